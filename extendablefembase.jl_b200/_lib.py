@@ -1,0 +1,268 @@
+"""ctypes binding of libfemb.so — one Python stub per ``ccall`` of julia/FEMBaseB200.jl.
+
+The product path fails loudly: if the shared library is missing or no B200 is usable,
+``load()`` / ``Context()`` raise; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libfemb.so")
+
+# enums of include/femb.h
+FAMILY = {"H1": 0, "Hdiv": 1, "L2": 2}
+OP_IDENTITY, OP_GRADIENT, OP_DIVERGENCE = 0, 1, 2
+RHS_NONE, RHS_AFFINE, RHS_QPVALUES, RHS_EX210 = 0, 1, 2, 3
+BIL_TRANSPOSE_COPY, BIL_SYMMETRIC_UPPER, BIL_NO_VOLUME = 1, 2, 4
+SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER = 0, 1, 2
+
+_i32, _i64, _f64 = C.c_int32, C.c_int64, C.c_double
+_p = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/femb.h declares
+SIGNATURES = {
+    "femb_version": (_i32, []),
+    "femb_create": (_i32, [_i32, C.POINTER(_p)]),
+    "femb_destroy": (_i32, [_p]),
+    "femb_last_error": (C.c_char_p, [_p]),
+    "femb_sync": (_i32, [_p]),
+    "femb_host_register": (_i32, [_p, _p, _i64]),
+    "femb_host_unregister": (_i32, [_p, _p]),
+    "femb_mesh_set": (_i32, [_p, _i32, _i64, _p, _i32, _i64, _p, _p]),
+    "femb_space_set": (_i32, [_p, _i32, _i32, _i32, _i64, _i32, _i32, _i32, _p, _p, _p]),
+    "femb_quadrature_set": (_i32, [_p, _i32, _p, _p]),
+    "femb_evaluator_set": (_i32, [_p, _i32, _i32, _i32, _p, _p]),
+    "femb_evaluator_eval": (_i32, [_p, _i32, _i64, _i64, _p]),
+    "femb_qp_coords": (_i32, [_p, _p]),
+    "femb_matrix_layout": (_i32, [_p, _i32, _p, _i32, _p]),
+    "femb_pattern_build": (_i32, [_p, _i32, _p, _p, _i64, _p, C.POINTER(_i64)]),
+    "femb_pattern_adopt": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i32, _p, _p]),
+    "femb_pattern_get": (_i32, [_p, _p, _p]),
+    "femb_pattern_compress": (_i32, [_p, C.POINTER(_i64)]),
+    "femb_pattern_track": (_i32, [_p, _i32]),
+    "femb_matrix_zero": (_i32, [_p]),
+    "femb_vector_zero": (_i32, [_p]),
+    "femb_matrix_get": (_i32, [_p, _p]),
+    "femb_matrix_add_to": (_i32, [_p, _p]),
+    "femb_vector_get": (_i32, [_p, _p]),
+    "femb_vector_set": (_i32, [_p, _i32, _p]),
+    "femb_set_scatter": (_i32, [_p, _i32]),
+    "femb_assemble_bilinear": (_i32, [_p, _i32, _i32, _i32, _i32, _f64, _i32, _f64]),
+    "femb_assemble_linear": (_i32, [_p, _i32, _i32, _f64, _i32, _p]),
+    "femb_assemble_poisson": (_i32, [_p, _i32, _i32, _f64, _i32, _p, _f64]),
+    "femb_assemble_navierstokes": (_i32, [_p, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _p]),
+    "femb_last_kernel_ms": (_i32, [_p, C.POINTER(C.c_float), C.POINTER(_i32)]),
+    "femb_launch_count": (_i64, [_p]),
+    "femb_device_ptr": (_p, [_p, _i32]),
+    "femb_comm_unique_id": (_i32, [C.c_char_p]),
+    "femb_comm_init": (_i32, [_p, _i32, _i32, C.c_char_p]),
+    "femb_comm_set_ghosts": (_i32, [_p, _i32, _p, _p, _p, _p]),
+    "femb_exchange": (_i32, [_p]),
+    "femb_comm_destroy": (_i32, [_p]),
+}
+
+_lib = None
+
+
+class FembError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libfemb status {status}: {msg}")
+        self.status = status
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """dlopen libfemb.so and bind every declared symbol (raises if one is missing)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIBPATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not found — run `python __graft_entry__.py build` (no CPU fallback exists)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_p)
+
+
+def _arr(a, dtype):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class Context:
+    """Owns one ``femb_ctx`` (one CUDA device)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _p()
+        st = self.lib.femb_create(device, C.byref(h))
+        if st != 0:
+            raise FembError(st, self.lib.femb_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.femb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, st):
+        if st != 0:
+            raise FembError(st, self.lib.femb_last_error(self.h).decode())
+
+    # ---- registration ---------------------------------------------------
+    def mesh_set(self, coords, cellnodes, cellvolumes=None):
+        coords = _arr(coords, np.float64)
+        cellnodes = _arr(cellnodes, np.int32)
+        cellvolumes = _arr(cellvolumes, np.float64)
+        nn, dim = coords.shape
+        nc, nnpc = cellnodes.shape
+        self._ck(self.lib.femb_mesh_set(self.h, dim, nn, _ptr(coords), nnpc, nc, _ptr(cellnodes), _ptr(cellvolumes)))
+        self.dim, self.ncells = dim, nc
+
+    def space_set(self, sid, family, ncomp, ndofs, nd, nd_all, handler, celldofs=None, signs=None, orient=None):
+        celldofs, signs, orient = _arr(celldofs, np.int32), _arr(signs, np.int32), _arr(orient, np.int32)
+        self._ck(self.lib.femb_space_set(self.h, sid, family, ncomp, ndofs, nd, nd_all, handler, _ptr(celldofs), _ptr(signs), _ptr(orient)))
+
+    def quadrature_set(self, xref, w):
+        xref, w = _arr(xref, np.float64), _arr(w, np.float64)
+        self._ck(self.lib.femb_quadrature_set(self.h, w.shape[0], _ptr(xref), _ptr(w)))
+
+    def evaluator_set(self, eid, sid, op, refvals=None, refderivs=None):
+        refvals, refderivs = _arr(refvals, np.float64), _arr(refderivs, np.float64)
+        self._ck(self.lib.femb_evaluator_set(self.h, eid, sid, op, _ptr(refvals), _ptr(refderivs)))
+
+    def evaluator_eval(self, eid, c0, c1, nqp, nd, resultdim):
+        out = np.empty((c1 - c0, nqp, nd, resultdim), dtype=np.float64)
+        self._ck(self.lib.femb_evaluator_eval(self.h, eid, c0, c1, _ptr(out)))
+        return out
+
+    def qp_coords(self, nqp):
+        out = np.empty((self.ncells, nqp, self.dim), dtype=np.float64)
+        self._ck(self.lib.femb_qp_coords(self.h, _ptr(out)))
+        return out
+
+    # ---- pattern --------------------------------------------------------
+    def matrix_layout(self, row_spaces, col_spaces):
+        r, c = np.asarray(row_spaces, np.int32), np.asarray(col_spaces, np.int32)
+        self._ck(self.lib.femb_matrix_layout(self.h, r.shape[0], _ptr(r), c.shape[0], _ptr(c)))
+        self._nrs, self._ncs = r.shape[0], c.shape[0]
+
+    def pattern_build(self, blocks, extra_diag=None) -> int:
+        br = np.asarray([b[0] for b in blocks], np.int32)
+        bc = np.asarray([b[1] for b in blocks], np.int32)
+        ex = None if extra_diag is None else np.ascontiguousarray(extra_diag, dtype=np.int64)
+        nnz = _i64(0)
+        self._ck(self.lib.femb_pattern_build(self.h, br.shape[0], _ptr(br), _ptr(bc), 0 if ex is None else ex.shape[0], _ptr(ex), C.byref(nnz)))
+        self.nnz = nnz.value
+        return self.nnz
+
+    def pattern_adopt(self, nrows, ncols, colptr, rowval, blocks):
+        colptr, rowval = _arr(colptr, np.int64), _arr(rowval, np.int64)
+        br = np.asarray([b[0] for b in blocks], np.int32)
+        bc = np.asarray([b[1] for b in blocks], np.int32)
+        self.nnz = int(colptr[-1] - 1)
+        self._ck(self.lib.femb_pattern_adopt(self.h, nrows, ncols, self.nnz, _ptr(colptr), _ptr(rowval), br.shape[0], _ptr(br), _ptr(bc)))
+
+    def pattern_get(self, ncols):
+        colptr = np.empty(ncols + 1, dtype=np.int64)
+        rowval = np.empty(self.nnz, dtype=np.int64)
+        self._ck(self.lib.femb_pattern_get(self.h, _ptr(colptr), _ptr(rowval)))
+        return colptr, rowval
+
+    def pattern_track(self, enable=True):
+        self._ck(self.lib.femb_pattern_track(self.h, 1 if enable else 0))
+
+    def pattern_compress(self) -> int:
+        nnz = _i64(0)
+        self._ck(self.lib.femb_pattern_compress(self.h, C.byref(nnz)))
+        self.nnz = nnz.value
+        return self.nnz
+
+    # ---- values ---------------------------------------------------------
+    def matrix_zero(self):
+        self._ck(self.lib.femb_matrix_zero(self.h))
+
+    def vector_zero(self):
+        self._ck(self.lib.femb_vector_zero(self.h))
+
+    def matrix_get(self, out=None):
+        out = np.empty(self.nnz, dtype=np.float64) if out is None else out
+        self._ck(self.lib.femb_matrix_get(self.h, _ptr(out)))
+        return out
+
+    def matrix_add_to(self, inout):
+        self._ck(self.lib.femb_matrix_add_to(self.h, _ptr(inout)))
+
+    def vector_get(self, n=None, out=None):
+        out = np.empty(n, dtype=np.float64) if out is None else out
+        self._ck(self.lib.femb_vector_get(self.h, _ptr(out)))
+        return out
+
+    def vector_set(self, which, v):
+        v = _arr(v, np.float64)
+        self._ck(self.lib.femb_vector_set(self.h, which, _ptr(v)))
+
+    def set_scatter(self, policy):
+        self._ck(self.lib.femb_set_scatter(self.h, policy))
+
+    def sync(self):
+        self._ck(self.lib.femb_sync(self.h))
+
+    def host_register(self, a: np.ndarray):
+        self._ck(self.lib.femb_host_register(self.h, _ptr(a), a.nbytes))
+
+    def host_unregister(self, a: np.ndarray):
+        self._ck(self.lib.femb_host_unregister(self.h, _ptr(a)))
+
+    # ---- assembly -------------------------------------------------------
+    def assemble_bilinear(self, er, ec, brow, bcol, factor=1.0, flags=0, drop_tol=0.0):
+        self._ck(self.lib.femb_assemble_bilinear(self.h, er, ec, brow, bcol, factor, flags, drop_tol))
+
+    def assemble_linear(self, ev, brow, factor, rhs_kind, data):
+        data = _arr(data, np.float64)
+        self._ck(self.lib.femb_assemble_linear(self.h, ev, brow, factor, rhs_kind, _ptr(data)))
+
+    def assemble_poisson(self, eg, ei, mu, rhs_kind, data, drop_tol):
+        data = _arr(data, np.float64)
+        self._ck(self.lib.femb_assemble_poisson(self.h, eg, ei, mu, rhs_kind, _ptr(data), drop_tol))
+
+    def assemble_navierstokes(self, egu, eiu, eip, mu, linear, nonlinear, rhs_kind, data):
+        data = _arr(data, np.float64)
+        self._ck(self.lib.femb_assemble_navierstokes(self.h, egu, eiu, eip, mu, int(linear), int(nonlinear), rhs_kind, _ptr(data)))
+
+    def last_kernel_ms(self):
+        ms, n = C.c_float(0), _i32(0)
+        self._ck(self.lib.femb_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.femb_launch_count(self.h))
+
+    def device_ptr(self, which) -> int:
+        return self.lib.femb_device_ptr(self.h, which) or 0

@@ -1,0 +1,747 @@
+// Numeric phase: the five stages of the reference's cell loop, batched over all cells.
+//   stage 1  affine map / determinant          (L2GTransformer; feevaluator.jl:344-363)
+//   stage 2  push-forward / Piola               (feevaluator_h1.jl, feevaluator_hdiv.jl)
+//   stage 3  quadrature-weighted contraction    (Example200:139-146, Example210:284-301,322-355)
+//   stage 4  scatter into the CSC image         (Example200:149-161, Example210:368-382)
+//   stage 5  right-hand side                    (Example200:165-178, Example210:304-318,358-363)
+#include <algorithm>
+
+#include "femb_device.cuh"
+#include "femb_internal.h"
+
+// ---------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------
+int femb_timer_begin(femb_ctx* ctx) {
+    ctx->last_launches = 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return FEMB_OK;
+}
+int femb_timer_end(femb_ctx* ctx) {
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return FEMB_OK;
+}
+
+static SpaceDev space_dev(const FembSpace& s) {
+    SpaceDev d;
+    d.family = s.family; d.ncomp = s.ncomp; d.nd = s.nd; d.nd_all = s.nd_all; d.handler = s.handler; d.nsign = s.nsign;
+    d.celldofs = s.celldofs; d.signs = s.signs; d.orient = s.orient;
+    return d;
+}
+
+// apply the lazy zeroing requested by femb_matrix_zero / femb_vector_zero for kernels that accumulate
+int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec) {
+    if (mat && ctx->zero_pending_A) {
+        if (ctx->nzval) CUDA_TRY(ctx, cudaMemsetAsync(ctx->nzval, 0, sizeof(double) * ctx->nnz, ctx->stream));
+        ctx->zero_pending_A = false;
+    }
+    if (vec && ctx->zero_pending_b) {
+        if (ctx->bvec) CUDA_TRY(ctx, cudaMemsetAsync(ctx->bvec, 0, sizeof(double) * ctx->nrows, ctx->stream));
+        ctx->zero_pending_b = false;
+    }
+    return FEMB_OK;
+}
+
+static int make_rhs(femb_ctx* ctx, int kind, const double* p, int ncomp, int nqp, RhsDev& r, double** dev_fvals) {
+    r.kind = kind;
+    r.ncomp = ncomp;
+    r.fvals = nullptr;
+    *dev_fvals = nullptr;
+    for (double& v : r.p) v = 0.0;
+    if (kind == FEMB_RHS_NONE) return FEMB_OK;
+    if (!p) return femb_fail(ctx, FEMB_ERR_ARG, "rhs data pointer is NULL");
+    if (kind == FEMB_RHS_AFFINE) {
+        int n = ncomp * (ctx->dim + 1);
+        if (n > 16) return femb_fail(ctx, FEMB_ERR_ARG, "too many affine rhs coefficients");
+        for (int i = 0; i < n; i++) r.p[i] = p[i];
+    } else if (kind == FEMB_RHS_EX210) {
+        if (ctx->dim != 2 || ncomp != 2) return femb_fail(ctx, FEMB_ERR_ARG, "FEMB_RHS_EX210 is the 2-D two-component f! of Example210");
+        r.p[0] = p[0];
+        r.p[1] = p[1];
+    } else if (kind == FEMB_RHS_QPVALUES) {
+        size_t n = (size_t)ctx->ncells * nqp * ncomp;
+        FEMB_TRY(femb_alloc(ctx, dev_fvals, n));
+        FEMB_TRY(femb_h2d(ctx, *dev_fvals, p, n));
+        r.fvals = *dev_fvals;
+    } else {
+        return femb_fail(ctx, FEMB_ERR_ARG, "unknown rhs kind %d", kind);
+    }
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batched update_basis! and quadrature-point coordinates (parity probes for stages 1-2)
+// ---------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_eval_basis(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
+                             SpaceDev s, int op, int R, int nqp, const double* __restrict__ rv, const double* __restrict__ rd, int64_t c0, int64_t c1,
+                             double* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t per = (int64_t)nqp * s.nd;
+    if (t >= (c1 - c0) * per) return;
+    int64_t cl = t / per;
+    int rem = (int)(t - cl * per);
+    int qp = rem / s.nd, dof = rem - qp * s.nd;
+    Geo<DIM> g;
+    load_geo<DIM>(coords, cellnodes, cellvol, c0 + cl, g);
+    double v[9];
+    for (int r = 0; r < R; r++) v[r] = 0.0;
+    eval_op<DIM>(s, op, g, c0 + cl, dof, qp, rv, rd, v);
+    for (int r = 0; r < R; r++) out[t * R + r] = v[r];
+}
+
+struct QuadDev {
+    int nqp;
+    double xref[FEMB_MAX_QP * 3];
+    double w[FEMB_MAX_QP];
+};
+
+template <int DIM>
+__global__ void k_qp_coords(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, int64_t ncells, QuadDev q, double* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ncells * q.nqp) return;
+    int64_t cell = t / q.nqp;
+    int qp = (int)(t - cell * q.nqp);
+    Geo<DIM> g;
+    load_geo<DIM>(coords, cellnodes, nullptr, cell, g);
+    double x[DIM];
+    eval_trafo<DIM>(g, q.xref + qp * DIM, x);
+    for (int d = 0; d < DIM; d++) out[t * DIM + d] = x[d];
+}
+
+static QuadDev quad_dev(const FembEval& e, int dim) {
+    QuadDev q;
+    q.nqp = e.nqp;
+    for (int i = 0; i < e.nqp * dim; i++) q.xref[i] = e.xref[i];
+    for (int i = 0; i < e.nqp; i++) q.w[i] = e.w[i];
+    return q;
+}
+
+extern "C" int32_t femb_evaluator_eval(femb_ctx* ctx, int32_t id, int64_t c0, int64_t c1, double* out) {
+    FEMB_CHECK_CTX(ctx);
+    if (id < 0 || id >= FEMB_MAX_EVALS || !ctx->evals[id].set) return femb_fail(ctx, FEMB_ERR_ARG, "unknown evaluator");
+    if (c0 < 0 || c1 > ctx->ncells || c0 > c1 || !out) return femb_fail(ctx, FEMB_ERR_ARG, "bad cell range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const FembEval& e = ctx->evals[id];
+    const FembSpace& s = ctx->spaces[e.space];
+    int64_t n = (c1 - c0) * e.nqp * s.nd;
+    if (n == 0) return FEMB_OK;
+    double* dout = nullptr;
+    FEMB_TRY(femb_alloc(ctx, &dout, (size_t)n * e.resultdim));
+    unsigned grid = (unsigned)((n + 127) / 128);
+    if (ctx->dim == 2)
+        k_eval_basis<2><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), e.op, e.resultdim, e.nqp, e.refvals, e.refderivs, c0, c1, dout);
+    else
+        k_eval_basis<3><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), e.op, e.resultdim, e.nqp, e.refvals, e.refderivs, c0, c1, dout);
+    ctx->launches++;
+    int st = femb_d2h(ctx, out, dout, (size_t)n * e.resultdim);
+    if (st == FEMB_OK) st = femb_sync(ctx);
+    cudaFree(dout);
+    return st;
+}
+
+extern "C" int32_t femb_qp_coords(femb_ctx* ctx, double* out) {
+    FEMB_CHECK_CTX(ctx);
+    if (!out || !ctx->nqp) return femb_fail(ctx, FEMB_ERR_ARG, "femb_qp_coords: quadrature not set");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    QuadDev q;
+    q.nqp = ctx->nqp;
+    for (int i = 0; i < ctx->nqp * ctx->dim; i++) q.xref[i] = ctx->xref[i];
+    int64_t n = ctx->ncells * ctx->nqp;
+    double* dout = nullptr;
+    FEMB_TRY(femb_alloc(ctx, &dout, (size_t)n * ctx->dim));
+    unsigned grid = (unsigned)((n + 127) / 128);
+    if (ctx->dim == 2) k_qp_coords<2><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->ncells, q, dout);
+    else k_qp_coords<3><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->ncells, q, dout);
+    ctx->launches++;
+    int st = femb_d2h(ctx, out, dout, (size_t)n * ctx->dim);
+    if (st == FEMB_OK) st = femb_sync(ctx);
+    cudaFree(dout);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic cell-parallel bilinear form: CTA = CPB cells; cvals staged in shared memory
+// ---------------------------------------------------------------------------------------------------
+struct BilArgs {
+    const double* coords;
+    const int32_t* cellnodes;
+    const double* cellvol;
+    int64_t ncells;
+    SpaceDev rs, cs;
+    int op_r, op_c, R, nqp, same;
+    const double *rv_r, *rd_r, *rv_c, *rd_c;
+    double w[FEMB_MAX_QP];
+    const int32_t* slots;    // [cell][ndr][ndc]
+    const int32_t* slots_t;  // [cell][ndc][ndr] (transpose block) or null
+    double* nzval;
+    uint8_t* touched;
+    int32_t* errflag;
+    double factor, drop_tol;
+    int flags, cpb;
+    const int32_t* perm;  // cell permutation (colouring) or null
+    int64_t p0, p1;       // range in perm / cells
+    int atomic;
+};
+
+__device__ __forceinline__ void scatter_add(double* nzval, uint8_t* touched, int32_t* errflag, int32_t slot, double v, int atomic) {
+    if (slot < 0) {
+        if (v != 0.0) atomicAdd(errflag, 1);
+        return;
+    }
+    if (atomic) atomicAdd(nzval + slot, v);
+    else nzval[slot] += v;
+    if (touched) touched[slot] = 1;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_bilinear(BilArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Geo<DIM>* geo = reinterpret_cast<Geo<DIM>*>(smem_raw);
+    double* rowv = reinterpret_cast<double*>(geo + a.cpb);
+    const int ndr = a.rs.nd, ndc = a.cs.nd;
+    const int per_r = a.nqp * a.R * ndr, per_c = a.nqp * a.R * ndc;
+    double* colv = a.same ? rowv : rowv + (size_t)a.cpb * per_r;
+    const int64_t base = a.p0 + (int64_t)blockIdx.x * a.cpb;
+    const int ncl = (int)min((int64_t)a.cpb, a.p1 - base);
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    for (int cl = tid; cl < ncl; cl += nt) {
+        int64_t cell = a.perm ? a.perm[base + cl] : base + cl;
+        load_geo<DIM>(a.coords, a.cellnodes, a.cellvol, cell, geo[cl]);
+    }
+    __syncthreads();
+    for (int i = tid; i < ncl * a.nqp * ndr; i += nt) {
+        int cl = i / (a.nqp * ndr), rem = i - cl * (a.nqp * ndr);
+        int qp = rem / ndr, dof = rem - qp * ndr;
+        int64_t cell = a.perm ? a.perm[base + cl] : base + cl;
+        double v[9];
+        eval_op<DIM>(a.rs, a.op_r, geo[cl], cell, dof, qp, a.rv_r, a.rd_r, v);
+        for (int r = 0; r < a.R; r++) rowv[(size_t)cl * per_r + (qp * a.R + r) * ndr + dof] = v[r];
+    }
+    if (!a.same) {
+        for (int i = tid; i < ncl * a.nqp * ndc; i += nt) {
+            int cl = i / (a.nqp * ndc), rem = i - cl * (a.nqp * ndc);
+            int qp = rem / ndc, dof = rem - qp * ndc;
+            int64_t cell = a.perm ? a.perm[base + cl] : base + cl;
+            double v[9];
+            eval_op<DIM>(a.cs, a.op_c, geo[cl], cell, dof, qp, a.rv_c, a.rd_c, v);
+            for (int r = 0; r < a.R; r++) colv[(size_t)cl * per_c + (qp * a.R + r) * ndc + dof] = v[r];
+        }
+    }
+    __syncthreads();
+    const int per = ndr * ndc;
+    const bool sym = a.flags & FEMB_BIL_SYMMETRIC_UPPER;
+    for (int i = tid; i < ncl * per; i += nt) {
+        int cl = i / per, jk = i - cl * per;
+        int j = jk / ndc, k = jk - j * ndc;
+        if (sym && j > k) continue;
+        int64_t cell = a.perm ? a.perm[base + cl] : base + cl;
+        const double* rp = rowv + (size_t)cl * per_r + j;
+        const double* cp = colv + (size_t)cl * per_c + k;
+        double temp = 0.0;
+        for (int qp = 0; qp < a.nqp; qp++) {
+            double d = 0.0;
+            for (int r = 0; r < a.R; r++) d += rp[(qp * a.R + r) * ndr] * cp[(qp * a.R + r) * ndc];
+            temp += a.w[qp] * d;
+        }
+        const double vol = (a.flags & FEMB_BIL_NO_VOLUME) ? 1.0 : geo[cl].vol;
+        double val = sym ? temp * (a.factor * vol) : (a.factor * temp) * vol;
+        if (sym && !(fabs(val) > a.drop_tol)) continue;
+        scatter_add(a.nzval, a.touched, a.errflag, a.slots[cell * per + jk], val, a.atomic);
+        if (sym && k > j) scatter_add(a.nzval, a.touched, a.errflag, a.slots[cell * per + k * ndc + j], val, a.atomic);
+        if (a.slots_t) scatter_add(a.nzval, a.touched, a.errflag, a.slots_t[cell * per + k * ndr + j], val, a.atomic);
+    }
+}
+
+static const FembBlock* find_block(const femb_ctx* ctx, int brow, int bcol) {
+    for (auto& b : ctx->blocks)
+        if (b.brow == brow && b.bcol == bcol) return &b;
+    return nullptr;
+}
+
+static int launch_bilinear(femb_ctx* ctx, int er, int ec, int op_r, int op_c, int brow, int bcol, double factor, int flags, double drop_tol) {
+    const FembEval& ER = ctx->evals[er];
+    const FembEval& EC = ctx->evals[ec];
+    const FembSpace& rs = ctx->spaces[ER.space];
+    const FembSpace& cs = ctx->spaces[EC.space];
+    if (brow < 0 || brow >= ctx->nrs || bcol < 0 || bcol >= ctx->ncs || ctx->row_spaces[brow] != ER.space || ctx->col_spaces[bcol] != EC.space)
+        return femb_fail(ctx, FEMB_ERR_ARG, "evaluator spaces do not match block (%d,%d)", brow, bcol);
+    const FembBlock* blk = find_block(ctx, brow, bcol);
+    if (!blk || !blk->slots) return femb_fail(ctx, FEMB_ERR_ARG, "block (%d,%d) is not part of the pattern", brow, bcol);
+    const FembBlock* blk_t = nullptr;
+    if (flags & FEMB_BIL_TRANSPOSE_COPY) {
+        // transposed block: row space list index of the column space and vice versa
+        int tr = -1, tc = -1;
+        for (int i = 0; i < ctx->nrs; i++) if (ctx->row_spaces[i] == EC.space) tr = i;
+        for (int i = 0; i < ctx->ncs; i++) if (ctx->col_spaces[i] == ER.space) tc = i;
+        blk_t = (tr >= 0 && tc >= 0) ? find_block(ctx, tr, tc) : nullptr;
+        if (!blk_t) return femb_fail(ctx, FEMB_ERR_ARG, "transposed block of (%d,%d) is not part of the pattern", brow, bcol);
+    }
+    int Rr = result_dim(op_r, ctx->dim, rs.ncomp), Rc = result_dim(op_c, ctx->dim, cs.ncomp);
+    if (Rr != Rc) return femb_fail(ctx, FEMB_ERR_ARG, "operator result lengths differ (%d vs %d)", Rr, Rc);
+    if (ER.nqp != EC.nqp) return femb_fail(ctx, FEMB_ERR_ARG, "evaluators use different quadrature rules");
+    if ((flags & FEMB_BIL_SYMMETRIC_UPPER) && (er != ec)) return femb_fail(ctx, FEMB_ERR_ARG, "SYMMETRIC_UPPER needs identical evaluators");
+    BilArgs a;
+    a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.ncells = ctx->ncells;
+    a.rs = space_dev(rs); a.cs = space_dev(cs);
+    a.op_r = op_r; a.op_c = op_c; a.R = Rr; a.nqp = ER.nqp; a.same = (er == ec && op_r == op_c);
+    a.rv_r = ER.refvals; a.rd_r = ER.refderivs; a.rv_c = EC.refvals; a.rd_c = EC.refderivs;
+    for (int i = 0; i < ER.nqp; i++) a.w[i] = ER.w[i];
+    a.slots = blk->slots; a.slots_t = blk_t ? blk_t->slots : nullptr;
+    a.nzval = ctx->nzval; a.touched = ctx->touched; a.errflag = ctx->errflag;
+    a.factor = factor; a.drop_tol = drop_tol; a.flags = flags;
+    size_t per_cell = ((size_t)a.nqp * a.R * rs.nd + (a.same ? 0 : (size_t)a.nqp * a.R * cs.nd)) * sizeof(double);
+    size_t geo_bytes = ctx->dim == 2 ? sizeof(Geo<2>) : sizeof(Geo<3>);
+    int cpb = (int)std::min<size_t>(32, (96 * 1024) / (per_cell + geo_bytes));
+    if (cpb < 1) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "local tables too large for shared memory");
+    a.cpb = cpb;
+    size_t smem = cpb * (per_cell + geo_bytes);
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    auto kern = ctx->dim == 2 ? k_bilinear<2> : k_bilinear<3>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->scatter == FEMB_SCATTER_COLORED) {
+        FEMB_TRY(femb_build_coloring(ctx));
+        a.perm = ctx->color_perm;
+        a.atomic = 0;
+        for (int c = 0; c < ctx->ncolors; c++) {
+            a.p0 = ctx->color_ptr[c];
+            a.p1 = ctx->color_ptr[c + 1];
+            if (a.p1 == a.p0) continue;
+            kern<<<(unsigned)((a.p1 - a.p0 + cpb - 1) / cpb), 128, smem, ctx->stream>>>(a);
+            KERNEL_CHECK(ctx);
+        }
+    } else {
+        a.perm = nullptr;
+        a.atomic = 1;
+        a.p0 = 0;
+        a.p1 = ctx->ncells;
+        if (ctx->ncells) {
+            kern<<<(unsigned)((ctx->ncells + cpb - 1) / cpb), 128, smem, ctx->stream>>>(a);
+            KERNEL_CHECK(ctx);
+        }
+    }
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// linear form: owner-computes gather over the dof -> cell adjacency (write-once, fixed order)
+// ---------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) k_linear_gather(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes,
+                                                       const double* __restrict__ cellvol, SpaceDev s, int op, int R, QuadDev q,
+                                                       const double* __restrict__ rv, const double* __restrict__ rd,
+                                                       const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj, int64_t ndofs,
+                                                       RhsDev rhs, double factor, double* __restrict__ b) {
+    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= ndofs) return;
+    double sum = 0.0;
+    for (int32_t e = adj_ptr[d]; e < adj_ptr[d + 1]; e++) {
+        uint32_t av = adj[e];
+        int64_t cell = av / (uint32_t)s.nd;
+        int k = (int)(av - cell * s.nd);
+        Geo<DIM> g;
+        load_geo<DIM>(coords, cellnodes, cellvol, cell, g);
+        double temp = 0.0;
+        for (int qp = 0; qp < q.nqp; qp++) {
+            double x[DIM], f[3], v[9];
+            eval_trafo<DIM>(g, q.xref + qp * DIM, x);
+            eval_rhs<DIM>(rhs, x, cell, qp, q.nqp, f);
+            eval_op<DIM>(s, op, g, cell, k, qp, rv, rd, v);
+            double dt = 0.0;
+            for (int r = 0; r < R; r++) dt += v[r] * f[r];
+            temp += q.w[qp] * dt;
+        }
+        sum += temp * g.vol;
+    }
+    b[d] += factor * sum;
+}
+
+static int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const RhsDev& rhs) {
+    const FembEval& E = ctx->evals[ev];
+    const FembSpace& s = ctx->spaces[E.space];
+    if (brow < 0 || brow >= ctx->nrs || ctx->row_spaces[brow] != E.space) return femb_fail(ctx, FEMB_ERR_ARG, "evaluator space does not match block row %d", brow);
+    if (E.resultdim != rhs.ncomp) return femb_fail(ctx, FEMB_ERR_ARG, "rhs has %d components, operator %d", rhs.ncomp, E.resultdim);
+    FEMB_TRY(femb_build_adjacency(ctx, E.space));
+    FEMB_TRY(femb_flush_zero(ctx, false, true));
+    unsigned grid = (unsigned)((s.ndofs + 127) / 128);
+    QuadDev q = quad_dev(E, ctx->dim);
+    if (ctx->dim == 2)
+        k_linear_gather<2><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, E.resultdim, q, E.refvals, E.refderivs,
+                                                          s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow]);
+    else
+        k_linear_gather<3><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, E.resultdim, q, E.refvals, E.refderivs,
+                                                          s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow]);
+    KERNEL_CHECK(ctx);
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused P1 Poisson, owner-computes by column (stages 1-5 in one kernel, write-once)
+// ---------------------------------------------------------------------------------------------------
+struct P1Tab {
+    int nqp;
+    double w[FEMB_MAX_QP];
+    double xref[FEMB_MAX_QP * 3];
+    double phi[FEMB_MAX_QP * 4];  // Identity table [qp][dof]
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_p1_poisson_gather(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes,
+                                                           const double* __restrict__ cellvol, const int32_t* __restrict__ adj_ptr,
+                                                           const uint2* __restrict__ gmap, const int64_t* __restrict__ colptr, int64_t ndofs,
+                                                           double* __restrict__ nzval, uint8_t* __restrict__ touched, double* __restrict__ bvec,
+                                                           int32_t* __restrict__ errflag, double mu, double drop_tol, RhsDev rhs, P1Tab tab,
+                                                           int acc_A, int acc_b) {
+    constexpr int ND = DIM + 1;
+    extern __shared__ double acc[];  // [maxlen][blockDim.x]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t c = blockIdx.x * (int64_t)nt + tid;
+    if (c >= ndofs) return;
+    const int64_t base = colptr[c] - 1;
+    const int len = (int)(colptr[c + 1] - 1 - base);
+    for (int i = 0; i < len; i++) acc[i * nt + tid] = 0.0;
+    unsigned long long mask = 0ull;
+    double bsum = 0.0;
+    const int e1 = adj_ptr[c + 1];
+    for (int e = adj_ptr[c]; e < e1; e++) {
+        const uint2 gm = __ldg(gmap + e);
+        const int64_t cell = gm.x;
+        const int k = (DIM == 2) ? (gm.y & 0xFF) : (gm.y & 3);
+        Geo<DIM> g;
+        load_geo<DIM>(coords, cellnodes, cellvol, cell, g);
+        // grad phi_0 = -sum_j M[:,j]; grad phi_i = M[:,i-1]   (feevaluator_h1.jl:69-72 with the P1 table)
+        double gr[ND][DIM];
+#pragma unroll
+        for (int kk = 0; kk < DIM; kk++) {
+            double s0 = 0.0;
+#pragma unroll
+            for (int j = 0; j < DIM; j++) {
+                s0 += g.M[kk][j] * -1.0;
+                gr[j + 1][kk] = g.M[kk][j];
+            }
+            gr[0][kk] = s0;
+        }
+        const double scale = mu * g.vol;
+#pragma unroll
+        for (int j = 0; j < ND; j++) {
+            // dot(grad_j, grad_k): select k without dynamic register indexing
+            double d = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < DIM; kk++) {
+                double gk = gr[0][kk];
+#pragma unroll
+                for (int m = 1; m < ND; m++) gk = (k == m) ? gr[m][kk] : gk;
+                d += gr[j][kk] * gk;
+            }
+            double temp = 0.0;
+            for (int qp = 0; qp < tab.nqp; qp++) temp += tab.w[qp] * d;
+            const double val = temp * scale;
+            if (fabs(val) > drop_tol) {
+                const unsigned pos = (DIM == 2) ? ((gm.y >> (8 * (j + 1))) & 0xFF) : ((gm.y >> (2 + 6 * j)) & 0x3F);
+                if (pos == ((DIM == 2) ? 0xFFu : 0x3Fu)) {
+                    atomicAdd(errflag, 1);
+                } else {
+                    acc[pos * nt + tid] += val;
+                    if (pos < 64) mask |= 1ull << pos;
+                }
+            }
+        }
+        if (rhs.kind != FEMB_RHS_NONE) {
+            double temp = 0.0;
+            for (int qp = 0; qp < tab.nqp; qp++) {
+                double x[DIM], f[3];
+                eval_trafo<DIM>(g, tab.xref + qp * DIM, x);
+                eval_rhs<DIM>(rhs, x, cell, qp, tab.nqp, f);
+                temp += tab.w[qp] * tab.phi[qp * ND + k] * f[0];
+            }
+            bsum += temp * g.vol;
+        }
+    }
+    if (acc_A) {
+        for (int i = 0; i < len; i++) nzval[base + i] += acc[i * nt + tid];
+    } else {
+        for (int i = 0; i < len; i++) nzval[base + i] = acc[i * nt + tid];
+    }
+    if (touched)
+        for (int i = 0; i < len; i++)
+            if ((mask >> i) & 1ull) touched[base + i] = 1;
+    if (rhs.kind != FEMB_RHS_NONE) {
+        if (acc_b) bvec[c] += bsum;
+        else bvec[c] = bsum;
+    }
+}
+
+static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
+    const FembEval& EG = ctx->evals[eg];
+    const FembSpace& s = ctx->spaces[EG.space];
+    P1Tab tab;
+    tab.nqp = EG.nqp;
+    const int ND = ctx->dim + 1;
+    std::vector<double> phi((size_t)EG.nqp * ND, 0.0);
+    if (rhs.kind != FEMB_RHS_NONE) {
+        const FembEval& EI = ctx->evals[ei];
+        if (EI.h_refvals.size() != phi.size()) return femb_fail(ctx, FEMB_ERR_ARG, "Identity table has the wrong size for P1");
+        phi = EI.h_refvals;
+    }
+    for (int i = 0; i < EG.nqp; i++) tab.w[i] = EG.w[i];
+    for (int i = 0; i < EG.nqp * ctx->dim; i++) tab.xref[i] = EG.xref[i];
+    for (int i = 0; i < EG.nqp * ND; i++) tab.phi[i] = phi[i];
+    int acc_A = ctx->zero_pending_A ? 0 : 1, acc_b = ctx->zero_pending_b ? 0 : 1;
+    ctx->zero_pending_A = false;
+    if (rhs.kind != FEMB_RHS_NONE) ctx->zero_pending_b = false;
+    const int nt = 128;
+    size_t smem = (size_t)std::max(1, ctx->max_collen) * nt * sizeof(double);
+    unsigned grid = (unsigned)((s.ndofs + nt - 1) / nt);
+    if (ctx->dim == 2) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_p1_poisson_gather<2><<<grid, nt, smem, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.adj_ptr, ctx->gmap, ctx->colptr, s.ndofs, ctx->nzval,
+                                                                ctx->touched, ctx->bvec, ctx->errflag, mu, drop_tol, rhs, tab, acc_A, acc_b);
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_p1_poisson_gather<3><<<grid, nt, smem, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.adj_ptr, ctx->gmap, ctx->colptr, s.ndofs, ctx->nzval,
+                                                                ctx->touched, ctx->bvec, ctx->errflag, mu, drop_tol, rhs, tab, acc_A, acc_b);
+    }
+    KERNEL_CHECK(ctx);
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Example210 convection (Newton linearisation), 2-D, two components   (Example210:322-365)
+// ---------------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const double* coords;
+    const int32_t* cellnodes;
+    const double* cellvol;
+    int64_t ncells;
+    SpaceDev us;
+    int nqp, cpb;
+    const double *rv, *rd;  // Identity / Gradient tables of the velocity space
+    double w[FEMB_MAX_QP];
+    const double* sol;
+    const int32_t* slots;  // (u,u) block
+    double* nzval;
+    uint8_t* touched;
+    int32_t* errflag;
+    double* b;  // velocity part of the rhs
+};
+
+__global__ void __launch_bounds__(128) k_convection2d(ConvArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Geo<2>* geo = reinterpret_cast<Geo<2>*>(smem_raw);
+    const int nd = a.us.nd, nq = a.nqp;
+    double* G = reinterpret_cast<double*>(geo + a.cpb);  // [cl][qp][4][nd]
+    double* I = G + (size_t)a.cpb * nq * 4 * nd;         // [cl][qp][2][nd]
+    double* T = I + (size_t)a.cpb * nq * 2 * nd;         // [cl][qp][2][nd]   tempV_j
+    double* IN = T + (size_t)a.cpb * nq * 2 * nd;        // [cl][qp][8]       input(6), rhs tempV(2)
+    const int64_t base = (int64_t)blockIdx.x * a.cpb;
+    const int ncl = (int)min((int64_t)a.cpb, a.ncells - base);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int cl = tid; cl < ncl; cl += nt) load_geo<2>(a.coords, a.cellnodes, a.cellvol, base + cl, geo[cl]);
+    __syncthreads();
+    for (int i = tid; i < ncl * nq * nd; i += nt) {
+        int cl = i / (nq * nd), rem = i - cl * (nq * nd);
+        int qp = rem / nd, dof = rem - qp * nd;
+        double v[4];
+        eval_op<2>(a.us, FEMB_OP_GRADIENT, geo[cl], base + cl, dof, qp, a.rv, a.rd, v);
+        for (int r = 0; r < 4; r++) G[((size_t)(cl * nq + qp) * 4 + r) * nd + dof] = v[r];
+        eval_op<2>(a.us, FEMB_OP_IDENTITY, geo[cl], base + cl, dof, qp, a.rv, a.rd, v);
+        for (int r = 0; r < 2; r++) I[((size_t)(cl * nq + qp) * 2 + r) * nd + dof] = v[r];
+    }
+    __syncthreads();
+    // input = (u_h, grad u_h) at every (cell, qp)   (Example210:324-333)
+    for (int i = tid; i < ncl * nq; i += nt) {
+        int cl = i / nq, qp = i - cl * nq;
+        double in[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < nd; j++) {
+            double sj = a.sol[a.us.celldofs[(base + cl) * nd + j] - 1];
+            for (int d = 0; d < 2; d++) in[d] += sj * I[((size_t)i * 2 + d) * nd + j];
+            for (int d = 0; d < 4; d++) in[2 + d] += sj * G[((size_t)i * 4 + d) * nd + j];
+        }
+        // value = (u.grad)u ; jac = [[g11,g12,u1,u2,0,0],[g21,g22,0,0,u1,u2]] ; tempV = jac*input - value
+        double val0 = in[0] * in[2] + in[1] * in[3];
+        double val1 = in[0] * in[4] + in[1] * in[5];
+        double t0 = in[2] * in[0] + in[3] * in[1] + in[0] * in[2] + in[1] * in[3];
+        double t1 = in[4] * in[0] + in[5] * in[1] + in[0] * in[4] + in[1] * in[5];
+        double* o = IN + (size_t)i * 8;
+        for (int d = 0; d < 6; d++) o[d] = in[d];
+        o[6] = t0 - val0;
+        o[7] = t1 - val1;
+    }
+    __syncthreads();
+    // tempV_j = jac * [phi_j; grad phi_j]   (Example210:339-350)
+    for (int i = tid; i < ncl * nq * nd; i += nt) {
+        int cq = i / nd, j = i - cq * nd;
+        const double* in = IN + (size_t)cq * 8;
+        const double i0 = I[((size_t)cq * 2 + 0) * nd + j], i1 = I[((size_t)cq * 2 + 1) * nd + j];
+        const double g0 = G[((size_t)cq * 4 + 0) * nd + j], g1 = G[((size_t)cq * 4 + 1) * nd + j];
+        const double g2 = G[((size_t)cq * 4 + 2) * nd + j], g3 = G[((size_t)cq * 4 + 3) * nd + j];
+        double t0 = 0.0, t1 = 0.0;
+        t0 += in[2] * i0; t1 += in[4] * i0;
+        t0 += in[3] * i1; t1 += in[5] * i1;
+        t0 += in[0] * g0; t1 += 0.0 * g0;
+        t0 += in[1] * g1; t1 += 0.0 * g1;
+        t0 += 0.0 * g2;   t1 += in[0] * g2;
+        t0 += 0.0 * g3;   t1 += in[1] * g3;
+        T[((size_t)cq * 2 + 0) * nd + j] = t0;
+        T[((size_t)cq * 2 + 1) * nd + j] = t1;
+    }
+    __syncthreads();
+    const int per = nd * nd;
+    for (int i = tid; i < ncl * per; i += nt) {
+        int cl = i / per, rc = i - cl * per;
+        int r = rc / nd, c = rc - r * nd;  // row = test function k, column = ansatz j
+        double s = 0.0;
+        for (int qp = 0; qp < nq; qp++) {
+            size_t cq = (size_t)cl * nq + qp;
+            double d = T[(cq * 2 + 0) * nd + c] * I[(cq * 2 + 0) * nd + r] + T[(cq * 2 + 1) * nd + c] * I[(cq * 2 + 1) * nd + r];
+            s += d * a.w[qp];
+        }
+        scatter_add(a.nzval, a.touched, a.errflag, a.slots[(base + cl) * per + rc], s * geo[cl].vol, 1);
+    }
+    for (int i = tid; i < ncl * nd; i += nt) {
+        int cl = i / nd, j = i - cl * nd;
+        double vol = geo[cl].vol;
+        double s = 0.0;
+        for (int qp = 0; qp < nq; qp++) {
+            size_t cq = (size_t)cl * nq + qp;
+            const double* in = IN + cq * 8;
+            s += (in[6] * I[(cq * 2 + 0) * nd + j] + in[7] * I[(cq * 2 + 1) * nd + j]) * a.w[qp] * vol;
+        }
+        atomicAdd(a.b + a.us.celldofs[(base + cl) * nd + j] - 1, s);
+    }
+}
+
+int femb_build_coloring(femb_ctx* ctx) {
+    return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "FEMB_SCATTER_COLORED is not built yet; use FEMB_SCATTER_ATOMIC or FEMB_SCATTER_GATHER");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI entry points
+// ---------------------------------------------------------------------------------------------------
+static int check_eval(femb_ctx* ctx, int id) {
+    if (id < 0 || id >= FEMB_MAX_EVALS || !ctx->evals[id].set) return femb_fail(ctx, FEMB_ERR_ARG, "unknown evaluator %d", id);
+    return FEMB_OK;
+}
+
+static int require_pattern(femb_ctx* ctx) {
+    if (!ctx->colptr || ctx->blocks.empty()) return femb_fail(ctx, FEMB_ERR_ARG, "no pattern: call femb_pattern_build or femb_pattern_adopt first");
+    return FEMB_OK;
+}
+
+extern "C" int32_t femb_assemble_bilinear(femb_ctx* ctx, int32_t er, int32_t ec, int32_t brow, int32_t bcol, double factor, int32_t flags,
+                                          double drop_tol) {
+    FEMB_CHECK_CTX(ctx);
+    FEMB_TRY(check_eval(ctx, er));
+    FEMB_TRY(check_eval(ctx, ec));
+    FEMB_TRY(require_pattern(ctx));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FEMB_TRY(femb_timer_begin(ctx));
+    FEMB_TRY(launch_bilinear(ctx, er, ec, ctx->evals[er].op, ctx->evals[ec].op, brow, bcol, factor, flags, drop_tol));
+    return femb_timer_end(ctx);
+}
+
+extern "C" int32_t femb_assemble_linear(femb_ctx* ctx, int32_t ev, int32_t brow, double factor, int32_t rhs_kind, const double* data) {
+    FEMB_CHECK_CTX(ctx);
+    FEMB_TRY(check_eval(ctx, ev));
+    if (!ctx->bvec) return femb_fail(ctx, FEMB_ERR_ARG, "femb_matrix_layout must precede femb_assemble_linear");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RhsDev rhs;
+    double* dev_f = nullptr;
+    FEMB_TRY(make_rhs(ctx, rhs_kind, data, ctx->evals[ev].resultdim, ctx->evals[ev].nqp, rhs, &dev_f));
+    int st = femb_timer_begin(ctx);
+    if (st == FEMB_OK && rhs_kind != FEMB_RHS_NONE) st = launch_linear(ctx, ev, brow, factor, rhs);
+    if (st == FEMB_OK) st = femb_timer_end(ctx);
+    cudaFree(dev_f);
+    return st;
+}
+
+extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, double mu, int32_t rhs_kind, const double* data, double drop_tol) {
+    FEMB_CHECK_CTX(ctx);
+    FEMB_TRY(check_eval(ctx, eg));
+    if (rhs_kind != FEMB_RHS_NONE) FEMB_TRY(check_eval(ctx, ei));
+    FEMB_TRY(require_pattern(ctx));
+    const FembEval& EG = ctx->evals[eg];
+    if (EG.op != FEMB_OP_GRADIENT) return femb_fail(ctx, FEMB_ERR_ARG, "eval_grad must be a Gradient evaluator");
+    if (rhs_kind != FEMB_RHS_NONE && (ctx->evals[ei].op != FEMB_OP_IDENTITY || ctx->evals[ei].space != EG.space || ctx->evals[ei].nqp != EG.nqp))
+        return femb_fail(ctx, FEMB_ERR_ARG, "eval_id must be the Identity evaluator of the same space and rule");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RhsDev rhs;
+    double* dev_f = nullptr;
+    FEMB_TRY(make_rhs(ctx, rhs_kind, data, ctx->spaces[EG.space].ncomp, EG.nqp, rhs, &dev_f));
+    int st = femb_timer_begin(ctx);
+    if (st == FEMB_OK) {
+        if (ctx->scatter == FEMB_SCATTER_GATHER && ctx->gmap && ctx->gmap_space == EG.space && (!ctx->touched || ctx->max_collen <= 64)) {
+            st = launch_p1_gather(ctx, eg, ei, mu, rhs, drop_tol);
+        } else {
+            st = launch_bilinear(ctx, eg, eg, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, FEMB_BIL_SYMMETRIC_UPPER, drop_tol);
+            if (st == FEMB_OK && rhs_kind != FEMB_RHS_NONE) st = launch_linear(ctx, ei, 0, 1.0, rhs);
+        }
+    }
+    if (st == FEMB_OK) st = femb_timer_end(ctx);
+    cudaFree(dev_f);
+    return st;
+}
+
+extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_t eiu, int32_t eip, double mu, int32_t linear, int32_t nonlinear,
+                                              int32_t rhs_kind, const double* data) {
+    FEMB_CHECK_CTX(ctx);
+    FEMB_TRY(check_eval(ctx, egu));
+    FEMB_TRY(check_eval(ctx, eiu));
+    FEMB_TRY(check_eval(ctx, eip));
+    FEMB_TRY(require_pattern(ctx));
+    const FembEval& EG = ctx->evals[egu];
+    const FembEval& EI = ctx->evals[eiu];
+    const FembEval& EP = ctx->evals[eip];
+    const FembSpace& us = ctx->spaces[EG.space];
+    if (ctx->dim != 2 || us.ncomp != 2 || EG.op != FEMB_OP_GRADIENT || EI.op != FEMB_OP_IDENTITY || EP.op != FEMB_OP_IDENTITY || EI.space != EG.space)
+        return femb_fail(ctx, FEMB_ERR_ARG, "femb_assemble_navierstokes expects (Gradient u, Identity u, Identity p) of a 2-D two-component velocity space");
+    if (ctx->nrs != 2 || ctx->ncs != 2 || ctx->row_spaces[0] != EG.space || ctx->row_spaces[1] != EP.space || ctx->col_spaces[0] != EG.space ||
+        ctx->col_spaces[1] != EP.space)
+        return femb_fail(ctx, FEMB_ERR_ARG, "layout must be FEMatrix([FES_u, FES_p])");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RhsDev rhs;
+    double* dev_f = nullptr;
+    FEMB_TRY(make_rhs(ctx, linear ? rhs_kind : FEMB_RHS_NONE, data, 2, EG.nqp, rhs, &dev_f));
+    int st = femb_timer_begin(ctx);
+    if (st == FEMB_OK && linear) {
+        // Aloc[k,j] = mu * sum_qp w <grad_j, grad_k>, then * |T|                 (Example210:284-290,368)
+        st = launch_bilinear(ctx, egu, egu, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, 0, 0.0);
+        // Bloc[j,k] = -sum_qp w (g[1,j]+g[4,j]) psi_k * |T| into (u,p) and (p,u) (Example210:293-301,376-380)
+        if (st == FEMB_OK) st = launch_bilinear(ctx, egu, eip, FEMB_OP_GRADTRACE, FEMB_OP_IDENTITY, 0, 1, -1.0, FEMB_BIL_TRANSPOSE_COPY, 0.0);
+        if (st == FEMB_OK && rhs.kind != FEMB_RHS_NONE) st = launch_linear(ctx, eiu, 0, 1.0, rhs);
+    }
+    if (st == FEMB_OK && nonlinear) {
+        const FembBlock* blk = find_block(ctx, 0, 0);
+        if (!blk || !blk->slots) st = femb_fail(ctx, FEMB_ERR_ARG, "(u,u) block missing from the pattern");
+        if (st == FEMB_OK) st = femb_flush_zero(ctx, true, true);
+        if (st == FEMB_OK) {
+            ConvArgs a;
+            a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.ncells = ctx->ncells;
+            a.us = space_dev(us); a.nqp = EG.nqp; a.rv = EI.refvals; a.rd = EG.refderivs;
+            for (int i = 0; i < EG.nqp; i++) a.w[i] = EG.w[i];
+            a.sol = ctx->sol; a.slots = blk->slots; a.nzval = ctx->nzval; a.touched = ctx->touched; a.errflag = ctx->errflag; a.b = ctx->bvec;
+            size_t per_cell = ((size_t)EG.nqp * 8 * us.nd + (size_t)EG.nqp * 8) * sizeof(double) + sizeof(Geo<2>);
+            int cpb = (int)std::min<size_t>(16, (160 * 1024) / per_cell);
+            if (cpb < 1) st = femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "convection tables too large for shared memory");
+            if (st == FEMB_OK) {
+                a.cpb = cpb;
+                size_t smem = cpb * per_cell;
+                cudaError_t e = cudaFuncSetAttribute(k_convection2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) st = femb_fail(ctx, FEMB_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                if (st == FEMB_OK && ctx->ncells) {
+                    k_convection2d<<<(unsigned)((ctx->ncells + cpb - 1) / cpb), 128, smem, ctx->stream>>>(a);
+                    ctx->launches++;
+                    ctx->last_launches++;
+                    e = cudaGetLastError();
+                    if (e != cudaSuccess) st = femb_fail(ctx, FEMB_ERR_CUDA, "k_convection2d: %s", cudaGetErrorString(e));
+                }
+            }
+        }
+    }
+    if (st == FEMB_OK) st = femb_timer_end(ctx);
+    cudaFree(dev_f);
+    return st;
+}

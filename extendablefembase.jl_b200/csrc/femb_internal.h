@@ -1,0 +1,196 @@
+// Internal state of libfemb (not part of the C ABI; see include/femb.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "femb.h"
+
+#define FEMB_MAX_SPACES 8
+#define FEMB_MAX_EVALS 16
+#define FEMB_MAX_QP 32
+#define FEMB_MAX_BLOCKS 16
+
+// extra operator codes used internally by femb_assemble_navierstokes
+#define FEMB_OP_GRADTRACE 3   // g[1] + g[4] of the Gradient (Example210:296)
+#define FEMB_OP_CONVECTION 4  // J(u_h) * [phi; grad phi]  (Example210:339-350)
+
+struct FembSpace {
+    bool set = false;
+    int family = 0, ncomp = 0, nd = 0, nd_all = 0, handler = 0;
+    int64_t ndofs = 0;
+    int32_t* celldofs = nullptr;  // device, nd x ncells, 1-based (may alias mesh.cellnodes)
+    bool celldofs_owned = false;
+    int32_t* signs = nullptr;     // device
+    int32_t* orient = nullptr;    // device
+    int nsign = 0;                // rows of signs (faces or edges per cell)
+    // dof -> (cell, local index) adjacency, sorted by (dof, cell): adj[e] = cell*nd + k
+    int32_t* adj_ptr = nullptr;   // ndofs+1
+    uint32_t* adj = nullptr;      // ncells*nd
+    int max_deg = 0;
+};
+
+struct FembEval {
+    bool set = false;
+    int space = -1, op = 0, nqp = 0, resultdim = 0;
+    double* refvals = nullptr;    // device [nqp][nd_all][ncomp]
+    double* refderivs = nullptr;  // device [nqp][nd_all][ncomp][dim]
+    std::vector<double> h_refvals; // host copy (P1 gather kernel takes the Identity table by value)
+    double xref[FEMB_MAX_QP * 3];
+    double w[FEMB_MAX_QP];
+};
+
+struct FembBlock {
+    int brow = 0, bcol = 0;       // indices into layout row/col space lists
+    int32_t* slots = nullptr;     // device [ncells][ndr][ndc] -> 0-based nz index, -1 = absent
+};
+
+struct femb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int last_launches = 0;
+    float last_ms = 0.f;
+    int scatter = FEMB_SCATTER_GATHER;
+    int sm_count = 148;
+
+    // mesh
+    int dim = 0, nnpc = 0;
+    int64_t nnodes = 0, ncells = 0;
+    double* coords = nullptr;     // dim x nnodes
+    int32_t* cellnodes = nullptr; // nnpc x ncells
+    double* cellvol = nullptr;    // ncells or null
+
+    FembSpace spaces[FEMB_MAX_SPACES];
+    FembEval evals[FEMB_MAX_EVALS];
+
+    // quadrature
+    int nqp = 0;
+    double xref[FEMB_MAX_QP * 3];
+    double w[FEMB_MAX_QP];
+
+    // layout
+    int nrs = 0, ncs = 0;
+    int row_spaces[FEMB_MAX_SPACES], col_spaces[FEMB_MAX_SPACES];
+    int64_t row_off[FEMB_MAX_SPACES + 1], col_off[FEMB_MAX_SPACES + 1];
+    int64_t nrows = 0, ncols = 0;
+
+    // pattern (device, 1-based int64 like Julia)
+    int64_t nnz = 0;
+    int64_t* colptr = nullptr;
+    int64_t* rowval = nullptr;
+    int max_collen = 0;
+    std::vector<FembBlock> blocks;
+    std::vector<int64_t> extra_diag;
+    // P1 gather map: per adjacency entry of the (single) space: packed (cell, k, pos[])
+    uint2* gmap = nullptr;
+    int gmap_space = -1;
+
+    double* nzval = nullptr;      // nnz
+    bool zero_pending_A = false;  // femb_matrix_zero is lazy: write-once kernels skip the memset
+    bool zero_pending_b = false;
+    uint8_t* touched = nullptr;   // nnz (only when tracking)
+    bool track = false;
+    double* bvec = nullptr;       // nrows
+    double* sol = nullptr;        // ncols (current solution)
+    int32_t* errflag = nullptr;   // device int: contributions that found no slot
+
+    // colouring of cells (FEMB_SCATTER_COLORED)
+    int ncolors = 0;
+    int32_t* color_perm = nullptr;          // cells sorted by colour
+    std::vector<int64_t> color_ptr;
+
+    // pinned staging
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    // NCCL
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+    std::vector<int> peers;
+    std::vector<int64_t> ghost_ptr;
+    int64_t* ghost_local = nullptr;   // device
+    int64_t* ghost_remote = nullptr;  // device (remote column ids we will RECEIVE contributions for)
+    std::vector<int64_t> recv_ptr;
+    double* sendbuf = nullptr;
+    double* recvbuf = nullptr;
+    int64_t* send_slots = nullptr;
+    int64_t* recv_slots = nullptr;
+    int64_t nsend = 0, nrecv = 0;
+    std::vector<int64_t> send_off, recv_off;
+};
+
+int femb_fail(femb_ctx* ctx, int code, const char* fmt, ...);
+
+#define FEMB_CHECK_CTX(ctx) \
+    do {                    \
+        if (!(ctx)) return FEMB_ERR_ARG; \
+    } while (0)
+
+#define CUDA_TRY(ctx, expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return femb_fail((ctx), FEMB_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                             cudaGetErrorString(_e));                                            \
+    } while (0)
+
+#define FEMB_TRY(expr)              \
+    do {                            \
+        int _s = (expr);            \
+        if (_s != FEMB_OK) return _s; \
+    } while (0)
+
+// after a kernel launch
+#define KERNEL_CHECK(ctx)                          \
+    do {                                           \
+        (ctx)->launches++;                         \
+        (ctx)->last_launches++;                    \
+        CUDA_TRY((ctx), cudaGetLastError());       \
+    } while (0)
+
+template <typename T>
+static inline int femb_alloc(femb_ctx* ctx, T** p, size_t n) {
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (n == 0) return FEMB_OK;
+    CUDA_TRY(ctx, cudaMalloc((void**)p, n * sizeof(T)));
+    return FEMB_OK;
+}
+
+template <typename T>
+static inline void femb_free(T** p) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+}
+
+// host -> device copy of n elements through the ctx stream (pageable or registered memory)
+template <typename T>
+static inline int femb_h2d(femb_ctx* ctx, T* dst, const T* src, size_t n) {
+    if (n == 0) return FEMB_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return FEMB_OK;
+}
+template <typename T>
+static inline int femb_d2h(femb_ctx* ctx, T* dst, const T* src, size_t n) {
+    if (n == 0) return FEMB_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return FEMB_OK;
+}
+
+// pattern.cu
+int femb_build_adjacency(femb_ctx* ctx, int space_id);
+int femb_build_slotmaps(femb_ctx* ctx);
+int femb_build_gmap(femb_ctx* ctx);
+void femb_free_pattern(femb_ctx* ctx);
+// assemble.cu
+int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec);
+int femb_build_coloring(femb_ctx* ctx);
+int femb_timer_begin(femb_ctx* ctx);
+int femb_timer_end(femb_ctx* ctx);

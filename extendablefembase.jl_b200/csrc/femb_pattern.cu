@@ -1,0 +1,557 @@
+// Symbolic phase: dof->cell adjacency, CSC pattern of the FEMatrix, cell->slot maps, P1 gather map.
+// Replaces what the reference gets from ExtendableSparse's linked-list insert + flush!
+// (call sites Example200:155-157,182; Example210:373-379,391; fematrix.jl:108-118).
+// Sort / scan / select primitives come from CUB (shipped with the CUDA toolkit); this phase runs
+// once per mesh, the numeric kernels in femb_assemble.cu run every assembly.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+#include "femb_internal.h"
+
+void femb_free_pattern(femb_ctx* ctx) {
+    femb_free(&ctx->colptr);
+    femb_free(&ctx->rowval);
+    femb_free(&ctx->nzval);
+    femb_free(&ctx->touched);
+    femb_free(&ctx->gmap);
+    ctx->gmap_space = -1;
+    for (auto& b : ctx->blocks) femb_free(&b.slots);
+    ctx->blocks.clear();
+    ctx->nnz = 0;
+    ctx->max_collen = 0;
+    femb_free(&ctx->color_perm);
+    ctx->ncolors = 0;
+    ctx->color_ptr.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dof -> (cell, local index) adjacency
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_adj_keys(const int32_t* __restrict__ celldofs, int64_t n, int32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = celldofs[i] - 1;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void k_adj_ptr(const int32_t* __restrict__ sorted_keys, int64_t n, int64_t ndofs, int32_t* __restrict__ adj_ptr, int* __restrict__ maxdeg) {
+    int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d > ndofs) return;
+    // lower_bound(sorted_keys, d)
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < (int32_t)d) lo = mid + 1;
+        else hi = mid;
+    }
+    adj_ptr[d] = (int32_t)lo;
+    if (d < ndofs) {
+        int64_t lo2 = lo, hi2 = n;
+        while (lo2 < hi2) {
+            int64_t mid = (lo2 + hi2) >> 1;
+            if (sorted_keys[mid] <= (int32_t)d) lo2 = mid + 1;
+            else hi2 = mid;
+        }
+        atomicMax(maxdeg, (int)(lo2 - lo));
+    }
+}
+
+int femb_build_adjacency(femb_ctx* ctx, int sid) {
+    FembSpace& s = ctx->spaces[sid];
+    if (s.adj_ptr) return FEMB_OK;
+    int64_t n = ctx->ncells * s.nd;
+    if (n >= ((int64_t)1 << 31)) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "ncells*nd_local >= 2^31: adjacency needs 64-bit packing");
+    int32_t *k0 = nullptr, *k1 = nullptr;
+    uint32_t* v0 = nullptr;
+    void* tmp = nullptr;
+    int* maxdeg = nullptr;
+    int st = FEMB_OK;
+    auto cleanup = [&]() {
+        cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(tmp); cudaFree(maxdeg);
+    };
+#define TRY_A(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return femb_fail(ctx, FEMB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    TRY_A(cudaMalloc(&k0, n * sizeof(int32_t)));
+    TRY_A(cudaMalloc(&k1, n * sizeof(int32_t)));
+    TRY_A(cudaMalloc(&v0, n * sizeof(uint32_t)));
+    if ((st = femb_alloc(ctx, &s.adj, (size_t)n)) != FEMB_OK) { cleanup(); return st; }
+    if ((st = femb_alloc(ctx, &s.adj_ptr, (size_t)s.ndofs + 1)) != FEMB_OK) { cleanup(); return st; }
+    TRY_A(cudaMalloc(&maxdeg, sizeof(int)));
+    TRY_A(cudaMemsetAsync(maxdeg, 0, sizeof(int), ctx->stream));
+    k_adj_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s.celldofs, n, k0, v0);
+    ctx->launches++;
+    int end_bit = 1;
+    while (((int64_t)1 << end_bit) < s.ndofs + 1 && end_bit < 31) end_bit++;
+    size_t tb = 0;
+    TRY_A(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, s.adj, (int)n, 0, end_bit, ctx->stream));
+    TRY_A(cudaMalloc(&tmp, tb));
+    TRY_A(cub::DeviceRadixSort::SortPairs(tmp, tb, k0, k1, v0, s.adj, (int)n, 0, end_bit, ctx->stream));  // stable: cells ascending per dof
+    k_adj_ptr<<<(unsigned)((s.ndofs + 1 + 255) / 256), 256, 0, ctx->stream>>>(k1, n, s.ndofs, s.adj_ptr, maxdeg);
+    ctx->launches += 2;
+    TRY_A(cudaMemcpyAsync(&s.max_deg, maxdeg, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY_A(cudaStreamSynchronize(ctx->stream));
+    TRY_A(cudaGetLastError());
+#undef TRY_A
+    cleanup();
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// structural pattern
+// ---------------------------------------------------------------------------------------------------
+struct RowSrc {
+    const int32_t* celldofs;
+    int nd;
+    int64_t off;
+};
+struct RowSrcList {
+    RowSrc s[FEMB_MAX_SPACES];
+    int n;
+    int total;  // sum of nd
+};
+
+// one thread per (adjacency entry of the chunk, candidate row): key = (dof - d0) * nrows + row
+__global__ void k_pattern_keys(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int nd_c, int64_t e0, int64_t ne,
+                               int64_t d0, int64_t d1, RowSrcList rows, int64_t nrows, int64_t* __restrict__ keys) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ne * rows.total) return;
+    int64_t e = t / rows.total;
+    int r = (int)(t - e * rows.total);
+    // dof of entry e0+e: upper_bound in adj_ptr[d0..d1]
+    int64_t lo = d0, hi = d1;
+    int32_t target = (int32_t)(e0 + e);
+    while (lo < hi) {
+        int64_t mid = (lo + hi + 1) >> 1;
+        if (adj_ptr[mid] <= target) lo = mid;
+        else hi = mid - 1;
+    }
+    int64_t cell = adj[e0 + e] / (uint32_t)nd_c;
+    int i = 0;
+    while (r >= rows.s[i].nd) {
+        r -= rows.s[i].nd;
+        i++;
+    }
+    int64_t row = rows.s[i].off + rows.s[i].celldofs[cell * rows.s[i].nd + r] - 1;
+    keys[t] = (lo - d0) * nrows + row;
+}
+
+__global__ void k_pattern_emit(const int64_t* __restrict__ ukeys, int64_t nu, int64_t nrows, int64_t col0, int64_t* __restrict__ rowval,
+                               unsigned long long* __restrict__ colcount) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nu) return;
+    int64_t k = ukeys[i];
+    int64_t c = k / nrows;
+    rowval[i] = k - c * nrows + 1;
+    atomicAdd(colcount + col0 + c, 1ULL);
+}
+
+__global__ void k_colptr_finish(const unsigned long long* __restrict__ scanned, int64_t ncols, int64_t nnz, int64_t* __restrict__ colptr,
+                                int* __restrict__ maxlen) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > ncols) return;
+    int64_t v = (c == ncols) ? nnz : (int64_t)scanned[c];
+    colptr[c] = v + 1;
+    if (c < ncols) {
+        int64_t nx = (c + 1 == ncols) ? nnz : (int64_t)scanned[c + 1];
+        atomicMax(maxlen, (int)(nx - v));
+    }
+}
+
+__global__ void k_max_collen(const int64_t* __restrict__ colptr, int64_t ncols, int* __restrict__ maxlen) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c < ncols) atomicMax(maxlen, (int)(colptr[c + 1] - colptr[c]));
+}
+
+static int set_blocks(femb_ctx* ctx, int nblocks, const int32_t* brows, const int32_t* bcols) {
+    if (nblocks <= 0 || nblocks > FEMB_MAX_BLOCKS || !brows || !bcols) return femb_fail(ctx, FEMB_ERR_ARG, "bad block list");
+    for (int b = 0; b < nblocks; b++) {
+        if (brows[b] < 0 || brows[b] >= ctx->nrs || bcols[b] < 0 || bcols[b] >= ctx->ncs) return femb_fail(ctx, FEMB_ERR_ARG, "block (%d,%d) outside the layout", brows[b], bcols[b]);
+        FembBlock blk;
+        blk.brow = brows[b];
+        blk.bcol = bcols[b];
+        ctx->blocks.push_back(blk);
+    }
+    return FEMB_OK;
+}
+
+static int finish_pattern(femb_ctx* ctx) {
+    FEMB_TRY(femb_alloc(ctx, &ctx->nzval, (size_t)ctx->nnz));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->nzval, 0, sizeof(double) * ctx->nnz, ctx->stream));
+    if (ctx->track) {
+        FEMB_TRY(femb_alloc(ctx, &ctx->touched, (size_t)ctx->nnz));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 0, ctx->nnz, ctx->stream));
+    }
+    for (int i = 0; i < ctx->ncs; i++) FEMB_TRY(femb_build_adjacency(ctx, ctx->col_spaces[i]));
+    for (int i = 0; i < ctx->nrs; i++) FEMB_TRY(femb_build_adjacency(ctx, ctx->row_spaces[i]));
+    FEMB_TRY(femb_build_slotmaps(ctx));
+    FEMB_TRY(femb_build_gmap(ctx));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FEMB_OK;
+}
+
+extern "C" int32_t femb_pattern_track(femb_ctx* ctx, int32_t enable) {
+    FEMB_CHECK_CTX(ctx);
+    ctx->track = enable != 0;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->track && ctx->nnz && !ctx->touched) {
+        FEMB_TRY(femb_alloc(ctx, &ctx->touched, (size_t)ctx->nnz));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 0, ctx->nnz, ctx->stream));
+    }
+    if (!ctx->track) femb_free(&ctx->touched);
+    return FEMB_OK;
+}
+
+extern "C" int32_t femb_pattern_build(femb_ctx* ctx, int32_t nblocks, const int32_t* brows, const int32_t* bcols, int64_t nextra,
+                                      const int64_t* extra, int64_t* nnz_out) {
+    FEMB_CHECK_CTX(ctx);
+    if (!ctx->nrs) return femb_fail(ctx, FEMB_ERR_ARG, "femb_matrix_layout must precede femb_pattern_build");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    femb_free_pattern(ctx);
+    FEMB_TRY(set_blocks(ctx, nblocks, brows, bcols));
+    ctx->extra_diag.assign(extra ? extra : nullptr, extra ? extra + nextra : nullptr);
+    std::sort(ctx->extra_diag.begin(), ctx->extra_diag.end());
+    const int64_t nrows = ctx->nrows, ncols = ctx->ncols;
+
+    unsigned long long* colcount = nullptr;
+    FEMB_TRY(femb_alloc(ctx, &colcount, (size_t)ncols + 1));
+    CUDA_TRY(ctx, cudaMemsetAsync(colcount, 0, sizeof(unsigned long long) * (ncols + 1), ctx->stream));
+
+    int64_t cap = 0, nnz = 0;
+    int64_t* rowval = nullptr;
+    int64_t *kin = nullptr, *kout = nullptr, *kuniq = nullptr, *nsel = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int64_t kcap = 0;
+    int st = FEMB_OK;
+    auto cleanup = [&]() {
+        cudaFree(colcount); cudaFree(kin); cudaFree(kout); cudaFree(kuniq); cudaFree(nsel); cudaFree(tmp);
+    };
+#define TRY_P(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); cudaFree(rowval); return femb_fail(ctx, FEMB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    TRY_P(cudaMalloc(&nsel, sizeof(int64_t)));
+    const int64_t budget = (int64_t)1 << 27;  // keys per chunk
+
+    for (int bc = 0; bc < ctx->ncs; bc++) {
+        int sid = ctx->col_spaces[bc];
+        FembSpace& cs = ctx->spaces[sid];
+        RowSrcList rows;
+        rows.n = 0;
+        rows.total = 0;
+        for (auto& b : ctx->blocks)
+            if (b.bcol == bc) {
+                FembSpace& rs = ctx->spaces[ctx->row_spaces[b.brow]];
+                rows.s[rows.n++] = RowSrc{rs.celldofs, rs.nd, ctx->row_off[b.brow]};
+                rows.total += rs.nd;
+            }
+        // extra diagonal entries falling into this column block
+        std::vector<int64_t> ex;
+        for (int64_t g : ctx->extra_diag)
+            if (g > ctx->col_off[bc] && g <= ctx->col_off[bc + 1]) ex.push_back(g - 1 - ctx->col_off[bc]);
+        if (rows.n == 0 && ex.empty()) continue;
+        if ((st = femb_build_adjacency(ctx, sid)) != FEMB_OK) { cleanup(); cudaFree(rowval); return st; }
+        int64_t total_keys = ctx->ncells * cs.nd * (int64_t)rows.total;
+        int nchunks = (int)std::max<int64_t>(1, (total_keys + budget - 1) / budget);
+        size_t exi = 0;
+        for (int ch = 0; ch < nchunks; ch++) {
+            int64_t d0 = cs.ndofs * ch / nchunks, d1 = cs.ndofs * (ch + 1) / nchunks;
+            if (d1 == d0) continue;
+            int32_t e01[2];
+            TRY_P(cudaMemcpyAsync(&e01[0], cs.adj_ptr + d0, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            TRY_P(cudaMemcpyAsync(&e01[1], cs.adj_ptr + d1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            TRY_P(cudaStreamSynchronize(ctx->stream));
+            int64_t e0 = e01[0], ne = e01[1] - e01[0];
+            std::vector<int64_t> exkeys;
+            while (exi < ex.size() && ex[exi] < d1) {
+                exkeys.push_back((ex[exi] - d0) * nrows + (ctx->col_off[bc] + ex[exi]));  // row == column (diagonal of a square layout)
+                exi++;
+            }
+            int64_t nk = ne * rows.total + (int64_t)exkeys.size();
+            if (nk == 0) continue;
+            if (nk > kcap) {
+                cudaFree(kin); cudaFree(kout); cudaFree(kuniq); cudaFree(tmp);
+                kin = kout = kuniq = nullptr; tmp = nullptr;
+                kcap = nk + nk / 8;
+                TRY_P(cudaMalloc(&kin, kcap * sizeof(int64_t)));
+                TRY_P(cudaMalloc(&kout, kcap * sizeof(int64_t)));
+                TRY_P(cudaMalloc(&kuniq, kcap * sizeof(int64_t)));
+                size_t t1 = 0, t2 = 0;
+                TRY_P(cub::DeviceRadixSort::SortKeys(nullptr, t1, kin, kout, kcap, 0, 64, ctx->stream));
+                TRY_P(cub::DeviceSelect::Unique(nullptr, t2, kout, kuniq, nsel, kcap, ctx->stream));
+                tmp_bytes = std::max(t1, t2);
+                TRY_P(cudaMalloc(&tmp, tmp_bytes));
+            }
+            if (ne * rows.total > 0) {
+                int64_t nt = ne * rows.total;
+                k_pattern_keys<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(cs.adj, cs.adj_ptr, cs.nd, e0, ne, d0, d1, rows, nrows, kin);
+                ctx->launches++;
+            }
+            if (!exkeys.empty())
+                TRY_P(cudaMemcpyAsync(kin + ne * rows.total, exkeys.data(), exkeys.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+            int end_bit = 1;
+            {
+                double maxkey = (double)(d1 - d0) * (double)nrows;
+                while (end_bit < 64 && (double)((uint64_t)1 << end_bit) <= maxkey) end_bit++;
+            }
+            size_t tb = tmp_bytes;
+            TRY_P(cub::DeviceRadixSort::SortKeys(tmp, tb, kin, kout, nk, 0, end_bit, ctx->stream));
+            tb = tmp_bytes;
+            TRY_P(cub::DeviceSelect::Unique(tmp, tb, kout, kuniq, nsel, nk, ctx->stream));
+            int64_t nu = 0;
+            TRY_P(cudaMemcpyAsync(&nu, nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            TRY_P(cudaStreamSynchronize(ctx->stream));
+            ctx->launches += 4;
+            if (nnz + nu > cap) {
+                int64_t ncap = std::max<int64_t>(nnz + nu, cap + cap / 2);
+                if (ch + 1 < nchunks || bc + 1 < ctx->ncs) ncap = std::max<int64_t>(ncap, (int64_t)((double)(nnz + nu) * 1.05 * nchunks / (ch + 1)));
+                int64_t* nr = nullptr;
+                TRY_P(cudaMalloc(&nr, ncap * sizeof(int64_t)));
+                if (nnz) TRY_P(cudaMemcpyAsync(nr, rowval, nnz * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+                TRY_P(cudaStreamSynchronize(ctx->stream));
+                cudaFree(rowval);
+                rowval = nr;
+                cap = ncap;
+            }
+            k_pattern_emit<<<(unsigned)((nu + 255) / 256), 256, 0, ctx->stream>>>(kuniq, nu, nrows, ctx->col_off[bc] + d0, rowval + nnz, colcount);
+            ctx->launches++;
+            nnz += nu;
+        }
+    }
+    // colptr = 1 + exclusive scan of the column counts
+    {
+        unsigned long long* scanned = nullptr;
+        TRY_P(cudaMalloc(&scanned, sizeof(unsigned long long) * (ncols + 1)));
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, colcount, scanned, (int64_t)ncols + 1, ctx->stream);
+        void* t2 = nullptr;
+        cudaMalloc(&t2, tb);
+        cub::DeviceScan::ExclusiveSum(t2, tb, colcount, scanned, (int64_t)ncols + 1, ctx->stream);
+        st = femb_alloc(ctx, &ctx->colptr, (size_t)ncols + 1);
+        int* maxlen = nullptr;
+        cudaMalloc(&maxlen, sizeof(int));
+        cudaMemsetAsync(maxlen, 0, sizeof(int), ctx->stream);
+        if (st == FEMB_OK) {
+            k_colptr_finish<<<(unsigned)((ncols + 1 + 255) / 256), 256, 0, ctx->stream>>>(scanned, ncols, nnz, ctx->colptr, maxlen);
+            ctx->launches += 2;
+            cudaMemcpyAsync(&ctx->max_collen, maxlen, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(scanned); cudaFree(t2); cudaFree(maxlen);
+        if (st != FEMB_OK) { cleanup(); cudaFree(rowval); return st; }
+        TRY_P(e);
+    }
+#undef TRY_P
+    cleanup();
+    ctx->rowval = rowval;
+    ctx->nnz = nnz;
+    if (nnz_out) *nnz_out = nnz;
+    return finish_pattern(ctx);
+}
+
+extern "C" int32_t femb_pattern_adopt(femb_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* colptr, const int64_t* rowval,
+                                      int32_t nblocks, const int32_t* brows, const int32_t* bcols) {
+    FEMB_CHECK_CTX(ctx);
+    if (!ctx->nrs) return femb_fail(ctx, FEMB_ERR_ARG, "femb_matrix_layout must precede femb_pattern_adopt");
+    if (nrows != ctx->nrows || ncols != ctx->ncols) return femb_fail(ctx, FEMB_ERR_ARG, "pattern is %lld x %lld but the layout is %lld x %lld", (long long)nrows, (long long)ncols, (long long)ctx->nrows, (long long)ctx->ncols);
+    if (!colptr || (!rowval && nnz) || colptr[0] != 1 || colptr[ncols] != nnz + 1) return femb_fail(ctx, FEMB_ERR_ARG, "colptr must be 1-based with colptr[end] == nnz+1");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    femb_free_pattern(ctx);
+    FEMB_TRY(set_blocks(ctx, nblocks, brows, bcols));
+    ctx->extra_diag.clear();
+    ctx->nnz = nnz;
+    FEMB_TRY(femb_alloc(ctx, &ctx->colptr, (size_t)ncols + 1));
+    FEMB_TRY(femb_alloc(ctx, &ctx->rowval, (size_t)nnz));
+    FEMB_TRY(femb_h2d(ctx, ctx->colptr, colptr, (size_t)ncols + 1));
+    FEMB_TRY(femb_h2d(ctx, ctx->rowval, rowval, (size_t)nnz));
+    int* maxlen = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&maxlen, sizeof(int)));
+    cudaMemsetAsync(maxlen, 0, sizeof(int), ctx->stream);
+    k_max_collen<<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(ctx->colptr, ncols, maxlen);
+    ctx->launches++;
+    cudaMemcpyAsync(&ctx->max_collen, maxlen, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(maxlen);
+    CUDA_TRY(ctx, e);
+    return finish_pattern(ctx);
+}
+
+extern "C" int32_t femb_pattern_get(femb_ctx* ctx, int64_t* colptr_out, int64_t* rowval_out) {
+    FEMB_CHECK_CTX(ctx);
+    if (!ctx->colptr) return femb_fail(ctx, FEMB_ERR_ARG, "no pattern");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (colptr_out) FEMB_TRY(femb_d2h(ctx, colptr_out, ctx->colptr, (size_t)ctx->ncols + 1));
+    if (rowval_out) FEMB_TRY(femb_d2h(ctx, rowval_out, ctx->rowval, (size_t)ctx->nnz));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// compress: Example200's value filter decides the pattern (Example200:153)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_keep_flags(const uint8_t* __restrict__ touched, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int64_t ncols,
+                             const int64_t* __restrict__ extra, int64_t nextra, uint8_t* __restrict__ keep, unsigned long long* __restrict__ colcount) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    bool diag_forced = false;
+    {
+        int64_t lo = 0, hi = nextra;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (extra[mid] < c + 1) lo = mid + 1;
+            else hi = mid;
+        }
+        diag_forced = lo < nextra && extra[lo] == c + 1;
+    }
+    unsigned long long cnt = 0;
+    for (int64_t p = colptr[c] - 1; p < colptr[c + 1] - 1; p++) {
+        uint8_t k = touched[p] || (diag_forced && rowval[p] == c + 1);
+        keep[p] = k;
+        cnt += k;
+    }
+    colcount[c] = cnt;
+}
+
+extern "C" int32_t femb_pattern_compress(femb_ctx* ctx, int64_t* nnz_out) {
+    FEMB_CHECK_CTX(ctx);
+    if (!ctx->touched || !ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "femb_pattern_compress needs femb_pattern_track(ctx,1) before the assembly");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t ncols = ctx->ncols, nnz = ctx->nnz;
+    uint8_t* keep = nullptr;
+    unsigned long long *colcount = nullptr, *scanned = nullptr;
+    int64_t *extra = nullptr, *rv2 = nullptr, *nsel = nullptr;
+    double* nz2 = nullptr;
+    void* tmp = nullptr;
+    int* maxlen = nullptr;
+    auto cleanup = [&]() { cudaFree(keep); cudaFree(colcount); cudaFree(scanned); cudaFree(extra); cudaFree(nsel); cudaFree(tmp); cudaFree(maxlen); };
+#define TRY_C(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); cudaFree(rv2); cudaFree(nz2); return femb_fail(ctx, FEMB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    TRY_C(cudaMalloc(&keep, nnz));
+    TRY_C(cudaMalloc(&colcount, sizeof(unsigned long long) * (ncols + 1)));
+    TRY_C(cudaMalloc(&scanned, sizeof(unsigned long long) * (ncols + 1)));
+    TRY_C(cudaMemsetAsync(colcount, 0, sizeof(unsigned long long) * (ncols + 1), ctx->stream));
+    int64_t nextra = (int64_t)ctx->extra_diag.size();
+    TRY_C(cudaMalloc(&extra, sizeof(int64_t) * std::max<int64_t>(1, nextra)));
+    if (nextra) TRY_C(cudaMemcpyAsync(extra, ctx->extra_diag.data(), sizeof(int64_t) * nextra, cudaMemcpyHostToDevice, ctx->stream));
+    k_keep_flags<<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(ctx->touched, ctx->colptr, ctx->rowval, ncols, extra, nextra, keep, colcount);
+    TRY_C(cudaMalloc(&rv2, sizeof(int64_t) * nnz));
+    TRY_C(cudaMalloc(&nz2, sizeof(double) * nnz));
+    TRY_C(cudaMalloc(&nsel, sizeof(int64_t)));
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    cub::DeviceSelect::Flagged(nullptr, t1, ctx->rowval, keep, rv2, nsel, nnz, ctx->stream);
+    cub::DeviceSelect::Flagged(nullptr, t2, ctx->nzval, keep, nz2, nsel, nnz, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t3, colcount, scanned, ncols + 1, ctx->stream);
+    size_t tb = std::max(t1, std::max(t2, t3));
+    TRY_C(cudaMalloc(&tmp, tb));
+    size_t t = tb;
+    TRY_C(cub::DeviceSelect::Flagged(tmp, t, ctx->rowval, keep, rv2, nsel, nnz, ctx->stream));
+    t = tb;
+    TRY_C(cub::DeviceSelect::Flagged(tmp, t, ctx->nzval, keep, nz2, nsel, nnz, ctx->stream));
+    t = tb;
+    TRY_C(cub::DeviceScan::ExclusiveSum(tmp, t, colcount, scanned, ncols + 1, ctx->stream));
+    int64_t nnz2 = 0;
+    TRY_C(cudaMemcpyAsync(&nnz2, nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY_C(cudaStreamSynchronize(ctx->stream));
+    TRY_C(cudaMalloc(&maxlen, sizeof(int)));
+    TRY_C(cudaMemsetAsync(maxlen, 0, sizeof(int), ctx->stream));
+    k_colptr_finish<<<(unsigned)((ncols + 1 + 255) / 256), 256, 0, ctx->stream>>>(scanned, ncols, nnz2, ctx->colptr, maxlen);
+    TRY_C(cudaMemcpyAsync(&ctx->max_collen, maxlen, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY_C(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 6;
+#undef TRY_C
+    cleanup();
+    // swap in the compressed arrays (keep exact-size copies)
+    std::vector<FembBlock> blocks = ctx->blocks;
+    for (auto& b : ctx->blocks) femb_free(&b.slots);
+    femb_free(&ctx->gmap);
+    femb_free(&ctx->rowval);
+    femb_free(&ctx->nzval);
+    femb_free(&ctx->touched);
+    ctx->rowval = rv2;
+    ctx->nzval = nz2;
+    ctx->nnz = nnz2;
+    FEMB_TRY(femb_alloc(ctx, &ctx->touched, (size_t)nnz2));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 1, nnz2, ctx->stream));
+    FEMB_TRY(femb_build_slotmaps(ctx));
+    FEMB_TRY(femb_build_gmap(ctx));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nnz_out) *nnz_out = nnz2;
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cell -> slot maps and the P1 gather map
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t find_slot(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int64_t col, int64_t row1) {
+    int64_t lo = colptr[col] - 1, hi = colptr[col + 1] - 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowval[mid] < row1) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < colptr[col + 1] - 1 && rowval[lo] == row1) ? lo : -1;
+}
+
+__global__ void k_slotmap(const int32_t* __restrict__ rdofs, int ndr, int64_t roff, const int32_t* __restrict__ cdofs, int ndc, int64_t coff,
+                          int64_t ncells, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int32_t* __restrict__ slots) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t per = (int64_t)ndr * ndc;
+    if (t >= ncells * per) return;
+    int64_t cell = t / per;
+    int jk = (int)(t - cell * per);
+    int j = jk / ndc, k = jk - j * ndc;
+    int64_t row1 = roff + rdofs[cell * ndr + j];
+    int64_t col = coff + cdofs[cell * ndc + k] - 1;
+    slots[t] = (int32_t)find_slot(colptr, rowval, col, row1);
+}
+
+int femb_build_slotmaps(femb_ctx* ctx) {
+    if (ctx->nnz >= ((int64_t)1 << 31)) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "nnz >= 2^31 needs 64-bit slot maps (not built in this round)");
+    for (auto& b : ctx->blocks) {
+        const FembSpace& rs = ctx->spaces[ctx->row_spaces[b.brow]];
+        const FembSpace& cs = ctx->spaces[ctx->col_spaces[b.bcol]];
+        int64_t n = ctx->ncells * rs.nd * cs.nd;
+        FEMB_TRY(femb_alloc(ctx, &b.slots, (size_t)n));
+        if (n == 0) continue;
+        k_slotmap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(rs.celldofs, rs.nd, ctx->row_off[b.brow], cs.celldofs, cs.nd, ctx->col_off[b.bcol],
+                                                                       ctx->ncells, ctx->colptr, ctx->rowval, b.slots);
+        KERNEL_CHECK(ctx);
+    }
+    return FEMB_OK;
+}
+
+// gather map for scalar P1: entry e of column c (adjacency order) -> (cell, k | pos[0..nd) packed)
+template <int ND>
+__global__ void k_gmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, const int32_t* __restrict__ celldofs,
+                       const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, uint2* __restrict__ gmap) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ndofs) return;
+    const int64_t base = colptr[c] - 1;
+    for (int32_t e = adj_ptr[c]; e < adj_ptr[c + 1]; e++) {
+        uint32_t a = adj[e];
+        uint32_t cell = a / ND, k = a - cell * ND;
+        uint32_t packed = (ND == 3) ? k : k;
+#pragma unroll
+        for (int j = 0; j < ND; j++) {
+            int64_t p = find_slot(colptr, rowval, c, (int64_t)celldofs[(int64_t)cell * ND + j]);
+            uint32_t pos = (p < 0) ? ((ND == 3) ? 0xFFu : 0x3Fu) : (uint32_t)(p - base);
+            packed |= (ND == 3) ? (pos << (8 * (j + 1))) : (pos << (2 + 6 * j));
+        }
+        gmap[e] = make_uint2(cell, packed);
+    }
+}
+
+int femb_build_gmap(femb_ctx* ctx) {
+    femb_free(&ctx->gmap);
+    ctx->gmap_space = -1;
+    if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
+    int sid = ctx->row_spaces[0];
+    const FembSpace& s = ctx->spaces[sid];
+    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.nd != ctx->nnpc || s.handler != FEMB_HANDLER_NONE) return FEMB_OK;
+    int maxpos = (s.nd == 3) ? 254 : 62;
+    if (ctx->max_collen > maxpos) return FEMB_OK;  // fall back to the cell-parallel kernels
+    FEMB_TRY(femb_alloc(ctx, &ctx->gmap, (size_t)ctx->ncells * s.nd));
+    unsigned grid = (unsigned)((s.ndofs + 127) / 128);
+    if (s.nd == 3) k_gmap<3><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, s.celldofs, ctx->colptr, ctx->rowval, ctx->gmap);
+    else k_gmap<4><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, s.celldofs, ctx->colptr, ctx->rowval, ctx->gmap);
+    KERNEL_CHECK(ctx);
+    ctx->gmap_space = sid;
+    return FEMB_OK;
+}

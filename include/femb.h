@@ -1,0 +1,206 @@
+/*
+ * femb.h — C ABI of libfemb: batched cell-wise finite-element assembly on one B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of WIAS-PDELib/ExtendableFEMBase.jl named in
+ * BASELINE.json: the per-cell loops of
+ *     examples/Example200_LowLevelPoisson.jl:103-184   (assemble!)
+ *     examples/Example210_LowLevelNavierStokes.jl:218-394 (prepare_assembly!/update_system!)
+ * and the per-cell evaluators they call (src/feevaluator.jl:344-387, src/feevaluator_h1.jl,
+ * src/feevaluator_hdiv.jl) plus the sparse insert they end in (ExtendableSparse rawupdateindex!/
+ * flush!, call sites Example200:155-157,182; Example210:373-379,391).
+ *
+ * The reference has no FFI of its own (it is pure Julia); each entry point below states which
+ * reference object or call it takes its data from / replaces.  The Julia-side `ccall` stubs are in
+ * julia/FEMBaseB200.jl and INTEGRATION.md; the Python ctypes mirror is extendablefembase.jl_b200/_lib.py.
+ *
+ * Conventions
+ *   - every function returns int32 status (0 = FEMB_OK); femb_last_error() gives the message.
+ *     Nothing throws, aborts or longjmps across this boundary.
+ *   - Julia arrays are passed AS IS: column-major, 1-based Int32 grid/dof indices, 1-based Int64
+ *     CSC indices; kernels subtract 1.  A Julia `k x n` matrix is `n` contiguous groups of `k`.
+ *   - all pointers are HOST pointers unless the name ends in `_dev`.  The library copies inputs
+ *     into device buffers it owns; outputs are written into caller-provided host buffers.
+ *   - a femb_ctx is bound to one CUDA device and is not thread-safe; use one per thread / GPU.
+ *   - there is no CPU fallback: every entry point that computes fails with FEMB_ERR_CUDA if no
+ *     sm_100-class device is usable.
+ */
+#ifndef FEMB_H
+#define FEMB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct femb_ctx femb_ctx;
+
+enum {
+    FEMB_OK = 0,
+    FEMB_ERR_ARG = 1,      /* invalid argument / call order */
+    FEMB_ERR_CUDA = 2,     /* CUDA runtime error (message has cudaGetErrorString) */
+    FEMB_ERR_UNSUPPORTED = 3,
+    FEMB_ERR_PATTERN = 4,  /* a contribution has no slot in the adopted pattern */
+    FEMB_ERR_NCCL = 5
+};
+
+/* FE class of a space: selects the push-forward (src/feevaluator_h1.jl vs feevaluator_hdiv.jl) */
+enum { FEMB_FAMILY_H1 = 0, FEMB_FAMILY_HDIV = 1, FEMB_FAMILY_L2 = 2 };
+
+/* per-cell coefficient / subset handlers (get_coefficients / get_basissubset of src/fedefs/*.jl) */
+enum {
+    FEMB_HANDLER_NONE = 0,
+    FEMB_HANDLER_H1_FACESWAP2D = 1, /* h1_p3.jl:200-217, h1_pk.jl:280-304 */
+    FEMB_HANDLER_H1_EDGESWAP3D = 2, /* h1_p3.jl:220-241 */
+    FEMB_HANDLER_RT0_SIGNS = 3,     /* hdiv_rt0.jl:114-124 */
+    FEMB_HANDLER_BDM1_2D = 4,       /* hdiv_bdm1.jl:200-212 */
+    FEMB_HANDLER_BDM1_3D = 5        /* hdiv_bdm1.jl:215-249 */
+};
+
+/* function operators implemented on the device (src/functionoperators.jl:132-196) */
+enum { FEMB_OP_IDENTITY = 0, FEMB_OP_GRADIENT = 1, FEMB_OP_DIVERGENCE = 2 };
+
+/* right-hand-side data kinds (the Julia closures rhs(x) / f!(fval,x,t) cannot be called from
+ * the device; Example200:38,173 and Example210:44-48,311 are covered by these) */
+enum {
+    FEMB_RHS_NONE = 0,
+    FEMB_RHS_AFFINE = 1, /* f_c(x) = params[c*(dim+1)] + sum_d params[c*(dim+1)+1+d] * x_d          */
+    FEMB_RHS_QPVALUES = 2, /* fvals[ncomp x nqp x ncells] evaluated by the host at x_qp (femb_qp_coords) */
+    FEMB_RHS_EX210 = 3   /* Example210 f!: params = {mu, t}                                         */
+};
+
+/* flags of femb_assemble_bilinear */
+enum {
+    FEMB_BIL_TRANSPOSE_COPY = 1, /* also add the transposed local matrix into block (bcol,brow): Example210:376-380 */
+    FEMB_BIL_SYMMETRIC_UPPER = 2, /* Example200:139-158: compute j<=k, mirror, skip |v| <= drop_tol   */
+    FEMB_BIL_NO_VOLUME = 4       /* do not multiply by |T|                                           */
+};
+
+/* scatter policy for the cell-parallel kernels */
+enum {
+    FEMB_SCATTER_ATOMIC = 0,   /* red.global.add.f64 (fastest; summation order not fixed)            */
+    FEMB_SCATTER_COLORED = 1,  /* cell colouring, plain read-modify-write per colour (bit-reproducible) */
+    FEMB_SCATTER_GATHER = 2    /* owner-computes column gather, write-once (bit-reproducible; P1 only) */
+};
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+int32_t femb_version(void);
+int32_t femb_create(int32_t device, femb_ctx** out);
+int32_t femb_destroy(femb_ctx* ctx);
+const char* femb_last_error(const femb_ctx* ctx); /* valid until the next call on ctx; ctx may be NULL */
+int32_t femb_sync(femb_ctx* ctx);
+/* pin / unpin a caller-owned host range so that copies run at full PCIe rate and overlap */
+int32_t femb_host_register(femb_ctx* ctx, void* ptr, int64_t bytes);
+int32_t femb_host_unregister(femb_ctx* ctx, void* ptr);
+
+/* ---- stage-1 inputs: xgrid[Coordinates], xgrid[CellNodes], xgrid[CellVolumes] ----------------
+ * (ExtendableGrids components read at Example200:107,114; Example210:227-228; feevaluator.jl:94-97)
+ * coords: dim x nnodes Float64; cellnodes: nnpc x ncells Int32 1-based; cellvolumes: ncells or NULL
+ * (NULL: |T| = |det A|/dim! is computed on the device). */
+int32_t femb_mesh_set(femb_ctx* ctx, int32_t dim, int64_t nnodes, const double* coords, int32_t nnpc,
+                      int64_t ncells, const int32_t* cellnodes, const double* cellvolumes_or_null);
+
+/* ---- FESpace: fe_space[CellDofs] (+ xgrid[CellFaceSigns], xgrid[CellFaceOrientations]) --------
+ * (finiteelements.jl:376-388, dofmaps.jl:419-627; handler inputs hdiv_rt0.jl:115, hdiv_bdm1.jl:201,235)
+ * celldofs: nd_local x ncells Int32 1-based, constant stride (single cell geometry);
+ * celldofs == NULL means "identical to cellnodes" (H1P1{1}).  signs/orient: nfaces x ncells Int32 or
+ * NULL.  For FEMB_HANDLER_H1_EDGESWAP3D `signs` is xgrid[CellEdgeSigns] (6 x ncells). */
+int32_t femb_space_set(femb_ctx* ctx, int32_t space_id, int32_t family, int32_t ncomp, int64_t ndofs,
+                       int32_t nd_local, int32_t nd_all, int32_t handler, const int32_t* celldofs_or_null,
+                       const int32_t* signs_or_null, const int32_t* orient_or_null);
+
+/* ---- QuadratureRule: qf.xref (dim x nqp), qf.w (nqp)   (quadrature.jl:38-42) ------------------ */
+int32_t femb_quadrature_set(femb_ctx* ctx, int32_t nqp, const double* xref, const double* w);
+
+/* ---- FEEvaluator(FES, op, qf): the reference tables built once by the constructor -------------
+ * (feevaluator.jl:83-215, :233-291).  refvals: [nqp][nd_all][ncomp]; refderivs:
+ * [nqp][nd_all][ncomp][dim] = d(phi_{dof,comp})/d(xref_j) (either may be NULL if the operator does
+ * not need it).  Uses the quadrature rule current at the time of the call. */
+int32_t femb_evaluator_set(femb_ctx* ctx, int32_t eval_id, int32_t space_id, int32_t op,
+                           const double* refvals_or_null, const double* refderivs_or_null);
+
+/* batched update_basis!(FEB, cell) for cells [cell_begin, cell_end) (0-based range):
+ * out[(cell-cell_begin)][qp][dof][r] = FEB.cvals[r, dof, qp] after update_basis!(FEB, cell+1)
+ * (feevaluator.jl:381-387 -> feevaluator_h1.jl:2-14,61-74,119-130; feevaluator_hdiv.jl:2-19,66-83) */
+int32_t femb_evaluator_eval(femb_ctx* ctx, int32_t eval_id, int64_t cell_begin, int64_t cell_end, double* out);
+
+/* physical quadrature points eval_trafo!(x, L2G, xref[qp]) for all cells: out[cell][qp][dim]
+ * (Example200:171, Example210:310) — lets the host evaluate rhs closures for FEMB_RHS_QPVALUES */
+int32_t femb_qp_coords(femb_ctx* ctx, double* out);
+
+/* ---- FEMatrix(FESX, FESY): block layout + CSC pattern ------------------------------------------
+ * (fematrix.jl:226-290: row offsets follow space_rows, column offsets space_cols) */
+int32_t femb_matrix_layout(femb_ctx* ctx, int32_t nrow_spaces, const int32_t* row_spaces,
+                           int32_t ncol_spaces, const int32_t* col_spaces);
+/* structural pattern  U_cells dofs_row(cell) x dofs_col(cell)  for the listed blocks — what the first
+ * assembly + flush! of the reference produces when nothing is filtered (Example210; and
+ * apply_nonzero_pattern!, fematrix.jl:108-118).  extra_diag: 1-based global dofs whose diagonal entry
+ * must exist (Dirichlet penalties, Example200:86-93, Example210:172,197-199). */
+int32_t femb_pattern_build(femb_ctx* ctx, int32_t nblocks, const int32_t* block_rows, const int32_t* block_cols,
+                           int64_t n_extra_diag, const int64_t* extra_diag_or_null, int64_t* nnz_out);
+/* use an already flushed Julia pattern A.cscmatrix.colptr / rowval (steady state, Example200:205-211) */
+int32_t femb_pattern_adopt(femb_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* colptr,
+                           const int64_t* rowval, int32_t nblocks, const int32_t* block_rows, const int32_t* block_cols);
+int32_t femb_pattern_get(femb_ctx* ctx, int64_t* colptr_out, int64_t* rowval_out);
+/* Example200's value filter (|Aloc[j,k]| > 1e-15, Example200:153) decides the pattern: drop every
+ * slot that received no contribution in the assemblies since the last femb_matrix_zero, keeping
+ * extra_diag entries.  Rebuilds the cell->slot maps.  */
+int32_t femb_pattern_compress(femb_ctx* ctx, int64_t* nnz_out);
+/* enable/disable the per-slot "received a contribution" flags that femb_pattern_compress reads */
+int32_t femb_pattern_track(femb_ctx* ctx, int32_t enable);
+
+/* ---- device-resident FEMatrix.entries.cscmatrix.nzval and FEVector.entries ---------------------- */
+int32_t femb_matrix_zero(femb_ctx* ctx);
+int32_t femb_vector_zero(femb_ctx* ctx);
+int32_t femb_matrix_get(femb_ctx* ctx, double* nzval_out);           /* nnz doubles, Julia CSC order */
+int32_t femb_matrix_add_to(femb_ctx* ctx, double* nzval_inout);      /* nzval_inout += device values  */
+int32_t femb_vector_get(femb_ctx* ctx, double* b_out);               /* sum of row-space ndofs        */
+int32_t femb_vector_set(femb_ctx* ctx, int32_t which, const double* v); /* which: 0 = b, 1 = current solution (Example210:328-331) */
+int32_t femb_set_scatter(femb_ctx* ctx, int32_t policy);
+
+/* ---- stages 3-5 ----------------------------------------------------------------------------------
+ * generic quadrature-weighted contraction of two evaluators + scatter into block (brow,bcol):
+ *   Aloc[j,k] = factor * |T| * sum_qp w_qp <op_row_j(qp), op_col_k(qp)>      (Example210:284-301)
+ * brow/bcol index into the row/col space lists of femb_matrix_layout (0-based). */
+int32_t femb_assemble_bilinear(femb_ctx* ctx, int32_t eval_row, int32_t eval_col, int32_t brow, int32_t bcol,
+                               double factor, int32_t flags, double drop_tol);
+/* b[off(brow)+dof_j] += factor * |T| * sum_qp w_qp <op_j(qp), f(x_qp)>   (Example200:165-178, Example210:304-318) */
+int32_t femb_assemble_linear(femb_ctx* ctx, int32_t eval_id, int32_t brow, double factor, int32_t rhs_kind,
+                             const double* params_or_fvals);
+/* Example200.assemble!(A, b, fe_space, rhs, mu) in one call (Example200:103-184): stiffness with the
+ * upper-triangle/mirror/drop_tol rule + rhs.  For H1P1 with FEMB_SCATTER_GATHER this is ONE fused
+ * kernel (stages 1-5). */
+int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id, double mu, int32_t rhs_kind,
+                              const double* params_or_fvals, double drop_tol);
+/* Example210 update_system!(linear, nonlinear) (Example210:276-385): Laplacian + div-pressure blocks +
+ * rhs (linear) and the Newton-linearised convection term + its rhs (nonlinear; uses vector 1 =
+ * current solution).  evals: grad u, id u, id p. */
+int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t eval_grad_u, int32_t eval_id_u, int32_t eval_id_p,
+                                   double mu, int32_t linear, int32_t nonlinear, int32_t rhs_kind,
+                                   const double* params_or_fvals);
+
+/* ---- timing / introspection (bench + tests) ------------------------------------------------------ */
+/* CUDA-event time of the kernels launched by the last femb_assemble_* call, in ms, and their count */
+int32_t femb_last_kernel_ms(femb_ctx* ctx, float* ms_out, int32_t* nlaunches_out);
+int64_t femb_launch_count(const femb_ctx* ctx); /* kernels launched by this ctx so far */
+/* raw device pointers (for harnesses that keep data resident): 0 nzval, 1 b, 2 colptr, 3 rowval */
+void* femb_device_ptr(femb_ctx* ctx, int32_t which);
+
+/* ---- multi-GPU: cells partitioned across ranks, interface columns exchanged over NCCL ------------
+ * (no counterpart in the reference, which is single-process: SURVEY.md §8(e)).  One process per GPU.
+ * Each rank sets its LOCAL mesh part (owned cells) with LOCAL dof numbering in which the dofs it
+ * owns come first; ghost dofs (owned by a peer) are listed per peer with the owner's local index. */
+int32_t femb_comm_unique_id(char id_out[128]);
+int32_t femb_comm_init(femb_ctx* ctx, int32_t nranks, int32_t rank, const char id[128]);
+/* peer lists: for peer p, ghost columns [ghost_ptr[p], ghost_ptr[p+1]) of `ghost_local` (1-based local
+ * global-matrix column on this rank) are owned by p.  After assembly femb_exchange() sends every ghost
+ * column's values to its owner, which adds them in ascending peer order (reproducible). */
+int32_t femb_comm_set_ghosts(femb_ctx* ctx, int32_t npeers, const int32_t* peers, const int64_t* ghost_ptr,
+                             const int64_t* ghost_local, const int64_t* ghost_remote);
+int32_t femb_exchange(femb_ctx* ctx);
+int32_t femb_comm_destroy(femb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEMB_H */
