@@ -164,21 +164,21 @@ def _face_orientation(local: np.ndarray, glob: np.ndarray) -> np.ndarray:
     """Orientation code of a local triangular face (node triple ``local`` in the
     cell's outward order) relative to the global face's node triple ``glob``.
 
-    1: local == glob (creating cell).  The neighbour sees the face reversed; the
-    code says which local position carries the global first node:
-    2: glob == (l1, l3, l2), 3: glob == (l3, l2, l1), 4: glob == (l2, l1, l3).
-    The numbering of 2..4 is fixed by requiring that the subset/coefficient
+    1: local == glob (creating cell).  The neighbour sees the face reversed:
+    2: glob == (l3, l2, l1), 3: glob == (l2, l1, l3), 4: glob == (l1, l3, l2).
+    The numbering of 2..4 is the ONLY one for which the subset/coefficient
     tables of HDIVBDM1{3} (/root/reference/src/fedefs/hdiv_bdm1.jl:215-249) give a
-    basis dual to the face functionals of hdiv_bdm1.jl:47-54; this is checked in
-    tests/test_oracle_pins.py (interpolation round trip).
+    basis dual to the face functionals of hdiv_bdm1.jl:47-54 (all 4 local faces
+    agree); pinned by tests/test_oracle_pins.py (test_bdm1_orientation_codes) and
+    the interpolation round trip there.
     """
     l1, l2, l3 = local[:, 0], local[:, 1], local[:, 2]
     g1, g2, g3 = glob[:, 0], glob[:, 1], glob[:, 2]
     out = np.zeros(local.shape[0], dtype=np.int32)
     out[(g1 == l1) & (g2 == l2) & (g3 == l3)] = 1
-    out[(g1 == l1) & (g2 == l3) & (g3 == l2)] = 2
-    out[(g1 == l3) & (g2 == l2) & (g3 == l1)] = 3
-    out[(g1 == l2) & (g2 == l1) & (g3 == l3)] = 4
+    out[(g1 == l3) & (g2 == l2) & (g3 == l1)] = 2
+    out[(g1 == l2) & (g2 == l1) & (g3 == l3)] = 3
+    out[(g1 == l1) & (g2 == l3) & (g3 == l2)] = 4
     if (out == 0).any():
         raise ValueError("inconsistent face orientation (non-manifold or same-handed neighbour faces)")
     return out
