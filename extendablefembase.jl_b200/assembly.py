@@ -195,7 +195,7 @@ def prepare_assembly(A: FEMatrix, b: FEVector, FESu, FESp, sol: FEVector, *, tev
         ctx.vector_zero()
         ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, mu, linear, nonlinear, kind, data)
         ctx.matrix_add_to(Ae.nzval)
-        be += ctx.vector_get(be.shape[0])
+        np.add(be, ctx.vector_get(be.shape[0]), out=be)
 
     update_system.session = S
     return update_system

@@ -60,7 +60,17 @@ def quadrature(geometry: str, order: int):
         if order == 2:  # :358-368
             a, b = 0.1381966011250105, 0.5854101966249685
             return np.array([[a, a, a], [b, a, a], [a, b, a], [a, a, b]]), np.full(4, 0.25)
-        raise NotImplementedError("tet rules of order > 2 are not used by the assembly configs")
+        if order <= 3:  # :369-381 (Keast)
+            s = 1.0 / 6.0
+            return (np.array([[0.25, 0.25, 0.25], [0.5, s, s], [s, s, s], [s, s, 0.5], [s, 0.5, s]]),
+                    np.array([-4.0 / 5.0, 9.0 / 20.0, 9.0 / 20.0, 9.0 / 20.0, 9.0 / 20.0]))
+        if order <= 4:  # :382-401 (Keast, 11 points)
+            p, q = 0.7857142857142857, 0.0714285714285714
+            u, v = 0.1005964238332008, 0.3994035761667992
+            xr = np.array([[0.25, 0.25, 0.25], [p, q, q], [q, q, q], [q, q, p], [q, p, q],
+                           [u, v, v], [v, u, v], [v, v, u], [v, u, u], [u, v, u], [u, u, v]])
+            return xr, np.array([-0.0789333333333333] + [0.0457333333333333] * 4 + [0.1493333333333333] * 6)
+        raise NotImplementedError("symmetric tet rules of order > 4 are not used by the assembly configs")
     raise ValueError(geometry)
 
 
