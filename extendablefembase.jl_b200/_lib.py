@@ -58,6 +58,8 @@ SIGNATURES = {
     "femb_last_kernel_ms": (_i32, [_p, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "femb_launch_count": (_i64, [_p]),
     "femb_device_ptr": (_p, [_p, _i32]),
+    "femb_region_begin": (_i32, [_p]),
+    "femb_region_end": (_i32, [_p, C.POINTER(C.c_float)]),
     "femb_comm_unique_id": (_i32, [C.c_char_p]),
     "femb_comm_init": (_i32, [_p, _i32, _i32, C.c_char_p]),
     "femb_comm_set_ghosts": (_i32, [_p, _i32, _p, _p, _p, _p]),
@@ -260,6 +262,14 @@ class Context:
         ms, n = C.c_float(0), _i32(0)
         self._ck(self.lib.femb_last_kernel_ms(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def region_begin(self):
+        self._ck(self.lib.femb_region_begin(self.h))
+
+    def region_end(self) -> float:
+        ms = C.c_float(0)
+        self._ck(self.lib.femb_region_end(self.h, C.byref(ms)))
+        return ms.value
 
     def launch_count(self) -> int:
         return int(self.lib.femb_launch_count(self.h))

@@ -64,9 +64,10 @@ def _register_space(ctx, sid, fes):
         signs = grid["CellEdgeSigns"]
     if handler == 5:
         orient = grid["CellFaceOrientations"]
-    celldofs = fes["CellDofs"]
     if ft.family == "H1" and ft.ncomponents == 1 and ft.order == 1:
-        celldofs = None  # identical to CellNodes: no second copy in HBM
+        celldofs = None  # CellDofs of scalar P1 is CellNodes itself (pattern "N1"): no second copy in HBM
+    else:
+        celldofs = fes["CellDofs"]
     ctx.space_set(sid, _lib.FAMILY[ft.family], ft.ncomponents, fes.ndofs, ft.get_ndofs(g), ft.get_ndofs_all(g), handler, celldofs, signs, orient)
 
 

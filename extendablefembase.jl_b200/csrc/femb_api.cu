@@ -50,6 +50,7 @@ int32_t femb_create(int32_t device, femb_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev2)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev3)) != cudaSuccess ||
         (e = cudaMalloc((void**)&ctx->errflag, sizeof(int32_t))) != cudaSuccess ||
         (e = cudaMemset(ctx->errflag, 0, sizeof(int32_t))) != cudaSuccess) {
         g_err = cudaGetErrorString(e);
@@ -88,6 +89,8 @@ int32_t femb_destroy(femb_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FEMB_OK;
@@ -358,6 +361,25 @@ int32_t femb_last_kernel_ms(femb_ctx* ctx, float* ms, int32_t* n) {
 }
 
 int64_t femb_launch_count(const femb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t femb_region_begin(femb_ctx* ctx) {
+    FEMB_CHECK_CTX(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev2, ctx->stream));
+    return FEMB_OK;
+}
+
+int32_t femb_region_end(femb_ctx* ctx, float* ms) {
+    FEMB_CHECK_CTX(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev3));
+    float t = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev2, ctx->ev3));
+    if (ms) *ms = t;
+    return FEMB_OK;
+}
 
 void* femb_device_ptr(femb_ctx* ctx, int32_t which) {
     if (!ctx) return nullptr;

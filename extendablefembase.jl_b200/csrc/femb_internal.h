@@ -50,7 +50,7 @@ struct FembBlock {
 struct femb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     std::string err;
     int64_t launches = 0;
     int last_launches = 0;

@@ -184,20 +184,26 @@ def _face_orientation(local: np.ndarray, glob: np.ndarray) -> np.ndarray:
     return out
 
 
-def cell_volumes(coords: np.ndarray, cellnodes: np.ndarray) -> np.ndarray:
-    """|T| per simplex cell = |det A| / d!  ([EXT E1] ``xgrid[CellVolumes]``)."""
-    x = coords[cellnodes - 1]  # (nc, d+1, d)
-    a = x[:, 1:, :] - x[:, :1, :]
+def cell_volumes(coords: np.ndarray, cellnodes: np.ndarray, chunk: int = 1 << 22) -> np.ndarray:
+    """|T| per simplex cell = |det A| / d!  ([EXT E1] ``xgrid[CellVolumes]``); chunked so that a 64M-cell
+    grid does not need multi-GB temporaries."""
     d = coords.shape[1]
-    if d == 2:
-        det = a[:, 0, 0] * a[:, 1, 1] - a[:, 0, 1] * a[:, 1, 0]
-        return np.abs(det) / 2.0
-    det = (
-        a[:, 0, 0] * (a[:, 1, 1] * a[:, 2, 2] - a[:, 1, 2] * a[:, 2, 1])
-        - a[:, 0, 1] * (a[:, 1, 0] * a[:, 2, 2] - a[:, 1, 2] * a[:, 2, 0])
-        + a[:, 0, 2] * (a[:, 1, 0] * a[:, 2, 1] - a[:, 1, 1] * a[:, 2, 0])
-    )
-    return np.abs(det) / 6.0
+    nc = cellnodes.shape[0]
+    out = np.empty(nc, dtype=np.float64)
+    for c0 in range(0, nc, chunk):
+        x = coords[cellnodes[c0:c0 + chunk] - 1]  # (n, d+1, d)
+        a = x[:, 1:, :] - x[:, :1, :]
+        if d == 2:
+            det = a[:, 0, 0] * a[:, 1, 1] - a[:, 0, 1] * a[:, 1, 0]
+            out[c0:c0 + chunk] = np.abs(det) / 2.0
+        else:
+            det = (
+                a[:, 0, 0] * (a[:, 1, 1] * a[:, 2, 2] - a[:, 1, 2] * a[:, 2, 1])
+                - a[:, 0, 1] * (a[:, 1, 0] * a[:, 2, 2] - a[:, 1, 2] * a[:, 2, 0])
+                + a[:, 0, 2] * (a[:, 1, 0] * a[:, 2, 1] - a[:, 1, 1] * a[:, 2, 0])
+            )
+            out[c0:c0 + chunk] = np.abs(det) / 6.0
+    return out
 
 
 # ----------------------------------------------------------------------

@@ -47,7 +47,7 @@ enum {
 /* FE class of a space: selects the push-forward (src/feevaluator_h1.jl vs feevaluator_hdiv.jl) */
 enum { FEMB_FAMILY_H1 = 0, FEMB_FAMILY_HDIV = 1, FEMB_FAMILY_L2 = 2 };
 
-/* per-cell coefficient / subset handlers (get_coefficients / get_basissubset of src/fedefs/*.jl) */
+/* per-cell coefficient / subset handlers (get_coefficients, get_basissubset of src/fedefs) */
 enum {
     FEMB_HANDLER_NONE = 0,
     FEMB_HANDLER_H1_FACESWAP2D = 1, /* h1_p3.jl:200-217, h1_pk.jl:280-304 */
@@ -183,6 +183,11 @@ int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t eval_grad_u, int32_t e
 /* CUDA-event time of the kernels launched by the last femb_assemble_* call, in ms, and their count */
 int32_t femb_last_kernel_ms(femb_ctx* ctx, float* ms_out, int32_t* nlaunches_out);
 int64_t femb_launch_count(const femb_ctx* ctx); /* kernels launched by this ctx so far */
+/* CUDA events on the library's own stream bracketing an arbitrary sequence of calls (bench.py's timed
+ * region; the reference's counterpart is the @elapsed around assemble!, Example200:82-94).  _end
+ * synchronises and returns the device time between the two events. */
+int32_t femb_region_begin(femb_ctx* ctx);
+int32_t femb_region_end(femb_ctx* ctx, float* ms_out);
 /* raw device pointers (for harnesses that keep data resident): 0 nzval, 1 b, 2 colptr, 3 rowval */
 void* femb_device_ptr(femb_ctx* ctx, int32_t which);
 
