@@ -383,95 +383,178 @@ static int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const R
 // ---------------------------------------------------------------------------------------------------
 struct P1Tab {
     int nqp;
+    double wsum;                  // sum_qp w_qp  (P1 gradients do not depend on qp: Example200:139-145 collapses to wsum * dot)
     double w[FEMB_MAX_QP];
     double xref[FEMB_MAX_QP * 3];
     double phi[FEMB_MAX_QP * 4];  // Identity table [qp][dof]
 };
 
-template <int DIM>
-__global__ void __launch_bounds__(128) k_p1_poisson_gather(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes,
-                                                           const double* __restrict__ cellvol, const int32_t* __restrict__ adj_ptr,
-                                                           const uint2* __restrict__ gmap, const int64_t* __restrict__ colptr, int64_t ndofs,
-                                                           double* __restrict__ nzval, uint8_t* __restrict__ touched, double* __restrict__ bvec,
-                                                           int32_t* __restrict__ errflag, double mu, double drop_tol, RhsDev rhs, P1Tab tab,
-                                                           int acc_A, int acc_b) {
+struct P1Args {
+    const double* coords;
+    const int32_t* cellnodes;
+    const double* cellvol;
+    const int32_t* adj_ptr;
+    const uint2* gmap;
+    const int64_t* colptr;
+    int64_t ndofs;
+    double* nzval;
+    uint8_t* touched;
+    double* bvec;
+    int32_t* errflag;
+    double mu, drop_tol;
+    int acc_A, acc_b;
+};
+
+// One thread per matrix column c (= dof).  For every cell e adjacent to c (dof -> cell adjacency, ascending
+// cell order) the thread recomputes the cell's affine map from CellNodes/Coordinates and adds column k_e of the
+// local stiffness matrix into the <= 64 slots of column c (accumulated in shared memory, written ONCE, fixed
+// order => bit-reproducible, no atomics, no memset).  Arithmetic: with C = cofactor matrix of the Jacobian A,
+// grad phi_j = C_j / det, so  Aloc[j,k] = mu |T| wsum (C_j . C_k) / det^2  — one division per cell instead of the
+// reference's four (mapderiv!) — equal to the reference's value up to a few ulp (tests: 1e-12).
+template <int DIM, bool TRACK, int RHS>  // RHS: FEMB_RHS_NONE / _AFFINE / _QPVALUES
+__global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const RhsDev rhs, const P1Tab tab) {
     constexpr int ND = DIM + 1;
     extern __shared__ double acc[];  // [maxlen][blockDim.x]
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned tid = threadIdx.x;
+    constexpr unsigned nt = 128;
     const int64_t c = blockIdx.x * (int64_t)nt + tid;
-    if (c >= ndofs) return;
-    const int64_t base = colptr[c] - 1;
-    const int len = (int)(colptr[c + 1] - 1 - base);
+    if (c >= a.ndofs) return;
+    const int64_t base = a.colptr[c] - 1;
+    const int len = (int)(a.colptr[c + 1] - 1 - base);
     for (int i = 0; i < len; i++) acc[i * nt + tid] = 0.0;
     unsigned long long mask = 0ull;
     double bsum = 0.0;
-    const int e1 = adj_ptr[c + 1];
-    for (int e = adj_ptr[c]; e < e1; e++) {
-        const uint2 gm = __ldg(gmap + e);
-        const int64_t cell = gm.x;
-        const int k = (DIM == 2) ? (gm.y & 0xFF) : (gm.y & 3);
-        Geo<DIM> g;
-        load_geo<DIM>(coords, cellnodes, cellvol, cell, g);
-        // grad phi_0 = -sum_j M[:,j]; grad phi_i = M[:,i-1]   (feevaluator_h1.jl:69-72 with the P1 table)
-        double gr[ND][DIM];
+    const int e1 = a.adj_ptr[c + 1];
+    for (int e = a.adj_ptr[c]; e < e1; e++) {
+        const uint2 gm = __ldg(a.gmap + e);
+        const unsigned cell = gm.x;
+        const unsigned k = (DIM == 2) ? (gm.y & 0xFFu) : (gm.y & 3u);
+        const int32_t* cn = a.cellnodes + (size_t)cell * ND;
+        double cf[ND][DIM];  // cofactor vectors: grad phi_j = cf[j] / det
+        double A[DIM][DIM], x0[DIM], det;
+        if (DIM == 2) {
+            const double2* xy = reinterpret_cast<const double2*>(a.coords);
+            const double2 p0 = __ldg(xy + (__ldg(cn) - 1)), p1 = __ldg(xy + (__ldg(cn + 1) - 1)), p2 = __ldg(xy + (__ldg(cn + 2) - 1));
+            A[0][0] = p1.x - p0.x; A[0][1] = p2.x - p0.x;
+            A[1][0] = p1.y - p0.y; A[1][1] = p2.y - p0.y;
+            x0[0] = p0.x; x0[1] = p0.y;
+            det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+            cf[1][0] = A[1][1];  cf[1][1] = -A[0][1];
+            cf[2][0] = -A[1][0]; cf[2][1] = A[0][0];
+        } else {
+            double x[4][3];
 #pragma unroll
-        for (int kk = 0; kk < DIM; kk++) {
+            for (int i = 0; i < 4; i++) {
+                const double* p = a.coords + (size_t)(__ldg(cn + i) - 1) * 3;
+                x[i][0] = __ldg(p); x[i][1] = __ldg(p + 1); x[i][2] = __ldg(p + 2);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                x0[d] = x[0][d];
+#pragma unroll
+                for (int i = 0; i < 3; i++) A[d][i] = x[i + 1][d] - x[0][d];
+            }
+            // cofactor C[r][j] of A[r][j]; cf[j+1][r] = C[r][j]
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const int r1 = (r + 1) % 3, r2 = (r + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                    cf[j + 1][r] = A[r1][j1] * A[r2][j2] - A[r1][j2] * A[r2][j1];
+                }
+            det = A[0][0] * cf[1][0] + A[0][1] * cf[2][0] + A[0][2] * cf[3][0];
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
             double s0 = 0.0;
 #pragma unroll
-            for (int j = 0; j < DIM; j++) {
-                s0 += g.M[kk][j] * -1.0;
-                gr[j + 1][kk] = g.M[kk][j];
-            }
-            gr[0][kk] = s0;
+            for (int j = 1; j < ND; j++) s0 -= cf[j][d];
+            cf[0][d] = s0;
         }
-        const double scale = mu * g.vol;
+        const double vol = a.cellvol ? __ldg(a.cellvol + cell) : fabs(det) * (DIM == 2 ? 0.5 : 1.0 / 6.0);
+        const double scale = (a.mu * vol) * tab.wsum / (det * det);
+        double ck[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            double v = cf[0][d];
+#pragma unroll
+            for (int m = 1; m < ND; m++) v = (k == (unsigned)m) ? cf[m][d] : v;
+            ck[d] = v;
+        }
 #pragma unroll
         for (int j = 0; j < ND; j++) {
-            // dot(grad_j, grad_k): select k without dynamic register indexing
             double d = 0.0;
 #pragma unroll
-            for (int kk = 0; kk < DIM; kk++) {
-                double gk = gr[0][kk];
-#pragma unroll
-                for (int m = 1; m < ND; m++) gk = (k == m) ? gr[m][kk] : gk;
-                d += gr[j][kk] * gk;
-            }
-            double temp = 0.0;
-            for (int qp = 0; qp < tab.nqp; qp++) temp += tab.w[qp] * d;
-            const double val = temp * scale;
-            if (fabs(val) > drop_tol) {
-                const unsigned pos = (DIM == 2) ? ((gm.y >> (8 * (j + 1))) & 0xFF) : ((gm.y >> (2 + 6 * j)) & 0x3F);
+            for (int kk = 0; kk < DIM; kk++) d += cf[j][kk] * ck[kk];
+            const double val = d * scale;
+            if (fabs(val) > a.drop_tol) {
+                const unsigned pos = (DIM == 2) ? ((gm.y >> (8 * (j + 1))) & 0xFFu) : ((gm.y >> (2 + 6 * j)) & 0x3Fu);
                 if (pos == ((DIM == 2) ? 0xFFu : 0x3Fu)) {
-                    atomicAdd(errflag, 1);
+                    atomicAdd(a.errflag, 1);
                 } else {
                     acc[pos * nt + tid] += val;
-                    if (pos < 64) mask |= 1ull << pos;
+                    if (TRACK) mask |= 1ull << (pos & 63u);
                 }
             }
         }
-        if (rhs.kind != FEMB_RHS_NONE) {
+        if (RHS != FEMB_RHS_NONE) {
             double temp = 0.0;
             for (int qp = 0; qp < tab.nqp; qp++) {
-                double x[DIM], f[3];
-                eval_trafo<DIM>(g, tab.xref + qp * DIM, x);
-                eval_rhs<DIM>(rhs, x, cell, qp, tab.nqp, f);
-                temp += tab.w[qp] * tab.phi[qp * ND + k] * f[0];
+                double f;
+                if (RHS == FEMB_RHS_AFFINE) {  // f(x_qp), x_qp = A xref_qp + x_1  (eval_trafo!, Example200:171)
+                    f = rhs.p[0];
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) {
+                        double sx = x0[d];
+#pragma unroll
+                        for (int i = 0; i < DIM; i++) sx += A[d][i] * tab.xref[qp * DIM + i];
+                        f += rhs.p[1 + d] * sx;
+                    }
+                } else {
+                    f = __ldg(rhs.fvals + (size_t)cell * tab.nqp + qp);
+                }
+                temp += tab.w[qp] * tab.phi[qp * ND + k] * f;
             }
-            bsum += temp * g.vol;
+            bsum += temp * vol;
         }
     }
-    if (acc_A) {
-        for (int i = 0; i < len; i++) nzval[base + i] += acc[i * nt + tid];
+    double* out = a.nzval + base;
+    if (a.acc_A) {
+        for (int i = 0; i < len; i++) out[i] += acc[i * nt + tid];
     } else {
-        for (int i = 0; i < len; i++) nzval[base + i] = acc[i * nt + tid];
+        for (int i = 0; i < len; i++) out[i] = acc[i * nt + tid];
     }
-    if (touched)
+    if (TRACK) {
         for (int i = 0; i < len; i++)
-            if ((mask >> i) & 1ull) touched[base + i] = 1;
-    if (rhs.kind != FEMB_RHS_NONE) {
-        if (acc_b) bvec[c] += bsum;
-        else bvec[c] = bsum;
+            if ((mask >> i) & 1ull) a.touched[base + i] = 1;
     }
+    if (RHS != FEMB_RHS_NONE) {
+        if (a.acc_b) a.bvec[c] += bsum;
+        else a.bvec[c] = bsum;
+    }
+}
+
+template <int DIM>
+static int launch_p1_gather_dim(femb_ctx* ctx, const P1Args& a, const RhsDev& rhs, const P1Tab& tab, unsigned grid, size_t smem) {
+    const bool track = a.touched != nullptr;
+#define FEMB_P1_LAUNCH(T, R)                                                                                                   \
+    do {                                                                                                                       \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather<DIM, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_p1_poisson_gather<DIM, T, R><<<grid, 128, smem, ctx->stream>>>(a, rhs, tab);                                           \
+    } while (0)
+    if (rhs.kind == FEMB_RHS_AFFINE) {
+        if (track) FEMB_P1_LAUNCH(true, FEMB_RHS_AFFINE);
+        else FEMB_P1_LAUNCH(false, FEMB_RHS_AFFINE);
+    } else if (rhs.kind == FEMB_RHS_QPVALUES) {
+        if (track) FEMB_P1_LAUNCH(true, FEMB_RHS_QPVALUES);
+        else FEMB_P1_LAUNCH(false, FEMB_RHS_QPVALUES);
+    } else {
+        if (track) FEMB_P1_LAUNCH(true, FEMB_RHS_NONE);
+        else FEMB_P1_LAUNCH(false, FEMB_RHS_NONE);
+    }
+#undef FEMB_P1_LAUNCH
+    KERNEL_CHECK(ctx);
+    return FEMB_OK;
 }
 
 static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
@@ -486,26 +569,26 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
         if (EI.h_refvals.size() != phi.size()) return femb_fail(ctx, FEMB_ERR_ARG, "Identity table has the wrong size for P1");
         phi = EI.h_refvals;
     }
-    for (int i = 0; i < EG.nqp; i++) tab.w[i] = EG.w[i];
+    tab.wsum = 0.0;
+    for (int i = 0; i < EG.nqp; i++) {
+        tab.w[i] = EG.w[i];
+        tab.wsum += EG.w[i];
+    }
     for (int i = 0; i < EG.nqp * ctx->dim; i++) tab.xref[i] = EG.xref[i];
     for (int i = 0; i < EG.nqp * ND; i++) tab.phi[i] = phi[i];
-    int acc_A = ctx->zero_pending_A ? 0 : 1, acc_b = ctx->zero_pending_b ? 0 : 1;
+    P1Args a;
+    a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.adj_ptr = s.adj_ptr; a.gmap = ctx->gmap;
+    a.colptr = ctx->colptr; a.ndofs = s.ndofs; a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag;
+    a.mu = mu; a.drop_tol = drop_tol;
+    a.acc_A = ctx->zero_pending_A ? 0 : 1;
+    a.acc_b = ctx->zero_pending_b ? 0 : 1;
     ctx->zero_pending_A = false;
     if (rhs.kind != FEMB_RHS_NONE) ctx->zero_pending_b = false;
     const int nt = 128;
     size_t smem = (size_t)std::max(1, ctx->max_collen) * nt * sizeof(double);
     unsigned grid = (unsigned)((s.ndofs + nt - 1) / nt);
-    if (ctx->dim == 2) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_p1_poisson_gather<2><<<grid, nt, smem, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.adj_ptr, ctx->gmap, ctx->colptr, s.ndofs, ctx->nzval,
-                                                                ctx->touched, ctx->bvec, ctx->errflag, mu, drop_tol, rhs, tab, acc_A, acc_b);
-    } else {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_p1_poisson_gather<3><<<grid, nt, smem, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.adj_ptr, ctx->gmap, ctx->colptr, s.ndofs, ctx->nzval,
-                                                                ctx->touched, ctx->bvec, ctx->errflag, mu, drop_tol, rhs, tab, acc_A, acc_b);
-    }
-    KERNEL_CHECK(ctx);
-    return FEMB_OK;
+    if (ctx->dim == 2) return launch_p1_gather_dim<2>(ctx, a, rhs, tab, grid, smem);
+    return launch_p1_gather_dim<3>(ctx, a, rhs, tab, grid, smem);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -673,7 +756,8 @@ extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, 
     FEMB_TRY(make_rhs(ctx, rhs_kind, data, ctx->spaces[EG.space].ncomp, EG.nqp, rhs, &dev_f));
     int st = femb_timer_begin(ctx);
     if (st == FEMB_OK) {
-        if (ctx->scatter == FEMB_SCATTER_GATHER && ctx->gmap && ctx->gmap_space == EG.space && (!ctx->touched || ctx->max_collen <= 64)) {
+        if (ctx->scatter == FEMB_SCATTER_GATHER && ctx->gmap && ctx->gmap_space == EG.space && (!ctx->touched || ctx->max_collen <= 64) &&
+            rhs_kind != FEMB_RHS_EX210) {
             st = launch_p1_gather(ctx, eg, ei, mu, rhs, drop_tol);
         } else {
             st = launch_bilinear(ctx, eg, eg, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, FEMB_BIL_SYMMETRIC_UPPER, drop_tol);
