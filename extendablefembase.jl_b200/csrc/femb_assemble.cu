@@ -391,10 +391,10 @@ struct P1Tab {
 
 struct P1Args {
     const double* coords;
-    const int32_t* cellnodes;
     const double* cellvol;
-    const int32_t* adj_ptr;
-    const uint2* gmap;
+    const int32_t* gslice_ptr;
+    const uint4* gmap;
+    const uint32_t* gmap_cell;
     const int64_t* colptr;
     int64_t ndofs;
     double* nzval;
@@ -403,64 +403,214 @@ struct P1Args {
     int32_t* errflag;
     double mu, drop_tol;
     int acc_A, acc_b;
+    int maxlen;  // longest CSC column: shared-memory row `maxlen` is the dump row of the 2-D kernel
 };
 
-// One thread per matrix column c (= dof).  For every cell e adjacent to c (dof -> cell adjacency, ascending
-// cell order) the thread recomputes the cell's affine map from CellNodes/Coordinates and adds column k_e of the
-// local stiffness matrix into the <= 64 slots of column c (accumulated in shared memory, written ONCE, fixed
-// order => bit-reproducible, no atomics, no memset).  Arithmetic: with C = cofactor matrix of the Jacobian A,
-// grad phi_j = C_j / det, so  Aloc[j,k] = mu |T| wsum (C_j . C_k) / det^2  — one division per cell instead of the
-// reference's four (mapderiv!) — equal to the reference's value up to a few ulp (tests: 1e-12).
-template <int DIM, bool TRACK, int RHS>  // RHS: FEMB_RHS_NONE / _AFFINE / _QPVALUES
-__global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const RhsDev rhs, const P1Tab tab) {
-    constexpr int ND = DIM + 1;
-    extern __shared__ double acc[];  // [maxlen][blockDim.x]
-    const unsigned tid = threadIdx.x;
+#define FEMB_P1_MAXQP 8
+struct P1Tab2 {
+    int nqp;
+    double mu_wsum;                     // mu * sum_qp w_qp
+    double t[3][FEMB_P1_MAXQP][4];      // [k][qp] = {w_qp phi_k, phi_k, phi_ja, phi_jb} at xref_qp; (ja, jb) = the other local indices
+};
+
+// ---- 2-D scalar P1, the headline kernel ------------------------------------------------------------------------
+// Same owner-computes scheme as the generic kernel below, specialised for triangles:
+//  * with u_self = x_a - x_b, u_a = x_b - x_self, u_b = x_self - x_a (edges opposite to each node, taken in the
+//    cell's cyclic local order up to one global sign that cancels in every product) the cofactor vectors are the
+//    rotated edges, so  Aloc[j,k] = mu |T| wsum (u_j . u_k) / det^2 : no local re-ordering, no selects;
+//  * det is the cross product of the same two edges the reference's A = [x2-x1 | x3-x1] uses (chosen by k), so
+//    every visitor of a cell gets bit-identical scale factors and the assembled matrix is exactly symmetric;
+//  * entries are software-pipelined: the gather-map entry two visits ahead and the coordinates / volume of the
+//    next visit are in flight while the current visit is computed;
+//  * accumulation into the column's slots is branch-free: filtered (|v| <= drop_tol) contributions go to a dump row.
+template <bool TRACK, int RHS, bool HAS_VOL>
+__global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
     constexpr unsigned nt = 128;
-    const int64_t c = blockIdx.x * (int64_t)nt + tid;
-    if (c >= a.ndofs) return;
-    const int64_t base = a.colptr[c] - 1;
-    const int len = (int)(a.colptr[c + 1] - 1 - base);
-    for (int i = 0; i < len; i++) acc[i * nt + tid] = 0.0;
+    extern __shared__ double acc[];  // [maxlen + 1][128]
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + (tid >> 5);
+    if (slice * 32 >= a.ndofs) return;  // whole warp out of range
+    const int64_t c = slice * 32 + lane;
+    const bool valid = c < a.ndofs;
+    const int row0 = __ldg(a.gslice_ptr + slice), nrows = __ldg(a.gslice_ptr + slice + 1) - row0;
+    const double2* __restrict__ xy = reinterpret_cast<const double2*>(a.coords);
+    int64_t base = 0;
+    int len = 0;
+    double2 self = make_double2(0.0, 0.0);
+    if (valid) {
+        base = a.colptr[c] - 1;
+        len = (int)(a.colptr[c + 1] - 1 - base);
+        self = __ldg(xy + c);
+    }
+    double* accp = acc + tid;
+    for (int i = 0; i < len; i++) accp[i * nt] = 0.0;
+    const unsigned dump = (unsigned)a.maxlen;
     unsigned long long mask = 0ull;
     double bsum = 0.0;
-    const int e1 = a.adj_ptr[c + 1];
-    for (int e = a.adj_ptr[c]; e < e1; e++) {
-        const uint2 gm = __ldg(a.gmap + e);
-        const unsigned cell = gm.x;
-        const unsigned k = (DIM == 2) ? (gm.y & 0xFFu) : (gm.y & 3u);
-        const int32_t* cn = a.cellnodes + (size_t)cell * ND;
-        double cf[ND][DIM];  // cofactor vectors: grad phi_j = cf[j] / det
-        double A[DIM][DIM], x0[DIM], det;
+    unsigned err = 0u;
+
+    const uint4 inv = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
+    const uint4* ep = a.gmap + ((size_t)row0 << 5) + lane;
+    uint4 e1 = nrows > 0 ? __ldg(ep) : inv;        // visit r
+    uint4 e2 = nrows > 1 ? __ldg(ep + 32) : inv;   // visit r + 1
+    double2 pa1 = __ldg(xy + e1.x), pb1 = __ldg(xy + e1.y);
+    double vol1 = HAS_VOL ? __ldg(a.cellvol + e1.z) : 0.0;
+    for (int r = 0; r < nrows; r++) {
+        const uint4 e = e1;
+        const double2 pa = pa1, pb = pb1;
+        const double volr = vol1;
+        e1 = e2;
+        e2 = (r + 2 < nrows) ? __ldg(ep + ((size_t)(r + 2) << 5)) : inv;
+        pa1 = __ldg(xy + e1.x);
+        pb1 = __ldg(xy + e1.y);
+        if (HAS_VOL) vol1 = __ldg(a.cellvol + e1.z);
+        if (e.w == 0xFFFFFFFFu) continue;
+        const unsigned k = e.w & 3u;
+        const double uax = pb.x - self.x, uay = pb.y - self.y;
+        const double ubx = self.x - pa.x, uby = self.y - pa.y;
+        const double usx = pa.x - pb.x, usy = pa.y - pb.y;
+        const double px = (k == 0u) ? uax : usx, py = (k == 0u) ? uay : usy;
+        const double det = px * uby - py * ubx;
+        const double vol = HAS_VOL ? volr : fabs(det) * 0.5;
+        const double scale = (tab.mu_wsum * vol) / (det * det);
+        const double vs = (usx * usx + usy * usy) * scale;
+        const double va = (uax * usx + uay * usy) * scale;
+        const double vb = (ubx * usx + uby * usy) * scale;
+        const unsigned ps = (e.w >> 8) & 0xFFu, pA = (e.w >> 16) & 0xFFu, pB = e.w >> 24;
+        const bool ks = fabs(vs) > a.drop_tol, ka = fabs(va) > a.drop_tol, kb = fabs(vb) > a.drop_tol;
+        err |= (unsigned)((ks && ps == 0xFFu) || (ka && pA == 0xFFu) || (kb && pB == 0xFFu));
+        const unsigned rs = (ks && ps != 0xFFu) ? ps : dump, ra = (ka && pA != 0xFFu) ? pA : dump, rb = (kb && pB != 0xFFu) ? pB : dump;
+        accp[rs * nt] += vs;
+        accp[ra * nt] += va;
+        accp[rb * nt] += vb;
+        if (TRACK) {
+            mask |= (rs != dump ? 1ull << (rs & 63u) : 0ull) | (ra != dump ? 1ull << (ra & 63u) : 0ull) | (rb != dump ? 1ull << (rb & 63u) : 0ull);
+        }
+        if (RHS != FEMB_RHS_NONE) {
+            double temp = 0.0;
+            for (int qp = 0; qp < tab.nqp; qp++) {
+                const double* t = tab.t[k][qp];
+                double f;
+                if (RHS == FEMB_RHS_AFFINE) {  // f(x_qp); x_qp = sum_j phi_j(xref_qp) x_j  (= A xref_qp + x_1, eval_trafo!, Example200:171)
+                    const double xq = t[1] * self.x + t[2] * pa.x + t[3] * pb.x;
+                    const double yq = t[1] * self.y + t[2] * pa.y + t[3] * pb.y;
+                    f = rhs.p[0] + rhs.p[1] * xq + rhs.p[2] * yq;
+                } else {
+                    f = __ldg(rhs.fvals + (size_t)e.z * tab.nqp + qp);
+                }
+                temp += t[0] * f;
+            }
+            bsum += temp * vol;
+        }
+    }
+    if (!valid) return;
+    if (err) atomicAdd(a.errflag, 1);
+    double* out = a.nzval + base;
+    if (a.acc_A) {
+        for (int i = 0; i < len; i++) out[i] += accp[i * nt];
+    } else {
+        for (int i = 0; i < len; i++) out[i] = accp[i * nt];
+    }
+    if (TRACK) {
+        for (int i = 0; i < len; i++)
+            if ((mask >> i) & 1ull) a.touched[base + i] = 1;
+    }
+    if (RHS != FEMB_RHS_NONE) {
+        if (a.acc_b) a.bvec[c] += bsum;
+        else a.bvec[c] = bsum;
+    }
+}
+
+// Fused stages 1-5 for scalar P1 (Example200:133-179), owner-computes by matrix column.
+// One thread per column c (= dof = node), one warp per slice of the sliced-ELL gather map (femb_pattern.cu):
+// the warp streams its slice's entries with fully coalesced 16-byte loads; every entry names one cell adjacent
+// to c by its two (three) other nodes, so the thread rebuilds the cell's affine map from Coordinates alone
+// (its own node is loaded once, coalesced), forms column k of the local stiffness matrix and adds it into the
+// <= 64 slots of CSC column c.  Slots are accumulated in shared memory (the diagonal in a register) and written
+// ONCE in a fixed order: bit-reproducible, no atomics, no memset of nzval.
+// Arithmetic: with C = cofactor matrix of the Jacobian A, grad phi_j = C_j / det, so
+//   Aloc[j,k] = mu |T| wsum (C_j . C_k) / det^2
+// — one division per cell visit instead of the reference's four (mapderiv!); the nodes are used in the cell's
+// own local order, so A[i,c] and A[c,i] are computed from identical operands and the matrix is exactly symmetric.
+template <int DIM, bool TRACK, int RHS>  // RHS: FEMB_RHS_NONE / _AFFINE / _QPVALUES.  Instantiated for DIM == 3 (tetrahedra) only.
+__global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const RhsDev rhs, const P1Tab tab) {
+    constexpr int ND = DIM + 1;
+    constexpr unsigned nt = 128;
+    constexpr unsigned MISSING = (DIM == 2) ? 0xFFu : 0x3Fu;
+    extern __shared__ double acc[];  // [maxlen][128]
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    const int64_t slice = (int64_t)blockIdx.x * 4 + (tid >> 5);
+    const int64_t c = slice * 32 + lane;
+    if (slice * 32 >= a.ndofs) return;  // whole warp out of range
+    const bool valid = c < a.ndofs;
+    const int row0 = __ldg(a.gslice_ptr + slice), row1 = __ldg(a.gslice_ptr + slice + 1);
+    int64_t base = 0;
+    int len = 0;
+    double self[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) self[d] = 0.0;
+    if (valid) {
+        base = a.colptr[c] - 1;
+        len = (int)(a.colptr[c + 1] - 1 - base);
         if (DIM == 2) {
+            const double2 p = __ldg(reinterpret_cast<const double2*>(a.coords) + c);
+            self[0] = p.x; self[1] = p.y;
+        } else {
+#pragma unroll
+            for (int d = 0; d < 3; d++) self[d] = __ldg(a.coords + c * 3 + d);
+        }
+    }
+    for (int i = 0; i < len; i++) acc[i * nt + tid] = 0.0;
+    unsigned long long mask = 0ull;
+    double bsum = 0.0, diag = 0.0;
+    unsigned dpos = MISSING, err = 0u;
+    const uint4* ent_p = a.gmap + ((size_t)row0 << 5) + lane;
+    for (int r = row0; r < row1; r++, ent_p += 32) {
+        const uint4 ent = __ldg(ent_p);
+        if (ent.w == 0xFFFFFFFFu) continue;
+        const unsigned k = ent.w & 3u;
+        unsigned cell;
+        double x[ND][DIM];  // the cell's nodes in local order
+        if (DIM == 2) {
+            cell = ent.z;
             const double2* xy = reinterpret_cast<const double2*>(a.coords);
-            const double2 p0 = __ldg(xy + (__ldg(cn) - 1)), p1 = __ldg(xy + (__ldg(cn + 1) - 1)), p2 = __ldg(xy + (__ldg(cn + 2) - 1));
-            A[0][0] = p1.x - p0.x; A[0][1] = p2.x - p0.x;
-            A[1][0] = p1.y - p0.y; A[1][1] = p2.y - p0.y;
-            x0[0] = p0.x; x0[1] = p0.y;
+            const double2 pa = __ldg(xy + ent.x), pb = __ldg(xy + ent.y);
+            x[0][0] = (k == 0) ? self[0] : pa.x; x[0][1] = (k == 0) ? self[1] : pa.y;
+            x[1][0] = (k == 0) ? pa.x : ((k == 1) ? self[0] : pb.x);
+            x[1][1] = (k == 0) ? pa.y : ((k == 1) ? self[1] : pb.y);
+            x[2][0] = (k == 2) ? self[0] : pb.x; x[2][1] = (k == 2) ? self[1] : pb.y;
+        } else {
+            cell = __ldg(a.gmap_cell + (ent_p - a.gmap));
+            double o[3][3];
+            const unsigned on[3] = {ent.x, ent.y, ent.z};
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int d = 0; d < 3; d++) o[i][d] = __ldg(a.coords + (size_t)on[i] * 3 + d);
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                x[0][d] = (k == 0) ? self[d] : o[0][d];
+                x[1][d] = (k == 0) ? o[0][d] : ((k == 1) ? self[d] : o[1][d]);
+                x[2][d] = (k <= 1) ? o[1][d] : ((k == 2) ? self[d] : o[2][d]);
+                x[3][d] = (k == 3) ? self[d] : o[2][d];
+            }
+        }
+        double A[DIM][DIM], cf[ND][DIM], det;  // cf[j] = cofactor vector: grad phi_j = cf[j] / det
+#pragma unroll
+        for (int d = 0; d < DIM; d++)
+#pragma unroll
+            for (int i = 0; i < DIM; i++) A[d][i] = x[i + 1][d] - x[0][d];
+        if (DIM == 2) {
             det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
             cf[1][0] = A[1][1];  cf[1][1] = -A[0][1];
             cf[2][0] = -A[1][0]; cf[2][1] = A[0][0];
         } else {
-            double x[4][3];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const double* p = a.coords + (size_t)(__ldg(cn + i) - 1) * 3;
-                x[i][0] = __ldg(p); x[i][1] = __ldg(p + 1); x[i][2] = __ldg(p + 2);
-            }
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                x0[d] = x[0][d];
-#pragma unroll
-                for (int i = 0; i < 3; i++) A[d][i] = x[i + 1][d] - x[0][d];
-            }
-            // cofactor C[r][j] of A[r][j]; cf[j+1][r] = C[r][j]
-#pragma unroll
-            for (int r = 0; r < 3; r++)
+            for (int r2 = 0; r2 < 3; r2++)
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
-                    const int r1 = (r + 1) % 3, r2 = (r + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-                    cf[j + 1][r] = A[r1][j1] * A[r2][j2] - A[r1][j2] * A[r2][j1];
+                    const int ra = (r2 + 1) % 3, rb = (r2 + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
+                    cf[j + 1][r2] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
                 }
             det = A[0][0] * cf[1][0] + A[0][1] * cf[2][0] + A[0][2] * cf[3][0];
         }
@@ -487,10 +637,13 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
 #pragma unroll
             for (int kk = 0; kk < DIM; kk++) d += cf[j][kk] * ck[kk];
             const double val = d * scale;
+            const unsigned pos = (DIM == 2) ? ((ent.w >> (8 * (j + 1))) & 0xFFu) : ((ent.w >> (2 + 6 * j)) & 0x3Fu);
             if (fabs(val) > a.drop_tol) {
-                const unsigned pos = (DIM == 2) ? ((gm.y >> (8 * (j + 1))) & 0xFFu) : ((gm.y >> (2 + 6 * j)) & 0x3Fu);
-                if (pos == ((DIM == 2) ? 0xFFu : 0x3Fu)) {
-                    atomicAdd(a.errflag, 1);
+                if (pos == MISSING) {
+                    err = 1u;
+                } else if (k == (unsigned)j) {  // diagonal entry A[c,c]: same slot on every visit
+                    diag += val;
+                    dpos = pos;
                 } else {
                     acc[pos * nt + tid] += val;
                     if (TRACK) mask |= 1ull << (pos & 63u);
@@ -505,7 +658,7 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
                     f = rhs.p[0];
 #pragma unroll
                     for (int d = 0; d < DIM; d++) {
-                        double sx = x0[d];
+                        double sx = x[0][d];
 #pragma unroll
                         for (int i = 0; i < DIM; i++) sx += A[d][i] * tab.xref[qp * DIM + i];
                         f += rhs.p[1 + d] * sx;
@@ -517,6 +670,12 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
             }
             bsum += temp * vol;
         }
+    }
+    if (!valid) return;
+    if (err) atomicAdd(a.errflag, 1);
+    if (dpos != MISSING) {
+        acc[dpos * nt + tid] += diag;
+        if (TRACK) mask |= 1ull << (dpos & 63u);
     }
     double* out = a.nzval + base;
     if (a.acc_A) {
@@ -577,7 +736,7 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
     for (int i = 0; i < EG.nqp * ctx->dim; i++) tab.xref[i] = EG.xref[i];
     for (int i = 0; i < EG.nqp * ND; i++) tab.phi[i] = phi[i];
     P1Args a;
-    a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.adj_ptr = s.adj_ptr; a.gmap = ctx->gmap;
+    a.coords = ctx->coords; a.cellvol = ctx->cellvol; a.gslice_ptr = ctx->gslice_ptr; a.gmap = ctx->gmap; a.gmap_cell = ctx->gmap_cell;
     a.colptr = ctx->colptr; a.ndofs = s.ndofs; a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag;
     a.mu = mu; a.drop_tol = drop_tol;
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
@@ -587,7 +746,49 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
     const int nt = 128;
     size_t smem = (size_t)std::max(1, ctx->max_collen) * nt * sizeof(double);
     unsigned grid = (unsigned)((s.ndofs + nt - 1) / nt);
-    if (ctx->dim == 2) return launch_p1_gather_dim<2>(ctx, a, rhs, tab, grid, smem);
+    a.maxlen = std::max(1, ctx->max_collen);
+    if (ctx->dim == 2) {
+        P1Tab2 t2;
+        t2.nqp = EG.nqp;
+        t2.mu_wsum = mu * tab.wsum;
+        static const int others[3][2] = {{1, 2}, {0, 2}, {0, 1}};
+        for (int k = 0; k < 3; k++)
+            for (int q = 0; q < FEMB_P1_MAXQP; q++) {
+                // P1 barycentric coordinates of xref_q (h1_p1.jl:64-76): needed even without a rhs? no — zero then
+                double lam[3] = {0.0, 0.0, 0.0};
+                if (q < EG.nqp) {
+                    lam[1] = EG.xref[q * 2];
+                    lam[2] = EG.xref[q * 2 + 1];
+                    lam[0] = 1.0 - lam[1] - lam[2];
+                }
+                double phik = (q < EG.nqp) ? phi[(size_t)q * 3 + k] : 0.0;  // Identity table of the evaluator (= lam[k] for P1)
+                t2.t[k][q][0] = (q < EG.nqp ? EG.w[q] : 0.0) * phik;
+                t2.t[k][q][1] = lam[k];
+                t2.t[k][q][2] = lam[others[k][0]];
+                t2.t[k][q][3] = lam[others[k][1]];
+            }
+        smem = (size_t)(a.maxlen + 1) * nt * sizeof(double);
+        const bool track = a.touched != nullptr, hv = a.cellvol != nullptr;
+#define FEMB_P1_LAUNCH2(T, R, V)                                                                                                    \
+    do {                                                                                                                            \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather2d<T, R, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        k_p1_poisson_gather2d<T, R, V><<<grid, 128, smem, ctx->stream>>>(a, rhs, t2);                                                \
+    } while (0)
+#define FEMB_P1_LAUNCH2_R(R)                                    \
+    do {                                                        \
+        if (track && hv) FEMB_P1_LAUNCH2(true, R, true);        \
+        else if (track) FEMB_P1_LAUNCH2(true, R, false);        \
+        else if (hv) FEMB_P1_LAUNCH2(false, R, true);           \
+        else FEMB_P1_LAUNCH2(false, R, false);                  \
+    } while (0)
+        if (rhs.kind == FEMB_RHS_AFFINE) FEMB_P1_LAUNCH2_R(FEMB_RHS_AFFINE);
+        else if (rhs.kind == FEMB_RHS_QPVALUES) FEMB_P1_LAUNCH2_R(FEMB_RHS_QPVALUES);
+        else FEMB_P1_LAUNCH2_R(FEMB_RHS_NONE);
+#undef FEMB_P1_LAUNCH2_R
+#undef FEMB_P1_LAUNCH2
+        KERNEL_CHECK(ctx);
+        return FEMB_OK;
+    }
     return launch_p1_gather_dim<3>(ctx, a, rhs, tab, grid, smem);
 }
 
@@ -757,7 +958,7 @@ extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, 
     int st = femb_timer_begin(ctx);
     if (st == FEMB_OK) {
         if (ctx->scatter == FEMB_SCATTER_GATHER && ctx->gmap && ctx->gmap_space == EG.space && (!ctx->touched || ctx->max_collen <= 64) &&
-            rhs_kind != FEMB_RHS_EX210) {
+            rhs_kind != FEMB_RHS_EX210 && (ctx->dim == 3 || EG.nqp <= FEMB_P1_MAXQP)) {
             st = launch_p1_gather(ctx, eg, ei, mu, rhs, drop_tol);
         } else {
             st = launch_bilinear(ctx, eg, eg, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, FEMB_BIL_SYMMETRIC_UPPER, drop_tol);

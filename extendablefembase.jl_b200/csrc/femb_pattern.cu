@@ -15,6 +15,9 @@ void femb_free_pattern(femb_ctx* ctx) {
     femb_free(&ctx->nzval);
     femb_free(&ctx->touched);
     femb_free(&ctx->gmap);
+    femb_free(&ctx->gmap_cell);
+    femb_free(&ctx->gslice_ptr);
+    ctx->gmap_rows = 0;
     ctx->gmap_space = -1;
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
@@ -460,7 +463,6 @@ extern "C" int32_t femb_pattern_compress(femb_ctx* ctx, int64_t* nnz_out) {
     // swap in the compressed arrays (keep exact-size copies)
     std::vector<FembBlock> blocks = ctx->blocks;
     for (auto& b : ctx->blocks) femb_free(&b.slots);
-    femb_free(&ctx->gmap);
     femb_free(&ctx->rowval);
     femb_free(&ctx->nzval);
     femb_free(&ctx->touched);
@@ -517,40 +519,107 @@ int femb_build_slotmaps(femb_ctx* ctx) {
     return FEMB_OK;
 }
 
-// gather map for scalar P1: entry e of column c (adjacency order) -> (cell, k | pos[0..nd) packed)
+// Gather map for scalar P1 (dof == node), sliced ELL with one slice per warp of 32 consecutive dofs.
+//   2-D entry {na, nb, cell, w}, w = k | pos_self << 8 | pos_a << 16 | pos_b << 24     (pos 0xFF = not in pattern)
+//   3-D entry {na, nb, nc, w} (+ gmap_cell), w = k | pos0 << 2 | ... | pos3 << 20       (pos 0x3F = not in pattern)
+// na.. are the cell's nodes other than the dof itself, in local order, 0-based; k is the dof's local index;
+// pos_j = position of global row celldofs[j] inside CSC column c.  Padding entries have w = 0xFFFFFFFF and node /
+// cell ids 0 (so that unconditional prefetches stay in bounds).
+#define FEMB_GMAP_INVALID 0xFFFFFFFFu
+
+__global__ void k_slice_deg(const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices, int32_t* __restrict__ deg) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nslices) return;
+    int m = 0;
+    for (int l = 0; l < 32; l++) {
+        int64_t c = s * 32 + l;
+        if (c < ndofs) m = max(m, adj_ptr[c + 1] - adj_ptr[c]);
+    }
+    deg[s] = m;
+}
+
 template <int ND>
-__global__ void k_gmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, const int32_t* __restrict__ celldofs,
-                       const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, uint2* __restrict__ gmap) {
+__global__ void k_gmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices,
+                       const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                       const int32_t* __restrict__ slice_ptr, uint4* __restrict__ gmap, uint32_t* __restrict__ gmap_cell) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= ndofs) return;
-    const int64_t base = colptr[c] - 1;
-    for (int32_t e = adj_ptr[c]; e < adj_ptr[c + 1]; e++) {
-        uint32_t a = adj[e];
-        uint32_t cell = a / ND, k = a - cell * ND;
-        uint32_t packed = (ND == 3) ? k : k;
+    if (c >= nslices * 32) return;
+    const int64_t slice = c >> 5;
+    const int lane = (int)(c & 31);
+    const int row0 = slice_ptr[slice], nrows = slice_ptr[slice + 1] - row0;
+    const int e0 = c < ndofs ? adj_ptr[c] : 0;
+    const int deg = c < ndofs ? adj_ptr[c + 1] - e0 : 0;
+    const int64_t base = c < ndofs ? colptr[c] - 1 : 0;
+    for (int r = 0; r < nrows; r++) {
+        uint4 ent = make_uint4(0u, 0u, 0u, FEMB_GMAP_INVALID);
+        uint32_t cell = 0;
+        if (r < deg) {
+            uint32_t a = adj[e0 + r];
+            cell = a / ND;
+            uint32_t k = a - cell * ND;
+            uint32_t w = k, others[3] = {0u, 0u, 0u}, opos[3] = {0u, 0u, 0u}, spos = 0u;
+            int no = 0;
 #pragma unroll
-        for (int j = 0; j < ND; j++) {
-            int64_t p = find_slot(colptr, rowval, c, (int64_t)celldofs[(int64_t)cell * ND + j]);
-            uint32_t pos = (p < 0) ? ((ND == 3) ? 0xFFu : 0x3Fu) : (uint32_t)(p - base);
-            packed |= (ND == 3) ? (pos << (8 * (j + 1))) : (pos << (2 + 6 * j));
+            for (int j = 0; j < ND; j++) {
+                int32_t dof = celldofs[(int64_t)cell * ND + j];
+                int64_t p = find_slot(colptr, rowval, c, (int64_t)dof);
+                uint32_t pos = (p < 0) ? ((ND == 3) ? 0xFFu : 0x3Fu) : (uint32_t)(p - base);
+                if (ND == 4) w |= pos << (2 + 6 * j);
+                if ((uint32_t)j != k) {
+                    opos[no] = pos;
+                    others[no++] = (uint32_t)(dof - 1);
+                } else {
+                    spos = pos;
+                }
+            }
+            if (ND == 3) w |= (spos << 8) | (opos[0] << 16) | (opos[1] << 24);  // 2-D: positions in (self, a, b) order
+            ent = (ND == 3) ? make_uint4(others[0], others[1], cell, w) : make_uint4(others[0], others[1], others[2], w);
         }
-        gmap[e] = make_uint2(cell, packed);
+        size_t idx = ((size_t)(row0 + r) << 5) + lane;
+        gmap[idx] = ent;
+        if (ND == 4) gmap_cell[idx] = cell;
     }
 }
 
 int femb_build_gmap(femb_ctx* ctx) {
     femb_free(&ctx->gmap);
+    femb_free(&ctx->gmap_cell);
+    femb_free(&ctx->gslice_ptr);
+    ctx->gmap_rows = 0;
     ctx->gmap_space = -1;
     if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
     int sid = ctx->row_spaces[0];
     const FembSpace& s = ctx->spaces[sid];
-    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.nd != ctx->nnpc || s.handler != FEMB_HANDLER_NONE) return FEMB_OK;
+    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.nd != ctx->nnpc || s.handler != FEMB_HANDLER_NONE || s.ndofs != ctx->nnodes) return FEMB_OK;
     int maxpos = (s.nd == 3) ? 254 : 62;
     if (ctx->max_collen > maxpos) return FEMB_OK;  // fall back to the cell-parallel kernels
-    FEMB_TRY(femb_alloc(ctx, &ctx->gmap, (size_t)ctx->ncells * s.nd));
-    unsigned grid = (unsigned)((s.ndofs + 127) / 128);
-    if (s.nd == 3) k_gmap<3><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, s.celldofs, ctx->colptr, ctx->rowval, ctx->gmap);
-    else k_gmap<4><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, s.celldofs, ctx->colptr, ctx->rowval, ctx->gmap);
+    const int64_t nslices = (s.ndofs + 31) / 32;
+    int32_t* deg = nullptr;
+    void* tmp = nullptr;
+    FEMB_TRY(femb_alloc(ctx, &deg, (size_t)nslices + 1));
+    FEMB_TRY(femb_alloc(ctx, &ctx->gslice_ptr, (size_t)nslices + 1));
+    CUDA_TRY(ctx, cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nslices + 1), ctx->stream));
+    k_slice_deg<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(s.adj_ptr, s.ndofs, nslices, deg);
+    KERNEL_CHECK(ctx);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, ctx->gslice_ptr, nslices + 1, ctx->stream);
+    cudaError_t e = cudaMalloc(&tmp, tb);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, deg, ctx->gslice_ptr, nslices + 1, ctx->stream);
+    int32_t rows = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&rows, ctx->gslice_ptr + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    cudaFree(deg);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, e);
+    ctx->gmap_rows = rows;
+    FEMB_TRY(femb_alloc(ctx, &ctx->gmap, (size_t)rows * 32));
+    if (s.nd == 4) FEMB_TRY(femb_alloc(ctx, &ctx->gmap_cell, (size_t)rows * 32));
+    unsigned grid = (unsigned)((nslices * 32 + 127) / 128);
+    if (s.nd == 3)
+        k_gmap<3><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.celldofs, ctx->colptr, ctx->rowval, ctx->gslice_ptr, ctx->gmap, ctx->gmap_cell);
+    else
+        k_gmap<4><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.celldofs, ctx->colptr, ctx->rowval, ctx->gslice_ptr, ctx->gmap, ctx->gmap_cell);
     KERNEL_CHECK(ctx);
     ctx->gmap_space = sid;
     return FEMB_OK;
