@@ -101,7 +101,7 @@ def make_problem(n, jitter):
     return grid, vol
 
 
-def setup_device(grid, vol, device):
+def setup_device(grid, vol, device, use_vol=True):
     """Symbolic phase (once): register mesh / space / rule / evaluators, build the structural pattern on the
     device, run the reference's FIRST assembly (value filter decides the pattern) and compress."""
     import femb_b200 as fb
@@ -111,7 +111,7 @@ def setup_device(grid, vol, device):
     fes = fb.FESpace(fb.H1Pk(1, 2, 1), grid)
     qf = fb.QuadratureRule(grid.geometry, 0)  # Example200:110 with order 1 -> midpoint rule
     t0 = time.time()
-    S = _Session([fes], qf, device)
+    S = _Session([fes], qf, device, cellvolumes=use_vol)
     ctx = S.ctx
     eg, ei = S.evaluator(0, fb.Gradient), S.evaluator(0, fb.Identity)
     ctx.pattern_track(True)
@@ -151,7 +151,8 @@ def run_ours(args):
 
     fbuild.build()
     grid, vol = make_problem(args.n, args.jitter)
-    S, fes, eg, ei, rhsp, nnz = setup_device(grid, vol, local)
+    use_vol = args.cellvol == "given"
+    S, fes, eg, ei, rhsp, nnz = setup_device(grid, vol, local, use_vol)
     ctx = S.ctx
     ncells, nnodes = grid.ncells, grid.nnodes
 
@@ -186,12 +187,13 @@ def run_ours(args):
     coords, cn = grid["Coordinates"], grid["CellNodes"]
     nz_host = np.empty(nnz, dtype=np.float64)
     b_host = np.empty(nnodes, dtype=np.float64)
-    pinned = [coords, cn, vol, nz_host, b_host]
+    vol_in = vol if use_vol else None
+    pinned = [coords, cn, nz_host, b_host] + ([vol] if use_vol else [])
     for a in pinned:
         ctx.host_register(a)
 
     def step_e2e():
-        ctx.mesh_set(coords, cn, vol)
+        ctx.mesh_set(coords, cn, vol_in)
         step_resident(ctx, eg, ei, rhsp)
         ctx.matrix_get(nz_host)
         ctx.vector_get(out=b_host)
@@ -212,7 +214,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * ncells / (e2e_ms / args.steps * 1e-3)
-    h2d = coords.nbytes + cn.nbytes + vol.nbytes
+    h2d = coords.nbytes + cn.nbytes + (vol.nbytes if use_vol else 0)
     d2h = nz_host.nbytes + b_host.nbytes
     checks = sanity_checks(nz_host, b_host, S, nnodes)
     for a in pinned:
@@ -224,19 +226,20 @@ def run_ours(args):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    bpc = algorithmic_bytes_per_cell(nnodes, ncells, nnz)
+    bpc = algorithmic_bytes_per_cell(nnodes, ncells, nnz, use_vol)
     kernel_ms = float(np.mean(kms))
     achieved = bpc * ncells / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
-                "kernel": "k_p1_poisson_gather<2>", "kernel_ms": round(kernel_ms, 4), "algorithmic_bytes_per_cell": round(bpc, 2)}
+                "kernel": "k_p1_poisson_gather2d", "kernel_ms": round(kernel_ms, 4), "algorithmic_bytes_per_cell": round(bpc, 2)}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"H1P1 2-D Poisson stiffness+rhs, simplexgrid n={args.n} ({ncells} triangles, {nnodes} nodes) per GPU" + (", jittered" if args.jitter else ""),
                    "nnz": nnz, "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" % (bpc * ncells / 1e9),
-                   "partition": "one slab per rank" if world > 1 else "single GPU", "scatter": "owner-computes gather (write-once, bit-reproducible)"},
+                   "partition": "one slab per rank" if world > 1 else "single GPU", "scatter": "owner-computes gather (write-once, bit-reproducible)",
+                   "cellvolumes": "xgrid[CellVolumes] passed in" if use_vol else "NULL: |det A|/2 on the device"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
         "roofline": roofline, "checks": checks,
@@ -366,6 +369,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_DEFAULT, help="quads per side (cells = 2 n^2)")
     ap.add_argument("--jitter", action="store_true", help="perturb interior nodes (full 7-point pattern)")
+    ap.add_argument("--cellvol", default="given", choices=["given", "device"], help="pass xgrid[CellVolumes] (as Example200:114 reads it) or NULL")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-cells", type=float, default=16e6, help="cells per step of the --impl reference sample")

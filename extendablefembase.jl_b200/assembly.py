@@ -88,11 +88,12 @@ def _rhs_args(ctx, rhs, nqp, ncomp):
 class _Session:
     """Device-resident state for one (grid, FE spaces, quadrature rule) combination."""
 
-    def __init__(self, spaces, qf, device=0):
+    def __init__(self, spaces, qf, device=0, cellvolumes=True):
+        """``cellvolumes=False`` passes NULL for xgrid[CellVolumes]: the kernels then use |det A| / d!."""
         self.ctx = _lib.Context(device)
         grid = spaces[0].xgrid
         self.grid, self.spaces, self.qf = grid, spaces, qf
-        self.ctx.mesh_set(grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"])
+        self.ctx.mesh_set(grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"] if cellvolumes else None)
         for sid, fes in enumerate(spaces):
             _register_space(self.ctx, sid, fes)
         self.ctx.quadrature_set(qf.xref, qf.w)

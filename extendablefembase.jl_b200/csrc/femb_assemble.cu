@@ -393,8 +393,8 @@ struct P1Args {
     const double* coords;
     const double* cellvol;
     const int32_t* gslice_ptr;
-    const uint4* gmap;
-    const uint32_t* gmap_cell;
+    const uint32_t* gmap;  // SoA planes na, nb, w, cell (, nc): femb_internal.h
+    size_t gstride;
     const int64_t* colptr;
     int64_t ndofs;
     double* nzval;
@@ -413,19 +413,42 @@ struct P1Tab2 {
     double t[3][FEMB_P1_MAXQP][4];      // [k][qp] = {w_qp phi_k, phi_k, phi_ja, phi_jb} at xref_qp; (ja, jb) = the other local indices
 };
 
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (no denormal / special-case slow path: x = det^2 > 0 of a
+// non-degenerate cell).  Every visitor of a cell evaluates this on identical bits, so symmetry is preserved.
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double lds64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
 // ---- 2-D scalar P1, the headline kernel ------------------------------------------------------------------------
-// Same owner-computes scheme as the generic kernel below, specialised for triangles:
+// Fused stages 1-5 (Example200:133-179), owner-computes by matrix column: one thread per column c (= dof = node),
+// one warp per slice of the sliced-ELL gather map (femb_pattern.cu), streamed with fully coalesced loads.  Every
+// entry names one cell adjacent to c by its two other nodes; the thread rebuilds the cell's affine map from
+// Coordinates alone (its own node is loaded once), forms column k of the local stiffness matrix and adds it into
+// the <= 255 slots of CSC column c, accumulated in shared memory and written ONCE in a fixed order:
+// bit-reproducible, no atomics, no memset of nzval.
 //  * with u_self = x_a - x_b, u_a = x_b - x_self, u_b = x_self - x_a (edges opposite to each node, taken in the
 //    cell's cyclic local order up to one global sign that cancels in every product) the cofactor vectors are the
-//    rotated edges, so  Aloc[j,k] = mu |T| wsum (u_j . u_k) / det^2 : no local re-ordering, no selects;
+//    rotated edges, so  Aloc[j,k] = mu |T| wsum (u_j . u_k) / det^2 : one reciprocal per visit instead of the
+//    reference's four divisions (mapderiv!), no local re-ordering;
 //  * det is the cross product of the same two edges the reference's A = [x2-x1 | x3-x1] uses (chosen by k), so
 //    every visitor of a cell gets bit-identical scale factors and the assembled matrix is exactly symmetric;
-//  * entries are software-pipelined: the gather-map entry two visits ahead and the coordinates / volume of the
-//    next visit are in flight while the current visit is computed;
-//  * accumulation into the column's slots is branch-free: filtered (|v| <= drop_tol) contributions go to a dump row.
-template <bool TRACK, int RHS, bool HAS_VOL>
+//  * software pipeline: the gather-map entry two visits ahead and the coordinates / volume of the next visit are
+//    in flight while the current visit is computed;
+//  * accumulation is branch-free: filtered (|v| <= drop_tol, Example200:153) contributions go to a dump row.
+template <bool TRACK, int RHS, bool HAS_VOL, int NQP>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
 __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
     constexpr unsigned nt = 128;
+    constexpr bool NEED_CELL = HAS_VOL || RHS == FEMB_RHS_QPVALUES;
     extern __shared__ double acc[];  // [maxlen + 1][128]
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const int64_t slice = (int64_t)blockIdx.x * 4 + (tid >> 5);
@@ -442,53 +465,75 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
         len = (int)(a.colptr[c + 1] - 1 - base);
         self = __ldg(xy + c);
     }
-    double* accp = acc + tid;
-    for (int i = 0; i < len; i++) accp[i * nt] = 0.0;
+    const unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + tid * 8u;
+    for (int i = 0; i < len; i++) sts64(sacc + i * (nt * 8u), 0.0);
     const unsigned dump = (unsigned)a.maxlen;
     unsigned long long mask = 0ull;
     double bsum = 0.0;
     unsigned err = 0u;
+    const double drop_tol = a.drop_tol, mu_wsum = tab.mu_wsum;
 
-    const uint4 inv = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
-    const uint4* ep = a.gmap + ((size_t)row0 << 5) + lane;
-    uint4 e1 = nrows > 0 ? __ldg(ep) : inv;        // visit r
-    uint4 e2 = nrows > 1 ? __ldg(ep + 32) : inv;   // visit r + 1
-    double2 pa1 = __ldg(xy + e1.x), pb1 = __ldg(xy + e1.y);
-    double vol1 = HAS_VOL ? __ldg(a.cellvol + e1.z) : 0.0;
+    const uint32_t* __restrict__ ga = a.gmap + ((size_t)row0 << 5) + lane;
+    const uint32_t* __restrict__ gb = ga + a.gstride;
+    const uint32_t* __restrict__ gw = gb + a.gstride;
+    const uint32_t* __restrict__ gc = gw + a.gstride;
+    // pipeline registers: (w1, a1, b1, c1) = entry of visit r, (w2, ...) = visit r + 1; pa1/pb1/vol1 = data of visit r
+    unsigned w1 = 0xFFFFFFFFu, a1 = 0u, b1 = 0u, c1 = 0u, w2 = 0xFFFFFFFFu, a2 = 0u, b2 = 0u, c2 = 0u;
+    if (nrows > 0) {
+        w1 = __ldg(gw); a1 = __ldg(ga); b1 = __ldg(gb);
+        if (NEED_CELL) c1 = __ldg(gc);
+    }
+    if (nrows > 1) {
+        w2 = __ldg(gw + 32); a2 = __ldg(ga + 32); b2 = __ldg(gb + 32);
+        if (NEED_CELL) c2 = __ldg(gc + 32);
+    }
+    double2 pa1 = __ldg(xy + a1), pb1 = __ldg(xy + b1);
+    double vol1 = HAS_VOL ? __ldg(a.cellvol + c1) : 0.0;
     for (int r = 0; r < nrows; r++) {
-        const uint4 e = e1;
+        const unsigned w = w1, cell = c1;
         const double2 pa = pa1, pb = pb1;
         const double volr = vol1;
-        e1 = e2;
-        e2 = (r + 2 < nrows) ? __ldg(ep + ((size_t)(r + 2) << 5)) : inv;
-        pa1 = __ldg(xy + e1.x);
-        pb1 = __ldg(xy + e1.y);
-        if (HAS_VOL) vol1 = __ldg(a.cellvol + e1.z);
-        if (e.w == 0xFFFFFFFFu) continue;
-        const unsigned k = e.w & 3u;
+        w1 = w2; a1 = a2; b1 = b2; c1 = c2;
+        if (r + 2 < nrows) {
+            const size_t o = (size_t)(r + 2) << 5;
+            w2 = __ldg(gw + o); a2 = __ldg(ga + o); b2 = __ldg(gb + o);
+            if (NEED_CELL) c2 = __ldg(gc + o);
+        } else {
+            w2 = 0xFFFFFFFFu; a2 = 0u; b2 = 0u; c2 = 0u;
+        }
+        pa1 = __ldg(xy + a1);
+        pb1 = __ldg(xy + b1);
+        if (HAS_VOL) vol1 = __ldg(a.cellvol + c1);
+        if (w == 0xFFFFFFFFu) continue;
+        const unsigned k = w & 3u;
         const double uax = pb.x - self.x, uay = pb.y - self.y;
         const double ubx = self.x - pa.x, uby = self.y - pa.y;
         const double usx = pa.x - pb.x, usy = pa.y - pb.y;
         const double px = (k == 0u) ? uax : usx, py = (k == 0u) ? uay : usy;
         const double det = px * uby - py * ubx;
         const double vol = HAS_VOL ? volr : fabs(det) * 0.5;
-        const double scale = (tab.mu_wsum * vol) / (det * det);
+        const double scale = (mu_wsum * vol) * rcp_newton(det * det);
         const double vs = (usx * usx + usy * usy) * scale;
         const double va = (uax * usx + uay * usy) * scale;
         const double vb = (ubx * usx + uby * usy) * scale;
-        const unsigned ps = (e.w >> 8) & 0xFFu, pA = (e.w >> 16) & 0xFFu, pB = e.w >> 24;
-        const bool ks = fabs(vs) > a.drop_tol, ka = fabs(va) > a.drop_tol, kb = fabs(vb) > a.drop_tol;
+        const unsigned ps = (w >> 8) & 0xFFu, pA = (w >> 16) & 0xFFu, pB = w >> 24;
+        const bool ks = fabs(vs) > drop_tol, ka = fabs(va) > drop_tol, kb = fabs(vb) > drop_tol;
         err |= (unsigned)((ks && ps == 0xFFu) || (ka && pA == 0xFFu) || (kb && pB == 0xFFu));
         const unsigned rs = (ks && ps != 0xFFu) ? ps : dump, ra = (ka && pA != 0xFFu) ? pA : dump, rb = (kb && pB != 0xFFu) ? pB : dump;
-        accp[rs * nt] += vs;
-        accp[ra * nt] += va;
-        accp[rb * nt] += vb;
+        const unsigned as = sacc + rs * (nt * 8u), aa = sacc + ra * (nt * 8u), ab = sacc + rb * (nt * 8u);
+        // the three rows are distinct unless they are the dump row, so the loads may be issued together
+        const double s0 = lds64(as), s1 = lds64(aa), s2 = lds64(ab);
+        sts64(as, s0 + vs);
+        sts64(aa, s1 + va);
+        sts64(ab, s2 + vb);
         if (TRACK) {
             mask |= (rs != dump ? 1ull << (rs & 63u) : 0ull) | (ra != dump ? 1ull << (ra & 63u) : 0ull) | (rb != dump ? 1ull << (rb & 63u) : 0ull);
         }
         if (RHS != FEMB_RHS_NONE) {
             double temp = 0.0;
-            for (int qp = 0; qp < tab.nqp; qp++) {
+            const int nqp = NQP ? NQP : tab.nqp;
+#pragma unroll
+            for (int qp = 0; qp < nqp; qp++) {
                 const double* t = tab.t[k][qp];
                 double f;
                 if (RHS == FEMB_RHS_AFFINE) {  // f(x_qp); x_qp = sum_j phi_j(xref_qp) x_j  (= A xref_qp + x_1, eval_trafo!, Example200:171)
@@ -496,7 +541,7 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
                     const double yq = t[1] * self.y + t[2] * pa.y + t[3] * pb.y;
                     f = rhs.p[0] + rhs.p[1] * xq + rhs.p[2] * yq;
                 } else {
-                    f = __ldg(rhs.fvals + (size_t)e.z * tab.nqp + qp);
+                    f = __ldg(rhs.fvals + (size_t)cell * nqp + qp);
                 }
                 temp += t[0] * f;
             }
@@ -507,9 +552,9 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
     if (err) atomicAdd(a.errflag, 1);
     double* out = a.nzval + base;
     if (a.acc_A) {
-        for (int i = 0; i < len; i++) out[i] += accp[i * nt];
+        for (int i = 0; i < len; i++) out[i] += lds64(sacc + i * (nt * 8u));
     } else {
-        for (int i = 0; i < len; i++) out[i] = accp[i * nt];
+        for (int i = 0; i < len; i++) out[i] = lds64(sacc + i * (nt * 8u));
     }
     if (TRACK) {
         for (int i = 0; i < len; i++)
@@ -521,22 +566,15 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
     }
 }
 
-// Fused stages 1-5 for scalar P1 (Example200:133-179), owner-computes by matrix column.
-// One thread per column c (= dof = node), one warp per slice of the sliced-ELL gather map (femb_pattern.cu):
-// the warp streams its slice's entries with fully coalesced 16-byte loads; every entry names one cell adjacent
-// to c by its two (three) other nodes, so the thread rebuilds the cell's affine map from Coordinates alone
-// (its own node is loaded once, coalesced), forms column k of the local stiffness matrix and adds it into the
-// <= 64 slots of CSC column c.  Slots are accumulated in shared memory (the diagonal in a register) and written
-// ONCE in a fixed order: bit-reproducible, no atomics, no memset of nzval.
-// Arithmetic: with C = cofactor matrix of the Jacobian A, grad phi_j = C_j / det, so
-//   Aloc[j,k] = mu |T| wsum (C_j . C_k) / det^2
-// — one division per cell visit instead of the reference's four (mapderiv!); the nodes are used in the cell's
-// own local order, so A[i,c] and A[c,i] are computed from identical operands and the matrix is exactly symmetric.
-template <int DIM, bool TRACK, int RHS>  // RHS: FEMB_RHS_NONE / _AFFINE / _QPVALUES.  Instantiated for DIM == 3 (tetrahedra) only.
+// ---- generic scalar P1 (instantiated for tetrahedra) ------------------------------------------------------------
+// Same owner-computes scheme; the cell's nodes are put back into local order (selects on k) and
+//   Aloc[j,k] = mu |T| wsum (C_j . C_k) / det^2,   C = cofactor matrix of the Jacobian A (grad phi_j = C_j / det).
+template <int DIM, bool TRACK, int RHS>  // RHS: FEMB_RHS_NONE / _AFFINE / _QPVALUES
 __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const RhsDev rhs, const P1Tab tab) {
+    static_assert(DIM == 3, "the 2-D case has its own kernel");
     constexpr int ND = DIM + 1;
     constexpr unsigned nt = 128;
-    constexpr unsigned MISSING = (DIM == 2) ? 0xFFu : 0x3Fu;
+    constexpr unsigned MISSING = 0x3Fu;
     extern __shared__ double acc[];  // [maxlen][128]
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const int64_t slice = (int64_t)blockIdx.x * 4 + (tid >> 5);
@@ -552,68 +590,45 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
     if (valid) {
         base = a.colptr[c] - 1;
         len = (int)(a.colptr[c + 1] - 1 - base);
-        if (DIM == 2) {
-            const double2 p = __ldg(reinterpret_cast<const double2*>(a.coords) + c);
-            self[0] = p.x; self[1] = p.y;
-        } else {
 #pragma unroll
-            for (int d = 0; d < 3; d++) self[d] = __ldg(a.coords + c * 3 + d);
-        }
+        for (int d = 0; d < 3; d++) self[d] = __ldg(a.coords + c * 3 + d);
     }
     for (int i = 0; i < len; i++) acc[i * nt + tid] = 0.0;
     unsigned long long mask = 0ull;
-    double bsum = 0.0, diag = 0.0;
-    unsigned dpos = MISSING, err = 0u;
-    const uint4* ent_p = a.gmap + ((size_t)row0 << 5) + lane;
-    for (int r = row0; r < row1; r++, ent_p += 32) {
-        const uint4 ent = __ldg(ent_p);
-        if (ent.w == 0xFFFFFFFFu) continue;
-        const unsigned k = ent.w & 3u;
-        unsigned cell;
-        double x[ND][DIM];  // the cell's nodes in local order
-        if (DIM == 2) {
-            cell = ent.z;
-            const double2* xy = reinterpret_cast<const double2*>(a.coords);
-            const double2 pa = __ldg(xy + ent.x), pb = __ldg(xy + ent.y);
-            x[0][0] = (k == 0) ? self[0] : pa.x; x[0][1] = (k == 0) ? self[1] : pa.y;
-            x[1][0] = (k == 0) ? pa.x : ((k == 1) ? self[0] : pb.x);
-            x[1][1] = (k == 0) ? pa.y : ((k == 1) ? self[1] : pb.y);
-            x[2][0] = (k == 2) ? self[0] : pb.x; x[2][1] = (k == 2) ? self[1] : pb.y;
-        } else {
-            cell = __ldg(a.gmap_cell + (ent_p - a.gmap));
-            double o[3][3];
-            const unsigned on[3] = {ent.x, ent.y, ent.z};
+    double bsum = 0.0;
+    unsigned err = 0u;
+    const uint32_t* __restrict__ ga = a.gmap + ((size_t)row0 << 5) + lane;
+    for (int r = row0; r < row1; r++, ga += 32) {
+        const unsigned w = __ldg(ga + 2 * a.gstride);
+        if (w == 0xFFFFFFFFu) continue;
+        const unsigned k = w & 3u;
+        const unsigned cell = __ldg(ga + 3 * a.gstride);
+        const unsigned on[3] = {__ldg(ga), __ldg(ga + a.gstride), __ldg(ga + 4 * a.gstride)};
+        double x[ND][DIM], o[3][3];  // x: the cell's nodes in local order
 #pragma unroll
-            for (int i = 0; i < 3; i++)
+        for (int i = 0; i < 3; i++)
 #pragma unroll
-                for (int d = 0; d < 3; d++) o[i][d] = __ldg(a.coords + (size_t)on[i] * 3 + d);
+            for (int d = 0; d < 3; d++) o[i][d] = __ldg(a.coords + (size_t)on[i] * 3 + d);
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                x[0][d] = (k == 0) ? self[d] : o[0][d];
-                x[1][d] = (k == 0) ? o[0][d] : ((k == 1) ? self[d] : o[1][d]);
-                x[2][d] = (k <= 1) ? o[1][d] : ((k == 2) ? self[d] : o[2][d]);
-                x[3][d] = (k == 3) ? self[d] : o[2][d];
-            }
+        for (int d = 0; d < 3; d++) {
+            x[0][d] = (k == 0) ? self[d] : o[0][d];
+            x[1][d] = (k == 0) ? o[0][d] : ((k == 1) ? self[d] : o[1][d]);
+            x[2][d] = (k <= 1) ? o[1][d] : ((k == 2) ? self[d] : o[2][d]);
+            x[3][d] = (k == 3) ? self[d] : o[2][d];
         }
         double A[DIM][DIM], cf[ND][DIM], det;  // cf[j] = cofactor vector: grad phi_j = cf[j] / det
 #pragma unroll
         for (int d = 0; d < DIM; d++)
 #pragma unroll
             for (int i = 0; i < DIM; i++) A[d][i] = x[i + 1][d] - x[0][d];
-        if (DIM == 2) {
-            det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
-            cf[1][0] = A[1][1];  cf[1][1] = -A[0][1];
-            cf[2][0] = -A[1][0]; cf[2][1] = A[0][0];
-        } else {
 #pragma unroll
-            for (int r2 = 0; r2 < 3; r2++)
+        for (int r2 = 0; r2 < 3; r2++)
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const int ra = (r2 + 1) % 3, rb = (r2 + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
-                    cf[j + 1][r2] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
-                }
-            det = A[0][0] * cf[1][0] + A[0][1] * cf[2][0] + A[0][2] * cf[3][0];
-        }
+            for (int j = 0; j < 3; j++) {
+                const int ra = (r2 + 1) % 3, rb = (r2 + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
+                cf[j + 1][r2] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
+            }
+        det = A[0][0] * cf[1][0] + A[0][1] * cf[2][0] + A[0][2] * cf[3][0];
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             double s0 = 0.0;
@@ -621,7 +636,7 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
             for (int j = 1; j < ND; j++) s0 -= cf[j][d];
             cf[0][d] = s0;
         }
-        const double vol = a.cellvol ? __ldg(a.cellvol + cell) : fabs(det) * (DIM == 2 ? 0.5 : 1.0 / 6.0);
+        const double vol = a.cellvol ? __ldg(a.cellvol + cell) : fabs(det) * (1.0 / 6.0);
         const double scale = (a.mu * vol) * tab.wsum / (det * det);
         double ck[DIM];
 #pragma unroll
@@ -637,13 +652,10 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
 #pragma unroll
             for (int kk = 0; kk < DIM; kk++) d += cf[j][kk] * ck[kk];
             const double val = d * scale;
-            const unsigned pos = (DIM == 2) ? ((ent.w >> (8 * (j + 1))) & 0xFFu) : ((ent.w >> (2 + 6 * j)) & 0x3Fu);
+            const unsigned pos = (w >> (2 + 6 * j)) & 0x3Fu;
             if (fabs(val) > a.drop_tol) {
                 if (pos == MISSING) {
                     err = 1u;
-                } else if (k == (unsigned)j) {  // diagonal entry A[c,c]: same slot on every visit
-                    diag += val;
-                    dpos = pos;
                 } else {
                     acc[pos * nt + tid] += val;
                     if (TRACK) mask |= 1ull << (pos & 63u);
@@ -673,10 +685,6 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
     }
     if (!valid) return;
     if (err) atomicAdd(a.errflag, 1);
-    if (dpos != MISSING) {
-        acc[dpos * nt + tid] += diag;
-        if (TRACK) mask |= 1ull << (dpos & 63u);
-    }
     double* out = a.nzval + base;
     if (a.acc_A) {
         for (int i = 0; i < len; i++) out[i] += acc[i * nt + tid];
@@ -736,7 +744,7 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
     for (int i = 0; i < EG.nqp * ctx->dim; i++) tab.xref[i] = EG.xref[i];
     for (int i = 0; i < EG.nqp * ND; i++) tab.phi[i] = phi[i];
     P1Args a;
-    a.coords = ctx->coords; a.cellvol = ctx->cellvol; a.gslice_ptr = ctx->gslice_ptr; a.gmap = ctx->gmap; a.gmap_cell = ctx->gmap_cell;
+    a.coords = ctx->coords; a.cellvol = ctx->cellvol; a.gslice_ptr = ctx->gslice_ptr; a.gmap = ctx->gmap; a.gstride = ctx->gmap_stride;
     a.colptr = ctx->colptr; a.ndofs = s.ndofs; a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag;
     a.mu = mu; a.drop_tol = drop_tol;
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
@@ -769,10 +777,15 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
             }
         smem = (size_t)(a.maxlen + 1) * nt * sizeof(double);
         const bool track = a.touched != nullptr, hv = a.cellvol != nullptr;
-#define FEMB_P1_LAUNCH2(T, R, V)                                                                                                    \
-    do {                                                                                                                            \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather2d<T, R, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        k_p1_poisson_gather2d<T, R, V><<<grid, 128, smem, ctx->stream>>>(a, rhs, t2);                                                \
+#define FEMB_P1_LAUNCH2Q(T, R, V, Q)                                                                                                  \
+    do {                                                                                                                              \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather2d<T, R, V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_p1_poisson_gather2d<T, R, V, Q><<<grid, 128, smem, ctx->stream>>>(a, rhs, t2);                                               \
+    } while (0)
+#define FEMB_P1_LAUNCH2(T, R, V)                 \
+    do {                                         \
+        if (t2.nqp == 1) FEMB_P1_LAUNCH2Q(T, R, V, 1); \
+        else FEMB_P1_LAUNCH2Q(T, R, V, 0);       \
     } while (0)
 #define FEMB_P1_LAUNCH2_R(R)                                    \
     do {                                                        \
@@ -786,6 +799,7 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
         else FEMB_P1_LAUNCH2_R(FEMB_RHS_NONE);
 #undef FEMB_P1_LAUNCH2_R
 #undef FEMB_P1_LAUNCH2
+#undef FEMB_P1_LAUNCH2Q
         KERNEL_CHECK(ctx);
         return FEMB_OK;
     }

@@ -86,11 +86,12 @@ struct femb_ctx {
     int max_collen = 0;
     std::vector<FembBlock> blocks;
     std::vector<int64_t> extra_diag;
-    // P1 gather map, sliced ELL (slice = 32 consecutive dofs = one warp): entry [row][lane] of a dof's e-th
-    // adjacent cell = {the cell's other nodes in local order (0-based), cell (2-D) , w}; w packs the local index k
-    // of the dof in that cell and the position of every local row in the dof's CSC column (see femb_pattern.cu)
-    uint4* gmap = nullptr;
-    uint32_t* gmap_cell = nullptr;   // 3-D only (the 2-D entry has room for the cell id)
+    // P1 gather map, sliced ELL (slice = 32 consecutive dofs = one warp), structure of arrays: plane p lives at
+    // gmap + p * gmap_stride, element [row][lane].  Planes: 0 = na, 1 = nb (the e-th adjacent cell's other nodes in
+    // local order, 0-based), 2 = w (local index k of the dof + positions of the local rows in the dof's CSC
+    // column, see femb_pattern.cu), 3 = cell, 4 = nc (tetrahedra only)
+    uint32_t* gmap = nullptr;
+    size_t gmap_stride = 0;
     int32_t* gslice_ptr = nullptr;   // nslices + 1 row offsets
     int64_t gmap_rows = 0;
     int gmap_space = -1;

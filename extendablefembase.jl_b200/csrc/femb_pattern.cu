@@ -15,9 +15,9 @@ void femb_free_pattern(femb_ctx* ctx) {
     femb_free(&ctx->nzval);
     femb_free(&ctx->touched);
     femb_free(&ctx->gmap);
-    femb_free(&ctx->gmap_cell);
     femb_free(&ctx->gslice_ptr);
     ctx->gmap_rows = 0;
+    ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
@@ -520,8 +520,9 @@ int femb_build_slotmaps(femb_ctx* ctx) {
 }
 
 // Gather map for scalar P1 (dof == node), sliced ELL with one slice per warp of 32 consecutive dofs.
-//   2-D entry {na, nb, cell, w}, w = k | pos_self << 8 | pos_a << 16 | pos_b << 24     (pos 0xFF = not in pattern)
-//   3-D entry {na, nb, nc, w} (+ gmap_cell), w = k | pos0 << 2 | ... | pos3 << 20       (pos 0x3F = not in pattern)
+// Structure of arrays, planes na, nb, w, cell (, nc): element [row][lane] at plane + (row << 5) + lane.
+//   2-D: w = k | pos_self << 8 | pos_a << 16 | pos_b << 24     (pos 0xFF = not in pattern)
+//   3-D: w = k | pos0 << 2 | ... | pos3 << 20                  (pos 0x3F = not in pattern; local order)
 // na.. are the cell's nodes other than the dof itself, in local order, 0-based; k is the dof's local index;
 // pos_j = position of global row celldofs[j] inside CSC column c.  Padding entries have w = 0xFFFFFFFF and node /
 // cell ids 0 (so that unconditional prefetches stay in bounds).
@@ -541,7 +542,7 @@ __global__ void k_slice_deg(const int32_t* __restrict__ adj_ptr, int64_t ndofs, 
 template <int ND>
 __global__ void k_gmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices,
                        const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
-                       const int32_t* __restrict__ slice_ptr, uint4* __restrict__ gmap, uint32_t* __restrict__ gmap_cell) {
+                       const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ gmap, size_t stride) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nslices * 32) return;
     const int64_t slice = c >> 5;
@@ -551,8 +552,7 @@ __global__ void k_gmap(const uint32_t* __restrict__ adj, const int32_t* __restri
     const int deg = c < ndofs ? adj_ptr[c + 1] - e0 : 0;
     const int64_t base = c < ndofs ? colptr[c] - 1 : 0;
     for (int r = 0; r < nrows; r++) {
-        uint4 ent = make_uint4(0u, 0u, 0u, FEMB_GMAP_INVALID);
-        uint32_t cell = 0;
+        uint32_t cell = 0, ww = FEMB_GMAP_INVALID, oo[3] = {0u, 0u, 0u};
         if (r < deg) {
             uint32_t a = adj[e0 + r];
             cell = a / ND;
@@ -573,19 +573,23 @@ __global__ void k_gmap(const uint32_t* __restrict__ adj, const int32_t* __restri
                 }
             }
             if (ND == 3) w |= (spos << 8) | (opos[0] << 16) | (opos[1] << 24);  // 2-D: positions in (self, a, b) order
-            ent = (ND == 3) ? make_uint4(others[0], others[1], cell, w) : make_uint4(others[0], others[1], others[2], w);
+            ww = w;
+            oo[0] = others[0]; oo[1] = others[1]; oo[2] = others[2];
         }
         size_t idx = ((size_t)(row0 + r) << 5) + lane;
-        gmap[idx] = ent;
-        if (ND == 4) gmap_cell[idx] = cell;
+        gmap[idx] = oo[0];
+        gmap[stride + idx] = oo[1];
+        gmap[2 * stride + idx] = ww;
+        gmap[3 * stride + idx] = cell;
+        if (ND == 4) gmap[4 * stride + idx] = oo[2];
     }
 }
 
 int femb_build_gmap(femb_ctx* ctx) {
     femb_free(&ctx->gmap);
-    femb_free(&ctx->gmap_cell);
     femb_free(&ctx->gslice_ptr);
     ctx->gmap_rows = 0;
+    ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
     if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
     int sid = ctx->row_spaces[0];
@@ -613,13 +617,13 @@ int femb_build_gmap(femb_ctx* ctx) {
     ctx->launches += 2;
     CUDA_TRY(ctx, e);
     ctx->gmap_rows = rows;
-    FEMB_TRY(femb_alloc(ctx, &ctx->gmap, (size_t)rows * 32));
-    if (s.nd == 4) FEMB_TRY(femb_alloc(ctx, &ctx->gmap_cell, (size_t)rows * 32));
+    ctx->gmap_stride = (size_t)rows * 32;
+    FEMB_TRY(femb_alloc(ctx, &ctx->gmap, ctx->gmap_stride * (s.nd == 4 ? 5 : 4)));
     unsigned grid = (unsigned)((nslices * 32 + 127) / 128);
     if (s.nd == 3)
-        k_gmap<3><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.celldofs, ctx->colptr, ctx->rowval, ctx->gslice_ptr, ctx->gmap, ctx->gmap_cell);
+        k_gmap<3><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.celldofs, ctx->colptr, ctx->rowval, ctx->gslice_ptr, ctx->gmap, ctx->gmap_stride);
     else
-        k_gmap<4><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.celldofs, ctx->colptr, ctx->rowval, ctx->gslice_ptr, ctx->gmap, ctx->gmap_cell);
+        k_gmap<4><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.celldofs, ctx->colptr, ctx->rowval, ctx->gslice_ptr, ctx->gmap, ctx->gmap_stride);
     KERNEL_CHECK(ctx);
     ctx->gmap_space = sid;
     return FEMB_OK;
