@@ -101,11 +101,12 @@ def make_problem(n, jitter):
     return grid, vol
 
 
-def setup_device(grid, vol, device, use_vol=True):
+def setup_device(grid, vol, device, use_vol=True, part=None):
     """Symbolic phase (once): register mesh / space / rule / evaluators, build the structural pattern on the
-    device, run the reference's FIRST assembly (value filter decides the pattern) and compress."""
+    device, run the reference's FIRST assembly (value filter decides the pattern) and compress.  With a partition
+    (`part`, N > 1): halo rows are added to the pattern and the NCCL exchange plan is installed."""
     import femb_b200 as fb
-    from femb_b200 import _lib
+    from femb_b200 import _lib, partition as pt
     from femb_b200.assembly import AffineFunction, _Session
 
     fes = fb.FESpace(fb.H1Pk(1, 2, 1), grid)
@@ -116,23 +117,50 @@ def setup_device(grid, vol, device, use_vol=True):
     eg, ei = S.evaluator(0, fb.Gradient), S.evaluator(0, fb.Identity)
     ctx.pattern_track(True)
     nnz_struct = ctx.pattern_build([(0, 0)])
+    if part is not None:
+        import torch.distributed as dist
+
+        uid = [_lib.Context.comm_unique_id() if part.rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(part.nranks, part.rank, uid[0])
+        colptr, rowval = ctx.pattern_get(grid.nnodes)
+        sent = pt.allgather(pt.ghost_columns(part, colptr, rowval), part.nranks)
+        er, ec = pt.extra_entries(part, sent)
+        if er.size:
+            ctx.pattern_extra(er, ec)
+            nnz_struct = ctx.pattern_build([(0, 0)])
+            colptr, rowval = ctx.pattern_get(grid.nnodes)
+        sent = pt.allgather(pt.ghost_columns(part, colptr, rowval), part.nranks)
+        ctx.comm_set_exchange(pt.exchange_plan(part, colptr, rowval, sent))
     rhs = AffineFunction([0.0], [[1.0, -1.0]])  # Example200:38
     ctx.matrix_zero()
     ctx.vector_zero()
     ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, rhs.params(), 1.0e-15)
+    if part is not None:
+        ctx.exchange()  # received non-zero contributions mark their slots as touched
     nnz = ctx.pattern_compress()
     ctx.pattern_track(False)
+    if part is not None:
+        colptr, rowval = ctx.pattern_get(grid.nnodes)
+        sent = pt.allgather(pt.ghost_columns(part, colptr, rowval), part.nranks)
+        plan = pt.exchange_plan(part, colptr, rowval, sent)
+        ctx.comm_set_exchange(plan)
+        S.exchange_bytes = 8 * int(plan.send_ptr[-1] + plan.sendb_ptr[-1])
     ctx.sync()
     log(f"[bench] symbolic phase: structural nnz={nnz_struct}, after Example200's 1e-15 filter nnz={nnz} ({time.time() - t0:.1f}s)")
     return S, fes, eg._eid, ei._eid, rhs.params(), nnz
 
 
-def step_resident(ctx, eg, ei, rhsp):
+def step_resident(ctx, eg, ei, rhsp, exchange=False):
     from femb_b200 import _lib
 
     ctx.matrix_zero()
     ctx.vector_zero()
     ctx.assemble_poisson(eg, ei, 1.0, _lib.RHS_AFFINE, rhsp, 1.0e-15)
+    ms = ctx.last_kernel_ms()[0]
+    if exchange:
+        ctx.exchange()  # interface columns -> owners (NCCL send/recv + add kernel)
+    return ms
 
 
 def run_ours(args):
@@ -150,11 +178,22 @@ def run_ours(args):
     from femb_b200 import build as fbuild
 
     fbuild.build()
-    grid, vol = make_problem(args.n, args.jitter)
+    part = None
+    if world > 1:
+        from femb_b200 import partition as pt
+
+        t0 = time.time()
+        part = pt.slab_partition_2d(args.n, rank, world)
+        grid = part.grid
+        vol = grid["CellVolumes"]
+        log(f"[bench] rank {rank}: slab n={args.n}: {grid.ncells} cells, {grid.nnodes} local nodes ({time.time() - t0:.1f}s host)")
+    else:
+        grid, vol = make_problem(args.n, args.jitter)
     use_vol = args.cellvol == "given"
-    S, fes, eg, ei, rhsp, nnz = setup_device(grid, vol, local, use_vol)
+    S, fes, eg, ei, rhsp, nnz = setup_device(grid, vol, local, use_vol, part)
     ctx = S.ctx
     ncells, nnodes = grid.ncells, grid.nnodes
+    xch = world > 1
 
     def barrier():
         if world > 1:
@@ -162,20 +201,19 @@ def run_ours(args):
         ctx.sync()
 
     # ---- value: device-resident ------------------------------------------------------------
+    clk = ClockSampler(local)
+    clk.__enter__()
     for _ in range(args.warmup):
-        step_resident(ctx, eg, ei, rhsp)
+        step_resident(ctx, eg, ei, rhsp, xch)
     barrier()
     l0 = ctx.launch_count()
     kms = []
-    with ClockSampler(local) as clk:
-        ctx.region_begin()
-        for _ in range(args.steps):
-            step_resident(ctx, eg, ei, rhsp)
-            kms.append(ctx.last_kernel_ms()[0])
-        ms_total = ctx.region_end()
+    ctx.region_begin()
+    for _ in range(args.steps):
+        kms.append(step_resident(ctx, eg, ei, rhsp, xch))
+    ms_total = ctx.region_end()
     barrier()
     launches = ctx.launch_count() - l0
-    clocks = clk.summary()
     if world > 1:
         t = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -194,7 +232,7 @@ def run_ours(args):
 
     def step_e2e():
         ctx.mesh_set(coords, cn, vol_in)
-        step_resident(ctx, eg, ei, rhsp)
+        step_resident(ctx, eg, ei, rhsp, xch)
         ctx.matrix_get(nz_host)
         ctx.vector_get(out=b_host)
 
@@ -214,9 +252,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * ncells / (e2e_ms / args.steps * 1e-3)
+    clk.__exit__()
+    clocks = clk.summary()  # sampled over warm-up + both timed regions
     h2d = coords.nbytes + cn.nbytes + (vol.nbytes if use_vol else 0)
     d2h = nz_host.nbytes + b_host.nbytes
-    checks = sanity_checks(nz_host, b_host, S, nnodes)
+    checks = sanity_checks(nz_host, b_host, S, nnodes, part)
     for a in pinned:
         ctx.host_unregister(a)
 
@@ -238,7 +278,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"H1P1 2-D Poisson stiffness+rhs, simplexgrid n={args.n} ({ncells} triangles, {nnodes} nodes) per GPU" + (", jittered" if args.jitter else ""),
                    "nnz": nnz, "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" % (bpc * ncells / 1e9),
-                   "partition": "one slab per rank" if world > 1 else "single GPU", "scatter": "owner-computes gather (write-once, bit-reproducible)",
+                   "partition": ("one %d-row slab per rank, interface columns owned by the lower rank, NCCL send/recv of %d bytes per rank per step" % (args.n, getattr(S, "exchange_bytes", 0))) if world > 1 else "single GPU", "scatter": "owner-computes gather (write-once, bit-reproducible)",
                    "cellvolumes": "xgrid[CellVolumes] passed in" if use_vol else "NULL: |det A|/2 on the device"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
@@ -252,14 +292,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def sanity_checks(nz, b, S, nnodes):
+def sanity_checks(nz, b, S, nnodes, part=None):
     """Size-independent properties of the full-size result (tests/ hold the oracle comparisons)."""
     colptr, rowval = S.ctx.pattern_get(nnodes)
     cols = np.repeat(np.arange(nnodes, dtype=np.int64), np.diff(colptr))
-    rowsum = np.bincount(rowval - 1, weights=nz, minlength=nnodes)  # A * 1
-    colsum = np.bincount(cols, weights=nz, minlength=nnodes)  # 1^T A
-    return {"max_abs_A_times_ones": float(np.abs(rowsum).max()), "max_abs_ones_times_A": float(np.abs(colsum).max()), "sum_b": float(b.sum()),
-            "diag_min": float(nz[rowval - 1 == cols].min())}
+    if part is None:
+        rowsum = np.bincount(rowval - 1, weights=nz, minlength=nnodes)  # A * 1
+        colsum = np.bincount(cols, weights=nz, minlength=nnodes)  # 1^T A
+        return {"max_abs_A_times_ones": float(np.abs(rowsum).max()), "max_abs_ones_times_A": float(np.abs(colsum).max()), "sum_b": float(b.sum()),
+                "diag_min": float(nz[rowval - 1 == cols].min())}
+    # distributed: every OWNED column is complete after the exchange -> its entries sum to 0 and, on this structured
+    # mesh, an owned interface node away from the boundary has the interior 5-point column (4; -1 -1 -1 -1)
+    owned = part.owner == part.rank
+    colsum = np.bincount(cols, weights=nz, minlength=nnodes)
+    diag = np.zeros(nnodes)
+    isd = rowval - 1 == cols
+    diag[cols[isd]] = nz[isd]
+    n1 = part.row_nodes
+    top = np.nonzero(owned)[0][-n1:]  # the rank's last owned node row = the cut (or the domain boundary on the last rank)
+    return {"max_abs_owned_colsum": float(np.abs(colsum[owned]).max()), "cut_row_diag_interior": float(np.median(diag[top][1:-1])),
+            "owned_diag_min": float(diag[owned].min())}
 
 
 # ---------------------------------------------------------------------------------------------

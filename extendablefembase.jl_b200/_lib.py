@@ -62,7 +62,8 @@ SIGNATURES = {
     "femb_region_end": (_i32, [_p, C.POINTER(C.c_float)]),
     "femb_comm_unique_id": (_i32, [C.c_char_p]),
     "femb_comm_init": (_i32, [_p, _i32, _i32, C.c_char_p]),
-    "femb_comm_set_ghosts": (_i32, [_p, _i32, _p, _p, _p, _p]),
+    "femb_comm_set_exchange": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "femb_pattern_extra": (_i32, [_p, _i64, _p, _p]),
     "femb_exchange": (_i32, [_p]),
     "femb_comm_destroy": (_i32, [_p]),
 }
@@ -184,6 +185,11 @@ class Context:
         self.nnz = nnz.value
         return self.nnz
 
+    def pattern_extra(self, rows, cols):
+        """Extra structural entries (1-based) merged into the next pattern_build (multi-GPU halo rows)."""
+        rows, cols = _arr(rows, np.int64), _arr(cols, np.int64)
+        self._ck(self.lib.femb_pattern_extra(self.h, rows.shape[0], _ptr(rows), _ptr(cols)))
+
     def pattern_adopt(self, nrows, ncols, colptr, rowval, blocks):
         colptr, rowval = _arr(colptr, np.int64), _arr(rowval, np.int64)
         br = np.asarray([b[0] for b in blocks], np.int32)
@@ -257,6 +263,31 @@ class Context:
     def assemble_navierstokes(self, egu, eiu, eip, mu, linear, nonlinear, rhs_kind, data):
         data = _arr(data, np.float64)
         self._ck(self.lib.femb_assemble_navierstokes(self.h, egu, eiu, eip, mu, int(linear), int(nonlinear), rhs_kind, _ptr(data)))
+
+    # ---- multi-GPU -------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        st = load().femb_comm_unique_id(buf)
+        if st != 0:
+            raise FembError(st, "ncclGetUniqueId failed (is libnccl.so.2 loadable?)")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        self._ck(self.lib.femb_comm_init(self.h, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    def comm_set_exchange(self, plan):
+        """plan: ExchangePlan of partition.py (0-based slot / vector index lists per peer)."""
+        a = lambda x: np.ascontiguousarray(x, dtype=np.int64)  # noqa: E731
+        peers = np.ascontiguousarray(plan.peers, dtype=np.int32)
+        arrs = [a(plan.send_ptr), a(plan.send_slots), a(plan.recv_ptr), a(plan.recv_slots), a(plan.sendb_ptr), a(plan.send_b), a(plan.recvb_ptr), a(plan.recv_b)]
+        self._ck(self.lib.femb_comm_set_exchange(self.h, peers.shape[0], _ptr(peers), *[_ptr(x) for x in arrs]))
+
+    def exchange(self):
+        self._ck(self.lib.femb_exchange(self.h))
+
+    def comm_destroy(self):
+        self._ck(self.lib.femb_comm_destroy(self.h))
 
     def last_kernel_ms(self):
         ms, n = C.c_float(0), _i32(0)

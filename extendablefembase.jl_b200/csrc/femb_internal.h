@@ -114,20 +114,21 @@ struct femb_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 
-    // NCCL
+    // extra structural entries for the next pattern build (multi-GPU halo rows), keys col * nrows + row (0-based)
+    std::vector<int64_t> extra_entries;
+
+    // NCCL (bound at run time with dlopen, femb_comm.cu)
     void* comm = nullptr;
     int nranks = 1, rank = 0;
     std::vector<int> peers;
-    std::vector<int64_t> ghost_ptr;
-    int64_t* ghost_local = nullptr;   // device
-    int64_t* ghost_remote = nullptr;  // device (remote column ids we will RECEIVE contributions for)
-    std::vector<int64_t> recv_ptr;
-    double* sendbuf = nullptr;
-    double* recvbuf = nullptr;
-    int64_t* send_slots = nullptr;
+    std::vector<int64_t> send_ptr, recv_ptr, sendb_ptr, recvb_ptr;  // per peer, in elements
+    int64_t* send_slots = nullptr;  // device
     int64_t* recv_slots = nullptr;
-    int64_t nsend = 0, nrecv = 0;
-    std::vector<int64_t> send_off, recv_off;
+    int64_t* send_b = nullptr;
+    int64_t* recv_b = nullptr;
+    double* sendbuf = nullptr;      // [matrix part | vector part] per peer, contiguous
+    double* recvbuf = nullptr;
+    int64_t nsend = 0, nrecv = 0, nsendb = 0, nrecvb = 0;
 };
 
 int femb_fail(femb_ctx* ctx, int code, const char* fmt, ...);

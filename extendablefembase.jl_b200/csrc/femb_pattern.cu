@@ -205,6 +205,19 @@ extern "C" int32_t femb_pattern_track(femb_ctx* ctx, int32_t enable) {
     return FEMB_OK;
 }
 
+extern "C" int32_t femb_pattern_extra(femb_ctx* ctx, int64_t n, const int64_t* rows, const int64_t* cols) {
+    FEMB_CHECK_CTX(ctx);
+    if (!ctx->nrs) return femb_fail(ctx, FEMB_ERR_ARG, "femb_matrix_layout must precede femb_pattern_extra");
+    ctx->extra_entries.clear();
+    if (n < 0 || (n && (!rows || !cols))) return femb_fail(ctx, FEMB_ERR_ARG, "femb_pattern_extra: bad arguments");
+    for (int64_t i = 0; i < n; i++) {
+        if (rows[i] < 1 || rows[i] > ctx->nrows || cols[i] < 1 || cols[i] > ctx->ncols)
+            return femb_fail(ctx, FEMB_ERR_ARG, "femb_pattern_extra: entry (%lld,%lld) outside the layout", (long long)rows[i], (long long)cols[i]);
+        ctx->extra_entries.push_back((cols[i] - 1) * ctx->nrows + (rows[i] - 1));
+    }
+    return FEMB_OK;
+}
+
 extern "C" int32_t femb_pattern_build(femb_ctx* ctx, int32_t nblocks, const int32_t* brows, const int32_t* bcols, int64_t nextra,
                                       const int64_t* extra, int64_t* nnz_out) {
     FEMB_CHECK_CTX(ctx);
@@ -246,10 +259,16 @@ extern "C" int32_t femb_pattern_build(femb_ctx* ctx, int32_t nblocks, const int3
                 rows.s[rows.n++] = RowSrc{rs.celldofs, rs.nd, ctx->row_off[b.brow]};
                 rows.total += rs.nd;
             }
-        // extra diagonal entries falling into this column block
-        std::vector<int64_t> ex;
+        // extra entries falling into this column block, as (local column, global 0-based row), sorted by column:
+        // forced diagonals (Dirichlet penalties) and halo rows registered with femb_pattern_extra (multi-GPU)
+        std::vector<std::pair<int64_t, int64_t>> ex;
         for (int64_t g : ctx->extra_diag)
-            if (g > ctx->col_off[bc] && g <= ctx->col_off[bc + 1]) ex.push_back(g - 1 - ctx->col_off[bc]);
+            if (g > ctx->col_off[bc] && g <= ctx->col_off[bc + 1]) ex.push_back({g - 1 - ctx->col_off[bc], g - 1});
+        for (int64_t key : ctx->extra_entries) {
+            int64_t col = key / nrows, row = key - col * nrows;
+            if (col >= ctx->col_off[bc] && col < ctx->col_off[bc + 1]) ex.push_back({col - ctx->col_off[bc], row});
+        }
+        std::sort(ex.begin(), ex.end());
         if (rows.n == 0 && ex.empty()) continue;
         if ((st = femb_build_adjacency(ctx, sid)) != FEMB_OK) { cleanup(); cudaFree(rowval); return st; }
         int64_t total_keys = ctx->ncells * cs.nd * (int64_t)rows.total;
@@ -264,8 +283,8 @@ extern "C" int32_t femb_pattern_build(femb_ctx* ctx, int32_t nblocks, const int3
             TRY_P(cudaStreamSynchronize(ctx->stream));
             int64_t e0 = e01[0], ne = e01[1] - e01[0];
             std::vector<int64_t> exkeys;
-            while (exi < ex.size() && ex[exi] < d1) {
-                exkeys.push_back((ex[exi] - d0) * nrows + (ctx->col_off[bc] + ex[exi]));  // row == column (diagonal of a square layout)
+            while (exi < ex.size() && ex[exi].first < d1) {
+                exkeys.push_back((ex[exi].first - d0) * nrows + ex[exi].second);
                 exi++;
             }
             int64_t nk = ne * rows.total + (int64_t)exkeys.size();

@@ -193,15 +193,22 @@ void* femb_device_ptr(femb_ctx* ctx, int32_t which);
 
 /* ---- multi-GPU: cells partitioned across ranks, interface columns exchanged over NCCL ------------
  * (no counterpart in the reference, which is single-process: SURVEY.md §8(e)).  One process per GPU.
- * Each rank sets its LOCAL mesh part (owned cells) with LOCAL dof numbering in which the dofs it
- * owns come first; ghost dofs (owned by a peer) are listed per peer with the owner's local index. */
-int32_t femb_comm_unique_id(char id_out[128]);
+ * Each rank registers its LOCAL mesh part with LOCAL dof numbering: the dofs of its own cells plus "halo" dofs
+ * (rows that peers contribute to columns this rank owns).  A dof on a cut is owned by exactly one rank; the other
+ * ranks hold it as a ghost: their contributions to its matrix column / vector entry are sent to the owner. */
+/* extra structural entries (1-based row / column in the layout's numbering) merged into the next
+ * femb_pattern_build: the rows a peer will contribute to columns owned here. */
+int32_t femb_pattern_extra(femb_ctx* ctx, int64_t n, const int64_t* rows, const int64_t* cols);
+int32_t femb_comm_unique_id(char id_out[128]);  /* ncclGetUniqueId; broadcast it to all ranks out of band */
 int32_t femb_comm_init(femb_ctx* ctx, int32_t nranks, int32_t rank, const char id[128]);
-/* peer lists: for peer p, ghost columns [ghost_ptr[p], ghost_ptr[p+1]) of `ghost_local` (1-based local
- * global-matrix column on this rank) are owned by p.  After assembly femb_exchange() sends every ghost
- * column's values to its owner, which adds them in ascending peer order (reproducible). */
-int32_t femb_comm_set_ghosts(femb_ctx* ctx, int32_t npeers, const int32_t* peers, const int64_t* ghost_ptr,
-                             const int64_t* ghost_local, const int64_t* ghost_remote);
+/* exchange plan: for peer p (rank peers[p]) this rank SENDS nzval[send_slots[send_ptr[p] .. send_ptr[p+1])] and
+ * b[send_b[sendb_ptr[p] ..)] and ADDS what it receives from p into nzval[recv_slots[recv_ptr[p] ..)] /
+ * b[recv_b[recvb_ptr[p] ..)] (0-based positions; the two sides list the same entries in the same order). */
+int32_t femb_comm_set_exchange(femb_ctx* ctx, int32_t npeers, const int32_t* peers, const int64_t* send_ptr, const int64_t* send_slots,
+                               const int64_t* recv_ptr, const int64_t* recv_slots, const int64_t* sendb_ptr, const int64_t* send_b,
+                               const int64_t* recvb_ptr, const int64_t* recv_b);
+/* pack -> ncclSend/ncclRecv (one group) -> add in ascending peer order (reproducible).  Received non-zero matrix
+ * values also mark their slot as touched (femb_pattern_compress).  Sent ghost entries are left in place. */
 int32_t femb_exchange(femb_ctx* ctx);
 int32_t femb_comm_destroy(femb_ctx* ctx);
 
