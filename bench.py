@@ -145,7 +145,8 @@ def setup_device(grid, vol, device, use_vol=True, part=None):
         sent = pt.allgather(pt.ghost_columns(part, colptr, rowval), part.nranks)
         plan = pt.exchange_plan(part, colptr, rowval, sent)
         ctx.comm_set_exchange(plan)
-        S.exchange_bytes = 8 * int(plan.send_ptr[-1] + plan.sendb_ptr[-1])
+        S.plan = plan
+        S.exchange_bytes = 8 * int(plan.send_ptr[-1] + plan.sendb_ptr[-1] + plan.recv_ptr[-1] + plan.recvb_ptr[-1])
     ctx.sync()
     log(f"[bench] symbolic phase: structural nnz={nnz_struct}, after Example200's 1e-15 filter nnz={nnz} ({time.time() - t0:.1f}s)")
     return S, fes, eg._eid, ei._eid, rhs.params(), nnz
@@ -230,11 +231,22 @@ def run_ours(args):
     for a in pinned:
         ctx.host_register(a)
 
+    from femb_b200 import _lib
+
+    if xch:
+        plan = S.plan
+        r_lo, r_n = (int(plan.recv_slots.min()), int(plan.recv_slots.max() - plan.recv_slots.min() + 1)) if plan.recv_slots.size else (0, 0)
+        b_lo, b_n = (int(plan.recv_b.min()), int(plan.recv_b.max() - plan.recv_b.min() + 1)) if plan.recv_b.size else (0, 0)
+
     def step_e2e():
-        ctx.mesh_set(coords, cn, vol_in)
-        step_resident(ctx, eg, ei, rhsp, xch)
-        ctx.matrix_get(nz_host)
-        ctx.vector_get(out=b_host)
+        # upload the mesh, assemble, download nzval and b — pipelined over column chunks inside the library
+        ctx.assemble_poisson_host(eg, ei, 1.0, _lib.RHS_AFFINE, rhsp, 1.0e-15, coords, cn, vol_in, nz_host, b_host, args.chunks)
+        if xch:  # interface columns: exchange, then re-download the (small, contiguous) ranges that received contributions
+            ctx.exchange()
+            if r_n:
+                ctx.matrix_get_range(r_lo, r_n, nz_host[r_lo:r_lo + r_n])
+            if b_n:
+                ctx.vector_get_range(b_lo, b_n, b_host[b_lo:b_lo + b_n])
 
     for _ in range(min(args.warmup, 3)):
         step_e2e()
@@ -278,7 +290,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"H1P1 2-D Poisson stiffness+rhs, simplexgrid n={args.n} ({ncells} triangles, {nnodes} nodes) per GPU" + (", jittered" if args.jitter else ""),
                    "nnz": nnz, "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" % (bpc * ncells / 1e9),
-                   "partition": ("one %d-row slab per rank, interface columns owned by the lower rank, NCCL send/recv of %d bytes per rank per step" % (args.n, getattr(S, "exchange_bytes", 0))) if world > 1 else "single GPU", "scatter": "owner-computes gather (write-once, bit-reproducible)",
+                   "partition": ("one %d-row slab per rank, interface columns owned by the lower rank, NCCL send+recv of %d bytes on rank 0 per step" % (args.n, getattr(S, "exchange_bytes", 0))) if world > 1 else "single GPU", "scatter": "owner-computes gather (write-once, bit-reproducible)",
                    "cellvolumes": "xgrid[CellVolumes] passed in" if use_vol else "NULL: |det A|/2 on the device"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
@@ -419,9 +431,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_DEFAULT, help="quads per side (cells = 2 n^2)")
+    ap.add_argument("--size", "--n", dest="n", type=int, default=N_DEFAULT, help="quads per side (cells = 2 n^2)")
     ap.add_argument("--jitter", action="store_true", help="perturb interior nodes (full 7-point pattern)")
     ap.add_argument("--cellvol", default="given", choices=["given", "device"], help="pass xgrid[CellVolumes] (as Example200:114 reads it) or NULL")
+    ap.add_argument("--chunks", type=int, default=24, help="column chunks of the streamed host-to-host assembly (e2e)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-cells", type=float, default=16e6, help="cells per step of the --impl reference sample")

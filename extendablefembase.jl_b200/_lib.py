@@ -49,11 +49,14 @@ SIGNATURES = {
     "femb_matrix_get": (_i32, [_p, _p]),
     "femb_matrix_add_to": (_i32, [_p, _p]),
     "femb_vector_get": (_i32, [_p, _p]),
+    "femb_matrix_get_range": (_i32, [_p, _i64, _i64, _p]),
+    "femb_vector_get_range": (_i32, [_p, _i64, _i64, _p]),
     "femb_vector_set": (_i32, [_p, _i32, _p]),
     "femb_set_scatter": (_i32, [_p, _i32]),
     "femb_assemble_bilinear": (_i32, [_p, _i32, _i32, _i32, _i32, _f64, _i32, _f64]),
     "femb_assemble_linear": (_i32, [_p, _i32, _i32, _f64, _i32, _p]),
     "femb_assemble_poisson": (_i32, [_p, _i32, _i32, _f64, _i32, _p, _f64]),
+    "femb_assemble_poisson_host": (_i32, [_p, _i32, _i32, _f64, _i32, _p, _f64, _p, _p, _p, _p, _p, _i32]),
     "femb_assemble_navierstokes": (_i32, [_p, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _p]),
     "femb_last_kernel_ms": (_i32, [_p, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "femb_launch_count": (_i64, [_p]),
@@ -232,6 +235,13 @@ class Context:
         self._ck(self.lib.femb_vector_get(self.h, _ptr(out)))
         return out
 
+    def matrix_get_range(self, first, count, out):
+        """out must be a contiguous float64 array (view) of at least `count` elements"""
+        self._ck(self.lib.femb_matrix_get_range(self.h, first, count, _ptr(out)))
+
+    def vector_get_range(self, first, count, out):
+        self._ck(self.lib.femb_vector_get_range(self.h, first, count, _ptr(out)))
+
     def vector_set(self, which, v):
         v = _arr(v, np.float64)
         self._ck(self.lib.femb_vector_set(self.h, which, _ptr(v)))
@@ -259,6 +269,14 @@ class Context:
     def assemble_poisson(self, eg, ei, mu, rhs_kind, data, drop_tol):
         data = _arr(data, np.float64)
         self._ck(self.lib.femb_assemble_poisson(self.h, eg, ei, mu, rhs_kind, _ptr(data), drop_tol))
+
+    def assemble_poisson_host(self, eg, ei, mu, rhs_kind, data, drop_tol, coords, cellnodes, cellvolumes, nzval_out, b_out, nchunks=16):
+        """Streamed host-to-host assembly (H2D / kernel / D2H overlap); arrays must be C-contiguous of the right dtype."""
+        data = _arr(data, np.float64)
+        for a, dt in ((coords, np.float64), (cellnodes, np.int32), (nzval_out, np.float64)):
+            assert a.dtype == dt and a.flags.c_contiguous
+        self._ck(self.lib.femb_assemble_poisson_host(self.h, eg, ei, mu, rhs_kind, _ptr(data), drop_tol, _ptr(coords), _ptr(cellnodes), _ptr(cellvolumes),
+                                                     _ptr(nzval_out), _ptr(b_out), nchunks))
 
     def assemble_navierstokes(self, egu, eiu, eip, mu, linear, nonlinear, rhs_kind, data):
         data = _arr(data, np.float64)

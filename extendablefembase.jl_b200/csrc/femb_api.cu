@@ -91,6 +91,9 @@ int32_t femb_destroy(femb_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
+    if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FEMB_OK;
@@ -298,6 +301,24 @@ int32_t femb_matrix_get(femb_ctx* ctx, double* out) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     FEMB_TRY(femb_flush_zero(ctx, true, false));
     FEMB_TRY(femb_d2h(ctx, out, ctx->nzval, (size_t)ctx->nnz));
+    return femb_sync(ctx);
+}
+
+int32_t femb_matrix_get_range(femb_ctx* ctx, int64_t first, int64_t count, double* out) {
+    FEMB_CHECK_CTX(ctx);
+    if (!out || !ctx->nzval || first < 0 || count < 0 || first + count > ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "femb_matrix_get_range: bad range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    FEMB_TRY(femb_d2h(ctx, out, ctx->nzval + first, (size_t)count));
+    return femb_sync(ctx);
+}
+
+int32_t femb_vector_get_range(femb_ctx* ctx, int64_t first, int64_t count, double* out) {
+    FEMB_CHECK_CTX(ctx);
+    if (!out || !ctx->bvec || first < 0 || count < 0 || first + count > ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "femb_vector_get_range: bad range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FEMB_TRY(femb_flush_zero(ctx, false, true));
+    FEMB_TRY(femb_d2h(ctx, out, ctx->bvec + first, (size_t)count));
     return femb_sync(ctx);
 }
 

@@ -404,6 +404,7 @@ struct P1Args {
     double mu, drop_tol;
     int acc_A, acc_b;
     int maxlen;  // longest CSC column: shared-memory row `maxlen` is the dump row of the 2-D kernel
+    int64_t slice_begin, slice_end;  // slices [begin, end) handled by this launch (chunked / streamed assembly)
 };
 
 #define FEMB_P1_MAXQP 8
@@ -451,8 +452,8 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
     constexpr bool NEED_CELL = HAS_VOL || RHS == FEMB_RHS_QPVALUES;
     extern __shared__ double acc[];  // [maxlen + 1][128]
     const unsigned tid = threadIdx.x, lane = tid & 31u;
-    const int64_t slice = (int64_t)blockIdx.x * 4 + (tid >> 5);
-    if (slice * 32 >= a.ndofs) return;  // whole warp out of range
+    const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + (tid >> 5);
+    if (slice >= a.slice_end) return;  // whole warp out of range
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.gslice_ptr + slice), nrows = __ldg(a.gslice_ptr + slice + 1) - row0;
@@ -577,9 +578,9 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
     constexpr unsigned MISSING = 0x3Fu;
     extern __shared__ double acc[];  // [maxlen][128]
     const unsigned tid = threadIdx.x, lane = tid & 31u;
-    const int64_t slice = (int64_t)blockIdx.x * 4 + (tid >> 5);
+    const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + (tid >> 5);
     const int64_t c = slice * 32 + lane;
-    if (slice * 32 >= a.ndofs) return;  // whole warp out of range
+    if (slice >= a.slice_end) return;  // whole warp out of range
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.gslice_ptr + slice), row1 = __ldg(a.gslice_ptr + slice + 1);
     int64_t base = 0;
@@ -702,12 +703,12 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather(const P1Args a, const
 }
 
 template <int DIM>
-static int launch_p1_gather_dim(femb_ctx* ctx, const P1Args& a, const RhsDev& rhs, const P1Tab& tab, unsigned grid, size_t smem) {
+static int launch_p1_gather_dim(femb_ctx* ctx, const P1Args& a, const RhsDev& rhs, const P1Tab& tab, unsigned grid, size_t smem, cudaStream_t stream) {
     const bool track = a.touched != nullptr;
 #define FEMB_P1_LAUNCH(T, R)                                                                                                   \
     do {                                                                                                                       \
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather<DIM, T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_p1_poisson_gather<DIM, T, R><<<grid, 128, smem, ctx->stream>>>(a, rhs, tab);                                           \
+        k_p1_poisson_gather<DIM, T, R><<<grid, 128, smem, stream>>>(a, rhs, tab);                                           \
     } while (0)
     if (rhs.kind == FEMB_RHS_AFFINE) {
         if (track) FEMB_P1_LAUNCH(true, FEMB_RHS_AFFINE);
@@ -724,10 +725,19 @@ static int launch_p1_gather_dim(femb_ctx* ctx, const P1Args& a, const RhsDev& rh
     return FEMB_OK;
 }
 
-static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
+struct P1Launch {
+    P1Args a;
+    P1Tab tab;
+    P1Tab2 t2;
+    RhsDev rhs;
+    size_t smem;
+    int64_t nslices;
+};
+
+static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol, P1Launch& L) {
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
-    P1Tab tab;
+    P1Tab& tab = L.tab;
     tab.nqp = EG.nqp;
     const int ND = ctx->dim + 1;
     std::vector<double> phi((size_t)EG.nqp * ND, 0.0);
@@ -743,7 +753,7 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
     }
     for (int i = 0; i < EG.nqp * ctx->dim; i++) tab.xref[i] = EG.xref[i];
     for (int i = 0; i < EG.nqp * ND; i++) tab.phi[i] = phi[i];
-    P1Args a;
+    P1Args& a = L.a;
     a.coords = ctx->coords; a.cellvol = ctx->cellvol; a.gslice_ptr = ctx->gslice_ptr; a.gmap = ctx->gmap; a.gstride = ctx->gmap_stride;
     a.colptr = ctx->colptr; a.ndofs = s.ndofs; a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag;
     a.mu = mu; a.drop_tol = drop_tol;
@@ -751,19 +761,20 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
     ctx->zero_pending_A = false;
     if (rhs.kind != FEMB_RHS_NONE) ctx->zero_pending_b = false;
-    const int nt = 128;
-    size_t smem = (size_t)std::max(1, ctx->max_collen) * nt * sizeof(double);
-    unsigned grid = (unsigned)((s.ndofs + nt - 1) / nt);
     a.maxlen = std::max(1, ctx->max_collen);
+    L.nslices = (s.ndofs + 31) / 32;
+    a.slice_begin = 0;
+    a.slice_end = L.nslices;
+    L.rhs = rhs;
+    L.smem = (size_t)a.maxlen * 128 * sizeof(double);
     if (ctx->dim == 2) {
-        P1Tab2 t2;
+        P1Tab2& t2 = L.t2;
         t2.nqp = EG.nqp;
         t2.mu_wsum = mu * tab.wsum;
         static const int others[3][2] = {{1, 2}, {0, 2}, {0, 1}};
         for (int k = 0; k < 3; k++)
             for (int q = 0; q < FEMB_P1_MAXQP; q++) {
-                // P1 barycentric coordinates of xref_q (h1_p1.jl:64-76): needed even without a rhs? no — zero then
-                double lam[3] = {0.0, 0.0, 0.0};
+                double lam[3] = {0.0, 0.0, 0.0};  // P1 barycentric coordinates of xref_q (h1_p1.jl:64-76)
                 if (q < EG.nqp) {
                     lam[1] = EG.xref[q * 2];
                     lam[2] = EG.xref[q * 2 + 1];
@@ -775,12 +786,27 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
                 t2.t[k][q][2] = lam[others[k][0]];
                 t2.t[k][q][3] = lam[others[k][1]];
             }
-        smem = (size_t)(a.maxlen + 1) * nt * sizeof(double);
+        L.smem = (size_t)(a.maxlen + 1) * 128 * sizeof(double);
+    }
+    return FEMB_OK;
+}
+
+// launch the P1 gather kernel for slices [s0, s1) on `stream`
+static int launch_p1_slices(femb_ctx* ctx, P1Launch& L, int64_t s0, int64_t s1, cudaStream_t stream) {
+    if (s1 <= s0) return FEMB_OK;
+    P1Args& a = L.a;
+    a.slice_begin = s0;
+    a.slice_end = s1;
+    const unsigned grid = (unsigned)((s1 - s0 + 3) / 4);
+    const size_t smem = L.smem;
+    if (ctx->dim == 2) {
+        const P1Tab2& t2 = L.t2;
+        const RhsDev& rhs = L.rhs;
         const bool track = a.touched != nullptr, hv = a.cellvol != nullptr;
 #define FEMB_P1_LAUNCH2Q(T, R, V, Q)                                                                                                  \
     do {                                                                                                                              \
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather2d<T, R, V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_p1_poisson_gather2d<T, R, V, Q><<<grid, 128, smem, ctx->stream>>>(a, rhs, t2);                                               \
+        k_p1_poisson_gather2d<T, R, V, Q><<<grid, 128, smem, stream>>>(a, rhs, t2);                                                    \
     } while (0)
 #define FEMB_P1_LAUNCH2(T, R, V)                 \
     do {                                         \
@@ -803,7 +829,13 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
         KERNEL_CHECK(ctx);
         return FEMB_OK;
     }
-    return launch_p1_gather_dim<3>(ctx, a, rhs, tab, grid, smem);
+    return launch_p1_gather_dim<3>(ctx, a, L.rhs, L.tab, grid, smem, stream);
+}
+
+static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
+    P1Launch L;
+    FEMB_TRY(prepare_p1_gather(ctx, eg, ei, mu, rhs, drop_tol, L));
+    return launch_p1_slices(ctx, L, 0, L.nslices, ctx->stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -982,6 +1014,142 @@ extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, 
     if (st == FEMB_OK) st = femb_timer_end(ctx);
     cudaFree(dev_f);
     return st;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// streamed host-to-host P1 assembly: upload / kernel / download overlap over column chunks
+// ---------------------------------------------------------------------------------------------------
+// per chunk: largest node id and cell id referenced by the gather-map rows of the chunk's slices
+__global__ void k_chunk_ranges(const uint32_t* __restrict__ gmap, size_t stride, const int32_t* __restrict__ slice_ptr, const int64_t* __restrict__ chunk_slice,
+                               int nchunks, int planes_nc, unsigned long long* __restrict__ nmax, unsigned long long* __restrict__ cmax) {
+    const int k = blockIdx.x;
+    const size_t i0 = (size_t)slice_ptr[chunk_slice[k]] << 5, i1 = (size_t)slice_ptr[chunk_slice[k + 1]] << 5;
+    unsigned long long nm = 0ull, cm = 0ull;
+    for (size_t i = i0 + blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < i1; i += (size_t)gridDim.y * blockDim.x) {
+        if (gmap[2 * stride + i] == 0xFFFFFFFFu) continue;
+        unsigned long long a = gmap[i], b = gmap[stride + i];
+        nm = max(nm, max(a, b));
+        if (planes_nc) nm = max(nm, (unsigned long long)gmap[4 * stride + i]);
+        cm = max(cm, (unsigned long long)gmap[3 * stride + i]);
+    }
+    atomicMax(nmax + k, nm);
+    atomicMax(cmax + k, cm);
+}
+
+static int plan_chunks(femb_ctx* ctx, int nchunks, int64_t nslices, int64_t ndofs) {
+    if (ctx->chunk_n == nchunks) return FEMB_OK;
+    ctx->chunk_n = 0;
+    if (!ctx->stream_h2d) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking));
+    if (!ctx->stream_d2h) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking));
+    while ((int)ctx->chunk_ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_ev.push_back(e);
+    }
+    ctx->chunk_slice.assign(nchunks + 1, 0);
+    for (int k = 0; k <= nchunks; k++) {
+        int64_t s = nslices * k / nchunks;
+        ctx->chunk_slice[k] = (k == nchunks) ? nslices : (s / 4) * 4;  // CTA = 4 slices
+    }
+    int64_t* d_slice = nullptr;
+    unsigned long long* d_max = nullptr;
+    FEMB_TRY(femb_alloc(ctx, &d_slice, (size_t)nchunks + 1));
+    int st = femb_alloc(ctx, &d_max, (size_t)2 * nchunks);
+    if (st != FEMB_OK) { cudaFree(d_slice); return st; }
+    cudaMemcpyAsync(d_slice, ctx->chunk_slice.data(), sizeof(int64_t) * (nchunks + 1), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * 2 * nchunks, ctx->stream);
+    k_chunk_ranges<<<dim3(nchunks, 64), 256, 0, ctx->stream>>>(ctx->gmap, ctx->gmap_stride, ctx->gslice_ptr, d_slice, nchunks, ctx->dim == 3, d_max, d_max + nchunks);
+    ctx->launches++;
+    std::vector<unsigned long long> h(2 * nchunks);
+    cudaMemcpyAsync(h.data(), d_max, sizeof(unsigned long long) * 2 * nchunks, cudaMemcpyDeviceToHost, ctx->stream);
+    ctx->chunk_cp.assign(nchunks + 1, 0);
+    for (int k = 0; k <= nchunks; k++) {
+        int64_t d = std::min<int64_t>(ctx->chunk_slice[k] * 32, ndofs);
+        cudaMemcpyAsync(&ctx->chunk_cp[k], ctx->colptr + d, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_slice);
+    cudaFree(d_max);
+    CUDA_TRY(ctx, e);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->chunk_nmax.assign(nchunks, 0);
+    ctx->chunk_cmax.assign(nchunks, 0);
+    for (int k = 0; k < nchunks; k++) {
+        // the chunk's own dofs are nodes too (their coordinates are read as `self`)
+        int64_t dlast = std::min<int64_t>(ctx->chunk_slice[k + 1] * 32, ndofs) - 1;
+        ctx->chunk_nmax[k] = std::max<int64_t>((int64_t)h[k], dlast);
+        ctx->chunk_cmax[k] = (int64_t)h[nchunks + k];
+        ctx->chunk_cp[k] -= 1;
+    }
+    ctx->chunk_cp[nchunks] -= 1;
+    ctx->chunk_n = nchunks;
+    return FEMB_OK;
+}
+
+extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t ei, double mu, int32_t rhs_kind, const double* params, double drop_tol,
+                                              const double* coords, const int32_t* cellnodes, const double* cellvol, double* nzval_out, double* b_out,
+                                              int32_t nchunks) {
+    FEMB_CHECK_CTX(ctx);
+    FEMB_TRY(check_eval(ctx, eg));
+    if (rhs_kind != FEMB_RHS_NONE) FEMB_TRY(check_eval(ctx, ei));
+    FEMB_TRY(require_pattern(ctx));
+    if (!coords || !cellnodes || !nzval_out || (rhs_kind != FEMB_RHS_NONE && !b_out)) return femb_fail(ctx, FEMB_ERR_ARG, "femb_assemble_poisson_host: NULL buffer");
+    if ((cellvol != nullptr) != (ctx->cellvol != nullptr)) return femb_fail(ctx, FEMB_ERR_ARG, "cellvolumes must be given iff the registered mesh has them");
+    const FembEval& EG = ctx->evals[eg];
+    if (EG.op != FEMB_OP_GRADIENT) return femb_fail(ctx, FEMB_ERR_ARG, "eval_grad must be a Gradient evaluator");
+    if (!(ctx->gmap && ctx->gmap_space == EG.space) || ctx->touched || (rhs_kind != FEMB_RHS_NONE && rhs_kind != FEMB_RHS_AFFINE) ||
+        (ctx->dim == 2 && EG.nqp > FEMB_P1_MAXQP))
+        return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "the streamed path covers scalar P1 with rhs NONE/AFFINE and no pattern tracking; use femb_mesh_set + femb_assemble_poisson + femb_matrix_get");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RhsDev rhs;
+    double* dev_f = nullptr;
+    FEMB_TRY(make_rhs(ctx, rhs_kind, params, 1, EG.nqp, rhs, &dev_f));
+    const FembSpace& s = ctx->spaces[EG.space];
+    const int64_t nslices = (s.ndofs + 31) / 32;
+    nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, nslices / 4 > 0 ? nslices / 4 : 1));
+    FEMB_TRY(plan_chunks(ctx, nchunks, nslices, s.ndofs));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // earlier kernels may still read the mesh arrays
+    ctx->zero_pending_A = true;  // "zero + assemble": the write-once kernel overwrites
+    ctx->zero_pending_b = true;
+    P1Launch L;
+    FEMB_TRY(prepare_p1_gather(ctx, eg, ei, mu, rhs, drop_tol, L));
+    FEMB_TRY(femb_timer_begin(ctx));
+    const int dim = ctx->dim;
+    int64_t hi_n = 0, hi_c = 0;
+    for (int k = 0; k < nchunks; k++) {
+        const int64_t need_n = ctx->chunk_nmax[k] + 1, need_c = ctx->chunk_cmax[k] + 1;
+        if (need_n > hi_n) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coords + hi_n * dim, coords + hi_n * dim, sizeof(double) * (need_n - hi_n) * dim, cudaMemcpyHostToDevice, ctx->stream_h2d));
+            hi_n = need_n;
+        }
+        if (cellvol && need_c > hi_c) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellvol + hi_c, cellvol + hi_c, sizeof(double) * (need_c - hi_c), cudaMemcpyHostToDevice, ctx->stream_h2d));
+            hi_c = need_c;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2 * k], ctx->stream_h2d));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[2 * k], 0));
+        FEMB_TRY(launch_p1_slices(ctx, L, ctx->chunk_slice[k], ctx->chunk_slice[k + 1], ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[2 * k + 1], ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ctx->chunk_ev[2 * k + 1], 0));
+        const int64_t cp0 = ctx->chunk_cp[k], cp1 = ctx->chunk_cp[k + 1];
+        const int64_t d0 = std::min<int64_t>(ctx->chunk_slice[k] * 32, s.ndofs), d1 = std::min<int64_t>(ctx->chunk_slice[k + 1] * 32, s.ndofs);
+        if (cp1 > cp0) CUDA_TRY(ctx, cudaMemcpyAsync(nzval_out + cp0, ctx->nzval + cp0, sizeof(double) * (cp1 - cp0), cudaMemcpyDeviceToHost, ctx->stream_d2h));
+        if (rhs_kind != FEMB_RHS_NONE && d1 > d0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(b_out + d0, ctx->bvec + d0, sizeof(double) * (d1 - d0), cudaMemcpyDeviceToHost, ctx->stream_d2h));
+    }
+    // the rest of the mesh: nodes / volumes no chunk referenced, and the topology (not read by the numeric phase)
+    if (ctx->nnodes > hi_n)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coords + hi_n * dim, coords + hi_n * dim, sizeof(double) * (ctx->nnodes - hi_n) * dim, cudaMemcpyHostToDevice, ctx->stream_h2d));
+    if (cellvol && ctx->ncells > hi_c)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellvol + hi_c, cellvol + hi_c, sizeof(double) * (ctx->ncells - hi_c), cudaMemcpyHostToDevice, ctx->stream_h2d));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellnodes, cellnodes, sizeof(int32_t) * ctx->ncells * ctx->nnpc, cudaMemcpyHostToDevice, ctx->stream_h2d));
+    int st = femb_timer_end(ctx);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->stream_h2d), e2 = cudaStreamSynchronize(ctx->stream_d2h);
+    cudaFree(dev_f);
+    if (st != FEMB_OK) return st;
+    CUDA_TRY(ctx, e1);
+    CUDA_TRY(ctx, e2);
+    return femb_sync(ctx);
 }
 
 extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_t eiu, int32_t eip, double mu, int32_t linear, int32_t nonlinear,

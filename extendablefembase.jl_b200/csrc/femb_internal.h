@@ -51,6 +51,11 @@ struct femb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    // streamed host-to-host assembly (femb_assemble_poisson_host)
+    cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;          // 2 per chunk: upload done, kernel done
+    std::vector<int64_t> chunk_slice, chunk_nmax, chunk_cmax, chunk_cp;  // per chunk: first slice, max node / cell id referenced, colptr at the chunk start (0-based)
+    int chunk_n = 0;
     std::string err;
     int64_t launches = 0;
     int last_launches = 0;

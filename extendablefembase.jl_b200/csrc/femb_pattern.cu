@@ -19,6 +19,7 @@ void femb_free_pattern(femb_ctx* ctx) {
     ctx->gmap_rows = 0;
     ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
+    ctx->chunk_n = 0;
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
     ctx->nnz = 0;
@@ -610,6 +611,7 @@ int femb_build_gmap(femb_ctx* ctx) {
     ctx->gmap_rows = 0;
     ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
+    ctx->chunk_n = 0;  // chunk plan of the streamed assembly depends on the gather map
     if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
     int sid = ctx->row_spaces[0];
     const FembSpace& s = ctx->spaces[sid];

@@ -154,6 +154,10 @@ int32_t femb_matrix_zero(femb_ctx* ctx);
 int32_t femb_vector_zero(femb_ctx* ctx);
 int32_t femb_matrix_get(femb_ctx* ctx, double* nzval_out);           /* nnz doubles, Julia CSC order */
 int32_t femb_matrix_add_to(femb_ctx* ctx, double* nzval_inout);      /* nzval_inout += device values  */
+/* partial downloads: nzval[first .. first+count) / b[first .. first+count) (0-based) into out[0 .. count) —
+ * e.g. the interface columns after femb_exchange */
+int32_t femb_matrix_get_range(femb_ctx* ctx, int64_t first, int64_t count, double* out);
+int32_t femb_vector_get_range(femb_ctx* ctx, int64_t first, int64_t count, double* out);
 int32_t femb_vector_get(femb_ctx* ctx, double* b_out);               /* sum of row-space ndofs        */
 int32_t femb_vector_set(femb_ctx* ctx, int32_t which, const double* v); /* which: 0 = b, 1 = current solution (Example210:328-331) */
 int32_t femb_set_scatter(femb_ctx* ctx, int32_t policy);
@@ -172,6 +176,15 @@ int32_t femb_assemble_linear(femb_ctx* ctx, int32_t eval_id, int32_t brow, doubl
  * kernel (stages 1-5). */
 int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id, double mu, int32_t rhs_kind,
                               const double* params_or_fvals, double drop_tol);
+/* The same assembly with HOST buffers end to end, software-pipelined over `nchunks` column ranges on three streams:
+ * upload of Coordinates / CellVolumes (prefix needed by the next chunk) and CellNodes, the fused kernel per chunk,
+ * and download of the finished nzval / b ranges overlap.  Equivalent to femb_mesh_set (same shapes: the symbolic
+ * phase is reused) + femb_matrix_zero + femb_vector_zero + femb_assemble_poisson + femb_matrix_get +
+ * femb_vector_get, bit for bit.  Scalar P1 with rhs_kind NONE / AFFINE; pin the host arrays with
+ * femb_host_register for the copies to overlap.  cellvol must be given iff the registered mesh has volumes. */
+int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id, double mu, int32_t rhs_kind, const double* params,
+                                   double drop_tol, const double* coords, const int32_t* cellnodes, const double* cellvolumes_or_null,
+                                   double* nzval_out, double* b_out, int32_t nchunks);
 /* Example210 update_system!(linear, nonlinear) (Example210:276-385): Laplacian + div-pressure blocks +
  * rhs (linear) and the Newton-linearised convection term + its rhs (nonlinear; uses vector 1 =
  * current solution).  evals: grad u, id u, id p. */

@@ -319,3 +319,35 @@ def test_adopted_pattern_missing_entry_is_reported():
     with pytest.raises(_lib.FembError) as ei:
         fb.assemble_poisson(B.entries, bv.entries, fes2, None, 1.0)
     assert ei.value.status == 4
+
+
+@pytest.mark.parametrize("dim,n,nchunks,use_vol", [(2, 70, 5, True), (2, 33, 1, False), (2, 200, 16, True), (3, 9, 4, True)])
+def test_streamed_host_assembly_is_bit_identical(dim, n, nchunks, use_vol):
+    """femb_assemble_poisson_host (upload / kernel / download pipelined over column chunks) == mesh_set + assemble + get."""
+    from femb_b200.assembly import _Session
+
+    grid = _grid2d(n, True) if dim == 2 else _grid3d(n, True)
+    fes = fb.FESpace(fb.H1P1(1), grid)
+    qf = fb.QuadratureRule(grid.geometry, 0)
+    S = _Session([fes], qf, cellvolumes=use_vol)
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    nnz = ctx.pattern_build([(0, 0)])
+    p = np.array([0.3, 1.0, -1.0] if dim == 2 else [0.3, 1.0, -1.0, 0.5])
+    ctx.matrix_zero()
+    ctx.vector_zero()
+    ctx.assemble_poisson(eg._eid, ei._eid, 1.7, _lib.RHS_AFFINE, p, 1e-15)
+    nz1, b1 = ctx.matrix_get(), ctx.vector_get(fes.ndofs)
+    # new coordinates for the streamed call (same topology): results must follow the uploaded mesh
+    coords2 = np.ascontiguousarray(grid["Coordinates"] * 1.25 + 0.1)
+    vol2 = np.ascontiguousarray(grid["CellVolumes"] * 1.25 ** dim) if use_vol else None
+    nz2, b2 = np.full(nnz, np.nan), np.full(fes.ndofs, np.nan)
+    ctx.assemble_poisson_host(eg._eid, ei._eid, 1.7, _lib.RHS_AFFINE, p, 1e-15, coords2, grid["CellNodes"], vol2, nz2, b2, nchunks)
+    ctx.mesh_set(coords2, grid["CellNodes"], vol2)
+    ctx.matrix_zero()
+    ctx.vector_zero()
+    ctx.assemble_poisson(eg._eid, ei._eid, 1.7, _lib.RHS_AFFINE, p, 1e-15)
+    nz3, b3 = ctx.matrix_get(), ctx.vector_get(fes.ndofs)
+    assert np.array_equal(nz2, nz3) and np.array_equal(b2, b3)
+    assert not np.array_equal(nz1, nz3) or dim == 2  # 2-D stiffness is scale invariant, 3-D is not
+    assert not np.array_equal(b1, b3)
