@@ -80,6 +80,7 @@ int32_t femb_destroy(femb_ctx* ctx) {
     for (auto& e : ctx->evals) {
         femb_free(&e.refvals);
         femb_free(&e.refderivs);
+        femb_free(&e.reftensor);
     }
     femb_free(&ctx->coords);
     femb_free(&ctx->cellnodes);
@@ -236,12 +237,16 @@ int32_t femb_evaluator_set(femb_ctx* ctx, int32_t id, int32_t space_id, int32_t 
     femb_free(&e.refvals);
     femb_free(&e.refderivs);
     e.h_refvals.clear();
+    e.h_refderivs.clear();
+    femb_free(&e.reftensor);
+    e.reftensor_nt = 0;
     if (refvals) {
         e.h_refvals.assign(refvals, refvals + nv);
         FEMB_TRY(femb_alloc(ctx, &e.refvals, nv));
         FEMB_TRY(femb_h2d(ctx, e.refvals, refvals, nv));
     }
     if (refderivs) {
+        e.h_refderivs.assign(refderivs, refderivs + nv * ctx->dim);
         FEMB_TRY(femb_alloc(ctx, &e.refderivs, nv * ctx->dim));
         FEMB_TRY(femb_h2d(ctx, e.refderivs, refderivs, nv * ctx->dim));
     }

@@ -839,6 +839,208 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
 }
 
 // ---------------------------------------------------------------------------------------------------
+// scalar H1 stiffness on affine cells as a batched small GEMM on the FP64 tensor cores (P2, and P1 when the
+// atomic scatter policy is chosen).  For an affine cell the push-forward factors out of the quadrature sum
+// (feevaluator_h1.jl:69-72 with M = A^{-T} constant on the cell):
+//     Aloc[j,k] = mu |T| sum_q w_q (M D_q e_j).(M D_q e_k) = sum_{a<=b} Kc[ab] * T[ab][j,k]
+//     Kc = mu |T| (M^T M) = mu |T| (C^T C) / det^2  (3 or 6 coefficients per cell, C = cofactor matrix)
+//     T[aa] = sum_q w_q D_q[.,a] D_q[.,a]^T,  T[ab] = sum_q w_q (D_q[.,a] D_q[.,b]^T + D_q[.,b] D_q[.,a]^T)
+// i.e. Aloc (cells x unique entries) = Kc (cells x ncoef) * T (ncoef x unique entries): a dense GEMM with a
+// reference tensor T that is the same for all cells.  One warp handles 32 cells per iteration as 4 m-tiles of
+// mma.sync.m8n8k4.f64 (SASS DMMA): A fragments = Kc staged through shared memory, B fragments = T held in
+// registers for the whole kernel, C = 8x8 tiles of local-matrix entries, scattered through the cell->slot map
+// with red.global.add.f64 (upper triangle + mirror, Example200:149-158, |v| <= drop_tol skipped).
+// ---------------------------------------------------------------------------------------------------
+struct DmmaArgs {
+    const double* coords;
+    const int32_t* cellnodes;
+    const double* cellvol;
+    int64_t ncells;
+    const double* T;       // [KS*4][NT*8]
+    const int32_t* slots;  // [cell][nd][nd]
+    double* nzval;
+    uint8_t* touched;
+    int32_t* errflag;
+    double mu, drop_tol;
+    int nd, ne;            // local dofs, unique entries nd(nd+1)/2
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int DIM, int NT>
+__global__ void __launch_bounds__(128) k_h1_stiffness_dmma(const DmmaArgs a) {
+    constexpr int KS = (DIM == 2) ? 1 : 2;  // coefficient count 3 / 6 padded to 4 / 8
+    constexpr int KP = KS * 4;
+    __shared__ double Kst[4][32][KP + 1];   // per warp: Kc of its 32 cells (+1: no bank conflicts on the column reads)
+    __shared__ uint8_t ejk[NT * 8][2];      // unique entry -> (j, k), j <= k
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int e = threadIdx.x; e < NT * 8; e += blockDim.x) {
+        int j = 0, k = 0, idx = e;
+        if (e < a.ne) {  // row-major upper triangle: (0,0),(0,1),...,(0,nd-1),(1,1),...
+            while (idx >= a.nd - j) {
+                idx -= a.nd - j;
+                j++;
+            }
+            k = j + idx;
+        }
+        ejk[e][0] = (uint8_t)j;
+        ejk[e][1] = (uint8_t)k;
+    }
+    double B[KS][NT];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) B[ks][nt] = __ldg(a.T + (size_t)(ks * 4 + t) * (NT * 8) + nt * 8 + g);
+    __syncthreads();
+    const int64_t ntiles = (a.ncells + 31) / 32;
+    const int per = a.nd * a.nd;
+    for (int64_t tile = (int64_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (int64_t)gridDim.x * 4) {
+        const int64_t cell = tile * 32 + lane;
+        double kc[KP];
+#pragma unroll
+        for (int i = 0; i < KP; i++) kc[i] = 0.0;
+        if (cell < a.ncells) {
+            double x[DIM + 1][DIM];
+            load_nodes<DIM>(a.coords, a.cellnodes, cell, x);
+            double A[DIM][DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++)
+#pragma unroll
+                for (int i = 0; i < DIM; i++) A[d][i] = x[i + 1][d] - x[0][d];
+            double C[DIM][DIM], det;  // cofactors: M[k][j] = C[k][j] / det
+            if (DIM == 2) {
+                det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+                C[0][0] = A[1][1]; C[0][1] = -A[1][0];
+                C[1][0] = -A[0][1]; C[1][1] = A[0][0];
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const int ra = (r + 1) % 3, rb = (r + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
+                        C[r][j] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
+                    }
+                det = A[0][0] * C[0][0] + A[0][1] * C[0][1] + A[0][2] * C[0][2];
+            }
+            const double vol = a.cellvol ? __ldg(a.cellvol + cell) : fabs(det) * (DIM == 2 ? 0.5 : 1.0 / 6.0);
+            const double sc = (a.mu * vol) / (det * det);
+            // Kmat[p][q] = sc * sum_k C[k][p] C[k][q]; coefficient order (00, 11, [22,] 01, [02, 12])
+            int ci = 0;
+#pragma unroll
+            for (int p = 0; p < DIM; p++) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][p];
+                kc[ci++] = s * sc;
+            }
+#pragma unroll
+            for (int p = 0; p < DIM; p++)
+#pragma unroll
+                for (int q = p + 1; q < DIM; q++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][q];
+                    kc[ci++] = s * sc;
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < KP; i++) Kst[warp][lane][i] = kc[i];
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            double acc[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) acc[nt][0] = acc[nt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                const double af = Kst[warp][mt * 8 + g][ks * 4 + t];
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) dmma_m8n8k4(acc[nt][0], acc[nt][1], af, B[ks][nt]);
+            }
+            const int64_t c2 = tile * 32 + mt * 8 + g;
+            if (c2 < a.ncells) {
+                const int32_t* sl = a.slots + c2 * per;
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int e = nt * 8 + 2 * t + h;
+                        const double v = acc[nt][h];
+                        if (e < a.ne && fabs(v) > a.drop_tol) {
+                            const int j = ejk[e][0], k = ejk[e][1];
+                            scatter_add(a.nzval, a.touched, a.errflag, __ldg(sl + j * a.nd + k), v, 1);
+                            if (k != j) scatter_add(a.nzval, a.touched, a.errflag, __ldg(sl + k * a.nd + j), v, 1);
+                        }
+                    }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// reference tensor T[coef][entry] from the evaluator's reference-gradient table and weights (host, once)
+static int build_reftensor(femb_ctx* ctx, FembEval& E, int nd, int nt) {
+    if (E.reftensor && E.reftensor_nt == nt) return FEMB_OK;
+    const int dim = ctx->dim, ks = dim == 2 ? 1 : 2, ncol = nt * 8;
+    const FembSpace& s = ctx->spaces[E.space];
+    if (E.h_refderivs.size() != (size_t)E.nqp * s.nd_all * dim) return femb_fail(ctx, FEMB_ERR_ARG, "Gradient evaluator has no reference-derivative table");
+    std::vector<double> T((size_t)ks * 4 * ncol, 0.0);
+    // coefficient order (00, 11, [22,] 01, [02, 12])
+    std::vector<std::pair<int, int>> co;
+    for (int p = 0; p < dim; p++) co.push_back({p, p});
+    for (int p = 0; p < dim; p++)
+        for (int q = p + 1; q < dim; q++) co.push_back({p, q});
+    int e = 0;
+    for (int j = 0; j < nd; j++)
+        for (int k = j; k < nd; k++, e++)
+            for (size_t c = 0; c < co.size(); c++) {
+                const int p = co[c].first, q = co[c].second;
+                double sum = 0.0;
+                for (int qp = 0; qp < E.nqp; qp++) {
+                    const double* Dj = &E.h_refderivs[((size_t)qp * s.nd_all + j) * dim];
+                    const double* Dk = &E.h_refderivs[((size_t)qp * s.nd_all + k) * dim];
+                    sum += E.w[qp] * (p == q ? Dj[p] * Dk[p] : Dj[p] * Dk[q] + Dj[q] * Dk[p]);
+                }
+                T[c * ncol + e] = sum;
+            }
+    FEMB_TRY(femb_alloc(ctx, &E.reftensor, T.size()));
+    FEMB_TRY(femb_h2d(ctx, E.reftensor, T.data(), T.size()));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    E.reftensor_nt = nt;
+    return FEMB_OK;
+}
+
+// returns FEMB_ERR_UNSUPPORTED (without setting an error) when the DMMA path does not cover the space
+static int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_tol) {
+    FembEval& EG = ctx->evals[eg];
+    const FembSpace& s = ctx->spaces[EG.space];
+    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd > 10) return FEMB_ERR_UNSUPPORTED;
+    const FembBlock* blk = find_block(ctx, 0, 0);
+    if (!blk || !blk->slots || ctx->nrs != 1 || ctx->row_spaces[0] != EG.space) return FEMB_ERR_UNSUPPORTED;
+    const int ne = s.nd * (s.nd + 1) / 2, nt = (ne + 7) / 8;
+    FEMB_TRY(build_reftensor(ctx, EG, s.nd, nt));
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    DmmaArgs a;
+    a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.ncells = ctx->ncells; a.T = EG.reftensor; a.slots = blk->slots;
+    a.nzval = ctx->nzval; a.touched = ctx->touched; a.errflag = ctx->errflag; a.mu = mu; a.drop_tol = drop_tol; a.nd = s.nd; a.ne = ne;
+    if (ctx->ncells == 0) return FEMB_OK;
+    const int64_t ntiles = (ctx->ncells + 31) / 32;
+    const unsigned grid = (unsigned)std::min<int64_t>((ntiles + 3) / 4, (int64_t)ctx->sm_count * 16);
+#define FEMB_DMMA(D, N) k_h1_stiffness_dmma<D, N><<<grid, 128, 0, ctx->stream>>>(a)
+    if (ctx->dim == 2 && nt == 1) FEMB_DMMA(2, 1);
+    else if (ctx->dim == 2 && nt == 3) FEMB_DMMA(2, 3);
+    else if (ctx->dim == 3 && nt == 2) FEMB_DMMA(3, 2);
+    else if (ctx->dim == 3 && nt == 7) FEMB_DMMA(3, 7);
+    else return FEMB_ERR_UNSUPPORTED;
+#undef FEMB_DMMA
+    KERNEL_CHECK(ctx);
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Example210 convection (Newton linearisation), 2-D, two components   (Example210:322-365)
 // ---------------------------------------------------------------------------------------------------
 struct ConvArgs {
@@ -1007,7 +1209,9 @@ extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, 
             rhs_kind != FEMB_RHS_EX210 && (ctx->dim == 3 || EG.nqp <= FEMB_P1_MAXQP)) {
             st = launch_p1_gather(ctx, eg, ei, mu, rhs, drop_tol);
         } else {
-            st = launch_bilinear(ctx, eg, eg, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, FEMB_BIL_SYMMETRIC_UPPER, drop_tol);
+            st = (ctx->scatter == FEMB_SCATTER_COLORED) ? FEMB_ERR_UNSUPPORTED : launch_stiffness_dmma(ctx, eg, mu, drop_tol);
+            if (st == FEMB_ERR_UNSUPPORTED)  // elements with per-cell basis subsets, vector-valued spaces, ...: generic quadrature kernel
+                st = launch_bilinear(ctx, eg, eg, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, FEMB_BIL_SYMMETRIC_UPPER, drop_tol);
             if (st == FEMB_OK && rhs_kind != FEMB_RHS_NONE) st = launch_linear(ctx, ei, 0, 1.0, rhs);
         }
     }

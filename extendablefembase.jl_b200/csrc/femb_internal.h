@@ -38,6 +38,9 @@ struct FembEval {
     double* refvals = nullptr;    // device [nqp][nd_all][ncomp]
     double* refderivs = nullptr;  // device [nqp][nd_all][ncomp][dim]
     std::vector<double> h_refvals; // host copy (P1 gather kernel takes the Identity table by value)
+    std::vector<double> h_refderivs; // host copy (reference tensor of the DMMA stiffness kernel)
+    double* reftensor = nullptr;  // device [KS*4][NT*8], built lazily by the DMMA stiffness path
+    int reftensor_nt = 0;
     double xref[FEMB_MAX_QP * 3];
     double w[FEMB_MAX_QP];
 };

@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Secondary configs of BASELINE.json (C3 P2-3D stiffness, C4 Hdiv mass+div, C5 Taylor-Hood) timed on the device
+through the same C ABI as bench.py (device-resident inputs, CUDA events of the library).  Not the headline metric:
+prints one JSON line per config with cells/s and the per-call kernel time, for DESIGN.md / profiles/."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__  # noqa: E402,F401
+import femb_b200 as fb  # noqa: E402
+from femb_b200 import _lib  # noqa: E402
+from femb_b200.assembly import AffineFunction, Example210RHS, _Session  # noqa: E402
+
+
+def timeit(fn, ctx, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    ctx.sync()
+    ctx.region_begin()
+    for _ in range(steps):
+        fn()
+    ms = ctx.region_end() / steps
+    return ms
+
+
+def c3_p2_3d(m, steps, warmup, order=2):
+    X = np.linspace(0, 1, m + 1)
+    t0 = time.time()
+    grid = fb.simplexgrid(X, X, X)
+    ft = fb.H1P2(1, 3) if order == 2 else fb.H1P1(1)
+    fes = fb.FESpace(ft, grid)
+    qf = fb.QuadratureRule(grid.geometry, 2 * (order - 1))
+    S = _Session([fes], qf)
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    t1 = time.time()
+    nnz = ctx.pattern_build([(0, 0)])
+    ctx.sync()
+    t2 = time.time()
+    p = AffineFunction([0.0], [[1.0, -1.0, 0.5]]).params()
+
+    def step():
+        ctx.matrix_zero()
+        ctx.vector_zero()
+        ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0)
+
+    ms = timeit(step, ctx, steps, warmup)
+    return {"config": f"C3 H1P{order}{{1,3}} Poisson stiffness+rhs, Kuhn m={m}", "ncells": grid.ncells, "ndofs": fes.ndofs, "nnz": nnz, "ms_per_step": ms,
+            "cells_per_s": grid.ncells / (ms * 1e-3), "host_setup_s": t1 - t0, "pattern_s": t2 - t1}
+
+
+def c4_hdiv(m, steps, warmup, name):
+    X = np.linspace(0, 1, m + 1)
+    grid = fb.simplexgrid(X, X, X)
+    ft = fb.HDIVRT0(3) if name == "RT0" else fb.HDIVBDM1(3)
+    FESv, FESq = fb.FESpace(ft, grid), fb.FESpace(fb.L2P0(1), grid)
+    qf = fb.QuadratureRule(grid.geometry, 2)
+    S = _Session([FESv, FESq], qf)
+    ctx = S.ctx
+    eid, ediv, eq = S.evaluator(0, "Identity"), S.evaluator(0, "Divergence"), S.evaluator(1, "Identity")
+    nnz = ctx.pattern_build([(0, 0), (0, 1), (1, 0)])
+
+    def step():
+        ctx.matrix_zero()
+        ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
+        ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
+
+    ms = timeit(step, ctx, steps, warmup)
+    return {"config": f"C4 HDIV{name}{{3}} mass + (div v, q) vs L2P0, Kuhn m={m}", "ncells": grid.ncells, "ndofs": FESv.ndofs + FESq.ndofs, "nnz": nnz,
+            "ms_per_step": ms, "cells_per_s": grid.ncells / (ms * 1e-3)}
+
+
+def c5_taylor_hood(n, steps, warmup):
+    X = np.linspace(0, 1, n + 1)
+    grid = fb.simplexgrid(X, X)
+    FESu, FESp = fb.FESpace(fb.H1Pk(2, 2, 2), grid), fb.FESpace(fb.H1Pk(1, 2, 1), grid)
+    qf = fb.QuadratureRule(grid.geometry, 5)
+    S = _Session([FESu, FESp], qf)
+    ctx = S.ctx
+    egu, eiu, eip = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity"), S.evaluator(1, "Identity")
+    nnz = ctx.pattern_build([(0, 0), (0, 1), (1, 0)], [FESu.ndofs + 1])
+    sol = np.random.default_rng(1).uniform(-1, 1, FESu.ndofs + FESp.ndofs)
+    ctx.vector_set(1, sol)
+    rp = Example210RHS(1e-2, 0.0).params()
+    out = []
+    for label, lin, nonlin in (("linear (Laplacian + div-pressure + rhs)", True, False), ("nonlinear (Newton convection + rhs)", False, True)):
+        def step():
+            ctx.matrix_zero()
+            ctx.vector_zero()
+            ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, 1e-2, lin, nonlin, _lib.RHS_EX210 if lin else _lib.RHS_NONE, rp if lin else None)
+
+        ms = timeit(step, ctx, steps, warmup)
+        out.append({"config": f"C5 Example210 Taylor-Hood update_system! {label}, n={n}", "ncells": grid.ncells, "ndofs": FESu.ndofs + FESp.ndofs, "nnz": nnz,
+                    "ms_per_step": ms, "cells_per_s": grid.ncells / (ms * 1e-3)})
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--which", default="c3,c3p1,c4,c5")
+    ap.add_argument("--m3", type=int, default=96)
+    ap.add_argument("--m4", type=int, default=64)
+    ap.add_argument("--n5", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    a = ap.parse_args()
+    res = []
+    for w in a.which.split(","):
+        if w == "c3":
+            res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 2))
+        elif w == "c3p1":
+            res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 1))
+        elif w == "c4":
+            res.append(c4_hdiv(a.m4, a.steps, a.warmup, "RT0"))
+            res.append(c4_hdiv(a.m4, a.steps, a.warmup, "BDM1"))
+        elif w == "c5":
+            res += c5_taylor_hood(a.n5, a.steps, a.warmup)
+    for r in res:
+        print(json.dumps(r), flush=True)
