@@ -329,7 +329,8 @@ static int launch_bilinear(femb_ctx* ctx, int er, int ec, int op_r, int op_c, in
 // ---------------------------------------------------------------------------------------------------
 // linear form: owner-computes gather over the dof -> cell adjacency (write-once, fixed order)
 // ---------------------------------------------------------------------------------------------------
-template <int DIM>
+// LIGHT: H1 / L2 Identity needs no inverse map — only A (for x_qp) and |T|: skips the divisions of mapderiv!
+template <int DIM, bool LIGHT>
 __global__ void __launch_bounds__(128) k_linear_gather(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes,
                                                        const double* __restrict__ cellvol, SpaceDev s, int op, int R, QuadDev q,
                                                        const double* __restrict__ rv, const double* __restrict__ rd,
@@ -343,7 +344,26 @@ __global__ void __launch_bounds__(128) k_linear_gather(const double* __restrict_
         int64_t cell = av / (uint32_t)s.nd;
         int k = (int)(av - cell * s.nd);
         Geo<DIM> g;
-        load_geo<DIM>(coords, cellnodes, cellvol, cell, g);
+        if (LIGHT) {
+            double xn[DIM + 1][DIM];
+            load_nodes<DIM>(coords, cellnodes, cell, xn);
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                g.x0[d] = xn[0][d];
+#pragma unroll
+                for (int i = 0; i < DIM; i++) g.A[d][i] = xn[i + 1][d] - xn[0][d];
+            }
+            if (cellvol) {
+                g.vol = __ldg(cellvol + cell);
+            } else if (DIM == 2) {
+                g.vol = fabs(g.A[0][0] * g.A[1][1] - g.A[0][1] * g.A[1][0]) * 0.5;
+            } else {
+                g.vol = fabs(g.A[0][0] * (g.A[1][1] * g.A[2][2] - g.A[1][2] * g.A[2][1]) + g.A[0][1] * (g.A[1][2] * g.A[2][0] - g.A[1][0] * g.A[2][2]) +
+                             g.A[0][2] * (g.A[1][0] * g.A[2][1] - g.A[1][1] * g.A[2][0])) * (1.0 / 6.0);
+            }
+        } else {
+            load_geo<DIM>(coords, cellnodes, cellvol, cell, g);
+        }
         double temp = 0.0;
         for (int qp = 0; qp < q.nqp; qp++) {
             double x[DIM], f[3], v[9];
@@ -368,12 +388,18 @@ static int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const R
     FEMB_TRY(femb_flush_zero(ctx, false, true));
     unsigned grid = (unsigned)((s.ndofs + 127) / 128);
     QuadDev q = quad_dev(E, ctx->dim);
-    if (ctx->dim == 2)
-        k_linear_gather<2><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, E.resultdim, q, E.refvals, E.refderivs,
-                                                          s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow]);
-    else
-        k_linear_gather<3><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, E.resultdim, q, E.refvals, E.refderivs,
-                                                          s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow]);
+    const bool light = s.family != FEMB_FAMILY_HDIV && E.op == FEMB_OP_IDENTITY;
+#define FEMB_LIN(D, L)                                                                                                                          \
+    k_linear_gather<D, L><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, E.resultdim, q, E.refvals, \
+                                                         E.refderivs, s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow])
+    if (ctx->dim == 2) {
+        if (light) FEMB_LIN(2, true);
+        else FEMB_LIN(2, false);
+    } else {
+        if (light) FEMB_LIN(3, true);
+        else FEMB_LIN(3, false);
+    }
+#undef FEMB_LIN
     KERNEL_CHECK(ctx);
     return FEMB_OK;
 }
@@ -949,7 +975,7 @@ __global__ void __launch_bounds__(128) k_h1_stiffness_dmma(const DmmaArgs a) {
 #pragma unroll
         for (int i = 0; i < KP; i++) Kst[warp][lane][i] = kc[i];
         __syncwarp();
-#pragma unroll
+#pragma unroll 1
         for (int mt = 0; mt < 4; mt++) {
             double acc[NT][2];
 #pragma unroll
@@ -963,17 +989,25 @@ __global__ void __launch_bounds__(128) k_h1_stiffness_dmma(const DmmaArgs a) {
             const int64_t c2 = tile * 32 + mt * 8 + g;
             if (c2 < a.ncells) {
                 const int32_t* sl = a.slots + c2 * per;
+                // all slot loads of the m-tile first (independent, in flight together), then the reductions
+                int32_t s_up[NT][2], s_lo[NT][2];
 #pragma unroll
                 for (int nt = 0; nt < NT; nt++)
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int e = nt * 8 + 2 * t + h;
+                        const int j = ejk[e][0], k = ejk[e][1];
+                        const bool on = e < a.ne && fabs(acc[nt][h]) > a.drop_tol;
+                        s_up[nt][h] = on ? __ldg(sl + j * a.nd + k) : INT32_MIN;
+                        s_lo[nt][h] = (on && k != j) ? __ldg(sl + k * a.nd + j) : INT32_MIN;
+                    }
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
                         const double v = acc[nt][h];
-                        if (e < a.ne && fabs(v) > a.drop_tol) {
-                            const int j = ejk[e][0], k = ejk[e][1];
-                            scatter_add(a.nzval, a.touched, a.errflag, __ldg(sl + j * a.nd + k), v, 1);
-                            if (k != j) scatter_add(a.nzval, a.touched, a.errflag, __ldg(sl + k * a.nd + j), v, 1);
-                        }
+                        if (s_up[nt][h] != INT32_MIN) scatter_add(a.nzval, a.touched, a.errflag, s_up[nt][h], v, 1);
+                        if (s_lo[nt][h] != INT32_MIN) scatter_add(a.nzval, a.touched, a.errflag, s_lo[nt][h], v, 1);
                     }
             }
         }

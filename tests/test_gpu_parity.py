@@ -351,3 +351,53 @@ def test_streamed_host_assembly_is_bit_identical(dim, n, nchunks, use_vol):
     assert np.array_equal(nz2, nz3) and np.array_equal(b2, b3)
     assert not np.array_equal(nz1, nz3) or dim == 2  # 2-D stiffness is scale invariant, 3-D is not
     assert not np.array_equal(b1, b3)
+
+
+@pytest.mark.parametrize("n", [1500, 5657])
+def test_full_size_p1_against_c_oracle(n):
+    """BASELINE.json configs[1] at full size (n = 5657: 64,003,298 triangles): the device result against the C
+    restatement of the reference loop (all host threads) on the SAME pattern — every reference contribution finds
+    a slot (pattern >= reference), every slot is non-zero (pattern <= reference), values within 1e-12 — plus the
+    size-independent identities A 1 = 0, A = A^T, sum(b) = int f."""
+    import oracle_c
+    from femb_b200.assembly import _Session
+
+    X = np.linspace(0, 1, n + 1)
+    grid = fb.simplexgrid(X, X)
+    fes = fb.FESpace(fb.H1Pk(1, 2, 1), grid)
+    qf = fb.QuadratureRule(grid.geometry, 0)
+    S = _Session([fes], qf)
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    ctx.pattern_track(True)
+    ctx.pattern_build([(0, 0)])
+    p = np.array([0.0, 1.0, -1.0])
+    ctx.matrix_zero()
+    ctx.vector_zero()
+    ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 1e-15)
+    nnz = ctx.pattern_compress()
+    ctx.pattern_track(False)
+    ctx.matrix_zero()
+    ctx.vector_zero()
+    ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 1e-15)
+    nz, b = ctx.matrix_get(), ctx.vector_get(fes.ndofs)
+    colptr, rowval = ctx.pattern_get(fes.ndofs)
+    assert nnz == rowval.shape[0] and np.all(np.diff(colptr) >= 3) and np.all(np.diff(colptr) <= 5)  # 5-point stencil after the 1e-15 filter
+    el = orc.Element("H1Pk", 1, 1)
+    xref, w = orc.quadrature("Triangle2D", 0)
+    vals, der = el.tabulate("Triangle2D", xref)
+    nz2, b2 = np.zeros(nnz), np.zeros(fes.ndofs)
+    cn = grid["CellNodes"]
+    miss = oracle_c.example200(grid["Coordinates"], cn, grid["CellVolumes"], cn, w, xref, vals[:, :, 0], der[:, :, 0, :], 1.0, p, 1e-15, colptr, rowval, nz2, b2,
+                               oracle_c.max_threads())
+    assert miss == 0 and np.all(nz2 != 0.0)
+    assert np.abs(nz - nz2).max() <= RTOL * np.abs(nz2).max()
+    assert np.abs(b - b2).max() <= RTOL * np.abs(b2).max()
+    cols = np.repeat(np.arange(fes.ndofs, dtype=np.int64), np.diff(colptr))
+    assert np.abs(np.bincount(rowval - 1, weights=nz, minlength=fes.ndofs)).max() < 1e-13  # A 1 = 0
+    assert np.abs(np.bincount(cols, weights=nz, minlength=fes.ndofs)).max() < 1e-13  # 1^T A = 0
+    # exact symmetry: value of (i, j) equals value of (j, i)
+    key = cols * fes.ndofs + (rowval - 1)
+    keyT = (rowval - 1) * fes.ndofs + cols
+    assert np.array_equal(nz[np.searchsorted(key, keyT)], nz)
+    assert abs(b.sum()) < 1e-12  # int (x - y) over the unit square
