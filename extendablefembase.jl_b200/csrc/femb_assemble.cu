@@ -888,7 +888,8 @@ struct DmmaArgs {
     uint8_t* touched;
     int32_t* errflag;
     double mu, drop_tol;
-    int nd, ne;            // local dofs, unique entries nd(nd+1)/2
+    int nd, ne;            // scalar local dofs nds, unique entries nds(nds+1)/2
+    int ncomp;             // vector-valued H1: component-blocked basis (h1_p2.jl:133-141) -> the same scalar block on every diagonal block
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -922,7 +923,7 @@ __global__ void __launch_bounds__(128) k_h1_stiffness_dmma(const DmmaArgs a) {
         for (int nt = 0; nt < NT; nt++) B[ks][nt] = __ldg(a.T + (size_t)(ks * 4 + t) * (NT * 8) + nt * 8 + g);
     __syncthreads();
     const int64_t ntiles = (a.ncells + 31) / 32;
-    const int per = a.nd * a.nd;
+    const int per = a.nd * a.nd * a.ncomp * a.ncomp;
     for (int64_t tile = (int64_t)blockIdx.x * 4 + warp; tile < ntiles; tile += (int64_t)gridDim.x * 4) {
         const int64_t cell = tile * 32 + lane;
         double kc[KP];
@@ -988,27 +989,30 @@ __global__ void __launch_bounds__(128) k_h1_stiffness_dmma(const DmmaArgs a) {
             }
             const int64_t c2 = tile * 32 + mt * 8 + g;
             if (c2 < a.ncells) {
-                const int32_t* sl = a.slots + c2 * per;
-                // all slot loads of the m-tile first (independent, in flight together), then the reductions
-                int32_t s_up[NT][2], s_lo[NT][2];
+                const int ndl = a.nd * a.ncomp;  // local dofs of the (vector) space
+                for (int comp = 0; comp < a.ncomp; comp++) {
+                    const int32_t* sl = a.slots + c2 * per + (comp * a.nd) * ndl + comp * a.nd;
+                    // all slot loads of the m-tile first (independent, in flight together), then the reductions
+                    int32_t s_up[NT][2], s_lo[NT][2];
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++)
+                    for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int e = nt * 8 + 2 * t + h;
-                        const int j = ejk[e][0], k = ejk[e][1];
-                        const bool on = e < a.ne && fabs(acc[nt][h]) > a.drop_tol;
-                        s_up[nt][h] = on ? __ldg(sl + j * a.nd + k) : INT32_MIN;
-                        s_lo[nt][h] = (on && k != j) ? __ldg(sl + k * a.nd + j) : INT32_MIN;
-                    }
+                        for (int h = 0; h < 2; h++) {
+                            const int e = nt * 8 + 2 * t + h;
+                            const int j = ejk[e][0], k = ejk[e][1];
+                            const bool on = e < a.ne && fabs(acc[nt][h]) > a.drop_tol;
+                            s_up[nt][h] = on ? __ldg(sl + j * ndl + k) : INT32_MIN;
+                            s_lo[nt][h] = (on && k != j) ? __ldg(sl + k * ndl + j) : INT32_MIN;
+                        }
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++)
+                    for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const double v = acc[nt][h];
-                        if (s_up[nt][h] != INT32_MIN) scatter_add(a.nzval, a.touched, a.errflag, s_up[nt][h], v, 1);
-                        if (s_lo[nt][h] != INT32_MIN) scatter_add(a.nzval, a.touched, a.errflag, s_lo[nt][h], v, 1);
-                    }
+                        for (int h = 0; h < 2; h++) {
+                            const double v = acc[nt][h];
+                            if (s_up[nt][h] != INT32_MIN) scatter_add(a.nzval, a.touched, a.errflag, s_up[nt][h], v, 1);
+                            if (s_lo[nt][h] != INT32_MIN) scatter_add(a.nzval, a.touched, a.errflag, s_lo[nt][h], v, 1);
+                        }
+                }
             }
         }
         __syncwarp();
@@ -1016,11 +1020,11 @@ __global__ void __launch_bounds__(128) k_h1_stiffness_dmma(const DmmaArgs a) {
 }
 
 // reference tensor T[coef][entry] from the evaluator's reference-gradient table and weights (host, once)
-static int build_reftensor(femb_ctx* ctx, FembEval& E, int nd, int nt) {
+static int build_reftensor(femb_ctx* ctx, FembEval& E, int nd, int ncomp, int nt) {
     if (E.reftensor && E.reftensor_nt == nt) return FEMB_OK;
     const int dim = ctx->dim, ks = dim == 2 ? 1 : 2, ncol = nt * 8;
     const FembSpace& s = ctx->spaces[E.space];
-    if (E.h_refderivs.size() != (size_t)E.nqp * s.nd_all * dim) return femb_fail(ctx, FEMB_ERR_ARG, "Gradient evaluator has no reference-derivative table");
+    if (E.h_refderivs.size() != (size_t)E.nqp * s.nd_all * ncomp * dim) return femb_fail(ctx, FEMB_ERR_ARG, "Gradient evaluator has no reference-derivative table");
     std::vector<double> T((size_t)ks * 4 * ncol, 0.0);
     // coefficient order (00, 11, [22,] 01, [02, 12])
     std::vector<std::pair<int, int>> co;
@@ -1034,8 +1038,9 @@ static int build_reftensor(femb_ctx* ctx, FembEval& E, int nd, int nt) {
                 const int p = co[c].first, q = co[c].second;
                 double sum = 0.0;
                 for (int qp = 0; qp < E.nqp; qp++) {
-                    const double* Dj = &E.h_refderivs[((size_t)qp * s.nd_all + j) * dim];
-                    const double* Dk = &E.h_refderivs[((size_t)qp * s.nd_all + k) * dim];
+                    // component 0 of the first nd functions = the scalar basis (component-blocked vector spaces)
+                    const double* Dj = &E.h_refderivs[((size_t)qp * s.nd_all + j) * ncomp * dim];
+                    const double* Dk = &E.h_refderivs[((size_t)qp * s.nd_all + k) * ncomp * dim];
                     sum += E.w[qp] * (p == q ? Dj[p] * Dk[p] : Dj[p] * Dk[q] + Dj[q] * Dk[p]);
                 }
                 T[c * ncol + e] = sum;
@@ -1051,15 +1056,20 @@ static int build_reftensor(femb_ctx* ctx, FembEval& E, int nd, int nt) {
 static int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_tol) {
     FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
-    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd > 10) return FEMB_ERR_UNSUPPORTED;
-    const FembBlock* blk = find_block(ctx, 0, 0);
-    if (!blk || !blk->slots || ctx->nrs != 1 || ctx->row_spaces[0] != EG.space) return FEMB_ERR_UNSUPPORTED;
-    const int ne = s.nd * (s.nd + 1) / 2, nt = (ne + 7) / 8;
-    FEMB_TRY(build_reftensor(ctx, EG, s.nd, nt));
+    if (s.family != FEMB_FAMILY_H1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd % s.ncomp) return FEMB_ERR_UNSUPPORTED;
+    const int nds = s.nd / s.ncomp;
+    if (nds > 10) return FEMB_ERR_UNSUPPORTED;
+    int brow = -1;
+    for (int i = 0; i < ctx->nrs; i++)
+        if (ctx->row_spaces[i] == EG.space && i < ctx->ncs && ctx->col_spaces[i] == EG.space) brow = i;
+    const FembBlock* blk = brow >= 0 ? find_block(ctx, brow, brow) : nullptr;
+    if (!blk || !blk->slots) return FEMB_ERR_UNSUPPORTED;
+    const int ne = nds * (nds + 1) / 2, nt = (ne + 7) / 8;
+    FEMB_TRY(build_reftensor(ctx, EG, nds, s.ncomp, nt));
     FEMB_TRY(femb_flush_zero(ctx, true, false));
     DmmaArgs a;
     a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.ncells = ctx->ncells; a.T = EG.reftensor; a.slots = blk->slots;
-    a.nzval = ctx->nzval; a.touched = ctx->touched; a.errflag = ctx->errflag; a.mu = mu; a.drop_tol = drop_tol; a.nd = s.nd; a.ne = ne;
+    a.nzval = ctx->nzval; a.touched = ctx->touched; a.errflag = ctx->errflag; a.mu = mu; a.drop_tol = drop_tol; a.nd = nds; a.ne = ne; a.ncomp = s.ncomp;
     if (ctx->ncells == 0) return FEMB_OK;
     const int64_t ntiles = (ctx->ncells + 31) / 32;
     const unsigned grid = (unsigned)std::min<int64_t>((ntiles + 3) / 4, (int64_t)ctx->sm_count * 16);
@@ -1177,6 +1187,117 @@ __global__ void __launch_bounds__(128) k_convection2d(ConvArgs a) {
             s += (in[6] * I[(cq * 2 + 0) * nd + j] + in[7] * I[(cq * 2 + 1) * nd + j]) * a.w[qp] * vol;
         }
         atomicAdd(a.b + a.us.celldofs[(base + cl) * nd + j] - 1, s);
+    }
+}
+
+// Register-blocked version for component-blocked H1 velocity spaces without per-cell handlers (H1Pk{2,2,2}, H1P2{2,2}):
+// local dof (c, i) = e_c psi_i with the scalar basis psi.  With u_h, g[r][c] = d_c u_r at the quadrature point and
+// adv_j = u_h . grad psi_j the Newton terms of Example210:339-355 collapse to
+//     Aloc[(ck,k),(cj,j)] += w psi_k ( g[ck][cj] psi_j + delta(ck,cj) adv_j ),
+//     b[(c,j)]            += w |T| psi_j ( (jac . input)_c - value_c )          (Example210:358-363)
+// One thread per (cell, 6x6 block): 36 accumulators in registers, no shared-memory staging of cvals.
+struct Conv2Args {
+    const double* coords;
+    const int32_t* cellnodes;
+    const double* cellvol;
+    int64_t ncells;
+    const int32_t* celldofs;  // [cell][2*NDS]
+    int nqp;
+    const double* rv;         // Identity table [qp][2*NDS][2]
+    const double* rd;         // Gradient table [qp][2*NDS][2][2]
+    double w[FEMB_MAX_QP];
+    const double* sol;
+    const int32_t* slots;     // (u,u) block [cell][2*NDS][2*NDS]
+    double* nzval;
+    uint8_t* touched;
+    int32_t* errflag;
+    double* b;
+};
+
+template <int NDS>
+__global__ void __launch_bounds__(128) k_convection2d_blocks(const Conv2Args a) {
+    __shared__ double tab[FEMB_MAX_QP][NDS][3];  // psi, dpsi/dxref_0, dpsi/dxref_1
+    for (int i = threadIdx.x; i < a.nqp * NDS; i += blockDim.x) {
+        const int q = i / NDS, d = i - q * NDS;
+        tab[q][d][0] = __ldg(a.rv + ((size_t)q * 2 * NDS + d) * 2);
+        tab[q][d][1] = __ldg(a.rd + (((size_t)q * 2 * NDS + d) * 2) * 2);
+        tab[q][d][2] = __ldg(a.rd + (((size_t)q * 2 * NDS + d) * 2) * 2 + 1);
+    }
+    __syncthreads();
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t cell = t >> 2;
+    if (cell >= a.ncells) return;
+    const int ck = (int)(t & 3) >> 1, cj = (int)(t & 1);
+    double x[3][2];
+    load_nodes<2>(a.coords, a.cellnodes, cell, x);
+    const double A00 = x[1][0] - x[0][0], A01 = x[2][0] - x[0][0], A10 = x[1][1] - x[0][1], A11 = x[2][1] - x[0][1];
+    const double det = A00 * A11 - A01 * A10;
+    const double M00 = A11 / det, M01 = -A10 / det, M10 = -A01 / det, M11 = A00 / det;  // mapderiv!: A^{-T}
+    const double vol = a.cellvol ? __ldg(a.cellvol + cell) : fabs(det) * 0.5;
+    const int32_t* cd = a.celldofs + cell * (2 * NDS);
+    double su[2][NDS];
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int i = 0; i < NDS; i++) su[c][i] = __ldg(a.sol + (__ldg(cd + c * NDS + i) - 1));
+    double acc[NDS][NDS], rb[NDS];
+#pragma unroll
+    for (int k = 0; k < NDS; k++) {
+        rb[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NDS; j++) acc[k][j] = 0.0;
+    }
+    for (int q = 0; q < a.nqp; q++) {
+        double psi[NDS], adv[NDS];
+        double u0 = 0.0, u1 = 0.0, g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NDS; i++) {  // input = (u_h, grad u_h)   (Example210:324-333)
+            psi[i] = tab[q][i][0];
+            const double gx = M00 * tab[q][i][1] + M01 * tab[q][i][2], gy = M10 * tab[q][i][1] + M11 * tab[q][i][2];
+            u0 += su[0][i] * psi[i];
+            u1 += su[1][i] * psi[i];
+            g00 += su[0][i] * gx; g01 += su[0][i] * gy;
+            g10 += su[1][i] * gx; g11 += su[1][i] * gy;
+            adv[i] = gx;  // completed below once u_h is known
+        }
+#pragma unroll
+        for (int i = 0; i < NDS; i++) {
+            const double gy = M10 * tab[q][i][1] + M11 * tab[q][i][2];
+            adv[i] = u0 * adv[i] + u1 * gy;
+        }
+        const double gkj = ck == 0 ? (cj == 0 ? g00 : g01) : (cj == 0 ? g10 : g11);
+        const double wq = a.w[q];
+#pragma unroll
+        for (int k = 0; k < NDS; k++) {
+            const double pk = psi[k] * wq;
+#pragma unroll
+            for (int j = 0; j < NDS; j++) {
+                const double tv = (ck == cj) ? gkj * psi[j] + adv[j] : gkj * psi[j];
+                acc[k][j] += tv * pk;
+            }
+        }
+        if (cj == 0) {  // rhs of component ck: jac . input - value
+            const double gr0 = ck == 0 ? g00 : g10, gr1 = ck == 0 ? g01 : g11;
+            const double value = u0 * gr0 + u1 * gr1;
+            const double ji = gr0 * u0 + gr1 * u1 + u0 * gr0 + u1 * gr1;
+            const double tv = ji - value;
+#pragma unroll
+            for (int j = 0; j < NDS; j++) rb[j] += tv * psi[j] * wq * vol;
+        }
+    }
+    const int nd = 2 * NDS;
+    const int32_t* sl = a.slots + cell * (nd * nd) + (ck * NDS) * nd + cj * NDS;
+#pragma unroll
+    for (int k = 0; k < NDS; k++) {
+        int32_t sk[NDS];
+#pragma unroll
+        for (int j = 0; j < NDS; j++) sk[j] = __ldg(sl + k * nd + j);
+#pragma unroll
+        for (int j = 0; j < NDS; j++) scatter_add(a.nzval, a.touched, a.errflag, sk[j], acc[k][j] * vol, 1);
+    }
+    if (cj == 0) {
+#pragma unroll
+        for (int j = 0; j < NDS; j++) atomicAdd(a.b + (__ldg(cd + ck * NDS + j) - 1), rb[j]);
     }
 }
 
@@ -1413,7 +1534,10 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
     int st = femb_timer_begin(ctx);
     if (st == FEMB_OK && linear) {
         // Aloc[k,j] = mu * sum_qp w <grad_j, grad_k>, then * |T|                 (Example210:284-290,368)
-        st = launch_bilinear(ctx, egu, egu, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, 0, 0.0);
+        // component-blocked basis: the 12x12 local matrix is two copies of the scalar 6x6 P2 stiffness; its
+        // off-diagonal blocks are exact zeros (their slots stay in the pattern, adding 0.0 changes nothing)
+        st = launch_stiffness_dmma(ctx, egu, mu, -1.0);
+        if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, egu, egu, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, 0, 0.0);
         // Bloc[j,k] = -sum_qp w (g[1,j]+g[4,j]) psi_k * |T| into (u,p) and (p,u) (Example210:293-301,376-380)
         if (st == FEMB_OK) st = launch_bilinear(ctx, egu, eip, FEMB_OP_GRADTRACE, FEMB_OP_IDENTITY, 0, 1, -1.0, FEMB_BIL_TRANSPOSE_COPY, 0.0);
         if (st == FEMB_OK && rhs.kind != FEMB_RHS_NONE) st = launch_linear(ctx, eiu, 0, 1.0, rhs);
@@ -1422,7 +1546,20 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
         const FembBlock* blk = find_block(ctx, 0, 0);
         if (!blk || !blk->slots) st = femb_fail(ctx, FEMB_ERR_ARG, "(u,u) block missing from the pattern");
         if (st == FEMB_OK) st = femb_flush_zero(ctx, true, true);
-        if (st == FEMB_OK) {
+        const int nds = us.nd / 2;
+        if (st == FEMB_OK && us.handler == FEMB_HANDLER_NONE && us.nd == us.nd_all && nds == 6 && ctx->ncells) {
+            Conv2Args a;
+            a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.ncells = ctx->ncells; a.celldofs = us.celldofs; a.nqp = EG.nqp;
+            a.rv = EI.refvals; a.rd = EG.refderivs;
+            for (int i = 0; i < EG.nqp; i++) a.w[i] = EG.w[i];
+            a.sol = ctx->sol; a.slots = blk->slots; a.nzval = ctx->nzval; a.touched = ctx->touched; a.errflag = ctx->errflag; a.b = ctx->bvec;
+            const int64_t nthreads = ctx->ncells * 4;
+            k_convection2d_blocks<6><<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(a);
+            ctx->launches++;
+            ctx->last_launches++;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) st = femb_fail(ctx, FEMB_ERR_CUDA, "k_convection2d_blocks: %s", cudaGetErrorString(e));
+        } else if (st == FEMB_OK) {
             ConvArgs a;
             a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.cellvol = ctx->cellvol; a.ncells = ctx->ncells;
             a.us = space_dev(us); a.nqp = EG.nqp; a.rv = EI.refvals; a.rd = EG.refderivs;
