@@ -281,8 +281,16 @@ def run_ours(args):
     bpc = algorithmic_bytes_per_cell(nnodes, ncells, nnz, use_vol)
     kernel_ms = float(np.mean(kms))
     achieved = bpc * ncells / (kernel_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel, per cell, scaled to this launch
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "p1_gather2d_traffic.json")
+    if os.path.exists(tj):
+        t = json.load(open(tj))
+        key = "given" if use_vol else "device"
+        if key in t:
+            traffic = {"bytes_per_launch": round(t[key]["dram_bytes_per_cell"] * ncells), "bytes_per_cell": t[key]["dram_bytes_per_cell"], "source": t[key]["source"]}
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
+                "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)",
                 "kernel": "k_p1_poisson_gather2d", "kernel_ms": round(kernel_ms, 4), "algorithmic_bytes_per_cell": round(bpc, 2)}
 
     out = {
@@ -299,7 +307,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(grid, vol, S, nnz, args.cpu_seconds)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -357,15 +365,19 @@ def cpu_run(grid, vol, colptr, rowval, seconds, nthreads=None):
     run(s0)  # warm-up / page-in
     t = run(s0)
     sample = int(min(grid.ncells, max(s0, s0 * seconds / max(t, 1e-6))))
-    t = run(sample)
-    return sample / t, sample, nthreads, t
+    run(sample)  # touch every page of the sample once
+    reps = int(max(1, min(20, seconds / max(run(sample), 1e-6))))  # ~`seconds` of wall time in total
+    ts = [run(sample) for _ in range(reps)]
+    t = float(np.median(ts))
+    return sample / t, sample, nthreads, t, reps
 
 
 def cpu_baseline(grid, vol, S, nnz, seconds):
     colptr, rowval = S.ctx.pattern_get(grid.nnodes)
-    rate, sample, nthreads, t = cpu_run(grid, vol, colptr, rowval, seconds)
+    rate, sample, nthreads, t, reps = cpu_run(grid, vol, colptr, rowval, seconds)
     return {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": f"cells [0,{sample}) of the same mesh, C restatement of the reference loop (oracle/femb_oracle_c.c) with OpenMP atomics, {t:.2f}s"}
+            "sample": f"cells [0,{sample}) of the same mesh, C restatement of the reference loop (oracle/femb_oracle_c.c), OpenMP over cells with atomic adds, "
+                      f"median of {reps} passes of {t:.2f}s"}
 
 
 def run_reference(args):
@@ -422,10 +434,28 @@ def run_reference(args):
            "config": {"workload": f"H1P1 2-D Poisson stiffness+rhs, simplexgrid n={args.n} (bounded sample: {sample})"},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL banners, torchrun notes)
+    was redirected to stderr in main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
