@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libfemb.so")
+LIBPATH = os.environ.get("FEMB_LIB") or os.path.join(HERE, "libfemb.so")  # FEMB_LIB: alternative build (tuning experiments)
 
 # enums of include/femb.h
 FAMILY = {"H1": 0, "Hdiv": 1, "L2": 2}

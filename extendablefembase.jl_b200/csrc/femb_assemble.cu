@@ -434,6 +434,10 @@ struct P1Args {
 };
 
 #define FEMB_P1_MAXQP 8
+#ifndef FEMB_P1_PIPE
+#define FEMB_P1_PIPE 2  // software-pipeline depth of the 2-D gather kernel (1: entries only, 2: entries + coordinates).
+// Measured on B200 (32M triangles): depth 2 @ 62 regs / 8 CTAs per SM = depth 1 @ 48 regs / 10 CTAs = 0.77 ms; spilling variants are slower.
+#endif
 struct P1Tab2 {
     int nqp;
     double mu_wsum;                     // mu * sum_qp w_qp
@@ -472,8 +476,8 @@ __device__ __forceinline__ void sts64(unsigned addr, double v) { asm volatile("s
 //  * software pipeline: the gather-map entry two visits ahead and the coordinates / volume of the next visit are
 //    in flight while the current visit is computed;
 //  * accumulation is branch-free: filtered (|v| <= drop_tol, Example200:153) contributions go to a dump row.
-template <bool TRACK, int RHS, bool HAS_VOL, int NQP>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
-__global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
+template <bool TRACK, int RHS, bool HAS_VOL, int NQP, int MINB = 8>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
+__global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
     constexpr unsigned nt = 128;
     constexpr bool NEED_CELL = HAS_VOL || RHS == FEMB_RHS_QPVALUES;
     extern __shared__ double acc[];  // [maxlen + 1][128]
@@ -494,16 +498,33 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
     }
     const unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + tid * 8u;
     for (int i = 0; i < len; i++) sts64(sacc + i * (nt * 8u), 0.0);
-    const unsigned dump = (unsigned)a.maxlen;
     unsigned long long mask = 0ull;
-    double bsum = 0.0;
-    unsigned err = 0u;
+    double bsum = 0.0, diag = 0.0;
+    unsigned err = 0u, dpos = 0xFFu;
     const double drop_tol = a.drop_tol, mu_wsum = tab.mu_wsum;
 
     const uint32_t* __restrict__ ga = a.gmap + ((size_t)row0 << 5) + lane;
-    const uint32_t* __restrict__ gb = ga + a.gstride;
-    const uint32_t* __restrict__ gw = gb + a.gstride;
-    const uint32_t* __restrict__ gc = gw + a.gstride;
+    const size_t gs = a.gstride;
+#if FEMB_P1_PIPE == 1
+    // shallow pipeline: only the next visit's entry is in flight; coordinates are loaded at the top of the visit
+    unsigned w1 = 0xFFFFFFFFu, a1 = 0u, b1 = 0u, c1 = 0u;
+    if (nrows > 0) {
+        w1 = __ldg(ga + 2 * gs); a1 = __ldg(ga); b1 = __ldg(ga + gs);
+        if (NEED_CELL) c1 = __ldg(ga + 3 * gs);
+    }
+    for (int r = 0; r < nrows; r++) {
+        const unsigned w = w1, cell = c1;
+        const double2 pa = __ldg(xy + a1), pb = __ldg(xy + b1);
+        const double volr = HAS_VOL ? __ldg(a.cellvol + c1) : 0.0;
+        if (r + 1 < nrows) {
+            const uint32_t* g1 = ga + ((size_t)(r + 1) << 5);
+            w1 = __ldg(g1 + 2 * gs); a1 = __ldg(g1); b1 = __ldg(g1 + gs);
+            if (NEED_CELL) c1 = __ldg(g1 + 3 * gs);
+        }
+#else
+    const uint32_t* __restrict__ gb = ga + gs;
+    const uint32_t* __restrict__ gw = gb + gs;
+    const uint32_t* __restrict__ gc = gw + gs;
     // pipeline registers: (w1, a1, b1, c1) = entry of visit r, (w2, ...) = visit r + 1; pa1/pb1/vol1 = data of visit r
     unsigned w1 = 0xFFFFFFFFu, a1 = 0u, b1 = 0u, c1 = 0u, w2 = 0xFFFFFFFFu, a2 = 0u, b2 = 0u, c2 = 0u;
     if (nrows > 0) {
@@ -531,6 +552,7 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
         pa1 = __ldg(xy + a1);
         pb1 = __ldg(xy + b1);
         if (HAS_VOL) vol1 = __ldg(a.cellvol + c1);
+#endif
         if (w == 0xFFFFFFFFu) continue;
         const unsigned k = w & 3u;
         const double uax = pb.x - self.x, uay = pb.y - self.y;
@@ -546,15 +568,21 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
         const unsigned ps = (w >> 8) & 0xFFu, pA = (w >> 16) & 0xFFu, pB = w >> 24;
         const bool ks = fabs(vs) > drop_tol, ka = fabs(va) > drop_tol, kb = fabs(vb) > drop_tol;
         err |= (unsigned)((ks && ps == 0xFFu) || (ka && pA == 0xFFu) || (kb && pB == 0xFFu));
-        const unsigned rs = (ks && ps != 0xFFu) ? ps : dump, ra = (ka && pA != 0xFFu) ? pA : dump, rb = (kb && pB != 0xFFu) ? pB : dump;
-        const unsigned as = sacc + rs * (nt * 8u), aa = sacc + ra * (nt * 8u), ab = sacc + rb * (nt * 8u);
-        // the three rows are distinct unless they are the dump row, so the loads may be issued together
-        const double s0 = lds64(as), s1 = lds64(aa), s2 = lds64(ab);
-        sts64(as, s0 + vs);
-        sts64(aa, s1 + va);
-        sts64(ab, s2 + vb);
-        if (TRACK) {
-            mask |= (rs != dump ? 1ull << (rs & 63u) : 0ull) | (ra != dump ? 1ull << (ra & 63u) : 0ull) | (rb != dump ? 1ull << (rb & 63u) : 0ull);
+        // diagonal A[c,c]: the same slot on every visit -> a register; off-diagonals: shared-memory rows.  The
+        // branches are warp-uniform on structured meshes (same filtered edge in every lane) and cheap otherwise.
+        if (ks && ps != 0xFFu) {
+            diag += vs;
+            dpos = ps;
+        }
+        if (ka && pA != 0xFFu) {
+            const unsigned ad = sacc + pA * (nt * 8u);
+            sts64(ad, lds64(ad) + va);
+            if (TRACK) mask |= 1ull << (pA & 63u);
+        }
+        if (kb && pB != 0xFFu) {
+            const unsigned ad = sacc + pB * (nt * 8u);
+            sts64(ad, lds64(ad) + vb);
+            if (TRACK) mask |= 1ull << (pB & 63u);
         }
         if (RHS != FEMB_RHS_NONE) {
             double temp = 0.0;
@@ -577,6 +605,10 @@ __global__ void __launch_bounds__(128) k_p1_poisson_gather2d(const P1Args a, con
     }
     if (!valid) return;
     if (err) atomicAdd(a.errflag, 1);
+    if (dpos != 0xFFu) {
+        sts64(sacc + dpos * (nt * 8u), diag);  // the diagonal row received no shared-memory update
+        if (TRACK) mask |= 1ull << (dpos & 63u);
+    }
     double* out = a.nzval + base;
     if (a.acc_A) {
         for (int i = 0; i < len; i++) out[i] += lds64(sacc + i * (nt * 8u));
