@@ -1117,6 +1117,303 @@ static int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_t
 }
 
 // ---------------------------------------------------------------------------------------------------
+// scalar H1 stiffness + rhs, owner-computes by matrix column for general elements (P2, ...): write-once,
+// bit-reproducible, no atomics.  Two launches per assembly:
+//   k_cell_coef   (one thread per cell)  Kc = mu |T| (C^T C) / det^2 (3 / 6 coefficients) and |T| f(x_q): 80 B / cell
+//   k_h1_gather   (one thread per column c) for every cell e adjacent to c (gather map, femb_pattern.cu) with local
+//                 index k:  h[q] = w_q Kmat D_q[:,k]  (the cell-dependent factor moved to the column side), then
+//                 Aloc[j,k] = sum_q D_q[:,j] . h[q]  with UNIFORM table operands D_q[:,j] (compile-time indices into the
+//                 kernel-parameter table), accumulated in shared memory rows and written once.
+// The slices are launched in ranges of similar column length (vertex vs edge dofs) so that shared memory is sized per
+// range.  Column positions are 8-bit, the base comes from colptr (int64): nnz may exceed 2^31.
+// ---------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) k_cell_coef(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
+                                                   int64_t ncells, double mu, RhsDev rhs, QuadDev q, double* __restrict__ out) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cell >= ncells) return;
+    double x[DIM + 1][DIM];
+    load_nodes<DIM>(coords, cellnodes, cell, x);
+    double A[DIM][DIM], C[DIM][DIM], det;
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+#pragma unroll
+        for (int i = 0; i < DIM; i++) A[d][i] = x[i + 1][d] - x[0][d];
+    if (DIM == 2) {
+        det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+        C[0][0] = A[1][1]; C[0][1] = -A[1][0];
+        C[1][0] = -A[0][1]; C[1][1] = A[0][0];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int ra = (r + 1) % 3, rb = (r + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
+                C[r][j] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
+            }
+        det = A[0][0] * C[0][0] + A[0][1] * C[0][1] + A[0][2] * C[0][2];
+    }
+    const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * (DIM == 2 ? 0.5 : 1.0 / 6.0);
+    const double sc = (mu * vol) / (det * det);
+    double* o = out + cell * FEMB_COEF_STRIDE;
+    int ci = 0;
+#pragma unroll
+    for (int p = 0; p < DIM; p++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][p];
+        o[ci++] = s * sc;
+    }
+#pragma unroll
+    for (int p = 0; p < DIM; p++)
+#pragma unroll
+        for (int r = p + 1; r < DIM; r++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][r];
+            o[ci++] = s * sc;
+        }
+    if (rhs.kind != FEMB_RHS_NONE) {
+        for (int qp = 0; qp < q.nqp; qp++) {
+            double xq[DIM], f[3];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                double sx = x[0][d];
+#pragma unroll
+                for (int i = 0; i < DIM; i++) sx += A[d][i] * q.xref[qp * DIM + i];
+                xq[d] = sx;
+            }
+            eval_rhs<DIM>(rhs, xq, cell, qp, q.nqp, f);
+            o[6 + qp] = f[0] * vol;
+        }
+    }
+}
+
+template <int DIM, int ND, int NQ>
+struct HTab {
+    double D[NQ][DIM][ND];  // reference gradients d phi_j / d xref_a at xref_q
+    double wphi[NQ][ND];    // w_q phi_k(xref_q)
+    double w[NQ];
+};
+
+struct HArgs {
+    const double* coef;
+    const int32_t* hslice_ptr;
+    const uint32_t* hmap;
+    size_t hstride;
+    const int64_t* colptr;
+    int64_t ndofs;
+    double* nzval;
+    uint8_t* touched;
+    double* bvec;
+    int32_t* errflag;
+    double drop_tol;
+    int acc_A, acc_b, has_rhs;
+    int64_t slice_begin, slice_end;
+};
+
+// SPLIT = 1: one thread per column, 4 slices (warps) per CTA.  SPLIT = 4: one slice per CTA, the 4 warps share the
+// columns of the slice — warp w takes the visits r = w (mod 4), computes them in parallel and the shared-memory
+// accumulation is serialised in visit order between barriers, so the result is bit-identical to SPLIT = 1.
+template <int DIM, int ND, int NQ, int SPLIT>
+__global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM, ND, NQ> tab) {
+    constexpr unsigned ncol = 128 / SPLIT;  // columns per CTA
+    constexpr int NW = (ND + 3) / 4;
+    constexpr int KP = (DIM == 2) ? 3 : 6;
+    extern __shared__ double acc[];  // [maxlen of the range][ncol]
+    __shared__ double bpart[SPLIT == 1 ? 1 : 4][32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int64_t slice = a.slice_begin + (SPLIT == 1 ? (int64_t)blockIdx.x * 4 + warp : (int64_t)blockIdx.x);
+    if (SPLIT == 1 && slice >= a.slice_end) return;  // (SPLIT == 4: the grid is exact)
+    const int64_t c = slice * 32 + lane;
+    const bool valid = c < a.ndofs;
+    const int row0 = __ldg(a.hslice_ptr + slice), nrows = __ldg(a.hslice_ptr + slice + 1) - row0;
+    int64_t base = 0;
+    int len = 0;
+    if (valid) {
+        base = a.colptr[c] - 1;
+        len = (int)(a.colptr[c + 1] - 1 - base);
+    }
+    const unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + (SPLIT == 1 ? tid : lane) * 8u;
+    for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) sts64(sacc + i * (ncol * 8u), 0.0);
+    if (SPLIT > 1) __syncthreads();
+    double bsum = 0.0;
+    unsigned err = 0u;
+    const int niter = (nrows + SPLIT - 1) / SPLIT;
+    for (int it = 0; it < niter; it++) {
+        const int r = it * SPLIT + (SPLIT == 1 ? 0 : (int)warp);
+        const uint32_t* __restrict__ hp = a.hmap + ((size_t)(row0 + r) << 5) + lane;
+        const unsigned k = (r < nrows) ? __ldg(hp + a.hstride) : 0xFFFFFFFFu;
+        const bool on = k != 0xFFFFFFFFu;
+        double v[ND];
+        unsigned words[NW];
+        if (on) {
+            const unsigned cell = __ldg(hp);
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) words[wd] = __ldg(hp + (2 + wd) * a.hstride);
+            const double* cc = a.coef + (size_t)cell * FEMB_COEF_STRIDE;
+            double kc[KP];
+            if (DIM == 2) {
+                const double2 c01 = __ldg(reinterpret_cast<const double2*>(cc));
+                kc[0] = c01.x; kc[1] = c01.y; kc[2] = __ldg(cc + 2);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double2 cv = __ldg(reinterpret_cast<const double2*>(cc) + i);
+                    kc[2 * i] = cv.x; kc[2 * i + 1] = cv.y;
+                }
+            }
+            double Km[DIM][DIM];  // symmetric Kmat from the coefficient order (00, 11, [22,] 01, [02, 12])
+            if (DIM == 2) {
+                Km[0][0] = kc[0]; Km[1][1] = kc[1]; Km[0][1] = Km[1][0] = kc[2];
+            } else {
+                Km[0][0] = kc[0]; Km[1][1] = kc[1]; Km[2][2] = kc[2];
+                Km[0][1] = Km[1][0] = kc[3]; Km[0][2] = Km[2][0] = kc[4]; Km[1][2] = Km[2][1] = kc[5];
+            }
+            double h[NQ][DIM];
+#pragma unroll
+            for (int qp = 0; qp < NQ; qp++) {
+                double dk[DIM];
+#pragma unroll
+                for (int b = 0; b < DIM; b++) dk[b] = tab.D[qp][b][k];  // per-lane k: indexed constant-bank load
+#pragma unroll
+                for (int aa = 0; aa < DIM; aa++) {
+                    double s2 = 0.0;
+#pragma unroll
+                    for (int b = 0; b < DIM; b++) s2 += Km[aa][b] * dk[b];
+                    h[qp][aa] = s2 * tab.w[qp];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < ND; j++) {
+                double vj = 0.0;
+#pragma unroll
+                for (int qp = 0; qp < NQ; qp++)
+#pragma unroll
+                    for (int aa = 0; aa < DIM; aa++) vj += tab.D[qp][aa][j] * h[qp][aa];
+                v[j] = vj;
+            }
+            if (a.has_rhs) {
+                double t = 0.0;
+#pragma unroll
+                for (int qp = 0; qp < NQ; qp++) t += tab.wphi[qp][k] * __ldg(cc + 6 + qp);
+                bsum += t;
+            }
+        }
+#pragma unroll 1
+        for (int ph = 0; ph < SPLIT; ph++) {
+            if (on && (SPLIT == 1 || (int)warp == ph)) {
+#pragma unroll
+                for (int j = 0; j < ND; j++) {
+                    const unsigned pos = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    if (fabs(v[j]) > a.drop_tol) {
+                        if (pos == 0xFFu) {
+                            err = 1u;
+                        } else {
+                            const unsigned ad = sacc + pos * (ncol * 8u);
+                            sts64(ad, lds64(ad) + v[j]);
+                            if (a.touched) a.touched[base + pos] = 1;
+                        }
+                    }
+                }
+            }
+            if (SPLIT > 1) __syncthreads();
+        }
+    }
+    if (err) atomicAdd(a.errflag, 1);
+    if (SPLIT > 1) {
+        bpart[warp][lane] = bsum;
+        __syncthreads();
+        bsum = ((bpart[0][lane] + bpart[1][lane]) + bpart[2][lane]) + bpart[3][lane];
+    }
+    if (!valid) return;
+    double* out = a.nzval + base;
+    if (a.acc_A) {
+        for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) out[i] += lds64(sacc + i * (ncol * 8u));
+    } else {
+        for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) out[i] = lds64(sacc + i * (ncol * 8u));
+    }
+    if (a.has_rhs && (SPLIT == 1 || warp == 0)) {
+        if (a.acc_b) a.bvec[c] += bsum;
+        else a.bvec[c] = bsum;
+    }
+}
+
+template <int DIM, int ND, int NQ>
+static int launch_h1_gather_t(femb_ctx* ctx, const FembEval& EG, const FembEval* EI, HArgs a) {
+    const FembSpace& s = ctx->spaces[EG.space];
+    HTab<DIM, ND, NQ> tab;
+    for (int q = 0; q < NQ; q++) {
+        tab.w[q] = EG.w[q];
+        for (int j = 0; j < ND; j++) {
+            for (int d = 0; d < DIM; d++) tab.D[q][d][j] = EG.h_refderivs[((size_t)q * s.nd_all + j) * DIM + d];
+            tab.wphi[q][j] = EI ? EG.w[q] * EI->h_refvals[(size_t)q * s.nd_all + j] : 0.0;
+        }
+    }
+    auto kern1 = k_h1_gather<DIM, ND, NQ, 1>;
+    auto kern4 = k_h1_gather<DIM, ND, NQ, 4>;
+    size_t max1 = 0, max4 = 0;
+    for (auto& r : ctx->hranges) {
+        if (r.split == 4) max4 = std::max(max4, (size_t)std::max(1, r.maxlen) * 32 * sizeof(double));
+        else max1 = std::max(max1, (size_t)std::max(1, r.maxlen) * 128 * sizeof(double));
+    }
+    if (max1 > 200 * 1024) return FEMB_ERR_UNSUPPORTED;
+    // the accumulator rows are the occupancy limiter: ask for the largest shared-memory carve-out
+    if (max1) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max1));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    if (max4) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max4));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    for (auto& r : ctx->hranges) {
+        if (r.s1 <= r.s0) continue;
+        a.slice_begin = r.s0;
+        a.slice_end = r.s1;
+        if (r.split == 4) {
+            const size_t smem = (size_t)std::max(1, r.maxlen) * 32 * sizeof(double);
+            kern4<<<(unsigned)(r.s1 - r.s0), 128, smem, ctx->stream>>>(a, tab);
+        } else {
+            const size_t smem = (size_t)std::max(1, r.maxlen) * 128 * sizeof(double);
+            kern1<<<(unsigned)((r.s1 - r.s0 + 3) / 4), 128, smem, ctx->stream>>>(a, tab);
+        }
+        KERNEL_CHECK(ctx);
+    }
+    return FEMB_OK;
+}
+
+// returns FEMB_ERR_UNSUPPORTED (no error message) when the gather path does not cover the space / rule
+static int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
+    const FembEval& EG = ctx->evals[eg];
+    const FembSpace& s = ctx->spaces[EG.space];
+    if (!ctx->hmap || ctx->hmap_space != EG.space || EG.nqp > 10) return FEMB_ERR_UNSUPPORTED;
+    if (EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * ctx->dim) return FEMB_ERR_UNSUPPORTED;
+    const FembEval* EI = rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr;
+    if (EI && EI->h_refvals.size() != (size_t)EG.nqp * s.nd_all) return FEMB_ERR_UNSUPPORTED;
+    const int key = ctx->dim * 10000 + s.nd * 100 + EG.nqp;
+    if (key != 20603 && key != 31004) return FEMB_ERR_UNSUPPORTED;  // H1P2 on triangles (3-point rule) / tetrahedra (4-point rule)
+    if (!ctx->cellcoef) FEMB_TRY(femb_alloc(ctx, &ctx->cellcoef, (size_t)ctx->ncells * FEMB_COEF_STRIDE));
+    if (ctx->ncells == 0) return FEMB_OK;
+    QuadDev q = quad_dev(EG, ctx->dim);
+    const unsigned gridc = (unsigned)((ctx->ncells + 127) / 128);
+    if (ctx->dim == 2) k_cell_coef<2><<<gridc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, ctx->cellcoef);
+    else k_cell_coef<3><<<gridc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, ctx->cellcoef);
+    KERNEL_CHECK(ctx);
+    HArgs a;
+    a.coef = ctx->cellcoef; a.hslice_ptr = ctx->hslice_ptr; a.hmap = ctx->hmap; a.hstride = ctx->hmap_stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
+    a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag; a.drop_tol = drop_tol;
+    a.acc_A = ctx->zero_pending_A ? 0 : 1;
+    a.acc_b = ctx->zero_pending_b ? 0 : 1;
+    a.has_rhs = rhs.kind != FEMB_RHS_NONE;
+    a.slice_begin = a.slice_end = 0;
+    ctx->zero_pending_A = false;
+    if (a.has_rhs) ctx->zero_pending_b = false;
+    if (key == 20603) return launch_h1_gather_t<2, 6, 3>(ctx, EG, EI, a);
+    return launch_h1_gather_t<3, 10, 4>(ctx, EG, EI, a);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Example210 convection (Newton linearisation), 2-D, two components   (Example210:322-365)
 // ---------------------------------------------------------------------------------------------------
 struct ConvArgs {
@@ -1395,6 +1692,8 @@ extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, 
         if (ctx->scatter == FEMB_SCATTER_GATHER && ctx->gmap && ctx->gmap_space == EG.space && (!ctx->touched || ctx->max_collen <= 64) &&
             rhs_kind != FEMB_RHS_EX210 && (ctx->dim == 3 || EG.nqp <= FEMB_P1_MAXQP)) {
             st = launch_p1_gather(ctx, eg, ei, mu, rhs, drop_tol);
+        } else if (ctx->scatter == FEMB_SCATTER_GATHER && rhs_kind != FEMB_RHS_EX210 && (st = launch_h1_gather(ctx, eg, ei, mu, rhs, drop_tol)) != FEMB_ERR_UNSUPPORTED) {
+            // owner-computes gather for general scalar H1 elements (stiffness + rhs in one pass, write-once)
         } else {
             st = (ctx->scatter == FEMB_SCATTER_COLORED) ? FEMB_ERR_UNSUPPORTED : launch_stiffness_dmma(ctx, eg, mu, drop_tol);
             if (st == FEMB_ERR_UNSUPPORTED)  // elements with per-cell basis subsets, vector-valued spaces, ...: generic quadrature kernel

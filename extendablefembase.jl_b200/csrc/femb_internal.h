@@ -103,6 +103,16 @@ struct femb_ctx {
     int32_t* gslice_ptr = nullptr;   // nslices + 1 row offsets
     int64_t gmap_rows = 0;
     int gmap_space = -1;
+    // general scalar-H1 gather map (P2, ...; femb_pattern.cu): sliced ELL over (dof, adjacent cell) pairs, SoA planes
+    // 0 = cell, 1 = local index k of the dof in that cell, 2.. = positions of the cell's local rows in the dof's CSC
+    // column packed 4 x 8 bit per word (0xFF = not in the pattern)
+    uint32_t* hmap = nullptr;
+    size_t hmap_stride = 0;
+    int32_t* hslice_ptr = nullptr;
+    int hmap_space = -1, hmap_words = 0;
+    struct HRange { int64_t s0, s1; int maxlen; int split; };  // split: threads per column (1, or 4 for high-degree columns)
+    std::vector<HRange> hranges;   // contiguous slice ranges with their longest CSC column (shared-memory sizing)
+    double* cellcoef = nullptr;    // [cell][FEMB_COEF_STRIDE]: Kc (3 / 6) then |T| f(x_q) per quadrature point (pre-pass of the gather)
 
     double* nzval = nullptr;      // nnz
     bool zero_pending_A = false;  // femb_matrix_zero is lazy: write-once kernels skip the memset
@@ -203,6 +213,8 @@ static inline int femb_d2h(femb_ctx* ctx, T* dst, const T* src, size_t n) {
 int femb_build_adjacency(femb_ctx* ctx, int space_id);
 int femb_build_slotmaps(femb_ctx* ctx);
 int femb_build_gmap(femb_ctx* ctx);
+int femb_build_hmap(femb_ctx* ctx);
+#define FEMB_COEF_STRIDE 16  // doubles per cell in femb_ctx::cellcoef (6 + up to 10 quadrature points)
 void femb_free_pattern(femb_ctx* ctx);
 // assemble.cu
 int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec);

@@ -20,6 +20,12 @@ void femb_free_pattern(femb_ctx* ctx) {
     ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
     ctx->chunk_n = 0;
+    femb_free(&ctx->hmap);
+    femb_free(&ctx->hslice_ptr);
+    femb_free(&ctx->cellcoef);
+    ctx->hmap_stride = 0;
+    ctx->hmap_space = -1;
+    ctx->hranges.clear();
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
     ctx->nnz = 0;
@@ -190,6 +196,7 @@ static int finish_pattern(femb_ctx* ctx) {
     for (int i = 0; i < ctx->nrs; i++) FEMB_TRY(femb_build_adjacency(ctx, ctx->row_spaces[i]));
     FEMB_TRY(femb_build_slotmaps(ctx));
     FEMB_TRY(femb_build_gmap(ctx));
+    FEMB_TRY(femb_build_hmap(ctx));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return FEMB_OK;
 }
@@ -493,6 +500,7 @@ extern "C" int32_t femb_pattern_compress(femb_ctx* ctx, int64_t* nnz_out) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 1, nnz2, ctx->stream));
     FEMB_TRY(femb_build_slotmaps(ctx));
     FEMB_TRY(femb_build_gmap(ctx));
+    FEMB_TRY(femb_build_hmap(ctx));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (nnz_out) *nnz_out = nnz2;
     return FEMB_OK;
@@ -647,5 +655,138 @@ int femb_build_gmap(femb_ctx* ctx) {
         k_gmap<4><<<grid, 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.celldofs, ctx->colptr, ctx->rowval, ctx->gslice_ptr, ctx->gmap, ctx->gmap_stride);
     KERNEL_CHECK(ctx);
     ctx->gmap_space = sid;
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gather map for general scalar H1 spaces without per-cell handlers (P2 on triangles / tetrahedra, ...)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_slice_collen(const int64_t* __restrict__ colptr, int64_t ndofs, int64_t nslices, int32_t* __restrict__ maxlen) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= nslices) return;
+    int m = 0;
+    for (int l = 0; l < 32; l++) {
+        int64_t c = s * 32 + l;
+        if (c < ndofs) m = max(m, (int)(colptr[c + 1] - colptr[c]));
+    }
+    maxlen[s] = m;
+}
+
+__global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices, int nd, int nwords,
+                       const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+                       const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hmap, size_t stride) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nslices * 32) return;
+    const int64_t slice = c >> 5;
+    const int lane = (int)(c & 31);
+    const int row0 = slice_ptr[slice], nrows = slice_ptr[slice + 1] - row0;
+    const int e0 = c < ndofs ? adj_ptr[c] : 0;
+    const int deg = c < ndofs ? adj_ptr[c + 1] - e0 : 0;
+    const int64_t base = c < ndofs ? colptr[c] - 1 : 0;
+    for (int r = 0; r < nrows; r++) {
+        const size_t idx = ((size_t)(row0 + r) << 5) + lane;
+        uint32_t cell = 0, k = FEMB_GMAP_INVALID;
+        uint32_t words[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (r < deg) {
+            uint32_t a = adj[e0 + r];
+            cell = a / (uint32_t)nd;
+            k = a - cell * (uint32_t)nd;
+            for (int j = 0; j < nd; j++) {
+                int64_t p = find_slot(colptr, rowval, c, (int64_t)celldofs[(int64_t)cell * nd + j]);
+                uint32_t pos = (p < 0) ? 0xFFu : (uint32_t)(p - base);
+                words[j >> 2] = (words[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (pos << (8 * (j & 3)));
+            }
+        }
+        hmap[idx] = cell;
+        hmap[stride + idx] = k;
+        for (int wd = 0; wd < nwords; wd++) hmap[(2 + wd) * stride + idx] = words[wd];
+    }
+}
+
+int femb_build_hmap(femb_ctx* ctx) {
+    femb_free(&ctx->hmap);
+    femb_free(&ctx->hslice_ptr);
+    ctx->hmap_stride = 0;
+    ctx->hmap_space = -1;
+    ctx->hranges.clear();
+    if (ctx->gmap_space >= 0) return FEMB_OK;  // scalar P1 has its own map
+    if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
+    const int sid = ctx->row_spaces[0];
+    const FembSpace& s = ctx->spaces[sid];
+    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd > 16 || ctx->max_collen > 254) return FEMB_OK;
+    const int64_t nslices = (s.ndofs + 31) / 32;
+    const int nwords = (s.nd + 3) / 4;
+    int32_t *deg = nullptr, *clen = nullptr;
+    void* tmp = nullptr;
+    FEMB_TRY(femb_alloc(ctx, &deg, (size_t)nslices + 1));
+    FEMB_TRY(femb_alloc(ctx, &clen, (size_t)nslices));
+    FEMB_TRY(femb_alloc(ctx, &ctx->hslice_ptr, (size_t)nslices + 1));
+    CUDA_TRY(ctx, cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nslices + 1), ctx->stream));
+    k_slice_deg<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(s.adj_ptr, s.ndofs, nslices, deg);
+    k_slice_collen<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(ctx->colptr, s.ndofs, nslices, clen);
+    ctx->launches += 2;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, ctx->hslice_ptr, nslices + 1, ctx->stream);
+    cudaError_t e = cudaMalloc(&tmp, tb);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, deg, ctx->hslice_ptr, nslices + 1, ctx->stream);
+    int32_t rows = 0;
+    std::vector<int32_t> h_clen((size_t)nslices);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&rows, ctx->hslice_ptr + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_clen.data(), clen, sizeof(int32_t) * nslices, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    cudaFree(deg);
+    cudaFree(clen);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, e);
+    // contiguous slice ranges of similar column length (shared memory per thread = maxlen doubles): runs of equal
+    // class ceil(len / 32), short runs (< 1/64 of the slices) merged into their predecessor, at most 16 ranges
+    std::vector<femb_ctx::HRange> rg;
+    const int64_t minrun = std::max<int64_t>(512, nslices / 64);
+    for (int64_t sl = 0; sl < nslices; sl++) {
+        const int cls = (h_clen[sl] + 31) / 32;
+        if (!rg.empty() && ((rg.back().maxlen + 31) / 32 == cls || rg.back().s1 - rg.back().s0 < minrun)) {
+            rg.back().s1 = sl + 1;
+            rg.back().maxlen = std::max(rg.back().maxlen, h_clen[sl]);
+        } else {
+            rg.push_back({sl, sl + 1, h_clen[sl], 1});
+        }
+    }
+    while (rg.size() > 16) {  // merge the neighbouring pair with the smallest size
+        size_t best = 0;
+        int64_t bs = INT64_MAX;
+        for (size_t i = 0; i + 1 < rg.size(); i++) {
+            int64_t sz = rg[i + 1].s1 - rg[i].s0;
+            if (sz < bs) { bs = sz; best = i; }
+        }
+        rg[best].s1 = rg[best + 1].s1;
+        rg[best].maxlen = std::max(rg[best].maxlen, rg[best + 1].maxlen);
+        rg.erase(rg.begin() + best + 1);
+    }
+    // columns with many adjacent cells (vertex dofs of P2 tetrahedra: ~24) are split over 4 threads
+    {
+        std::vector<int32_t> h_ptr((size_t)nslices + 1);
+        CUDA_TRY(ctx, cudaMemcpy(h_ptr.data(), ctx->hslice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost));
+        for (auto& r : rg) r.split = ((double)(h_ptr[r.s1] - h_ptr[r.s0]) / (double)(r.s1 - r.s0) >= 12.0) ? 4 : 1;
+        // neighbours with the same split whose merged accumulator block stays small (<= 24 KB per CTA) become one launch
+        for (size_t i = 0; i + 1 < rg.size();) {
+            const int ml = std::max(rg[i].maxlen, rg[i + 1].maxlen);
+            if (rg[i].split == rg[i + 1].split && (size_t)ml * (128 / rg[i].split) * 8 <= 24 * 1024) {
+                rg[i].s1 = rg[i + 1].s1;
+                rg[i].maxlen = ml;
+                rg.erase(rg.begin() + i + 1);
+            } else {
+                i++;
+            }
+        }
+    }
+    ctx->hranges = rg;
+    ctx->hmap_stride = (size_t)rows * 32;
+    ctx->hmap_words = nwords;
+    FEMB_TRY(femb_alloc(ctx, &ctx->hmap, ctx->hmap_stride * (2 + nwords)));
+    k_hmap<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.nd, nwords, s.celldofs, ctx->colptr, ctx->rowval,
+                                                                            ctx->hslice_ptr, ctx->hmap, ctx->hmap_stride);
+    KERNEL_CHECK(ctx);
+    ctx->hmap_space = sid;
     return FEMB_OK;
 }
