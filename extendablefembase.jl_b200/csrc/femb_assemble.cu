@@ -269,6 +269,7 @@ static int launch_bilinear(femb_ctx* ctx, int er, int ec, int op_r, int op_c, in
     const FembSpace& cs = ctx->spaces[EC.space];
     if (brow < 0 || brow >= ctx->nrs || bcol < 0 || bcol >= ctx->ncs || ctx->row_spaces[brow] != ER.space || ctx->col_spaces[bcol] != EC.space)
         return femb_fail(ctx, FEMB_ERR_ARG, "evaluator spaces do not match block (%d,%d)", brow, bcol);
+    FEMB_TRY(femb_build_slotmaps(ctx));
     const FembBlock* blk = find_block(ctx, brow, bcol);
     if (!blk || !blk->slots) return femb_fail(ctx, FEMB_ERR_ARG, "block (%d,%d) is not part of the pattern", brow, bcol);
     const FembBlock* blk_t = nullptr;
@@ -1094,7 +1095,9 @@ static int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_t
     int brow = -1;
     for (int i = 0; i < ctx->nrs; i++)
         if (ctx->row_spaces[i] == EG.space && i < ctx->ncs && ctx->col_spaces[i] == EG.space) brow = i;
-    const FembBlock* blk = brow >= 0 ? find_block(ctx, brow, brow) : nullptr;
+    if (brow < 0 || !find_block(ctx, brow, brow)) return FEMB_ERR_UNSUPPORTED;
+    FEMB_TRY(femb_build_slotmaps(ctx));
+    const FembBlock* blk = find_block(ctx, brow, brow);
     if (!blk || !blk->slots) return FEMB_ERR_UNSUPPORTED;
     const int ne = nds * (nds + 1) / 2, nt = (ne + 7) / 8;
     FEMB_TRY(build_reftensor(ctx, EG, nds, s.ncomp, nt));
@@ -1874,8 +1877,9 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
         if (st == FEMB_OK && rhs.kind != FEMB_RHS_NONE) st = launch_linear(ctx, eiu, 0, 1.0, rhs);
     }
     if (st == FEMB_OK && nonlinear) {
+        st = femb_build_slotmaps(ctx);
         const FembBlock* blk = find_block(ctx, 0, 0);
-        if (!blk || !blk->slots) st = femb_fail(ctx, FEMB_ERR_ARG, "(u,u) block missing from the pattern");
+        if (st == FEMB_OK && (!blk || !blk->slots)) st = femb_fail(ctx, FEMB_ERR_ARG, "(u,u) block missing from the pattern");
         if (st == FEMB_OK) st = femb_flush_zero(ctx, true, true);
         const int nds = us.nd / 2;
         if (st == FEMB_OK && us.handler == FEMB_HANDLER_NONE && us.nd == us.nd_all && nds == 6 && ctx->ncells) {

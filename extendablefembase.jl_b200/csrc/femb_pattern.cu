@@ -194,7 +194,8 @@ static int finish_pattern(femb_ctx* ctx) {
     }
     for (int i = 0; i < ctx->ncs; i++) FEMB_TRY(femb_build_adjacency(ctx, ctx->col_spaces[i]));
     for (int i = 0; i < ctx->nrs; i++) FEMB_TRY(femb_build_adjacency(ctx, ctx->row_spaces[i]));
-    FEMB_TRY(femb_build_slotmaps(ctx));
+    // the cell->slot maps of the cell-parallel kernels are built lazily (femb_build_slotmaps): the owner-computes
+    // paths below do not need them, and they are what limits nnz to 2^31
     FEMB_TRY(femb_build_gmap(ctx));
     FEMB_TRY(femb_build_hmap(ctx));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -498,7 +499,6 @@ extern "C" int32_t femb_pattern_compress(femb_ctx* ctx, int64_t* nnz_out) {
     ctx->nnz = nnz2;
     FEMB_TRY(femb_alloc(ctx, &ctx->touched, (size_t)nnz2));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 1, nnz2, ctx->stream));
-    FEMB_TRY(femb_build_slotmaps(ctx));
     FEMB_TRY(femb_build_gmap(ctx));
     FEMB_TRY(femb_build_hmap(ctx));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -533,8 +533,10 @@ __global__ void k_slotmap(const int32_t* __restrict__ rdofs, int ndr, int64_t ro
 }
 
 int femb_build_slotmaps(femb_ctx* ctx) {
-    if (ctx->nnz >= ((int64_t)1 << 31)) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "nnz >= 2^31 needs 64-bit slot maps (not built in this round)");
+    if (ctx->nnz >= ((int64_t)1 << 31))
+        return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "nnz >= 2^31: the cell-parallel kernels use 32-bit slot maps (the owner-computes gather paths do not)");
     for (auto& b : ctx->blocks) {
+        if (b.slots) continue;  // built on first use
         const FembSpace& rs = ctx->spaces[ctx->row_spaces[b.brow]];
         const FembSpace& cs = ctx->spaces[ctx->col_spaces[b.bcol]];
         int64_t n = ctx->ncells * rs.nd * cs.nd;
