@@ -42,6 +42,7 @@ SIGNATURES = {
     "femb_pattern_build": (_i32, [_p, _i32, _p, _p, _i64, _p, C.POINTER(_i64)]),
     "femb_pattern_adopt": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i32, _p, _p]),
     "femb_pattern_get": (_i32, [_p, _p, _p]),
+    "femb_pattern_get_slots": (_i32, [_p, _i64, _p, _p]),
     "femb_pattern_compress": (_i32, [_p, C.POINTER(_i64)]),
     "femb_pattern_track": (_i32, [_p, _i32]),
     "femb_matrix_zero": (_i32, [_p]),
@@ -205,6 +206,18 @@ class Context:
         rowval = np.empty(self.nnz, dtype=np.int64)
         self._ck(self.lib.femb_pattern_get(self.h, _ptr(colptr), _ptr(rowval)))
         return colptr, rowval
+
+    def pattern_get_colptr(self, ncols):
+        colptr = np.empty(ncols + 1, dtype=np.int64)
+        self._ck(self.lib.femb_pattern_get(self.h, _ptr(colptr), None))
+        return colptr
+
+    def pattern_get_slots(self, slots):
+        """rowval (1-based) at the given 0-based nz positions"""
+        slots = _arr(slots, np.int64)
+        out = np.empty(slots.shape[0], dtype=np.int64)
+        self._ck(self.lib.femb_pattern_get_slots(self.h, slots.shape[0], _ptr(slots), _ptr(out)))
+        return out
 
     def pattern_track(self, enable=True):
         self._ck(self.lib.femb_pattern_track(self.h, 1 if enable else 0))

@@ -415,6 +415,36 @@ extern "C" int32_t femb_pattern_get(femb_ctx* ctx, int64_t* colptr_out, int64_t*
     return FEMB_OK;
 }
 
+__global__ void k_gather_i64(const int64_t* __restrict__ src, const int64_t* __restrict__ idx, int64_t n, int64_t* __restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+extern "C" int32_t femb_pattern_get_slots(femb_ctx* ctx, int64_t n, const int64_t* slots, int64_t* out) {
+    FEMB_CHECK_CTX(ctx);
+    if (!ctx->rowval) return femb_fail(ctx, FEMB_ERR_ARG, "no pattern");
+    if (n < 0 || (n && (!slots || !out))) return femb_fail(ctx, FEMB_ERR_ARG, "femb_pattern_get_slots: bad arguments");
+    if (n == 0) return FEMB_OK;
+    for (int64_t i = 0; i < n; i++)
+        if (slots[i] < 0 || slots[i] >= ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "slot out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int64_t *d_idx = nullptr, *d_out = nullptr;
+    FEMB_TRY(femb_alloc(ctx, &d_idx, (size_t)n));
+    int st = femb_alloc(ctx, &d_out, (size_t)n);
+    if (st == FEMB_OK) st = femb_h2d(ctx, d_idx, slots, (size_t)n);
+    if (st == FEMB_OK) {
+        k_gather_i64<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->rowval, d_idx, n, d_out);
+        ctx->launches++;
+        st = femb_d2h(ctx, out, d_out, (size_t)n);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_idx);
+    cudaFree(d_out);
+    if (st != FEMB_OK) return st;
+    CUDA_TRY(ctx, e);
+    return FEMB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // compress: Example200's value filter decides the pattern (Example200:153)
 // ---------------------------------------------------------------------------------------------------

@@ -141,7 +141,10 @@ int32_t femb_pattern_build(femb_ctx* ctx, int32_t nblocks, const int32_t* block_
 /* use an already flushed Julia pattern A.cscmatrix.colptr / rowval (steady state, Example200:205-211) */
 int32_t femb_pattern_adopt(femb_ctx* ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t* colptr,
                            const int64_t* rowval, int32_t nblocks, const int32_t* block_rows, const int32_t* block_cols);
-int32_t femb_pattern_get(femb_ctx* ctx, int64_t* colptr_out, int64_t* rowval_out);
+int32_t femb_pattern_get(femb_ctx* ctx, int64_t* colptr_out, int64_t* rowval_out); /* either may be NULL */
+/* rowval at the given 0-based nz positions (gathered on the device): the interface columns of a partitioned mesh
+ * without downloading the whole pattern */
+int32_t femb_pattern_get_slots(femb_ctx* ctx, int64_t n, const int64_t* slots, int64_t* rowval_out);
 /* Example200's value filter (|Aloc[j,k]| > 1e-15, Example200:153) decides the pattern: drop every
  * slot that received no contribution in the assemblies since the last femb_matrix_zero, keeping
  * extra_diag entries.  Rebuilds the cell->slot maps.  */

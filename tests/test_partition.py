@@ -142,3 +142,78 @@ def test_slab_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _p2_local(part, grid, ndofs_local, extra=None):
+    el = orc.Element("H1P2", 1)
+    fes = fb.FESpace(fb.H1P2(1, 3), grid)
+    cd = fes["CellDofs"]
+    rhs = lambda x: 0.25 + x[..., 0] - x[..., 1] + 0.5 * x[..., 2]  # noqa: E731
+    Aloc, bloc = orc.example200_local(el, "Tetrahedron3D", grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"], 1.0, rhs)
+    I, J, V = orc.example200_triplets(Aloc, cd, drop_tol=-1.0)  # structural pattern (no value filter)
+    if extra is not None and extra[0].size:
+        I, J, V = np.concatenate([I, extra[0]]), np.concatenate([J, extra[1]]), np.concatenate([V, np.zeros(extra[0].shape[0])])
+    colptr, rowval, nzval = orc.flush_csc(ndofs_local, ndofs_local, I, J, V)
+    b = np.zeros(ndofs_local)
+    np.add.at(b, cd.astype(np.int64).reshape(-1) - 1, bloc.reshape(-1))
+    return colptr, rowval, nzval, b, cd
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_exchange_3d_p2_in_process(nranks):
+    """H1P2{1,3} on z-slabs of the Kuhn mesh: ghost pattern from CellDofs on the host, halo dofs discovered from the
+    peers, exchange plan through the fetch interface (what the device path uses); result == single-domain oracle."""
+    m, L = 3, 2
+    parts, grids = zip(*[pt.slab_partition_3d(m, r, nranks, L) for r in range(nranks)])
+    fess = [fb.FESpace(fb.H1P2(1, 3), g) for g in grids]
+    sent0 = [pt.ghost_pattern_from_cells(p, f["CellDofs"]) for p, f in zip(parts, fess)]
+    nhalo = [pt.add_halo(p, sent0) for p in parts]
+    assert nhalo[0] > 0 and nhalo[-1] == 0  # the top rank has no upper neighbour
+    extras = [pt.extra_entries(p, sent0) for p in parts]
+    loc = [_p2_local(p, g, f.ndofs + h, e) for p, g, f, h, e in zip(parts, grids, fess, nhalo, extras)]
+    sent = [pt.ghost_columns(p, l[0], fetch=lambda sl, rv=l[1]: rv[sl]) for p, l in zip(parts, loc)]
+    plans = [pt.exchange_plan(p, l[0], None, sent, fetch=lambda sl, rv=l[1]: rv[sl]) for p, l in zip(parts, loc)]
+    packed = [{} for _ in range(nranks)]
+    for r, (pl, l) in enumerate(zip(plans, loc)):
+        for i, p in enumerate(pl.peers):
+            packed[r][int(p)] = (l[2][pl.send_slots[pl.send_ptr[i]:pl.send_ptr[i + 1]]].copy(), l[3][pl.send_b[pl.sendb_ptr[i]:pl.sendb_ptr[i + 1]]].copy())
+    for r, (pl, l) in enumerate(zip(plans, loc)):
+        for i, p in enumerate(pl.peers):
+            vals, bv = packed[int(p)][r]
+            l[2][pl.recv_slots[pl.recv_ptr[i]:pl.recv_ptr[i + 1]]] += vals
+            l[3][pl.recv_b[pl.recvb_ptr[i]:pl.recvb_ptr[i + 1]]] += bv
+    # single-domain reference with the same global dof keys
+    X = np.linspace(0, 1, m + 1)
+    gridG = fb.simplexgrid(X, X, np.arange(nranks * L + 1) / float(m))
+    fesG = fb.FESpace(fb.H1P2(1, 3), gridG)
+    cdG = fesG["CellDofs"]
+    elG = orc.Element("H1P2", 1)
+    Aloc, bloc = orc.example200_local(elG, "Tetrahedron3D", gridG["Coordinates"], gridG["CellNodes"], gridG["CellVolumes"], 1.0,
+                                      lambda x: 0.25 + x[..., 0] - x[..., 1] + 0.5 * x[..., 2])
+    I, J, V = orc.example200_triplets(Aloc, cdG, drop_tol=-1.0)
+    cG, rG, vG = orc.flush_csc(fesG.ndofs, fesG.ndofs, I, J, V)
+    Aref = sp.csc_matrix((vG, rG - 1, cG - 1), shape=(fesG.ndofs,) * 2)
+    bref = np.zeros(fesG.ndofs)
+    np.add.at(bref, cdG.astype(np.int64).reshape(-1) - 1, bloc.reshape(-1))
+    NN = gridG.nnodes
+    enG = gridG["EdgeNodes"].astype(np.int64) - 1
+    keyG = np.concatenate([np.arange(NN, dtype=np.int64), NN + np.minimum(enG[:, 0], enG[:, 1]) * NN + np.maximum(enG[:, 0], enG[:, 1])])
+    order = np.argsort(keyG)
+    to_ref = lambda keys: order[np.searchsorted(keyG[order], keys)]  # noqa: E731
+    nowned = 0
+    for p, l in zip(parts, loc):
+        colptr, rowval, nzval, b, _ = l
+        A = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(p.l2g.shape[0],) * 2)
+        owned = np.nonzero(p.owner == p.rank)[0]
+        nowned += owned.shape[0]
+        gi = to_ref(p.l2g)
+        for c in owned:
+            col = A.getcol(c).tocoo()
+            ref = Aref.getcol(int(gi[c])).tocoo()
+            got = dict(zip(gi[col.row].tolist(), col.data.tolist()))
+            want = dict(zip(ref.row.tolist(), ref.data.tolist()))
+            assert set(got) == set(want), (p.rank, c)
+            for k in want:
+                assert abs(got[k] - want[k]) <= 1e-13 * max(1.0, abs(want[k]))
+        assert np.abs(b[owned] - bref[gi[owned]]).max() <= 1e-13 * np.abs(bref).max()
+    assert nowned == fesG.ndofs

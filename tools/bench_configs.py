@@ -103,12 +103,95 @@ def c5_taylor_hood(n, steps, warmup):
     return out
 
 
+def c3_multi_gpu(m, layers, steps, warmup):
+    """C3 on z-slabs, one rank per GPU (launch with torchrun): weak scaling of the H1P2{1,3} stiffness + rhs assembly with
+    the NCCL exchange of the interface columns (vertex and edge dofs in the cut planes)."""
+    import torch
+    import torch.distributed as dist
+    from femb_b200 import partition as pt
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t0 = time.time()
+    part, grid = pt.slab_partition_3d(m, rank, world, layers)
+    fes = fb.FESpace(fb.H1P2(1, 3), grid)
+    cd = fes["CellDofs"]
+    ndofs_own_cells = fes.ndofs
+    if world > 1:
+        sent0 = pt.allgather(pt.ghost_pattern_from_cells(part, cd), world)
+        nhalo = pt.add_halo(part, sent0)
+        fes.ndofs += nhalo  # halo rows: dofs of the neighbour's first cell layer
+        er, ec = pt.extra_entries(part, sent0)
+    qf = fb.QuadratureRule(grid.geometry, 2)
+    S = _Session([fes], qf, local)
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    if world > 1 and er.size:
+        ctx.pattern_extra(er, ec)
+    nnz = ctx.pattern_build([(0, 0)])
+    xbytes = 0
+    if world > 1:
+        uid = [_lib.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+        colptr = ctx.pattern_get_colptr(fes.ndofs)
+        sent = pt.allgather(pt.ghost_columns(part, colptr, fetch=ctx.pattern_get_slots), world)
+        plan = pt.exchange_plan(part, colptr, None, sent, fetch=ctx.pattern_get_slots)
+        ctx.comm_set_exchange(plan)
+        xbytes = 8 * int(plan.send_ptr[-1] + plan.sendb_ptr[-1] + plan.recv_ptr[-1] + plan.recvb_ptr[-1])
+    setup_s = time.time() - t0
+    p = AffineFunction([0.25], [[1.0, -1.0, 0.5]]).params()
+
+    def step():
+        ctx.matrix_zero()
+        ctx.vector_zero()
+        ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0)
+        if world > 1:
+            ctx.exchange()
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    ctx.sync()
+    ctx.region_begin()
+    for _ in range(steps):
+        step()
+    ms = ctx.region_end() / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # check: every owned column of the stiffness matrix sums to zero once the interface contributions have arrived
+    nz = ctx.matrix_get()
+    colptr = ctx.pattern_get_colptr(fes.ndofs)
+    lens = np.diff(colptr)
+    colsum = np.zeros(fes.ndofs)
+    nzc = np.nonzero(lens)[0]
+    colsum[nzc] = np.add.reduceat(nz, colptr[nzc] - 1)
+    owned = part.owner == rank
+    scale = np.abs(nz).max()
+    res = {"config": f"C3 multi-GPU: H1P2{{1,3}} stiffness+rhs, Kuhn {m}x{m}x{layers} per rank, z-slabs", "n_gpus": world, "ncells_per_rank": grid.ncells,
+           "ndofs_local": fes.ndofs, "halo_dofs": fes.ndofs - ndofs_own_cells, "nnz_local": nnz, "ms_per_step": ms,
+           "cells_per_s": world * grid.ncells / (ms * 1e-3), "exchange_bytes_rank": xbytes, "setup_s": setup_s,
+           "max_rel_owned_colsum": float(np.abs(colsum[owned]).max() / scale), "max_rel_ghost_colsum": float(np.abs(colsum[~owned]).max() / scale) if (~owned).any() else 0.0}
+    if world > 1:
+        allres = [None] * world
+        dist.all_gather_object(allres, res)
+        res["max_rel_owned_colsum"] = max(r["max_rel_owned_colsum"] for r in allres)
+        dist.destroy_process_group()
+    return res if rank == 0 else None
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--which", default="c3,c3p1,c4,c5")
     ap.add_argument("--m3", type=int, default=96)
     ap.add_argument("--m4", type=int, default=64)
     ap.add_argument("--n5", type=int, default=1024)
+    ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     a = ap.parse_args()
@@ -123,5 +206,9 @@ if __name__ == "__main__":
             res.append(c4_hdiv(a.m4, a.steps, a.warmup, "BDM1"))
         elif w == "c5":
             res += c5_taylor_hood(a.n5, a.steps, a.warmup)
+        elif w == "c3mg":
+            r = c3_multi_gpu(a.m3, a.layers, a.steps, a.warmup)
+            if r:
+                res.append(r)
     for r in res:
         print(json.dumps(r), flush=True)
