@@ -1133,63 +1133,73 @@ static int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_t
 template <int DIM>
 __global__ void __launch_bounds__(128) k_cell_coef(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
                                                    int64_t ncells, double mu, RhsDev rhs, QuadDev q, double* __restrict__ out) {
-    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (cell >= ncells) return;
-    double x[DIM + 1][DIM];
-    load_nodes<DIM>(coords, cellnodes, cell, x);
-    double A[DIM][DIM], C[DIM][DIM], det;
+    __shared__ double tile[128][FEMB_COEF_STRIDE + 1];  // staged so that the 128-byte records leave the SM fully coalesced
+    const int64_t cell0 = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t cell = cell0 + threadIdx.x;
+    if (cell < ncells) {
+        double x[DIM + 1][DIM];
+        load_nodes<DIM>(coords, cellnodes, cell, x);
+        double A[DIM][DIM], C[DIM][DIM], det;
 #pragma unroll
-    for (int d = 0; d < DIM; d++)
+        for (int d = 0; d < DIM; d++)
 #pragma unroll
-        for (int i = 0; i < DIM; i++) A[d][i] = x[i + 1][d] - x[0][d];
-    if (DIM == 2) {
-        det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
-        C[0][0] = A[1][1]; C[0][1] = -A[1][0];
-        C[1][0] = -A[0][1]; C[1][1] = A[0][0];
-    } else {
+            for (int i = 0; i < DIM; i++) A[d][i] = x[i + 1][d] - x[0][d];
+        if (DIM == 2) {
+            det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+            C[0][0] = A[1][1]; C[0][1] = -A[1][0];
+            C[1][0] = -A[0][1]; C[1][1] = A[0][0];
+        } else {
 #pragma unroll
-        for (int r = 0; r < 3; r++)
+            for (int r = 0; r < 3; r++)
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const int ra = (r + 1) % 3, rb = (r + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
-                C[r][j] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
-            }
-        det = A[0][0] * C[0][0] + A[0][1] * C[0][1] + A[0][2] * C[0][2];
-    }
-    const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * (DIM == 2 ? 0.5 : 1.0 / 6.0);
-    const double sc = (mu * vol) / (det * det);
-    double* o = out + cell * FEMB_COEF_STRIDE;
-    int ci = 0;
+                for (int j = 0; j < 3; j++) {
+                    const int ra = (r + 1) % 3, rb = (r + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
+                    C[r][j] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
+                }
+            det = A[0][0] * C[0][0] + A[0][1] * C[0][1] + A[0][2] * C[0][2];
+        }
+        const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * (DIM == 2 ? 0.5 : 1.0 / 6.0);
+        const double sc = (mu * vol) / (det * det);
+        double* o = tile[threadIdx.x];
+        int ci = 0;
 #pragma unroll
-    for (int p = 0; p < DIM; p++) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][p];
-        o[ci++] = s * sc;
-    }
-#pragma unroll
-    for (int p = 0; p < DIM; p++)
-#pragma unroll
-        for (int r = p + 1; r < DIM; r++) {
+        for (int p = 0; p < DIM; p++) {
             double s = 0.0;
 #pragma unroll
-            for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][r];
+            for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][p];
             o[ci++] = s * sc;
         }
-    if (rhs.kind != FEMB_RHS_NONE) {
-        for (int qp = 0; qp < q.nqp; qp++) {
-            double xq[DIM], f[3];
 #pragma unroll
-            for (int d = 0; d < DIM; d++) {
-                double sx = x[0][d];
+        for (int p = 0; p < DIM; p++)
 #pragma unroll
-                for (int i = 0; i < DIM; i++) sx += A[d][i] * q.xref[qp * DIM + i];
-                xq[d] = sx;
+            for (int r = p + 1; r < DIM; r++) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; k++) s += C[k][p] * C[k][r];
+                o[ci++] = s * sc;
             }
-            eval_rhs<DIM>(rhs, xq, cell, qp, q.nqp, f);
-            o[6 + qp] = f[0] * vol;
+        for (; ci < 6; ci++) o[ci] = 0.0;
+        for (int qp = 0; qp < FEMB_COEF_STRIDE - 6; qp++) {
+            double f = 0.0;
+            if (qp < q.nqp && rhs.kind == FEMB_RHS_AFFINE) {  // f(x_qp), x_qp = A xref_qp + x_1
+                f = rhs.p[0];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) {
+                    double sx = x[0][d];
+#pragma unroll
+                    for (int i = 0; i < DIM; i++) sx += A[d][i] * q.xref[qp * DIM + i];
+                    f += rhs.p[1 + d] * sx;
+                }
+            } else if (qp < q.nqp && rhs.kind == FEMB_RHS_QPVALUES) {
+                f = __ldg(rhs.fvals + (size_t)cell * q.nqp + qp);
+            }
+            o[6 + qp] = f * vol;
         }
     }
+    __syncthreads();
+    const int64_t nloc = min((int64_t)128, ncells - cell0);
+    double* dst = out + cell0 * FEMB_COEF_STRIDE;
+    for (int i = threadIdx.x; i < nloc * FEMB_COEF_STRIDE; i += 128) dst[i] = tile[i / FEMB_COEF_STRIDE][i % FEMB_COEF_STRIDE];
 }
 
 template <int DIM, int ND, int NQ>
@@ -1243,29 +1253,78 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
     double bsum = 0.0;
     unsigned err = 0u;
     const int niter = (nrows + SPLIT - 1) / SPLIT;
-    for (int it = 0; it < niter; it++) {
-        const int r = it * SPLIT + (SPLIT == 1 ? 0 : (int)warp);
-        const uint32_t* __restrict__ hp = a.hmap + ((size_t)(row0 + r) << 5) + lane;
-        const unsigned k = (r < nrows) ? __ldg(hp + a.hstride) : 0xFFFFFFFFu;
-        const bool on = k != 0xFFFFFFFFu;
-        double v[ND];
-        unsigned words[NW];
-        if (on) {
-            const unsigned cell = __ldg(hp);
+    // software pipeline: the gather-map entry two visits ahead and the cell coefficients of the next visit are in
+    // flight while the current visit is computed (padding entries point at cell 0: their loads stay in bounds)
+    const int rfirst = (SPLIT == 1) ? 0 : (int)warp;
+    const uint32_t* __restrict__ hbase = a.hmap + ((size_t)row0 << 5) + lane;
+    unsigned k1 = 0xFFFFFFFFu, cell1 = 0u, k2 = 0xFFFFFFFFu, cell2 = 0u, w1[NW], w2[NW];
 #pragma unroll
-            for (int wd = 0; wd < NW; wd++) words[wd] = __ldg(hp + (2 + wd) * a.hstride);
-            const double* cc = a.coef + (size_t)cell * FEMB_COEF_STRIDE;
-            double kc[KP];
+    for (int wd = 0; wd < NW; wd++) w1[wd] = w2[wd] = 0xFFFFFFFFu;
+    if (rfirst < nrows) {
+        const uint32_t* hp = hbase + ((size_t)rfirst << 5);
+        k1 = __ldg(hp + a.hstride);
+        cell1 = __ldg(hp);
+#pragma unroll
+        for (int wd = 0; wd < NW; wd++) w1[wd] = __ldg(hp + (2 + wd) * a.hstride);
+    }
+    if (rfirst + SPLIT < nrows) {
+        const uint32_t* hp = hbase + ((size_t)(rfirst + SPLIT) << 5);
+        k2 = __ldg(hp + a.hstride);
+        cell2 = __ldg(hp);
+#pragma unroll
+        for (int wd = 0; wd < NW; wd++) w2[wd] = __ldg(hp + (2 + wd) * a.hstride);
+    }
+    double kc1[KP], f1[NQ];
+    {
+        const double* cc = a.coef + (size_t)cell1 * FEMB_COEF_STRIDE;
+#pragma unroll
+        for (int i = 0; i < KP; i++) kc1[i] = __ldg(cc + i);
+#pragma unroll
+        for (int qp = 0; qp < NQ; qp++) f1[qp] = a.has_rhs ? __ldg(cc + 6 + qp) : 0.0;
+    }
+    for (int it = 0; it < niter; it++) {
+        const int r = it * SPLIT + rfirst;
+        const unsigned k = k1;
+        const bool on = k != 0xFFFFFFFFu;
+        double v[ND], kc[KP], fq[NQ];
+        unsigned words[NW];
+#pragma unroll
+        for (int wd = 0; wd < NW; wd++) words[wd] = w1[wd];
+#pragma unroll
+        for (int i = 0; i < KP; i++) kc[i] = kc1[i];
+#pragma unroll
+        for (int qp = 0; qp < NQ; qp++) fq[qp] = f1[qp];
+        // rotate the pipeline
+        k1 = k2; cell1 = cell2;
+#pragma unroll
+        for (int wd = 0; wd < NW; wd++) w1[wd] = w2[wd];
+        if (r + 2 * SPLIT < nrows) {
+            const uint32_t* hp = hbase + ((size_t)(r + 2 * SPLIT) << 5);
+            k2 = __ldg(hp + a.hstride);
+            cell2 = __ldg(hp);
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) w2[wd] = __ldg(hp + (2 + wd) * a.hstride);
+        } else {
+            k2 = 0xFFFFFFFFu; cell2 = 0u;
+        }
+        {
+            const double* cc = a.coef + (size_t)cell1 * FEMB_COEF_STRIDE;
             if (DIM == 2) {
                 const double2 c01 = __ldg(reinterpret_cast<const double2*>(cc));
-                kc[0] = c01.x; kc[1] = c01.y; kc[2] = __ldg(cc + 2);
+                kc1[0] = c01.x; kc1[1] = c01.y; kc1[2] = __ldg(cc + 2);
             } else {
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     const double2 cv = __ldg(reinterpret_cast<const double2*>(cc) + i);
-                    kc[2 * i] = cv.x; kc[2 * i + 1] = cv.y;
+                    kc1[2 * i] = cv.x; kc1[2 * i + 1] = cv.y;
                 }
             }
+            if (a.has_rhs) {
+#pragma unroll
+                for (int qp = 0; qp < NQ; qp++) f1[qp] = __ldg(cc + 6 + qp);
+            }
+        }
+        if (on) {
             double Km[DIM][DIM];  // symmetric Kmat from the coefficient order (00, 11, [22,] 01, [02, 12])
             if (DIM == 2) {
                 Km[0][0] = kc[0]; Km[1][1] = kc[1]; Km[0][1] = Km[1][0] = kc[2];
@@ -1299,7 +1358,7 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
             if (a.has_rhs) {
                 double t = 0.0;
 #pragma unroll
-                for (int qp = 0; qp < NQ; qp++) t += tab.wphi[qp][k] * __ldg(cc + 6 + qp);
+                for (int qp = 0; qp < NQ; qp++) t += tab.wphi[qp][k] * fq[qp];
                 bsum += t;
             }
         }
@@ -1391,6 +1450,7 @@ static int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
     if (!ctx->hmap || ctx->hmap_space != EG.space || EG.nqp > 10) return FEMB_ERR_UNSUPPORTED;
+    if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return FEMB_ERR_UNSUPPORTED;
     if (EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * ctx->dim) return FEMB_ERR_UNSUPPORTED;
     const FembEval* EI = rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr;
     if (EI && EI->h_refvals.size() != (size_t)EG.nqp * s.nd_all) return FEMB_ERR_UNSUPPORTED;
