@@ -31,7 +31,7 @@ def timeit(fn, ctx, steps, warmup):
     return ms
 
 
-def c3_p2_3d(m, steps, warmup, order=2):
+def c3_p2_3d(m, steps, warmup, order=2, check=False):
     X = np.linspace(0, 1, m + 1)
     t0 = time.time()
     grid = fb.simplexgrid(X, X, X)
@@ -53,8 +53,17 @@ def c3_p2_3d(m, steps, warmup, order=2):
         ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0)
 
     ms = timeit(step, ctx, steps, warmup)
-    return {"config": f"C3 H1P{order}{{1,3}} Poisson stiffness+rhs, Kuhn m={m}", "ncells": grid.ncells, "ndofs": fes.ndofs, "nnz": nnz, "ms_per_step": ms,
-            "cells_per_s": grid.ncells / (ms * 1e-3), "host_setup_s": t1 - t0, "pattern_s": t2 - t1}
+    res = {"config": f"C3 H1P{order}{{1,3}} Poisson stiffness+rhs, Kuhn m={m}", "ncells": grid.ncells, "ndofs": fes.ndofs, "nnz": nnz, "ms_per_step": ms,
+           "cells_per_s": grid.ncells / (ms * 1e-3), "host_setup_s": t1 - t0, "pattern_s": t2 - t1}
+    if check:
+        # size-independent properties of the full result: 1^T A = 0 (every column sums to zero), diag > 0, sum(b) = int f
+        nz = ctx.matrix_get()
+        colptr = ctx.pattern_get_colptr(fes.ndofs)
+        colsum = np.add.reduceat(nz, colptr[:-1] - 1)
+        b = ctx.vector_get(fes.ndofs)
+        res.update({"check_max_abs_colsum": float(np.abs(colsum).max()), "check_max_abs_entry": float(np.abs(nz).max()), "check_nonzero_entries": int(np.count_nonzero(nz)),
+                    "check_sum_b": float(b.sum()), "check_int_f": 0.25})  # int over the unit cube of x - y + z/2
+    return res
 
 
 def c4_hdiv(m, steps, warmup, name):
@@ -192,13 +201,14 @@ if __name__ == "__main__":
     ap.add_argument("--m4", type=int, default=64)
     ap.add_argument("--n5", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=None)
+    ap.add_argument("--check", action="store_true")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     a = ap.parse_args()
     res = []
     for w in a.which.split(","):
         if w == "c3":
-            res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 2))
+            res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 2, a.check))
         elif w == "c3p1":
             res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 1))
         elif w == "c4":
