@@ -145,6 +145,7 @@ def setup_device(grid, vol, device, use_vol=True, part=None):
         sent = pt.allgather(pt.ghost_columns(part, colptr, rowval), part.nranks)
         plan = pt.exchange_plan(part, colptr, rowval, sent)
         ctx.comm_set_exchange(plan)
+        ctx.set_fused_exchange(True)  # from now on femb_assemble_poisson overlaps the exchange with the bulk of the assembly
         S.plan = plan
         S.exchange_bytes = 8 * int(plan.send_ptr[-1] + plan.sendb_ptr[-1] + plan.recv_ptr[-1] + plan.recvb_ptr[-1])
     ctx.sync()
@@ -204,14 +205,15 @@ def run_ours(args):
     # ---- value: device-resident ------------------------------------------------------------
     clk = ClockSampler(local)
     clk.__enter__()
+    # device-resident steps: the interface exchange is fused into (overlapped with) femb_assemble_poisson
     for _ in range(args.warmup):
-        step_resident(ctx, eg, ei, rhsp, xch)
+        step_resident(ctx, eg, ei, rhsp, False)
     barrier()
     l0 = ctx.launch_count()
     kms = []
     ctx.region_begin()
     for _ in range(args.steps):
-        kms.append(step_resident(ctx, eg, ei, rhsp, xch))
+        kms.append(step_resident(ctx, eg, ei, rhsp, False))
     ms_total = ctx.region_end()
     barrier()
     launches = ctx.launch_count() - l0

@@ -69,6 +69,7 @@ SIGNATURES = {
     "femb_comm_set_exchange": (_i32, [_p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "femb_pattern_extra": (_i32, [_p, _i64, _p, _p]),
     "femb_exchange": (_i32, [_p]),
+    "femb_set_fused_exchange": (_i32, [_p, _i32]),
     "femb_comm_destroy": (_i32, [_p]),
 }
 
@@ -313,6 +314,9 @@ class Context:
         peers = np.ascontiguousarray(plan.peers, dtype=np.int32)
         arrs = [a(plan.send_ptr), a(plan.send_slots), a(plan.recv_ptr), a(plan.recv_slots), a(plan.sendb_ptr), a(plan.send_b), a(plan.recvb_ptr), a(plan.recv_b)]
         self._ck(self.lib.femb_comm_set_exchange(self.h, peers.shape[0], _ptr(peers), *[_ptr(x) for x in arrs]))
+
+    def set_fused_exchange(self, enable=True):
+        self._ck(self.lib.femb_set_fused_exchange(self.h, 1 if enable else 0))
 
     def exchange(self):
         self._ck(self.lib.femb_exchange(self.h))

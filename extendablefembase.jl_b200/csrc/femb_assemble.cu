@@ -894,6 +894,41 @@ static int launch_p1_slices(femb_ctx* ctx, P1Launch& L, int64_t s0, int64_t s1, 
 static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
     P1Launch L;
     FEMB_TRY(prepare_p1_gather(ctx, eg, ei, mu, rhs, drop_tol, L));
+    if (ctx->fused_exchange && ctx->comm && !ctx->peers.empty() && ctx->stream_x) {
+        // overlapped interface exchange: assemble the slices holding ghost (send) and owned-interface (recv) columns
+        // first, run pack / NCCL / add on a second stream while the bulk of the columns is assembled
+        int64_t r[2][2] = {{ctx->xdof_send_lo / 32, ctx->xdof_send_hi / 32 + 1}, {ctx->xdof_recv_lo / 32, ctx->xdof_recv_hi / 32 + 1}};
+        if (ctx->xdof_send_hi < 0) r[0][0] = r[0][1] = 0;
+        if (ctx->xdof_recv_hi < 0) r[1][0] = r[1][1] = 0;
+        for (auto& q : r) {  // CTA granularity (4 slices)
+            q[0] = (q[0] / 4) * 4;
+            q[1] = std::min<int64_t>(((q[1] + 3) / 4) * 4, L.nslices);
+        }
+        if (r[1][1] > r[1][0] && (r[0][1] <= r[0][0] || r[1][0] < r[0][0])) std::swap(r[0], r[1]);  // ascending
+        if (r[0][1] > r[1][0] && r[1][1] > r[1][0]) {  // overlapping: merge
+            r[0][1] = std::max(r[0][1], r[1][1]);
+            r[1][0] = r[1][1] = 0;
+        }
+        const int64_t nb = (r[0][1] - r[0][0]) + (r[1][1] - r[1][0]);
+        if (nb > 0 && nb * 8 <= L.nslices) {
+            for (auto& q : r) FEMB_TRY(launch_p1_slices(ctx, L, q[0], q[1], ctx->stream));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_x0, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_x, ctx->ev_x0, 0));
+            FEMB_TRY(femb_exchange_on(ctx, ctx->stream_x));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_x1, ctx->stream_x));
+            int64_t pos = 0;  // the complement of the boundary ranges
+            for (auto& q : r) {
+                if (q[1] <= q[0]) continue;
+                FEMB_TRY(launch_p1_slices(ctx, L, pos, q[0], ctx->stream));
+                pos = q[1];
+            }
+            FEMB_TRY(launch_p1_slices(ctx, L, pos, L.nslices, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x1, 0));
+            return FEMB_OK;
+        }
+        FEMB_TRY(launch_p1_slices(ctx, L, 0, L.nslices, ctx->stream));  // interface too large to be worth splitting
+        return femb_exchange_on(ctx, ctx->stream);
+    }
     return launch_p1_slices(ctx, L, 0, L.nslices, ctx->stream);
 }
 

@@ -101,6 +101,45 @@ void free_exchange(femb_ctx* ctx) {
 
 }  // namespace
 
+int femb_exchange_on(femb_ctx* ctx, cudaStream_t stream) {
+    const int np = (int)ctx->peers.size();
+    // send buffer layout: [matrix entries of all peers | vector entries of all peers]
+    if (ctx->nsend) {
+        k_pack<<<(unsigned)((ctx->nsend + 255) / 256), 256, 0, stream>>>(ctx->nzval, ctx->send_slots, ctx->nsend, ctx->sendbuf);
+        KERNEL_CHECK(ctx);
+    }
+    if (ctx->nsendb) {
+        k_pack<<<(unsigned)((ctx->nsendb + 255) / 256), 256, 0, stream>>>(ctx->bvec, ctx->send_b, ctx->nsendb, ctx->sendbuf + ctx->nsend);
+        KERNEL_CHECK(ctx);
+    }
+    nccl_comm comm = (nccl_comm)ctx->comm;
+    NCCL_TRY(ctx, g_nccl.GroupStart());
+    for (int p = 0; p < np; p++) {
+        const int peer = ctx->peers[p];
+        const int64_t ns = ctx->send_ptr[p + 1] - ctx->send_ptr[p], nr = ctx->recv_ptr[p + 1] - ctx->recv_ptr[p];
+        const int64_t nsb = ctx->sendb_ptr[p + 1] - ctx->sendb_ptr[p], nrb = ctx->recvb_ptr[p + 1] - ctx->recvb_ptr[p];
+        if (ns) NCCL_TRY(ctx, g_nccl.Send(ctx->sendbuf + ctx->send_ptr[p], (size_t)ns, NCCL_FLOAT64, peer, comm, stream));
+        if (nsb) NCCL_TRY(ctx, g_nccl.Send(ctx->sendbuf + ctx->nsend + ctx->sendb_ptr[p], (size_t)nsb, NCCL_FLOAT64, peer, comm, stream));
+        if (nr) NCCL_TRY(ctx, g_nccl.Recv(ctx->recvbuf + ctx->recv_ptr[p], (size_t)nr, NCCL_FLOAT64, peer, comm, stream));
+        if (nrb) NCCL_TRY(ctx, g_nccl.Recv(ctx->recvbuf + ctx->nrecv + ctx->recvb_ptr[p], (size_t)nrb, NCCL_FLOAT64, peer, comm, stream));
+    }
+    NCCL_TRY(ctx, g_nccl.GroupEnd());
+    for (int p = 0; p < np; p++) {  // ascending peer order: the sum order of every slot is fixed
+        const int64_t nr = ctx->recv_ptr[p + 1] - ctx->recv_ptr[p], nrb = ctx->recvb_ptr[p + 1] - ctx->recvb_ptr[p];
+        if (nr) {
+            k_unpack_add<<<(unsigned)((nr + 255) / 256), 256, 0, stream>>>(ctx->nzval, ctx->recv_slots + ctx->recv_ptr[p], nr, ctx->recvbuf + ctx->recv_ptr[p],
+                                                                         ctx->touched);
+            KERNEL_CHECK(ctx);
+        }
+        if (nrb) {
+            k_unpack_add<<<(unsigned)((nrb + 255) / 256), 256, 0, stream>>>(ctx->bvec, ctx->recv_b + ctx->recvb_ptr[p], nrb,
+                                                                          ctx->recvbuf + ctx->nrecv + ctx->recvb_ptr[p], nullptr);
+            KERNEL_CHECK(ctx);
+        }
+    }
+    return FEMB_OK;
+}
+
 extern "C" {
 
 int32_t femb_comm_unique_id(char id_out[128]) {
@@ -159,6 +198,16 @@ int32_t femb_comm_set_exchange(femb_ctx* ctx, int32_t npeers, const int32_t* pee
         if (send_b[i] < 0 || send_b[i] >= ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "send vector index out of range");
     for (int64_t i = 0; i < ctx->nrecvb; i++)
         if (recv_b[i] < 0 || recv_b[i] >= ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "recv vector index out of range");
+    ctx->xdof_send_lo = ctx->xdof_recv_lo = 0;
+    ctx->xdof_send_hi = ctx->xdof_recv_hi = -1;
+    if (ctx->nsendb) {
+        ctx->xdof_send_lo = *std::min_element(send_b, send_b + ctx->nsendb);
+        ctx->xdof_send_hi = *std::max_element(send_b, send_b + ctx->nsendb);
+    }
+    if (ctx->nrecvb) {
+        ctx->xdof_recv_lo = *std::min_element(recv_b, recv_b + ctx->nrecvb);
+        ctx->xdof_recv_hi = *std::max_element(recv_b, recv_b + ctx->nrecvb);
+    }
     FEMB_TRY(femb_alloc(ctx, &ctx->send_slots, (size_t)ctx->nsend));
     FEMB_TRY(femb_alloc(ctx, &ctx->recv_slots, (size_t)ctx->nrecv));
     FEMB_TRY(femb_alloc(ctx, &ctx->send_b, (size_t)ctx->nsendb));
@@ -181,47 +230,32 @@ int32_t femb_exchange(femb_ctx* ctx) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     FEMB_TRY(femb_flush_zero(ctx, true, true));
     FEMB_TRY(femb_timer_begin(ctx));
-    const int np = (int)ctx->peers.size();
-    // send buffer layout: [matrix entries of all peers | vector entries of all peers]
-    if (ctx->nsend) {
-        k_pack<<<(unsigned)((ctx->nsend + 255) / 256), 256, 0, ctx->stream>>>(ctx->nzval, ctx->send_slots, ctx->nsend, ctx->sendbuf);
-        KERNEL_CHECK(ctx);
-    }
-    if (ctx->nsendb) {
-        k_pack<<<(unsigned)((ctx->nsendb + 255) / 256), 256, 0, ctx->stream>>>(ctx->bvec, ctx->send_b, ctx->nsendb, ctx->sendbuf + ctx->nsend);
-        KERNEL_CHECK(ctx);
-    }
-    nccl_comm comm = (nccl_comm)ctx->comm;
-    NCCL_TRY(ctx, g_nccl.GroupStart());
-    for (int p = 0; p < np; p++) {
-        const int peer = ctx->peers[p];
-        const int64_t ns = ctx->send_ptr[p + 1] - ctx->send_ptr[p], nr = ctx->recv_ptr[p + 1] - ctx->recv_ptr[p];
-        const int64_t nsb = ctx->sendb_ptr[p + 1] - ctx->sendb_ptr[p], nrb = ctx->recvb_ptr[p + 1] - ctx->recvb_ptr[p];
-        if (ns) NCCL_TRY(ctx, g_nccl.Send(ctx->sendbuf + ctx->send_ptr[p], (size_t)ns, NCCL_FLOAT64, peer, comm, ctx->stream));
-        if (nsb) NCCL_TRY(ctx, g_nccl.Send(ctx->sendbuf + ctx->nsend + ctx->sendb_ptr[p], (size_t)nsb, NCCL_FLOAT64, peer, comm, ctx->stream));
-        if (nr) NCCL_TRY(ctx, g_nccl.Recv(ctx->recvbuf + ctx->recv_ptr[p], (size_t)nr, NCCL_FLOAT64, peer, comm, ctx->stream));
-        if (nrb) NCCL_TRY(ctx, g_nccl.Recv(ctx->recvbuf + ctx->nrecv + ctx->recvb_ptr[p], (size_t)nrb, NCCL_FLOAT64, peer, comm, ctx->stream));
-    }
-    NCCL_TRY(ctx, g_nccl.GroupEnd());
-    for (int p = 0; p < np; p++) {  // ascending peer order: the sum order of every slot is fixed
-        const int64_t nr = ctx->recv_ptr[p + 1] - ctx->recv_ptr[p], nrb = ctx->recvb_ptr[p + 1] - ctx->recvb_ptr[p];
-        if (nr) {
-            k_unpack_add<<<(unsigned)((nr + 255) / 256), 256, 0, ctx->stream>>>(ctx->nzval, ctx->recv_slots + ctx->recv_ptr[p], nr, ctx->recvbuf + ctx->recv_ptr[p],
-                                                                               ctx->touched);
-            KERNEL_CHECK(ctx);
-        }
-        if (nrb) {
-            k_unpack_add<<<(unsigned)((nrb + 255) / 256), 256, 0, ctx->stream>>>(ctx->bvec, ctx->recv_b + ctx->recvb_ptr[p], nrb,
-                                                                                ctx->recvbuf + ctx->nrecv + ctx->recvb_ptr[p], nullptr);
-            KERNEL_CHECK(ctx);
-        }
-    }
+    FEMB_TRY(femb_exchange_on(ctx, ctx->stream));
     return femb_timer_end(ctx);
+}
+
+int32_t femb_set_fused_exchange(femb_ctx* ctx, int32_t enable) {
+    FEMB_CHECK_CTX(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (enable && !ctx->stream_x) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_x, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_x0, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_x1, cudaEventDisableTiming));
+    }
+    ctx->fused_exchange = enable != 0;
+    return FEMB_OK;
 }
 
 int32_t femb_comm_destroy(femb_ctx* ctx) {
     FEMB_CHECK_CTX(ctx);
     free_exchange(ctx);
+    if (ctx->stream_x) {
+        cudaStreamDestroy(ctx->stream_x);
+        cudaEventDestroy(ctx->ev_x0);
+        cudaEventDestroy(ctx->ev_x1);
+        ctx->stream_x = nullptr;
+    }
+    ctx->fused_exchange = false;
     if (ctx->comm && g_nccl.handle) g_nccl.CommDestroy((nccl_comm)ctx->comm);
     ctx->comm = nullptr;
     ctx->nranks = 1;

@@ -147,6 +147,11 @@ struct femb_ctx {
     double* sendbuf = nullptr;      // [matrix part | vector part] per peer, contiguous
     double* recvbuf = nullptr;
     int64_t nsend = 0, nrecv = 0, nsendb = 0, nrecvb = 0;
+    // fused (overlapped) exchange: dof ranges that must be assembled before the exchange may start
+    bool fused_exchange = false;
+    int64_t xdof_send_lo = 0, xdof_send_hi = -1, xdof_recv_lo = 0, xdof_recv_hi = -1;  // [lo, hi] of send_b / recv_b
+    cudaStream_t stream_x = nullptr;
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
 };
 
 int femb_fail(femb_ctx* ctx, int code, const char* fmt, ...);
@@ -221,3 +226,5 @@ int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec);
 int femb_build_coloring(femb_ctx* ctx);
 int femb_timer_begin(femb_ctx* ctx);
 int femb_timer_end(femb_ctx* ctx);
+// comm.cu: pack -> NCCL send/recv -> add on `stream` (no timing, no lazy-zero flush)
+int femb_exchange_on(femb_ctx* ctx, cudaStream_t stream);

@@ -226,6 +226,10 @@ int32_t femb_comm_set_exchange(femb_ctx* ctx, int32_t npeers, const int32_t* pee
 /* pack -> ncclSend/ncclRecv (one group) -> add in ascending peer order (reproducible).  Received non-zero matrix
  * values also mark their slot as touched (femb_pattern_compress).  Sent ghost entries are left in place. */
 int32_t femb_exchange(femb_ctx* ctx);
+/* enable = 1: femb_assemble_poisson (scalar P1 gather path) performs the exchange itself, overlapped with the bulk of
+ * the assembly: the slices holding ghost and owned-interface columns are launched first, the pack / NCCL / add
+ * sequence runs on a second stream while the remaining columns are assembled.  Do not call femb_exchange then. */
+int32_t femb_set_fused_exchange(femb_ctx* ctx, int32_t enable);
 int32_t femb_comm_destroy(femb_ctx* ctx);
 
 #ifdef __cplusplus
