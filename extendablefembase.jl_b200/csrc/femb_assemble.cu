@@ -911,9 +911,10 @@ static int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsD
         }
         const int64_t nb = (r[0][1] - r[0][0]) + (r[1][1] - r[1][0]);
         if (nb > 0 && nb * 8 <= L.nslices) {
-            for (auto& q : r) FEMB_TRY(launch_p1_slices(ctx, L, q[0], q[1], ctx->stream));
-            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_x0, ctx->stream));
+            // second (high-priority) stream: boundary slices -> pack / NCCL / add; main stream: all other slices, concurrently
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_x0, ctx->stream));  // everything queued so far on the main stream comes first
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_x, ctx->ev_x0, 0));
+            for (auto& q : r) FEMB_TRY(launch_p1_slices(ctx, L, q[0], q[1], ctx->stream_x));
             FEMB_TRY(femb_exchange_on(ctx, ctx->stream_x));
             CUDA_TRY(ctx, cudaEventRecord(ctx->ev_x1, ctx->stream_x));
             int64_t pos = 0;  // the complement of the boundary ranges

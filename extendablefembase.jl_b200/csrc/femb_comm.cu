@@ -238,7 +238,9 @@ int32_t femb_set_fused_exchange(femb_ctx* ctx, int32_t enable) {
     FEMB_CHECK_CTX(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (enable && !ctx->stream_x) {
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_x, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;  // highest priority: the few boundary CTAs should not queue behind the bulk grid
+        CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->stream_x, cudaStreamNonBlocking, hi));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_x0, cudaEventDisableTiming));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_x1, cudaEventDisableTiming));
     }
