@@ -401,3 +401,69 @@ def test_full_size_p1_against_c_oracle(n):
     keyT = (rowval - 1) * fes.ndofs + cols
     assert np.array_equal(nz[np.searchsorted(key, keyT)], nz)
     assert abs(b.sum()) < 1e-12  # int (x - y) over the unit square
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: tiny / ragged / mirrored inputs
+# ---------------------------------------------------------------------------------------------
+def _assemble_and_compare(grid, ft, rhs, mu=0.7):
+    fes = fb.FESpace(ft, grid)
+    (colptr, rowval, nzval, b), _ = _ex200_oracle(grid, ft, fes, mu, rhs)
+    scale = _local_scale(grid, ft, mu)
+    for scatter in (_lib.SCATTER_GATHER, _lib.SCATTER_ATOMIC):
+        A, bv = fb.FEMatrix(fes, fes), fb.FEVector(fes)
+        fes2 = fb.FESpace(ft, grid)  # fresh session per policy
+        fb.assemble_poisson(A.entries, bv.entries, fes2, rhs, mu, scatter=scatter)
+        E = A.entries
+        import scipy.sparse as sp
+
+        D = E.to_scipy() - sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=E.shape)
+        assert abs(D).max() <= RTOL * scale
+        assert np.abs(bv.entries - b).max() <= RTOL * max(np.abs(b).max(), 1e-300)
+        if ft.order == 1:
+            assert np.array_equal(E.colptr, colptr) and np.array_equal(E.rowval, rowval)
+
+
+def test_single_cells():
+    """one triangle (the non-reference triangle of test/test_operators.jl:83) and one stretched tetrahedron"""
+    _assemble_and_compare(fb.grid_triangle([[-1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), fb.H1Pk(1, 2, 1), rhs_affine())
+    _assemble_and_compare(fb.grid_triangle([[-1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), fb.H1Pk(1, 2, 2), rhs_affine())
+    tet = fb.grid_tetrahedron([[0.0, 0, 0], [2.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]])
+    _assemble_and_compare(tet, fb.H1P1(1), fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]]))
+    _assemble_and_compare(tet, fb.H1P2(1, 3), fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]]))
+    # Appendix C.1 golden: P1 stiffness of that triangle
+    fes = fb.FESpace(fb.H1P1(1), fb.grid_triangle([[-1.0, 0.0], [1.0, 0.0], [0.0, 1.0]]))
+    A, bv = fb.FEMatrix(fes, fes), fb.FEVector(fes)
+    fb.assemble_poisson(A.entries, bv.entries, fes, None, 1.0)
+    assert np.allclose(A.entries.to_scipy().toarray(), [[0.5, 0, -0.5], [0, 0.5, -0.5], [-0.5, -0.5, 1.0]], atol=1e-15)
+
+
+def test_mirrored_cells_and_ragged_sizes():
+    """negatively oriented cells (two nodes swapped: det A < 0), node counts that are not multiples of the 32-dof
+    slices, 2 cells only"""
+    for n in (1, 2, 5, 11):
+        grid = _grid2d(n, n > 2)
+        cn = grid["CellNodes"].copy()
+        cn[::2] = cn[::2][:, [0, 2, 1]]  # mirror every other cell
+        g2 = fb.ExtendableGrid(grid["Coordinates"], cn, "Triangle2D")
+        _assemble_and_compare(g2, fb.H1Pk(1, 2, 1), rhs_affine())
+    grid = _grid3d(2, True)
+    cn = grid["CellNodes"].copy()
+    cn[1::3] = cn[1::3][:, [0, 1, 3, 2]]
+    g3 = fb.ExtendableGrid(grid["Coordinates"], cn, "Tetrahedron3D")
+    _assemble_and_compare(g3, fb.H1P1(1), fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]]))
+
+
+def test_empty_cell_range_and_unused_nodes():
+    """nodes that belong to no cell (halo nodes of a partitioned mesh) get empty columns; evaluating an empty cell range is a no-op"""
+    grid = _grid2d(4, True)
+    coords = np.concatenate([grid["Coordinates"], [[2.0, 2.0], [3.0, 3.0], [4.0, 2.5]]])
+    g2 = fb.ExtendableGrid(coords, grid["CellNodes"], "Triangle2D")
+    fes = fb.FESpace(fb.H1P1(1), g2)
+    A, bv = fb.FEMatrix(fes, fes), fb.FEVector(fes)
+    fb.assemble_poisson(A.entries, bv.entries, fes, rhs_affine(), 1.0)
+    E = A.entries
+    assert np.all(np.diff(E.colptr)[-3:] == 0) and np.all(bv.entries[-3:] == 0.0)
+    S = getattr(fes, "_femb_session_0")
+    out = S.evaluator(0, "Gradient").update_basis_all(3, 3)
+    assert out.shape[0] == 0

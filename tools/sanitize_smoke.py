@@ -1,0 +1,45 @@
+"""Small end-to-end pass over every kernel family for compute-sanitizer (memcheck): tiny meshes, all paths."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__  # noqa
+import femb_b200 as fb
+from femb_b200 import _lib
+from femb_b200.assembly import _Session
+
+rhs2 = fb.AffineFunction([0.0], [[1.0, -1.0]])
+rhs3 = fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]])
+X = np.linspace(0, 1, 12)
+g2 = fb.jitter(fb.simplexgrid(X, X))
+g3 = fb.jitter(fb.simplexgrid(X[:6], X[:6], X[:6]), 0.1)
+for ft, g, rhs in [(fb.H1Pk(1, 2, 1), g2, rhs2), (fb.H1Pk(1, 2, 2), g2, rhs2), (fb.H1Pk(1, 2, 3), g2, rhs2), (fb.H1P1(1), g3, rhs3), (fb.H1P2(1, 3), g3, rhs3), (fb.H1P3(1, 3), g3, rhs3)]:
+    for sc in (_lib.SCATTER_GATHER, _lib.SCATTER_ATOMIC):
+        fes = fb.FESpace(ft, g)
+        A, b = fb.FEMatrix(fes, fes), fb.FEVector(fes)
+        fb.assemble_poisson(A.entries, b.entries, fes, rhs, 1.0, scatter=sc)
+        fb.assemble_poisson(A.entries, b.entries, fes, rhs, 1.0, scatter=sc)
+        print(ft, sc, A.entries.nnz, float(np.abs(A.entries.nzval).max()))
+# streamed path
+fes = fb.FESpace(fb.H1P1(1), g2)
+S = _Session([fes], fb.QuadratureRule(g2.geometry, 0))
+eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+nnz = S.ctx.pattern_build([(0, 0)])
+nz, bb = np.zeros(nnz), np.zeros(fes.ndofs)
+S.ctx.assemble_poisson_host(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, rhs2.params(), 1e-15, g2["Coordinates"], g2["CellNodes"], g2["CellVolumes"], nz, bb, 3)
+print("streamed", nnz, float(np.abs(nz).max()))
+# Example210
+FESu, FESp = fb.FESpace(fb.H1Pk(2, 2, 2), g2), fb.FESpace(fb.H1Pk(1, 2, 1), g2)
+sol = fb.FEVector([FESu, FESp]); sol.entries[:] = np.random.default_rng(0).uniform(-1, 1, sol.entries.shape[0])
+A, b = fb.FEMatrix([FESu, FESp]), fb.FEVector([FESu, FESp])
+upd = fb.prepare_assembly(A, b, FESu, FESp, sol)
+upd(True, True)
+print("TH", A.entries.nnz)
+# Hdiv
+for ft in (fb.HDIVRT0(3), fb.HDIVBDM1(3), fb.HDIVRT0(2), fb.HDIVBDM1(2)):
+    g = g3 if ft.edim == 3 else g2
+    FESv, FESq = fb.FESpace(ft, g), fb.FESpace(fb.L2P0(1), g)
+    A = fb.FEMatrix([FESv, FESq])
+    fb.assemble_hdiv_mixed(A, FESv, FESq)
+    print(ft, A.entries.nnz)
+print("done")
