@@ -85,6 +85,7 @@ int32_t femb_destroy(femb_ctx* ctx) {
     femb_free(&ctx->coords);
     femb_free(&ctx->cellnodes);
     femb_free(&ctx->cellvol);
+    femb_free(&ctx->cellrhs);
     femb_free(&ctx->errflag);
     femb_free(&ctx->color_perm);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

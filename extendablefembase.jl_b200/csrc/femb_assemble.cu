@@ -256,6 +256,72 @@ __global__ void __launch_bounds__(128) k_bilinear(BilArgs a) {
     }
 }
 
+// Row-blocked variant: one thread per (cell, row dof j).  The row-side operator values of (cell, j) stay in registers
+// (compile-time NQ x R), the column-side values of the cell are staged once in shared memory; every thread then forms
+// its row of the local matrix (one LDS per FMA, no index arithmetic per entry) and scatters it.  Same arithmetic order
+// as k_bilinear / the reference loops: temp = sum_qp w_qp (sum_r row * col), value = (factor * temp) * |T|.
+template <int DIM, int NQ, int R>
+__global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Geo<DIM>* geo = reinterpret_cast<Geo<DIM>*>(smem_raw);
+    double* colv = reinterpret_cast<double*>(geo + a.cpb);  // [cl][qp * R + r][k]
+    const int ndr = a.rs.nd, ndc = a.cs.nd;
+    const int64_t base = a.p0 + (int64_t)blockIdx.x * a.cpb;
+    const int ncl = (int)min((int64_t)a.cpb, a.p1 - base);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int cl = tid; cl < ncl; cl += nt) load_geo<DIM>(a.coords, a.cellnodes, a.cellvol, a.perm ? a.perm[base + cl] : base + cl, geo[cl]);
+    __syncthreads();
+    const int cl = tid / ndr, j = tid - cl * ndr;
+    const bool active = cl < ncl;
+    const int64_t cell = active ? (a.perm ? a.perm[base + cl] : base + cl) : 0;
+    double rv[NQ * R];
+    if (active) {
+#pragma unroll
+        for (int qp = 0; qp < NQ; qp++) {
+            double v[9];
+            eval_op<DIM>(a.rs, a.op_r, geo[cl], cell, j, qp, a.rv_r, a.rd_r, v);
+#pragma unroll
+            for (int r = 0; r < R; r++) rv[qp * R + r] = v[r];
+        }
+        if (a.same) {
+#pragma unroll
+            for (int i = 0; i < NQ * R; i++) colv[((size_t)cl * (NQ * R) + i) * ndc + j] = rv[i];
+        }
+    }
+    if (!a.same) {
+        for (int i = tid; i < ncl * NQ * ndc; i += nt) {
+            const int c2 = i / (NQ * ndc), rem = i - c2 * (NQ * ndc);
+            const int qp = rem / ndc, k = rem - qp * ndc;
+            double v[9];
+            eval_op<DIM>(a.cs, a.op_c, geo[c2], a.perm ? a.perm[base + c2] : base + c2, k, qp, a.rv_c, a.rd_c, v);
+#pragma unroll
+            for (int r = 0; r < R; r++) colv[((size_t)c2 * (NQ * R) + qp * R + r) * ndc + k] = v[r];
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    const bool sym = a.flags & FEMB_BIL_SYMMETRIC_UPPER;
+    const double vol = (a.flags & FEMB_BIL_NO_VOLUME) ? 1.0 : geo[cl].vol;
+    const int per = ndr * ndc;
+    const double* cv = colv + (size_t)cl * (NQ * R) * ndc;
+    const int32_t* sl = a.slots + cell * per + j * ndc;
+    for (int k = sym ? j : 0; k < ndc; k++) {
+        double temp = 0.0;
+#pragma unroll
+        for (int qp = 0; qp < NQ; qp++) {
+            double d = 0.0;
+#pragma unroll
+            for (int r = 0; r < R; r++) d += rv[qp * R + r] * cv[(qp * R + r) * ndc + k];
+            temp += a.w[qp] * d;
+        }
+        const double val = sym ? temp * (a.factor * vol) : (a.factor * temp) * vol;
+        if (sym && !(fabs(val) > a.drop_tol)) continue;
+        scatter_add(a.nzval, a.touched, a.errflag, __ldg(sl + k), val, a.atomic);
+        if (sym && k > j) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots + cell * per + k * ndc + j), val, a.atomic);
+        if (a.slots_t) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots_t + cell * per + k * ndr + j), val, a.atomic);
+    }
+}
+
 static const FembBlock* find_block(const femb_ctx* ctx, int brow, int bcol) {
     for (auto& b : ctx->blocks)
         if (b.brow == brow && b.bcol == bcol) return &b;
@@ -301,7 +367,28 @@ static int launch_bilinear(femb_ctx* ctx, int er, int ec, int op_r, int op_c, in
     a.cpb = cpb;
     size_t smem = cpb * (per_cell + geo_bytes);
     FEMB_TRY(femb_flush_zero(ctx, true, false));
-    auto kern = ctx->dim == 2 ? k_bilinear<2> : k_bilinear<3>;
+    void (*kern)(BilArgs) = ctx->dim == 2 ? k_bilinear<2> : k_bilinear<3>;
+    // row-blocked kernel for the common (dim, nqp, R) combinations: one thread per (cell, row dof)
+    void (*rows)(BilArgs) = nullptr;
+    const int key = ctx->dim * 10000 + a.nqp * 100 + a.R;
+    switch (key) {
+        case 20301: rows = k_bilinear_rows<2, 3, 1>; break;   // 2-D order-2 rule: divergences, P0
+        case 20302: rows = k_bilinear_rows<2, 3, 2>; break;   // 2-D Hdiv mass, P2 gradients
+        case 20901: rows = k_bilinear_rows<2, 9, 1>; break;   // Example210 div-pressure (9-point Stroud rule)
+        case 20902: rows = k_bilinear_rows<2, 9, 2>; break;   // P3 / Pk gradients in 2-D
+        case 30401: rows = k_bilinear_rows<3, 4, 1>; break;   // 3-D order-2 rule: divergences, P0
+        case 30403: rows = k_bilinear_rows<3, 4, 3>; break;   // 3-D Hdiv mass, P2 gradients
+        case 31103: rows = k_bilinear_rows<3, 11, 3>; break;  // P3 gradients on tetrahedra (11-point rule)
+        default: break;
+    }
+    if (rows && rs.nd <= 64) {
+        kern = rows;
+        cpb = std::max(1, 128 / rs.nd);
+        per_cell = (size_t)a.nqp * a.R * cs.nd * sizeof(double);
+        cpb = (int)std::min<size_t>(cpb, (96 * 1024) / (per_cell + geo_bytes));
+        a.cpb = cpb;
+        smem = cpb * (per_cell + geo_bytes);
+    }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (ctx->scatter == FEMB_SCATTER_COLORED) {
         FEMB_TRY(femb_build_coloring(ctx));
@@ -380,6 +467,64 @@ __global__ void __launch_bounds__(128) k_linear_gather(const double* __restrict_
     b[d] += factor * sum;
 }
 
+// Identity rhs of H1 / L2 spaces in two passes: the (possibly expensive) data f(x_q) is evaluated ONCE per cell and
+// quadrature point instead of once per (dof, cell) pair, then gathered per dof in a fixed order (write-once).
+template <int DIM>
+__global__ void __launch_bounds__(128) k_cell_rhs(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
+                                                  int64_t ncells, QuadDev q, RhsDev rhs, double factor, double* __restrict__ out) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cell >= ncells) return;
+    double xn[DIM + 1][DIM], A[DIM][DIM];
+    load_nodes<DIM>(coords, cellnodes, cell, xn);
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+#pragma unroll
+        for (int i = 0; i < DIM; i++) A[d][i] = xn[i + 1][d] - xn[0][d];
+    double vol;
+    if (cellvol) {
+        vol = __ldg(cellvol + cell);
+    } else if (DIM == 2) {
+        vol = fabs(A[0][0] * A[1][1] - A[0][1] * A[1][0]) * 0.5;
+    } else {
+        vol = fabs(A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) + A[0][1] * (A[1][2] * A[2][0] - A[1][0] * A[2][2]) +
+                   A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0])) * (1.0 / 6.0);
+    }
+    for (int qp = 0; qp < q.nqp; qp++) {
+        double x[DIM], f[3];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            double sx = xn[0][d];
+#pragma unroll
+            for (int i = 0; i < DIM; i++) sx += A[d][i] * q.xref[qp * DIM + i];
+            x[d] = sx;
+        }
+        eval_rhs<DIM>(rhs, x, cell, qp, q.nqp, f);
+        for (int c = 0; c < rhs.ncomp; c++) out[((size_t)cell * q.nqp + qp) * rhs.ncomp + c] = f[c] * (q.w[qp] * vol * factor);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_linear_gather_id(SpaceDev s, int nqp, int ncomp, const double* __restrict__ rv, const double* __restrict__ F,
+                                                          const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj, int64_t ndofs, double* __restrict__ b) {
+    const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= ndofs) return;
+    double sum = 0.0;
+    for (int32_t e = adj_ptr[d]; e < adj_ptr[d + 1]; e++) {
+        const uint32_t av = adj[e];
+        const int64_t cell = av / (uint32_t)s.nd;
+        const int k = (int)(av - cell * s.nd);
+        const int sub = subset_of(s, cell, k);
+        const double* Fc = F + (size_t)cell * nqp * ncomp;
+        double t = 0.0;
+        for (int qp = 0; qp < nqp; qp++)
+            for (int c = 0; c < ncomp; c++) {
+                const double phi = __ldg(rv + ((size_t)qp * s.nd_all + sub) * ncomp + c);
+                if (phi != 0.0) t += phi * __ldg(Fc + qp * ncomp + c);  // component-blocked bases: most entries are exact zeros
+            }
+        sum += t;
+    }
+    b[d] += sum;
+}
+
 static int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const RhsDev& rhs) {
     const FembEval& E = ctx->evals[ev];
     const FembSpace& s = ctx->spaces[E.space];
@@ -390,6 +535,21 @@ static int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const R
     unsigned grid = (unsigned)((s.ndofs + 127) / 128);
     QuadDev q = quad_dev(E, ctx->dim);
     const bool light = s.family != FEMB_FAMILY_HDIV && E.op == FEMB_OP_IDENTITY;
+    if (light && E.refvals && ctx->ncells) {
+        const size_t need = (size_t)ctx->ncells * E.nqp * rhs.ncomp;
+        if (ctx->cellrhs_n < need) {
+            FEMB_TRY(femb_alloc(ctx, &ctx->cellrhs, need));
+            ctx->cellrhs_n = need;
+        }
+        const unsigned gc = (unsigned)((ctx->ncells + 127) / 128);
+        if (ctx->dim == 2) k_cell_rhs<2><<<gc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, q, rhs, factor, ctx->cellrhs);
+        else k_cell_rhs<3><<<gc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, q, rhs, factor, ctx->cellrhs);
+        KERNEL_CHECK(ctx);
+        k_linear_gather_id<<<grid, 128, 0, ctx->stream>>>(space_dev(s), E.nqp, rhs.ncomp, E.refvals, ctx->cellrhs, s.adj_ptr, s.adj, s.ndofs,
+                                                          ctx->bvec + ctx->row_off[brow]);
+        KERNEL_CHECK(ctx);
+        return FEMB_OK;
+    }
 #define FEMB_LIN(D, L)                                                                                                                          \
     k_linear_gather<D, L><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, E.resultdim, q, E.refvals, \
                                                          E.refderivs, s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow])

@@ -112,6 +112,8 @@ struct femb_ctx {
     int hmap_space = -1, hmap_words = 0;
     struct HRange { int64_t s0, s1; int maxlen; int split; };  // split: threads per column (1, or 4 for high-degree columns)
     std::vector<HRange> hranges;   // contiguous slice ranges with their longest CSC column (shared-memory sizing)
+    double* cellrhs = nullptr;     // [cell][qp][comp]: factor w_q |T| f(x_q), pre-pass of the Identity rhs gather
+    size_t cellrhs_n = 0;
     double* cellcoef = nullptr;    // [cell][FEMB_COEF_STRIDE]: Kc (3 / 6) then |T| f(x_q) per quadrature point (pre-pass of the gather)
 
     double* nzval = nullptr;      // nnz
