@@ -467,3 +467,51 @@ def test_empty_cell_range_and_unused_nodes():
     S = getattr(fes, "_femb_session_0")
     out = S.evaluator(0, "Gradient").update_basis_all(3, 3)
     assert out.shape[0] == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# the examples end to end (device assembly + host solve), as SURVEY.md §8(c) asks
+# ---------------------------------------------------------------------------------------------
+def _load_example(name):
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", name + ".py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_example200_solution_matches_oracle_solution():
+    """Example200 main loop: the Poisson solution from the device-assembled system equals the one from the oracle system"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    ex = _load_example("example200_lowlevel_poisson")
+    X = np.linspace(0, 1, 17)
+    grid = fb.simplexgrid(X, X)
+    ft = fb.H1Pk(1, 2, 2)
+    fes = fb.FESpace(ft, grid)
+    rhs = rhs_affine()
+    solution, _, _ = ex.solve_poisson_lowlevel(fes, 1.0, rhs)
+    (colptr, rowval, nzval, b), _ = _ex200_oracle(grid, ft, fes, 1.0, rhs)
+    M = sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(fes.ndofs,) * 2).tolil()
+    for d in fb.boundarydofs(fes):
+        M[d - 1, d - 1] = 1.0e60
+        b[d - 1] = 0.0
+    u = spla.spsolve(M.tocsc(), b)
+    assert np.abs(solution.entries - u).max() <= 1e-10 * max(np.abs(u).max(), 1e-300)
+    assert np.abs(u).max() > 1e-4  # non-trivial solution
+
+
+def test_example210_newton_converges():
+    """Example210: Newton iteration on the device-assembled Taylor-Hood system reaches the reference's stopping criterion
+    (nonlinear residual < max(1e-12, 20 linres), Example210:207-209) and the discrete solution approximates the exact one"""
+    ex = _load_example("example210_lowlevel_navierstokes")
+    errs = []
+    for nref in (3, 4):
+        sol, nlres, its, err = ex.main(nref=nref)
+        assert its <= 12 and nlres < 1e-8
+        errs.append(err)
+    assert errs[1] < errs[0] / 4  # at least second-order decay of the nodal velocity error under refinement
