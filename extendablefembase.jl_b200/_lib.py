@@ -288,7 +288,7 @@ class Context:
         """Streamed host-to-host assembly (H2D / kernel / D2H overlap); arrays must be C-contiguous of the right dtype."""
         data = _arr(data, np.float64)
         for a, dt in ((coords, np.float64), (cellnodes, np.int32), (nzval_out, np.float64)):
-            assert a.dtype == dt and a.flags.c_contiguous
+            assert a is None or (a.dtype == dt and a.flags.c_contiguous)
         self._ck(self.lib.femb_assemble_poisson_host(self.h, eg, ei, mu, rhs_kind, _ptr(data), drop_tol, _ptr(coords), _ptr(cellnodes), _ptr(cellvolumes),
                                                      _ptr(nzval_out), _ptr(b_out), nchunks))
 

@@ -2042,7 +2042,7 @@ extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t
     FEMB_TRY(check_eval(ctx, eg));
     if (rhs_kind != FEMB_RHS_NONE) FEMB_TRY(check_eval(ctx, ei));
     FEMB_TRY(require_pattern(ctx));
-    if (!coords || !cellnodes || !nzval_out || (rhs_kind != FEMB_RHS_NONE && !b_out)) return femb_fail(ctx, FEMB_ERR_ARG, "femb_assemble_poisson_host: NULL buffer");
+    if (!coords || !nzval_out || (rhs_kind != FEMB_RHS_NONE && !b_out)) return femb_fail(ctx, FEMB_ERR_ARG, "femb_assemble_poisson_host: NULL buffer");
     if ((cellvol != nullptr) != (ctx->cellvol != nullptr)) return femb_fail(ctx, FEMB_ERR_ARG, "cellvolumes must be given iff the registered mesh has them");
     const FembEval& EG = ctx->evals[eg];
     if (EG.op != FEMB_OP_GRADIENT) return femb_fail(ctx, FEMB_ERR_ARG, "eval_grad must be a Gradient evaluator");
@@ -2091,7 +2091,8 @@ extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coords + hi_n * dim, coords + hi_n * dim, sizeof(double) * (ctx->nnodes - hi_n) * dim, cudaMemcpyHostToDevice, ctx->stream_h2d));
     if (cellvol && ctx->ncells > hi_c)
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellvol + hi_c, cellvol + hi_c, sizeof(double) * (ctx->ncells - hi_c), cudaMemcpyHostToDevice, ctx->stream_h2d));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellnodes, cellnodes, sizeof(int32_t) * ctx->ncells * ctx->nnpc, cudaMemcpyHostToDevice, ctx->stream_h2d));
+    if (cellnodes)  // NULL: topology unchanged since femb_mesh_set (it is what the reused pattern was built from)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellnodes, cellnodes, sizeof(int32_t) * ctx->ncells * ctx->nnpc, cudaMemcpyHostToDevice, ctx->stream_h2d));
     int st = femb_timer_end(ctx);
     cudaError_t e1 = cudaStreamSynchronize(ctx->stream_h2d), e2 = cudaStreamSynchronize(ctx->stream_d2h);
     cudaFree(dev_f);

@@ -184,7 +184,8 @@ int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id,
  * and download of the finished nzval / b ranges overlap.  Equivalent to femb_mesh_set (same shapes: the symbolic
  * phase is reused) + femb_matrix_zero + femb_vector_zero + femb_assemble_poisson + femb_matrix_get +
  * femb_vector_get, bit for bit.  Scalar P1 with rhs_kind NONE / AFFINE; pin the host arrays with
- * femb_host_register for the copies to overlap.  cellvol must be given iff the registered mesh has volumes. */
+ * femb_host_register for the copies to overlap.  cellvol must be given iff the registered mesh has volumes;
+ * cellnodes may be NULL (connectivity unchanged — the numeric phase reads the geometry only). */
 int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id, double mu, int32_t rhs_kind, const double* params,
                                    double drop_tol, const double* coords, const int32_t* cellnodes, const double* cellvolumes_or_null,
                                    double* nzval_out, double* b_out, int32_t nchunks);
