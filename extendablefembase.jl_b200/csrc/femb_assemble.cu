@@ -592,6 +592,7 @@ struct P1Args {
     int acc_A, acc_b;
     int maxlen;  // longest CSC column: shared-memory row `maxlen` is the dump row of the 2-D kernel
     int64_t slice_begin, slice_end;  // slices [begin, end) handled by this launch (chunked / streamed assembly)
+    int maxrows;  // longest slice of the gather map; > 0 selects the staged variant (entries copied to shared memory with cp.async)
 };
 
 #define FEMB_P1_MAXQP 8
@@ -621,6 +622,62 @@ __device__ __forceinline__ double lds64(unsigned addr) {
 }
 __device__ __forceinline__ void sts64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
+// one visit of the 2-D P1 gather: column k of the cell's local stiffness matrix (+ rhs) into the accumulators
+template <bool TRACK, int RHS, bool HAS_VOL, int NQP>
+__device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, const double2 self, const double2 pa, const double2 pb, const double volr,
+                                         const P1Tab2& tab, const RhsDev& rhs, const double drop_tol, const double mu_wsum, const unsigned sacc,
+                                         double& diag, unsigned& dpos, unsigned& err, unsigned long long& mask, double& bsum) {
+    constexpr unsigned nt = 128;
+    const unsigned k = w & 3u;
+    const double uax = pb.x - self.x, uay = pb.y - self.y;
+    const double ubx = self.x - pa.x, uby = self.y - pa.y;
+    const double usx = pa.x - pb.x, usy = pa.y - pb.y;
+    const double px = (k == 0u) ? uax : usx, py = (k == 0u) ? uay : usy;
+    const double det = px * uby - py * ubx;
+    const double vol = HAS_VOL ? volr : fabs(det) * 0.5;
+    const double scale = (mu_wsum * vol) * rcp_newton(det * det);
+    const double vs = (usx * usx + usy * usy) * scale;
+    const double va = (uax * usx + uay * usy) * scale;
+    const double vb = (ubx * usx + uby * usy) * scale;
+    const unsigned ps = (w >> 8) & 0xFFu, pA = (w >> 16) & 0xFFu, pB = w >> 24;
+    const bool ks = fabs(vs) > drop_tol, ka = fabs(va) > drop_tol, kb = fabs(vb) > drop_tol;
+    err |= (unsigned)((ks && ps == 0xFFu) || (ka && pA == 0xFFu) || (kb && pB == 0xFFu));
+    // diagonal A[c,c]: the same slot on every visit -> a register; off-diagonals: shared-memory rows.  The
+    // branches are warp-uniform on structured meshes (same filtered edge in every lane) and cheap otherwise.
+    if (ks && ps != 0xFFu) {
+        diag += vs;
+        dpos = ps;
+    }
+    if (ka && pA != 0xFFu) {
+        const unsigned ad = sacc + pA * (nt * 8u);
+        sts64(ad, lds64(ad) + va);
+        if (TRACK) mask |= 1ull << (pA & 63u);
+    }
+    if (kb && pB != 0xFFu) {
+        const unsigned ad = sacc + pB * (nt * 8u);
+        sts64(ad, lds64(ad) + vb);
+        if (TRACK) mask |= 1ull << (pB & 63u);
+    }
+    if (RHS != FEMB_RHS_NONE) {
+        double temp = 0.0;
+        const int nqp = NQP ? NQP : tab.nqp;
+#pragma unroll
+        for (int qp = 0; qp < nqp; qp++) {
+            const double* t = tab.t[k][qp];
+            double f;
+            if (RHS == FEMB_RHS_AFFINE) {  // f(x_qp); x_qp = sum_j phi_j(xref_qp) x_j  (= A xref_qp + x_1, eval_trafo!, Example200:171)
+                const double xq = t[1] * self.x + t[2] * pa.x + t[3] * pb.x;
+                const double yq = t[1] * self.y + t[2] * pa.y + t[3] * pb.y;
+                f = rhs.p[0] + rhs.p[1] * xq + rhs.p[2] * yq;
+            } else {
+                f = __ldg(rhs.fvals + (size_t)cell * nqp + qp);
+            }
+            temp += t[0] * f;
+        }
+        bsum += temp * vol;
+    }
+    }
+
 // ---- 2-D scalar P1, the headline kernel ------------------------------------------------------------------------
 // Fused stages 1-5 (Example200:133-179), owner-computes by matrix column: one thread per column c (= dof = node),
 // one warp per slice of the sliced-ELL gather map (femb_pattern.cu), streamed with fully coalesced loads.  Every
@@ -637,11 +694,14 @@ __device__ __forceinline__ void sts64(unsigned addr, double v) { asm volatile("s
 //  * software pipeline: the gather-map entry two visits ahead and the coordinates / volume of the next visit are
 //    in flight while the current visit is computed;
 //  * accumulation is branch-free: filtered (|v| <= drop_tol, Example200:153) contributions go to a dump row.
-template <bool TRACK, int RHS, bool HAS_VOL, int NQP, int MINB = 8>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
+//  * STAGE: the slice's gather-map entries (all visits) are copied to shared memory with cp.async (LDGSTS) at the very
+//    start, so the streamed part of the input arrives in ONE memory latency instead of one per visit and costs no
+//    registers; only the coordinate / volume loads of the next visit stay in a register pipeline.
+template <bool TRACK, int RHS, bool HAS_VOL, int NQP, bool STAGE, int MINB = 8>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
 __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
     constexpr unsigned nt = 128;
     constexpr bool NEED_CELL = HAS_VOL || RHS == FEMB_RHS_QPVALUES;
-    extern __shared__ double acc[];  // [maxlen + 1][128]
+    extern __shared__ double acc[];  // [maxlen + 1][128], then (STAGE) u32 [4 warps][4 planes][maxrows][32]
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + (tid >> 5);
     if (slice >= a.slice_end) return;  // whole warp out of range
@@ -666,6 +726,46 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
 
     const uint32_t* __restrict__ ga = a.gmap + ((size_t)row0 << 5) + lane;
     const size_t gs = a.gstride;
+    if (STAGE) {
+        const unsigned sst = (unsigned)__cvta_generic_to_shared(acc + (size_t)(a.maxlen + 1) * nt) + ((tid >> 5) * 4u * (unsigned)a.maxrows * 32u + lane) * 4u;
+        const unsigned pst = (unsigned)a.maxrows * 128u;  // plane stride in bytes
+        for (int r = 0; r < nrows; r++) {
+            const uint32_t* g = ga + ((size_t)r << 5);
+            const unsigned d = sst + (unsigned)r * 128u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + pst), "l"(g + gs) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 2u * pst), "l"(g + 2 * gs) : "memory");
+            if (NEED_CELL) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 3u * pst), "l"(g + 3 * gs) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        auto lds32 = [](unsigned addr) {
+            unsigned v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+            return v;
+        };
+        double2 pa1 = make_double2(0.0, 0.0), pb1 = pa1;
+        double vol1 = 0.0;
+        if (nrows > 0) {
+            pa1 = __ldg(xy + lds32(sst));
+            pb1 = __ldg(xy + lds32(sst + pst));
+            if (HAS_VOL) vol1 = __ldg(a.cellvol + lds32(sst + 3u * pst));
+        }
+        for (int r = 0; r < nrows; r++) {
+            const unsigned d = sst + (unsigned)r * 128u;
+            const unsigned w = lds32(d + 2u * pst);
+            const unsigned cell = NEED_CELL ? lds32(d + 3u * pst) : 0u;
+            const double2 pa = pa1, pb = pb1;
+            const double volr = vol1;
+            if (r + 1 < nrows) {  // coordinates / volume of the next visit
+                pa1 = __ldg(xy + lds32(d + 128u));
+                pb1 = __ldg(xy + lds32(d + 128u + pst));
+                if (HAS_VOL) vol1 = __ldg(a.cellvol + lds32(d + 128u + 3u * pst));
+            }
+            if (w == 0xFFFFFFFFu) continue;
+            p1_visit<TRACK, RHS, HAS_VOL, NQP>(w, cell, self, pa, pb, volr, tab, rhs, drop_tol, mu_wsum, sacc, diag, dpos, err, mask, bsum);
+        }
+    } else {
 #if FEMB_P1_PIPE == 1
     // shallow pipeline: only the next visit's entry is in flight; coordinates are loaded at the top of the visit
     unsigned w1 = 0xFFFFFFFFu, a1 = 0u, b1 = 0u, c1 = 0u;
@@ -715,54 +815,8 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
         if (HAS_VOL) vol1 = __ldg(a.cellvol + c1);
 #endif
         if (w == 0xFFFFFFFFu) continue;
-        const unsigned k = w & 3u;
-        const double uax = pb.x - self.x, uay = pb.y - self.y;
-        const double ubx = self.x - pa.x, uby = self.y - pa.y;
-        const double usx = pa.x - pb.x, usy = pa.y - pb.y;
-        const double px = (k == 0u) ? uax : usx, py = (k == 0u) ? uay : usy;
-        const double det = px * uby - py * ubx;
-        const double vol = HAS_VOL ? volr : fabs(det) * 0.5;
-        const double scale = (mu_wsum * vol) * rcp_newton(det * det);
-        const double vs = (usx * usx + usy * usy) * scale;
-        const double va = (uax * usx + uay * usy) * scale;
-        const double vb = (ubx * usx + uby * usy) * scale;
-        const unsigned ps = (w >> 8) & 0xFFu, pA = (w >> 16) & 0xFFu, pB = w >> 24;
-        const bool ks = fabs(vs) > drop_tol, ka = fabs(va) > drop_tol, kb = fabs(vb) > drop_tol;
-        err |= (unsigned)((ks && ps == 0xFFu) || (ka && pA == 0xFFu) || (kb && pB == 0xFFu));
-        // diagonal A[c,c]: the same slot on every visit -> a register; off-diagonals: shared-memory rows.  The
-        // branches are warp-uniform on structured meshes (same filtered edge in every lane) and cheap otherwise.
-        if (ks && ps != 0xFFu) {
-            diag += vs;
-            dpos = ps;
-        }
-        if (ka && pA != 0xFFu) {
-            const unsigned ad = sacc + pA * (nt * 8u);
-            sts64(ad, lds64(ad) + va);
-            if (TRACK) mask |= 1ull << (pA & 63u);
-        }
-        if (kb && pB != 0xFFu) {
-            const unsigned ad = sacc + pB * (nt * 8u);
-            sts64(ad, lds64(ad) + vb);
-            if (TRACK) mask |= 1ull << (pB & 63u);
-        }
-        if (RHS != FEMB_RHS_NONE) {
-            double temp = 0.0;
-            const int nqp = NQP ? NQP : tab.nqp;
-#pragma unroll
-            for (int qp = 0; qp < nqp; qp++) {
-                const double* t = tab.t[k][qp];
-                double f;
-                if (RHS == FEMB_RHS_AFFINE) {  // f(x_qp); x_qp = sum_j phi_j(xref_qp) x_j  (= A xref_qp + x_1, eval_trafo!, Example200:171)
-                    const double xq = t[1] * self.x + t[2] * pa.x + t[3] * pb.x;
-                    const double yq = t[1] * self.y + t[2] * pa.y + t[3] * pb.y;
-                    f = rhs.p[0] + rhs.p[1] * xq + rhs.p[2] * yq;
-                } else {
-                    f = __ldg(rhs.fvals + (size_t)cell * nqp + qp);
-                }
-                temp += t[0] * f;
-            }
-            bsum += temp * vol;
-        }
+        p1_visit<TRACK, RHS, HAS_VOL, NQP>(w, cell, self, pa, pb, volr, tab, rhs, drop_tol, mu_wsum, sacc, diag, dpos, err, mask, bsum);
+    }
     }
     if (!valid) return;
     if (err) atomicAdd(a.errflag, 1);
@@ -981,6 +1035,7 @@ static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const Rhs
     ctx->zero_pending_A = false;
     if (rhs.kind != FEMB_RHS_NONE) ctx->zero_pending_b = false;
     a.maxlen = std::max(1, ctx->max_collen);
+    a.maxrows = 0;
     L.nslices = (s.ndofs + 31) / 32;
     a.slice_begin = 0;
     a.slice_end = L.nslices;
@@ -1006,6 +1061,10 @@ static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const Rhs
                 t2.t[k][q][3] = lam[others[k][1]];
             }
         L.smem = (size_t)(a.maxlen + 1) * 128 * sizeof(double);
+        // staged variant: + u32 [4 warps][4 planes][maxrows][32] for the slice's gather-map entries
+        static const int stage_env = getenv("FEMB_P1_STAGE") ? atoi(getenv("FEMB_P1_STAGE")) : 1;
+        a.maxrows = (stage_env && ctx->gmap_maxrows > 0 && ctx->gmap_maxrows <= 12) ? ctx->gmap_maxrows : 0;
+        L.smem += (size_t)a.maxrows * 4 * 4 * 32 * sizeof(uint32_t);
     }
     return FEMB_OK;
 }
@@ -1022,10 +1081,15 @@ static int launch_p1_slices(femb_ctx* ctx, P1Launch& L, int64_t s0, int64_t s1, 
         const P1Tab2& t2 = L.t2;
         const RhsDev& rhs = L.rhs;
         const bool track = a.touched != nullptr, hv = a.cellvol != nullptr;
-#define FEMB_P1_LAUNCH2Q(T, R, V, Q)                                                                                                  \
-    do {                                                                                                                              \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather2d<T, R, V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_p1_poisson_gather2d<T, R, V, Q><<<grid, 128, smem, stream>>>(a, rhs, t2);                                                    \
+#define FEMB_P1_LAUNCH2S(T, R, V, Q, S)                                                                                                  \
+    do {                                                                                                                                 \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather2d<T, R, V, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_p1_poisson_gather2d<T, R, V, Q, S><<<grid, 128, smem, stream>>>(a, rhs, t2);                                                    \
+    } while (0)
+#define FEMB_P1_LAUNCH2Q(T, R, V, Q)                     \
+    do {                                                 \
+        if (a.maxrows > 0) FEMB_P1_LAUNCH2S(T, R, V, Q, true); \
+        else FEMB_P1_LAUNCH2S(T, R, V, Q, false);        \
     } while (0)
 #define FEMB_P1_LAUNCH2(T, R, V)                 \
     do {                                         \
@@ -1045,6 +1109,7 @@ static int launch_p1_slices(femb_ctx* ctx, P1Launch& L, int64_t s0, int64_t s1, 
 #undef FEMB_P1_LAUNCH2_R
 #undef FEMB_P1_LAUNCH2
 #undef FEMB_P1_LAUNCH2Q
+#undef FEMB_P1_LAUNCH2S
         KERNEL_CHECK(ctx);
         return FEMB_OK;
     }

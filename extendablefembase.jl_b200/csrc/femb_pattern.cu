@@ -670,14 +670,25 @@ int femb_build_gmap(femb_ctx* ctx) {
     cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, ctx->gslice_ptr, nslices + 1, ctx->stream);
     cudaError_t e = cudaMalloc(&tmp, tb);
     if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, deg, ctx->gslice_ptr, nslices + 1, ctx->stream);
-    int32_t rows = 0;
+    int32_t rows = 0, maxrows = 0;
+    int32_t* d_max = nullptr;
+    void* tmp2 = nullptr;
+    size_t tb2 = 0;
+    if (e == cudaSuccess) e = cudaMalloc(&d_max, sizeof(int32_t));
+    if (e == cudaSuccess) e = cub::DeviceReduce::Max(nullptr, tb2, deg, d_max, nslices, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp2, tb2);
+    if (e == cudaSuccess) e = cub::DeviceReduce::Max(tmp2, tb2, deg, d_max, nslices, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&maxrows, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&rows, ctx->gslice_ptr + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(tmp);
+    cudaFree(tmp2);
+    cudaFree(d_max);
     cudaFree(deg);
-    ctx->launches += 2;
+    ctx->launches += 3;
     CUDA_TRY(ctx, e);
     ctx->gmap_rows = rows;
+    ctx->gmap_maxrows = maxrows;
     ctx->gmap_stride = (size_t)rows * 32;
     FEMB_TRY(femb_alloc(ctx, &ctx->gmap, ctx->gmap_stride * (s.nd == 4 ? 5 : 4)));
     unsigned grid = (unsigned)((nslices * 32 + 127) / 128);
