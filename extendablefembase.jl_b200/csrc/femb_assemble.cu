@@ -593,12 +593,15 @@ struct P1Args {
     int maxlen;  // longest CSC column: shared-memory row `maxlen` is the dump row of the 2-D kernel
     int64_t slice_begin, slice_end;  // slices [begin, end) handled by this launch (chunked / streamed assembly)
     int maxrows;  // longest slice of the gather map; > 0 selects the staged variant (entries copied to shared memory with cp.async)
+    int uniform_rows;  // > 0: every slice has exactly this many rows (row0 = slice * uniform_rows)
 };
 
 #define FEMB_P1_MAXQP 8
 #ifndef FEMB_P1_PIPE
 #define FEMB_P1_PIPE 2  // software-pipeline depth of the 2-D gather kernel (1: entries only, 2: entries + coordinates).
 // Measured on B200 (32M triangles): depth 2 @ 62 regs / 8 CTAs per SM = depth 1 @ 48 regs / 10 CTAs = 0.77 ms; spilling variants are slower.
+// The staged variant (entries via cp.async into shared memory) runs 0.69 ms; a multi-slice, double-buffered variant of it
+// (2 or 4 slices per warp, next slice staged during the current one) measured 0.89-0.91 ms and was dropped.
 #endif
 struct P1Tab2 {
     int nqp;
@@ -697,7 +700,10 @@ __device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, 
 //  * STAGE: the slice's gather-map entries (all visits) are copied to shared memory with cp.async (LDGSTS) at the very
 //    start, so the streamed part of the input arrives in ONE memory latency instead of one per visit and costs no
 //    registers; only the coordinate / volume loads of the next visit stay in a register pipeline.
-template <bool TRACK, int RHS, bool HAS_VOL, int NQP, bool STAGE, int MINB = 8>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
+#ifndef FEMB_P1_MINB
+#define FEMB_P1_MINB 8  // resident CTAs per SM the 2-D gather kernel is compiled for (register cap 65536 / (128 * MINB))
+#endif
+template <bool TRACK, int RHS, bool HAS_VOL, int NQP, bool STAGE, int MINB = FEMB_P1_MINB>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
 __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
     constexpr unsigned nt = 128;
     constexpr bool NEED_CELL = HAS_VOL || RHS == FEMB_RHS_QPVALUES;
@@ -707,7 +713,14 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
     if (slice >= a.slice_end) return;  // whole warp out of range
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
-    const int row0 = __ldg(a.gslice_ptr + slice), nrows = __ldg(a.gslice_ptr + slice + 1) - row0;
+    int row0, nrows;
+    if (a.uniform_rows > 0) {
+        row0 = (int)slice * a.uniform_rows;
+        nrows = a.uniform_rows;
+    } else {
+        row0 = __ldg(a.gslice_ptr + slice);
+        nrows = __ldg(a.gslice_ptr + slice + 1) - row0;
+    }
     const double2* __restrict__ xy = reinterpret_cast<const double2*>(a.coords);
     int64_t base = 0;
     int len = 0;
@@ -1036,6 +1049,7 @@ static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const Rhs
     if (rhs.kind != FEMB_RHS_NONE) ctx->zero_pending_b = false;
     a.maxlen = std::max(1, ctx->max_collen);
     a.maxrows = 0;
+    a.uniform_rows = ctx->gmap_uniform ? ctx->gmap_maxrows : 0;
     L.nslices = (s.ndofs + 31) / 32;
     a.slice_begin = 0;
     a.slice_end = L.nslices;

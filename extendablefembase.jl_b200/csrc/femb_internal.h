@@ -102,6 +102,7 @@ struct femb_ctx {
     size_t gmap_stride = 0;
     int32_t* gslice_ptr = nullptr;   // nslices + 1 row offsets
     int64_t gmap_rows = 0;
+    bool gmap_uniform = false;       // every slice padded to gmap_maxrows rows (row0 = slice * maxrows, no indirection)
     int gmap_maxrows = 0;            // longest slice (rows) = largest number of cells around a dof
     int gmap_space = -1;
     // general scalar-H1 gather map (P2, ...; femb_pattern.cu): sliced ELL over (dof, adjacent cell) pairs, SoA planes
