@@ -206,7 +206,7 @@ def prepare_assembly(A: FEMatrix, b: FEVector, FESu, FESp, sol: FEVector, *, tev
 # --------------------------------------------------------------------------------------
 # Hdiv mixed blocks (config C4): mass (v,w) and divergence (div v, q) against L2P0
 # --------------------------------------------------------------------------------------
-def assemble_hdiv_mixed(A: FEMatrix, FESv, FESq, *, device=0):
+def assemble_hdiv_mixed(A: FEMatrix, FESv, FESq, *, device=0, scatter=None):
     """``A[1,1] += (v_i, v_j)``, ``A[1,2] += (div v_i, q_k)`` and its transpose in ``A[2,1]``, with
     contravariant-Piola evaluators (feevaluator_hdiv.jl:2-19,66-83) and the 4-point (3-D) /
     3-point (2-D) order-2 rule."""
@@ -215,6 +215,8 @@ def assemble_hdiv_mixed(A: FEMatrix, FESv, FESq, *, device=0):
     qf = QuadratureRule(g, 2)
     S = _session_for([FESv, FESq], qf, device)
     ctx = S.ctx
+    if scatter is not None:
+        ctx.set_scatter(scatter)
     eid, ediv, eq = S.evaluator(0, Identity), S.evaluator(0, Divergence), S.evaluator(1, Identity)
     fresh = S.ensure_pattern(Ae, [(0, 0), (0, 1), (1, 0)])
     if fresh:

@@ -550,9 +550,6 @@ int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const RhsDev& 
     return FEMB_OK;
 }
 
-int femb_build_coloring(femb_ctx* ctx) {
-    return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "FEMB_SCATTER_COLORED is not built yet; use FEMB_SCATTER_ATOMIC or FEMB_SCATTER_GATHER");
-}
 
 // ---------------------------------------------------------------------------------------------------
 // C ABI entry points

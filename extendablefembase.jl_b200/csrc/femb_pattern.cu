@@ -588,6 +588,11 @@ int femb_build_slotmaps(femb_ctx* ctx) {
 // cell ids 0 (so that unconditional prefetches stay in bounds).
 #define FEMB_GMAP_INVALID 0xFFFFFFFFu
 
+__global__ void k_iota_i32(int32_t* __restrict__ p, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+
 __global__ void k_fill_i32(int32_t* __restrict__ p, int64_t n, int32_t v) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -856,5 +861,132 @@ int femb_build_hmap(femb_ctx* ctx) {
                                                                             ctx->hslice_ptr, ctx->hmap, ctx->hmap_stride);
     KERNEL_CHECK(ctx);
     ctx->hmap_space = sid;
+    return FEMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cell colouring (FEMB_SCATTER_COLORED): no two cells of one colour share a dof of any space in the matrix layout, so a
+// colour can be scattered with plain read-modify-writes; colours are processed in order => bit-reproducible sums.
+// Jones-Plassmann rounds on the device: an uncoloured cell takes the smallest colour not used by its neighbours as soon
+// as it has the highest priority (hash of the cell id) among its uncoloured neighbours.  Deterministic: the result
+// depends only on the mesh.
+// ---------------------------------------------------------------------------------------------------
+struct ColorSpaces {
+    int n;
+    const int32_t* celldofs[2 * FEMB_MAX_SPACES];
+    const int32_t* adj_ptr[2 * FEMB_MAX_SPACES];
+    const uint32_t* adj[2 * FEMB_MAX_SPACES];
+    int nd[2 * FEMB_MAX_SPACES];
+};
+
+__device__ __forceinline__ uint32_t cell_prio(uint32_t c) {
+    uint32_t h = c * 2654435761u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    return h;
+}
+
+__global__ void k_color_round(ColorSpaces sp, int64_t ncells, int32_t* __restrict__ color, int* __restrict__ remaining, int* __restrict__ overflow) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ncells || color[c] >= 0) return;
+    const uint32_t pc = cell_prio((uint32_t)c);
+    unsigned long long used[4] = {0ull, 0ull, 0ull, 0ull};  // colours 0..255
+    bool blocked = false;
+    for (int s = 0; s < sp.n && !blocked; s++) {
+        const int nd = sp.nd[s];
+        for (int j = 0; j < nd && !blocked; j++) {
+            const int32_t dof = sp.celldofs[s][c * nd + j] - 1;
+            for (int32_t e = sp.adj_ptr[s][dof]; e < sp.adj_ptr[s][dof + 1]; e++) {
+                const uint32_t n = sp.adj[s][e] / (uint32_t)nd;
+                if (n == (uint32_t)c) continue;
+                const int32_t cn = color[n];
+                if (cn >= 0) {
+                    if (cn < 256) used[cn >> 6] |= 1ull << (cn & 63);
+                } else {
+                    const uint32_t pn = cell_prio(n);
+                    if (pn > pc || (pn == pc && n > (uint32_t)c)) {
+                        blocked = true;
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    if (blocked) {
+        atomicAdd(remaining, 1);
+        return;
+    }
+    int col = -1;
+    for (int w = 0; w < 4 && col < 0; w++)
+        if (~used[w]) col = w * 64 + __ffsll((long long)~used[w]) - 1;
+    if (col < 0) {
+        atomicExch(overflow, 1);
+        col = 255;
+    }
+    color[c] = col;
+}
+
+int femb_build_coloring(femb_ctx* ctx) {
+    if (ctx->color_perm) return FEMB_OK;
+    if (ctx->ncells == 0) {
+        ctx->ncolors = 0;
+        ctx->color_ptr.assign(1, 0);
+        return FEMB_OK;
+    }
+    ColorSpaces sp;
+    sp.n = 0;
+    bool seen[FEMB_MAX_SPACES] = {false};
+    for (int pass = 0; pass < 2; pass++)
+        for (int i = 0; i < (pass ? ctx->ncs : ctx->nrs); i++) {
+            const int sid = pass ? ctx->col_spaces[i] : ctx->row_spaces[i];
+            if (seen[sid]) continue;
+            seen[sid] = true;
+            FEMB_TRY(femb_build_adjacency(ctx, sid));
+            const FembSpace& s = ctx->spaces[sid];
+            sp.celldofs[sp.n] = s.celldofs; sp.adj_ptr[sp.n] = s.adj_ptr; sp.adj[sp.n] = s.adj; sp.nd[sp.n] = s.nd;
+            sp.n++;
+        }
+    int32_t *color = nullptr, *cells = nullptr, *color_sorted = nullptr;
+    int* flags = nullptr;
+    void* tmp = nullptr;
+    auto cleanup = [&]() { cudaFree(color); cudaFree(cells); cudaFree(color_sorted); cudaFree(flags); cudaFree(tmp); };
+#define TRY_K(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return femb_fail(ctx, FEMB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    const int64_t nc = ctx->ncells;
+    TRY_K(cudaMalloc(&color, nc * sizeof(int32_t)));
+    TRY_K(cudaMalloc(&flags, 2 * sizeof(int)));
+    TRY_K(cudaMemsetAsync(color, 0xFF, nc * sizeof(int32_t), ctx->stream));
+    TRY_K(cudaMemsetAsync(flags, 0, 2 * sizeof(int), ctx->stream));
+    int h[2] = {1, 0};
+    for (int round = 0; round < 4096 && h[0] > 0; round++) {
+        TRY_K(cudaMemsetAsync(flags, 0, sizeof(int), ctx->stream));
+        k_color_round<<<(unsigned)((nc + 127) / 128), 128, 0, ctx->stream>>>(sp, nc, color, flags, flags + 1);
+        ctx->launches++;
+        TRY_K(cudaMemcpyAsync(h, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        TRY_K(cudaStreamSynchronize(ctx->stream));
+    }
+    if (h[0] > 0 || h[1]) {
+        cleanup();
+        return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "cell colouring needs more than 256 colours (or did not converge)");
+    }
+    // perm = cells sorted by colour (stable: ascending cell id inside a colour)
+    TRY_K(cudaMalloc(&cells, nc * sizeof(int32_t)));
+    TRY_K(cudaMalloc(&color_sorted, nc * sizeof(int32_t)));
+    FEMB_TRY(femb_alloc(ctx, &ctx->color_perm, (size_t)nc));
+    k_iota_i32<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(cells, nc);
+    ctx->launches++;
+    size_t tb = 0;
+    TRY_K(cub::DeviceRadixSort::SortPairs(nullptr, tb, color, color_sorted, cells, ctx->color_perm, (int)nc, 0, 8, ctx->stream));
+    TRY_K(cudaMalloc(&tmp, tb));
+    TRY_K(cub::DeviceRadixSort::SortPairs(tmp, tb, color, color_sorted, cells, ctx->color_perm, (int)nc, 0, 8, ctx->stream));
+    std::vector<int32_t> hc((size_t)nc);
+    TRY_K(cudaMemcpyAsync(hc.data(), color_sorted, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY_K(cudaStreamSynchronize(ctx->stream));
+#undef TRY_K
+    cleanup();
+    ctx->ncolors = hc.back() + 1;
+    ctx->color_ptr.assign(ctx->ncolors + 1, 0);
+    for (int64_t i = 0; i < nc; i++) ctx->color_ptr[hc[i] + 1]++;
+    for (int c = 0; c < ctx->ncolors; c++) ctx->color_ptr[c + 1] += ctx->color_ptr[c];
     return FEMB_OK;
 }

@@ -515,3 +515,39 @@ def test_example210_newton_converges():
         assert its <= 12 and nlres < 1e-8
         errs.append(err)
     assert errs[1] < errs[0] / 4  # at least second-order decay of the nodal velocity error under refinement
+
+
+# ---------------------------------------------------------------------------------------------
+# FEMB_SCATTER_COLORED: cell colouring, plain read-modify-write per colour, bit-reproducible
+# ---------------------------------------------------------------------------------------------
+def test_colored_scatter_is_reproducible_and_correct():
+    import scipy.sparse as sp
+
+    # generic forms: Hdiv mass + divergence blocks (two spaces in the layout)
+    grid = _grid3d(4, True)
+    g = grid.geometry
+    runs = []
+    for _ in range(2):
+        FESv, FESq = fb.FESpace(fb.HDIVBDM1(3), grid), fb.FESpace(fb.L2P0(1), grid)
+        A = fb.FEMatrix([FESv, FESq])
+        fb.assemble_hdiv_mixed(A, FESv, FESq, scatter=_lib.SCATTER_COLORED)
+        runs.append(A.entries.nzval.copy())
+    assert np.array_equal(runs[0], runs[1])
+    FESv, FESq = fb.FESpace(fb.HDIVBDM1(3), grid), fb.FESpace(fb.L2P0(1), grid)
+    B = fb.FEMatrix([FESv, FESq])
+    fb.assemble_hdiv_mixed(B, FESv, FESq, scatter=_lib.SCATTER_ATOMIC)
+    assert np.abs(runs[0] - B.entries.nzval).max() <= RTOL * np.abs(runs[0]).max()
+    # Example200 with a P3 element (per-cell basis subsets -> generic kernel) and with P1 / P2 forced onto the coloured path
+    for ft, grid in ((fb.H1Pk(1, 2, 3), _grid2d(9, True)), (fb.H1Pk(1, 2, 1), _grid2d(14, True)), (fb.H1P2(1, 3), _grid3d(3, True))):
+        rhs = rhs_affine() if grid.dim == 2 else fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]])
+        outs = []
+        for _ in range(2):
+            fes = fb.FESpace(ft, grid)
+            A, bv = fb.FEMatrix(fes, fes), fb.FEVector(fes)
+            fb.assemble_poisson(A.entries, bv.entries, fes, rhs, 0.9, scatter=_lib.SCATTER_COLORED)
+            outs.append((A.entries.nzval.copy(), A.entries.rowval.copy()))
+        assert np.array_equal(outs[0][0], outs[1][0])
+        fes = fb.FESpace(ft, grid)
+        (colptr, rowval, nzval, b), _ = _ex200_oracle(grid, ft, fes, 0.9, rhs)
+        D = A.entries.to_scipy() - sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=A.entries.shape)
+        assert abs(D).max() <= RTOL * _local_scale(grid, ft, 0.9)
