@@ -307,6 +307,43 @@ __global__ void __launch_bounds__(128) k_cell_coef(const double* __restrict__ co
     for (int i = threadIdx.x; i < nloc * FEMB_COEF_STRIDE; i += 128) dst[i] = tile[i / FEMB_COEF_STRIDE][i % FEMB_COEF_STRIDE];
 }
 
+// 256-bit read-only load (sm_100: LDG.E.256).  A scattered 128-byte coefficient record costs one L1 tag look-up per
+// instruction and lane, and the L1 pipe is what bounds the gather: fewer, wider loads relieve it.
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// coefficient record of one cell (k_cell_coef): Kc[0..5], |T| f(x_q) at [6, 6 + NQ)
+template <int DIM, int KP, int NQ>
+__device__ __forceinline__ void load_coef(const double* __restrict__ cc, bool has_rhs, double (&kc)[KP], double (&f)[NQ]) {
+    if (DIM == 3 && NQ == 4) {
+        ldg256(cc, kc[0], kc[1], kc[2], kc[3]);
+        if (has_rhs) {
+            ldg256(cc + 4, kc[4], kc[5], f[0], f[1]);
+            const double2 fv = __ldg(reinterpret_cast<const double2*>(cc + 8));
+            f[2] = fv.x; f[3] = fv.y;
+        } else {
+            const double2 cv = __ldg(reinterpret_cast<const double2*>(cc + 4));
+            kc[4] = cv.x; kc[5] = cv.y;
+        }
+    } else {
+        if (DIM == 2) {
+            double unused;
+            ldg256(cc, kc[0], kc[1], kc[2], unused);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double2 cv = __ldg(reinterpret_cast<const double2*>(cc) + i);
+                kc[2 * i] = cv.x; kc[2 * i + 1] = cv.y;
+            }
+        }
+        if (has_rhs) {
+#pragma unroll
+            for (int qp = 0; qp < NQ; qp++) f[qp] = __ldg(cc + 6 + qp);
+        }
+    }
+}
+
 template <int DIM, int ND, int NQ>
 struct HTab {
     double D[NQ][DIM][ND];  // reference gradients d phi_j / d xref_a at xref_q
@@ -381,11 +418,9 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
     }
     double kc1[KP], f1[NQ];
     {
-        const double* cc = a.coef + (size_t)cell1 * FEMB_COEF_STRIDE;
 #pragma unroll
-        for (int i = 0; i < KP; i++) kc1[i] = __ldg(cc + i);
-#pragma unroll
-        for (int qp = 0; qp < NQ; qp++) f1[qp] = a.has_rhs ? __ldg(cc + 6 + qp) : 0.0;
+        for (int qp = 0; qp < NQ; qp++) f1[qp] = 0.0;
+        load_coef<DIM, KP, NQ>(a.coef + (size_t)cell1 * FEMB_COEF_STRIDE, a.has_rhs != 0, kc1, f1);
     }
     for (int it = 0; it < niter; it++) {
         const int r = it * SPLIT + rfirst;
@@ -412,23 +447,7 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
         } else {
             k2 = 0xFFFFFFFFu; cell2 = 0u;
         }
-        {
-            const double* cc = a.coef + (size_t)cell1 * FEMB_COEF_STRIDE;
-            if (DIM == 2) {
-                const double2 c01 = __ldg(reinterpret_cast<const double2*>(cc));
-                kc1[0] = c01.x; kc1[1] = c01.y; kc1[2] = __ldg(cc + 2);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    const double2 cv = __ldg(reinterpret_cast<const double2*>(cc) + i);
-                    kc1[2 * i] = cv.x; kc1[2 * i + 1] = cv.y;
-                }
-            }
-            if (a.has_rhs) {
-#pragma unroll
-                for (int qp = 0; qp < NQ; qp++) f1[qp] = __ldg(cc + 6 + qp);
-            }
-        }
+        load_coef<DIM, KP, NQ>(a.coef + (size_t)cell1 * FEMB_COEF_STRIDE, a.has_rhs != 0, kc1, f1);
         if (on) {
             double Km[DIM][DIM];  // symmetric Kmat from the coefficient order (00, 11, [22,] 01, [02, 12])
             if (DIM == 2) {
