@@ -19,6 +19,7 @@ OP_IDENTITY, OP_GRADIENT, OP_DIVERGENCE = 0, 1, 2
 RHS_NONE, RHS_AFFINE, RHS_QPVALUES, RHS_EX210 = 0, 1, 2, 3
 BIL_TRANSPOSE_COPY, BIL_SYMMETRIC_UPPER, BIL_NO_VOLUME = 1, 2, 4
 SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER = 0, 1, 2
+ENTITY_FACES, ENTITY_EDGES = 0, 1
 
 _i32, _i64, _f64 = C.c_int32, C.c_int64, C.c_double
 _p = C.c_void_p
@@ -34,6 +35,10 @@ SIGNATURES = {
     "femb_host_unregister": (_i32, [_p, _p]),
     "femb_mesh_set": (_i32, [_p, _i32, _i64, _p, _i32, _i64, _p, _p]),
     "femb_space_set": (_i32, [_p, _i32, _i32, _i32, _i64, _i32, _i32, _i32, _p, _p, _p]),
+    "femb_grid_entities": (_i32, [_p, _i32, C.POINTER(_i64)]),
+    "femb_grid_entities_get": (_i32, [_p, _i32, _p, _p, _p, _p, _p]),
+    "femb_space_set_from_pattern": (_i32, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "femb_space_get_celldofs": (_i32, [_p, _i32, _p]),
     "femb_quadrature_set": (_i32, [_p, _i32, _p, _p]),
     "femb_evaluator_set": (_i32, [_p, _i32, _i32, _i32, _p, _p]),
     "femb_evaluator_eval": (_i32, [_p, _i32, _i64, _i64, _p]),
@@ -156,6 +161,41 @@ class Context:
     def space_set(self, sid, family, ncomp, ndofs, nd, nd_all, handler, celldofs=None, signs=None, orient=None):
         celldofs, signs, orient = _arr(celldofs, np.int32), _arr(signs, np.int32), _arr(orient, np.int32)
         self._ck(self.lib.femb_space_set(self.h, sid, family, ncomp, ndofs, nd, nd_all, handler, _ptr(celldofs), _ptr(signs), _ptr(orient)))
+
+    # ---- grid components / dofmaps generated on the device ---------------
+    def grid_entities(self, kind):
+        """Enumerate the faces (ENTITY_FACES) or edges (ENTITY_EDGES) of the registered mesh on the device -> count."""
+        n = _i64(0)
+        self._ck(self.lib.femb_grid_entities(self.h, kind, C.byref(n)))
+        return int(n.value)
+
+    def grid_entities_get(self, kind):
+        """-> dict with cell_entities (ncells, per_cell), entity_nodes (n, k), signs, and for faces orientations, facecells."""
+        n = self.grid_entities(kind)
+        faces = kind == ENTITY_FACES or self.dim == 2
+        per = self.dim + 1 if faces else 6
+        k = 3 if (faces and self.dim == 3) else 2
+        out = {"cell_entities": np.empty((self.ncells, per), np.int32), "entity_nodes": np.empty((n, k), np.int32),
+               "signs": np.empty((self.ncells, per), np.int32)}
+        if faces:
+            out["orientations"] = np.empty((self.ncells, per), np.int32)
+            out["facecells"] = np.empty((n, 2), np.int32)
+        self._ck(self.lib.femb_grid_entities_get(self.h, kind, _ptr(out["cell_entities"]), _ptr(out["entity_nodes"]), _ptr(out["signs"]),
+                                                 _ptr(out.get("orientations")), _ptr(out.get("facecells"))))
+        return out
+
+    def space_set_from_pattern(self, sid, family, ncomp, nd, nd_all, handler, segs):
+        """segs: list of (type, each_component, q) with type in 'nfeic' -> (ndofs, coffset); CellDofs stay on the device."""
+        code = {"n": 0, "f": 1, "e": 2, "i": 3, "c": 3}
+        flat = np.array([[code[t], int(each), q] for t, each, q in segs], dtype=np.int32)
+        ndofs, coffset = _i64(0), _i64(0)
+        self._ck(self.lib.femb_space_set_from_pattern(self.h, sid, family, ncomp, nd, nd_all, handler, flat.shape[0], _ptr(flat), C.byref(ndofs), C.byref(coffset)))
+        return int(ndofs.value), int(coffset.value)
+
+    def space_get_celldofs(self, sid, nd):
+        out = np.empty((self.ncells, nd), np.int32)
+        self._ck(self.lib.femb_space_get_celldofs(self.h, sid, _ptr(out)))
+        return out
 
     def quadrature_set(self, xref, w):
         xref, w = _arr(xref, np.float64), _arr(w, np.float64)

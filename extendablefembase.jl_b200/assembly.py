@@ -53,10 +53,20 @@ class Example210RHS:
         return np.array([self.mu, self.t])
 
 
-def _register_space(ctx, sid, fes):
+def _register_space(ctx, sid, fes, device_dofmap=False):
+    """``device_dofmap=True``: faces / edges, signs and CellDofs are generated on the device from the dofmap pattern
+    (femb_space_set_from_pattern) — nothing but the pattern string crosses the boundary."""
     ft, grid = fes.fetype, fes.xgrid
     g = grid.geometry
     handler = ft.handler(g)
+    if device_dofmap:
+        from .fespace import parse_pattern
+
+        ndofs, coffset = ctx.space_set_from_pattern(sid, _lib.FAMILY[ft.family], ft.ncomponents, ft.get_ndofs(g), ft.get_ndofs_all(g), handler,
+                                                    parse_pattern(ft.get_dofmap_pattern(g)))
+        if (ndofs, coffset) != (fes.ndofs, fes.coffset):
+            raise RuntimeError(f"device dofmap: ndofs / coffset {ndofs, coffset} differ from the FESpace's {fes.ndofs, fes.coffset}")
+        return
     signs = orient = None
     if handler in (1, 3, 4, 5):
         signs = grid["CellFaceSigns"]
@@ -88,14 +98,15 @@ def _rhs_args(ctx, rhs, nqp, ncomp):
 class _Session:
     """Device-resident state for one (grid, FE spaces, quadrature rule) combination."""
 
-    def __init__(self, spaces, qf, device=0, cellvolumes=True):
-        """``cellvolumes=False`` passes NULL for xgrid[CellVolumes]: the kernels then use |det A| / d!."""
+    def __init__(self, spaces, qf, device=0, cellvolumes=True, device_dofmaps=False):
+        """``cellvolumes=False`` passes NULL for xgrid[CellVolumes]: the kernels then use |det A| / d!.
+        ``device_dofmaps=True`` generates CellDofs (and the face / edge components behind them) on the device."""
         self.ctx = _lib.Context(device)
         grid = spaces[0].xgrid
         self.grid, self.spaces, self.qf = grid, spaces, qf
         self.ctx.mesh_set(grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"] if cellvolumes else None)
         for sid, fes in enumerate(spaces):
-            _register_space(self.ctx, sid, fes)
+            _register_space(self.ctx, sid, fes, device_dofmaps)
         self.ctx.quadrature_set(qf.xref, qf.w)
         self.ctx.matrix_layout(list(range(len(spaces))), list(range(len(spaces))))
         self.evals = {}

@@ -61,7 +61,7 @@ int32_t femb_create(int32_t device, femb_ctx** out) {
     return FEMB_OK;
 }
 
-static void free_space(FembSpace& s) {
+extern "C++" void femb_free_space(FembSpace& s) {
     if (s.celldofs_owned) femb_free(&s.celldofs);
     s.celldofs = nullptr;
     femb_free(&s.signs);
@@ -76,12 +76,13 @@ int32_t femb_destroy(femb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     femb_comm_destroy(ctx);
     femb_free_pattern(ctx);
-    for (auto& s : ctx->spaces) free_space(s);
+    for (auto& s : ctx->spaces) femb_free_space(s);
     for (auto& e : ctx->evals) {
         femb_free(&e.refvals);
         femb_free(&e.refderivs);
         femb_free(&e.reftensor);
     }
+    femb_free_entities(ctx);
     femb_free(&ctx->coords);
     femb_free(&ctx->cellnodes);
     femb_free(&ctx->cellvol);
@@ -139,7 +140,8 @@ int32_t femb_mesh_set(femb_ctx* ctx, int32_t dim, int64_t nnodes, const double* 
     if (!same_shape) {
         // a new mesh invalidates everything derived from it
         femb_free_pattern(ctx);
-        for (auto& s : ctx->spaces) free_space(s);
+        for (auto& s : ctx->spaces) femb_free_space(s);
+        femb_free_entities(ctx);
         FEMB_TRY(femb_alloc(ctx, &ctx->coords, (size_t)nnodes * dim));
         FEMB_TRY(femb_alloc(ctx, &ctx->cellnodes, (size_t)ncells * nnpc));
         femb_free(&ctx->cellvol);
@@ -184,7 +186,7 @@ int32_t femb_space_set(femb_ctx* ctx, int32_t id, int32_t family, int32_t ncomp,
     bool same = s.set && s.nd == nd && s.ndofs == ndofs && s.family == family && s.ncomp == ncomp && s.nd_all == nd_all &&
                 s.handler == handler && (s.celldofs_owned == (celldofs != nullptr));
     if (!same) {
-        free_space(s);
+        femb_free_space(s);
         femb_free_pattern(ctx);
         if (celldofs) {
             FEMB_TRY(femb_alloc(ctx, &s.celldofs, (size_t)ctx->ncells * nd));

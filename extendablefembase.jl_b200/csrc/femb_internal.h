@@ -32,6 +32,20 @@ struct FembSpace {
     int max_deg = 0;
 };
 
+// grid entities enumerated on the device (femb_grid.cu): faces [0] and, in 3-D, edges [1]
+struct FembEntities {
+    bool built = false;
+    int64_t n = 0;                 // number of faces / edges
+    int per_cell = 0, nodes_per = 0;
+    int32_t* cell_ent = nullptr;   // per_cell x ncells, 1-based ids in order of first appearance (xgrid[CellFaces] / [CellEdges])
+    int32_t* ent_nodes = nullptr;  // nodes_per x n, 1-based, local order of the creating cell (xgrid[FaceNodes] / [EdgeNodes])
+    int32_t* signs = nullptr;      // per_cell x ncells (xgrid[CellFaceSigns] / [CellEdgeSigns])
+    int32_t* orient = nullptr;     // faces: xgrid[CellFaceOrientations]
+    int32_t* facecells = nullptr;  // faces: 2 x n, (creating cell, neighbour or 0) (xgrid[FaceCells])
+};
+
+#define FEMB_MAX_PATTERN_SEGS 8
+
 struct FembEval {
     bool set = false;
     int space = -1, op = 0, nqp = 0, resultdim = 0;
@@ -126,6 +140,8 @@ struct femb_ctx {
     double* bvec = nullptr;       // nrows
     double* sol = nullptr;        // ncols (current solution)
     int32_t* errflag = nullptr;   // device int: contributions that found no slot
+
+    FembEntities ent[2];
 
     // colouring of cells (FEMB_SCATTER_COLORED)
     int ncolors = 0;
@@ -225,6 +241,10 @@ int femb_build_gmap(femb_ctx* ctx);
 int femb_build_hmap(femb_ctx* ctx);
 #define FEMB_COEF_STRIDE 16  // doubles per cell in femb_ctx::cellcoef (6 + up to 10 quadrature points)
 void femb_free_pattern(femb_ctx* ctx);
+void femb_free_space(FembSpace& s);
+// femb_grid.cu
+int femb_build_entities(femb_ctx* ctx, int kind);
+void femb_free_entities(femb_ctx* ctx);
 // assemble.cu
 int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec);
 int femb_build_coloring(femb_ctx* ctx);

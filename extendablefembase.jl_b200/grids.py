@@ -97,6 +97,28 @@ class ExtendableGrid:
         else:
             raise KeyError(f"grid component {name!r} not available")
 
+    def instantiate_on_device(self, device: int = 0, components=("faces", "edges")):
+        """Enumerate faces / edges with the CUDA library (femb_grid_entities, csrc/femb_grid.cu) instead of the numpy
+        routines below and cache the same grid components: the device counterpart of the reference's lazy
+        ``xgrid[CellFaces]`` ... instantiation (timed at Example200_LowLevelPoisson.jl:55)."""
+        from . import _lib
+
+        ctx = _lib.Context(device)
+        try:
+            ctx.mesh_set(self._c["Coordinates"], self._c["CellNodes"], None)
+            if "faces" in components or self.dim == 2:
+                r = ctx.grid_entities_get(_lib.ENTITY_FACES)
+                self._c["CellFaces"], self._c["FaceNodes"], self._c["CellFaceSigns"] = r["cell_entities"], r["entity_nodes"], r["signs"]
+                self._c["CellFaceOrientations"], self._c["FaceCells"] = r["orientations"], r["facecells"]
+                if self.dim == 2:
+                    self._c["EdgeNodes"], self._c["CellEdges"], self._c["CellEdgeSigns"] = r["entity_nodes"], r["cell_entities"], r["signs"]
+            if "edges" in components and self.dim == 3:
+                r = ctx.grid_entities_get(_lib.ENTITY_EDGES)
+                self._c["CellEdges"], self._c["EdgeNodes"], self._c["CellEdgeSigns"] = r["cell_entities"], r["entity_nodes"], r["signs"]
+        finally:
+            ctx.close()
+        return self
+
     def _build_faces(self):
         lfn = LOCAL_CELLFACENODES[self.geometry] - 1
         cn = self._c["CellNodes"]
@@ -152,6 +174,8 @@ def _first_appearance_ids(sorted_rows: np.ndarray):
     nmax = int(sorted_rows.max()) + 1
     key = sorted_rows[:, 0].astype(np.int64)
     for j in range(1, k):
+        if float(key.max() + 1) * nmax >= 2.0 ** 62:  # 3 nodes of a large mesh: compress the partial key to dense ids first
+            key = np.unique(key, return_inverse=True)[1].astype(np.int64).reshape(-1)
         key = key * nmax + sorted_rows[:, j].astype(np.int64)
     _, first_idx, inv = np.unique(key, return_index=True, return_inverse=True)
     order = np.argsort(first_idx, kind="stable")  # unique-id -> appearance rank

@@ -109,6 +109,32 @@ int32_t femb_space_set(femb_ctx* ctx, int32_t space_id, int32_t family, int32_t 
                        int32_t nd_local, int32_t nd_all, int32_t handler, const int32_t* celldofs_or_null,
                        const int32_t* signs_or_null, const int32_t* orient_or_null);
 
+/* ---- grid components on the device: face / edge enumeration -----------------------------------
+ * Replaces the lazy instantiation of xgrid[CellFaces], xgrid[FaceNodes], xgrid[CellFaceSigns],
+ * xgrid[CellFaceOrientations], xgrid[FaceCells] (kind FACES) and xgrid[CellEdges], xgrid[EdgeNodes],
+ * xgrid[CellEdgeSigns] (kind EDGES; on triangles the edges are the faces) of ExtendableGrids for the mesh of
+ * femb_mesh_set (read at dofmaps.jl:448-458, hdiv_rt0.jl:115, hdiv_bdm1.jl:201,235; Example200:55 times it).
+ * Numbering = first appearance while looping cells and local entities in order; entity_nodes = node order of the
+ * creating cell; face sign +1 creator / -1 neighbour; edge sign +1 when the local edge starts at the global edge's
+ * first node; orientations 1..4 (3-D) as in hdiv_bdm1.jl:238-246.  All arrays Int32, 1-based, column-major
+ * (k x nitems).  femb_grid_entities_get: any pointer may be NULL; sizes: cell_entities / signs / orientations
+ * per_cell x ncells, entity_nodes nodes_per x n, facecells 2 x n (faces only). */
+enum { FEMB_ENTITY_FACES = 0, FEMB_ENTITY_EDGES = 1 };
+int32_t femb_grid_entities(femb_ctx* ctx, int32_t kind, int64_t* n_out);
+int32_t femb_grid_entities_get(femb_ctx* ctx, int32_t kind, int32_t* cell_entities, int32_t* entity_nodes, int32_t* signs,
+                               int32_t* orientations, int32_t* facecells);
+
+/* ---- FESpace with the dofmap generated on the device: init_dofmap_from_pattern! (dofmaps.jl:419-627) ----
+ * segs: nseg triples (type, each_component, q) of the parsed dofmap pattern (dofmaps.jl:263-301), type
+ * 0 = N/n nodes, 1 = F/f faces, 2 = E/e edges, 3 = I/i/C/c cell interior.  Faces / edges and the sign /
+ * orientation arrays the handler needs are taken from the device enumeration above.  Outputs ndofs and the
+ * component offset (count_ndofs, finiteelements.jl:395-449).  femb_space_get_celldofs downloads fe_space[CellDofs]
+ * (nd_local x ncells Int32, 1-based) of any registered space. */
+int32_t femb_space_set_from_pattern(femb_ctx* ctx, int32_t space_id, int32_t family, int32_t ncomp, int32_t nd_local,
+                                    int32_t nd_all, int32_t handler, int32_t nseg, const int32_t* segs, int64_t* ndofs_out,
+                                    int64_t* coffset_out);
+int32_t femb_space_get_celldofs(femb_ctx* ctx, int32_t space_id, int32_t* celldofs);
+
 /* ---- QuadratureRule: qf.xref (dim x nqp), qf.w (nqp)   (quadrature.jl:38-42) ------------------ */
 int32_t femb_quadrature_set(femb_ctx* ctx, int32_t nqp, const double* xref, const double* w);
 

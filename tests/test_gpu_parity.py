@@ -551,3 +551,90 @@ def test_colored_scatter_is_reproducible_and_correct():
         (colptr, rowval, nzval, b), _ = _ex200_oracle(grid, ft, fes, 0.9, rhs)
         D = A.entries.to_scipy() - sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=A.entries.shape)
         assert abs(D).max() <= RTOL * _local_scale(grid, ft, 0.9)
+
+
+# ---------------------------------------------------------------------------------------------
+# face / edge enumeration and the pattern-driven CellDofs generator on the device, bit-exact against
+# the host restatement (grids.py / fespace.py) — all integer work
+# ---------------------------------------------------------------------------------------------
+def _shuffled(grid, seed=3):
+    """Same mesh with the cells in random order and the local node order rotated (keeps the orientation)."""
+    rng = np.random.default_rng(seed)
+    cn = grid["CellNodes"][rng.permutation(grid.ncells)].copy()
+    if grid.dim == 2:
+        rot = rng.integers(0, 3, cn.shape[0])
+        cn = np.stack([np.roll(c, r) for c, r in zip(cn, rot)]).astype(np.int32)
+    else:
+        ev = np.array([[0, 1, 2, 3], [1, 2, 0, 3], [2, 0, 1, 3], [1, 0, 3, 2], [3, 2, 1, 0], [0, 3, 1, 2]])  # even permutations
+        cn = np.stack([c[ev[r]] for c, r in zip(cn, rng.integers(0, len(ev), cn.shape[0]))]).astype(np.int32)
+    return fb.ExtendableGrid(grid["Coordinates"], cn, grid.geometry)
+
+
+@pytest.mark.parametrize("dim,n,shuffle", [(2, 1, False), (2, 7, False), (2, 12, True), (3, 1, False), (3, 4, False), (3, 5, True)])
+def test_device_grid_entities_match_host(dim, n, shuffle):
+    grid = _grid2d(n) if dim == 2 else _grid3d(n)
+    if shuffle:
+        grid = _shuffled(grid)
+    dev = fb.ExtendableGrid(grid["Coordinates"], grid["CellNodes"], grid.geometry).instantiate_on_device()
+    names = ["CellFaces", "FaceNodes", "CellFaceSigns", "CellFaceOrientations", "FaceCells", "CellEdges", "EdgeNodes", "CellEdgeSigns"]
+    for name in names:
+        assert name in dev._c, name  # filled by the device, not lazily by numpy
+        host = grid[name]
+        assert dev[name].dtype == np.int32 and dev[name].shape == host.shape, name
+        assert np.array_equal(dev[name], host), name
+
+
+DOFMAP_CASES = [
+    (lambda: fb.H1P1(1), 2), (lambda: fb.H1P1(2), 2), (lambda: fb.H1P2(1, 2), 2), (lambda: fb.H1Pk(2, 2, 2), 2), (lambda: fb.H1P3(1, 2), 2),
+    (lambda: fb.H1Pk(1, 2, 4), 2), (lambda: fb.HDIVRT0(2), 2), (lambda: fb.HDIVBDM1(2), 2), (lambda: fb.L2P0(1), 2),
+    (lambda: fb.H1P1(1), 3), (lambda: fb.H1P2(1, 3), 3), (lambda: fb.H1P2(3, 3), 3), (lambda: fb.H1P3(1, 3), 3), (lambda: fb.HDIVRT0(3), 3),
+    (lambda: fb.HDIVBDM1(3), 3), (lambda: fb.L2P0(3), 3),
+]
+
+
+@pytest.mark.parametrize("mk,dim", DOFMAP_CASES)
+def test_device_celldofs_match_host(mk, dim):
+    from femb_b200.assembly import _register_space
+
+    ft = mk()
+    grid = _shuffled(_grid2d(6) if dim == 2 else _grid3d(3), seed=11)
+    fes = fb.FESpace(ft, grid)
+    ctx = _lib.Context(0)
+    ctx.mesh_set(grid["Coordinates"], grid["CellNodes"], None)
+    _register_space(ctx, 0, fes, device_dofmap=True)  # raises if ndofs / coffset differ
+    nd = ft.get_ndofs(grid.geometry)
+    assert np.array_equal(ctx.space_get_celldofs(0, nd), fes["CellDofs"])
+    ctx.close()
+
+
+def test_device_dofmaps_assemble_like_host_dofmaps():
+    """Example200 P2-3D and the Hdiv blocks with CellDofs / signs / orientations generated on the device: same matrix."""
+    from femb_b200.assembly import _Session
+
+    grid = _grid3d(3, True)
+    res = []
+    for dev in (False, True):
+        fes = fb.FESpace(fb.H1P2(1, 3), grid)
+        qf = fb.QuadratureRule(grid.geometry, 2)
+        S = _Session([fes], qf, device_dofmaps=dev)
+        eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+        S.ctx.pattern_build([(0, 0)])
+        S.ctx.matrix_zero(); S.ctx.vector_zero()
+        S.ctx.assemble_poisson(eg._eid, ei._eid, 0.7, _lib.RHS_AFFINE, fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]]).params(), 0.0)
+        res.append((S.ctx.pattern_get(fes.ndofs), S.ctx.matrix_get(), S.ctx.vector_get(fes.ndofs)))
+        S.ctx.close()
+    assert all(np.array_equal(a, b) for a, b in zip(res[0][0], res[1][0]))
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    res = []
+    for dev in (False, True):
+        FESv, FESq = fb.FESpace(fb.HDIVBDM1(3), grid), fb.FESpace(fb.L2P0(1), grid)
+        S = _Session([FESv, FESq], fb.QuadratureRule(grid.geometry, 2), device_dofmaps=dev)
+        eid, ediv, eq = S.evaluator(0, "Identity"), S.evaluator(0, "Divergence"), S.evaluator(1, "Identity")
+        S.ctx.pattern_build([(0, 0), (0, 1), (1, 0)])
+        S.ctx.set_scatter(_lib.SCATTER_COLORED)  # reproducible sums
+        S.ctx.matrix_zero()
+        S.ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
+        S.ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
+        res.append(S.ctx.matrix_get())
+        S.ctx.close()
+    assert np.array_equal(res[0], res[1])

@@ -36,9 +36,11 @@ def c3_p2_3d(m, steps, warmup, order=2, check=False):
     t0 = time.time()
     grid = fb.simplexgrid(X, X, X)
     ft = fb.H1P2(1, 3) if order == 2 else fb.H1P1(1)
+    if order == 2:
+        grid.instantiate_on_device(0, components=("edges",))  # xgrid[CellEdges] from the device enumeration (ndofs needs nedges)
     fes = fb.FESpace(ft, grid)
     qf = fb.QuadratureRule(grid.geometry, 2 * (order - 1))
-    S = _Session([fes], qf)
+    S = _Session([fes], qf, device_dofmaps=order == 2)  # CellDofs generated on the device from the pattern "N1E1"
     ctx = S.ctx
     eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
     t1 = time.time()
@@ -112,6 +114,45 @@ def c5_taylor_hood(n, steps, warmup):
     return out
 
 
+def topo(m, host_limit=128):
+    """face / edge enumeration + CellDofs of H1P2{1,3} on the device vs the numpy restatement (the host
+    side is only run up to m = host_limit; it needs minutes and tens of GB beyond)."""
+    from femb_b200.fespace import parse_pattern
+
+    X = np.linspace(0, 1, m + 1)
+    grid = fb.simplexgrid(X, X, X)
+    ctx = _lib.Context(0)
+    ctx.mesh_set(grid["Coordinates"], grid["CellNodes"], None)
+    ctx.sync()
+    res = {"config": f"topology of the Kuhn mesh m={m}: faces, edges, CellDofs(H1P2{{1,3}}) on the device", "ncells": grid.ncells}
+    for name, kind in (("faces", _lib.ENTITY_FACES), ("edges", _lib.ENTITY_EDGES)):
+        t0 = time.perf_counter()
+        n = ctx.grid_entities(kind)
+        ctx.sync()
+        res[f"n{name}"] = n
+        res[f"device_{name}_ms"] = (time.perf_counter() - t0) * 1e3
+    ft = fb.H1P2(1, 3)
+    t0 = time.perf_counter()
+    ndofs, _ = ctx.space_set_from_pattern(0, _lib.FAMILY["H1"], 1, 10, 10, 0, parse_pattern(ft.get_dofmap_pattern(grid.geometry)))
+    ctx.sync()
+    res["device_celldofs_ms"] = (time.perf_counter() - t0) * 1e3
+    res["ndofs"] = ndofs
+    res["device_items_per_s"] = grid.ncells * 10 / ((res["device_faces_ms"] + res["device_edges_ms"]) * 1e-3)
+    if m <= host_limit:
+        t0 = time.perf_counter()
+        grid["CellFaces"]
+        res["host_faces_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        grid["CellEdges"]
+        res["host_edges_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        cd = fb.FESpace(ft, grid)["CellDofs"]
+        res["host_celldofs_ms"] = (time.perf_counter() - t0) * 1e3
+        res["celldofs_equal"] = bool(np.array_equal(cd, ctx.space_get_celldofs(0, 10)))
+    ctx.close()
+    return res
+
+
 def c3_multi_gpu(m, layers, steps, warmup):
     """C3 on z-slabs, one rank per GPU (launch with torchrun): weak scaling of the H1P2{1,3} stiffness + rhs assembly with
     the NCCL exchange of the interface columns (vertex and edge dofs in the cut planes)."""
@@ -125,6 +166,7 @@ def c3_multi_gpu(m, layers, steps, warmup):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t0 = time.time()
     part, grid = pt.slab_partition_3d(m, rank, world, layers)
+    grid.instantiate_on_device(local, components=("edges",))
     fes = fb.FESpace(fb.H1P2(1, 3), grid)
     cd = fes["CellDofs"]
     ndofs_own_cells = fes.ndofs
@@ -216,6 +258,8 @@ if __name__ == "__main__":
             res.append(c4_hdiv(a.m4, a.steps, a.warmup, "BDM1"))
         elif w == "c5":
             res += c5_taylor_hood(a.n5, a.steps, a.warmup)
+        elif w == "topo":
+            res.append(topo(a.m3))
         elif w == "c3mg":
             r = c3_multi_gpu(a.m3, a.layers, a.steps, a.warmup)
             if r:
