@@ -80,6 +80,61 @@ def solve_stokes_lowlevel(FES, teval=0.0, maxits=20):
     return sol, nlres, it
 
 
+def solve_stokes_device(FES, teval=0.0, maxits=20):
+    """The same Newton loop with everything but the linear solve on the device: the linear part is kept there
+    (femb_system_save = `Alin = deepcopy(A)`), each iteration re-assembles the convection, adds the saved part, applies
+    the 1e60 penalisation to the boundary dofs enumerated on the device and evaluates both residual norms there
+    (Example210:175-212).  Only the penalised system travels to the host, for the linear solve."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from femb_b200 import _lib
+    from femb_b200.fespace import parse_pattern
+
+    FESu, FESp = FES
+    sol, A, b = fb.FEVector(FES), fb.FEMatrix(FES), fb.FEVector(FES)
+    update_system = fb.prepare_assembly(A, b, FESu, FESp, sol, teval=teval, mu=MU)
+    update_system(True, False)  # builds the pattern, assembles the linear part (device copy stays in the session)
+    S = update_system.session
+    ctx = S.ctx
+    ctx.system_save()
+    E = A.entries
+    n = E.shape[0]
+    u_init = np.zeros(n)
+    ue = u_exact(p2_nodal_points(FESu.xgrid), teval)
+    u_init[: FESu.ndofs] = np.concatenate([ue[:, 0], ue[:, 1]])
+    nb = ctx.boundary_dofs(0, parse_pattern(FESu.fetype.get_dofmap_pattern(FESu.xgrid.geometry)), download=False)
+    fx = np.concatenate([ctx.boundary_dofs(0, parse_pattern(FESu.fetype.get_dofmap_pattern(FESu.xgrid.geometry))), [FESu.ndofs + 1]]) - 1
+    assert fx.shape[0] == nb + 1
+    free = np.setdiff1d(np.arange(n), fx)
+    pin = np.array([FESu.ndofs + 1])
+    egu, eiu, eip = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity"), S.evaluator(1, "Identity")
+
+    def host_solve():
+        """the linear solve of the penalised system = elimination of the fixed dofs (see solve_stokes_lowlevel)."""
+        M = sp.csr_matrix(sp.csc_matrix((ctx.matrix_get(), E.rowval - 1, E.colptr - 1), shape=E.shape))
+        rhs = ctx.vector_get(n)
+        x = np.zeros(n)
+        x[fx] = u_init[fx]
+        x[free] = spla.spsolve(M[free][:, free].tocsc(), rhs[free] - M[free][:, fx] @ x[fx])
+        return x
+
+    ctx.dirichlet_apply(True, 0, pin, u_init, 1.0e60)  # also registers the fixed rows the residuals skip
+    nlres = np.inf
+    for it in range(1, maxits + 1):
+        sol.entries[:] = host_solve()
+        linres = ctx.residual(sol.entries, zero_fixed=True)  # uploads sol: it is also the linearisation point below
+        ctx.matrix_zero()
+        ctx.vector_zero()
+        ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, MU, False, True, _lib.RHS_NONE, None)
+        ctx.system_add_saved()
+        ctx.dirichlet_apply(True, 0, pin, u_init, 1.0e60)
+        nlres = ctx.residual(None, zero_fixed=True)
+        print(f"ITERATION {it}: linear residual = {linres:.3e}, nonlinear residual = {nlres:.3e}")
+        if nlres < max(1.0e-12, 20 * linres):
+            break
+    return sol, nlres, it
+
+
 def l2_errors(sol, FESu, FESp):
     """nodal-point (vertex rule) L2 errors like compute_error (Example210:112-154), velocity only at the P2 nodes"""
     pts = p2_nodal_points(FESu.xgrid)
@@ -88,15 +143,15 @@ def l2_errors(sol, FESu, FESp):
     return float(np.sqrt(np.mean(np.sum((uh - ue) ** 2, axis=1))))
 
 
-def main(nref=5, order=2):
+def main(nref=5, order=2, device_loop=False):
     X = np.linspace(0, 1, 2 ** nref + 1)
     xgrid = fb.simplexgrid(X, X)
     FES = [fb.FESpace(fb.H1Pk(2, 2, order), xgrid, "velocity space"), fb.FESpace(fb.H1Pk(1, 2, order - 1), xgrid, "pressure space")]
-    sol, nlres, its = solve_stokes_lowlevel(FES)
+    sol, nlres, its = (solve_stokes_device if device_loop else solve_stokes_lowlevel)(FES)
     err = l2_errors(sol, *FES)
     print(f"nodal l2 error velo = {err:.4e} after {its} Newton iterations")
     return sol, nlres, its, err
 
 
 if __name__ == "__main__":
-    main()
+    main(device_loop="--device-loop" in sys.argv)

@@ -39,6 +39,12 @@ SIGNATURES = {
     "femb_grid_entities_get": (_i32, [_p, _i32, _p, _p, _p, _p, _p]),
     "femb_space_set_from_pattern": (_i32, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, C.POINTER(_i64), C.POINTER(_i64)]),
     "femb_space_get_celldofs": (_i32, [_p, _i32, _p]),
+    "femb_boundary_dofs": (_i32, [_p, _i32, _i32, _p, C.POINTER(_i64)]),
+    "femb_boundary_dofs_get": (_i32, [_p, _p]),
+    "femb_dirichlet_apply": (_i32, [_p, _i32, _i64, _i64, _p, _p, _f64]),
+    "femb_residual": (_i32, [_p, _p, _i32, _p, C.POINTER(_f64)]),
+    "femb_system_save": (_i32, [_p]),
+    "femb_system_add_saved": (_i32, [_p]),
     "femb_quadrature_set": (_i32, [_p, _i32, _p, _p]),
     "femb_evaluator_set": (_i32, [_p, _i32, _i32, _i32, _p, _p]),
     "femb_evaluator_eval": (_i32, [_p, _i32, _i64, _i64, _p]),
@@ -196,6 +202,39 @@ class Context:
         out = np.empty((self.ncells, nd), np.int32)
         self._ck(self.lib.femb_space_get_celldofs(self.h, sid, _ptr(out)))
         return out
+
+    # ---- after the assembly: Dirichlet rows, residual ---------------------
+    _SEG_CODE = {"n": 0, "f": 1, "e": 2, "i": 3, "c": 3}
+
+    def boundary_dofs(self, sid, segs, download=True):
+        """boundarydofs(FES) on the device -> sorted unique 1-based dofs (int64 like the host mirror), or the count."""
+        flat = np.array([[self._SEG_CODE[t], int(each), q] for t, each, q in segs], dtype=np.int32)
+        n = _i64(0)
+        self._ck(self.lib.femb_boundary_dofs(self.h, sid, flat.shape[0], _ptr(flat), C.byref(n)))
+        if not download:
+            return int(n.value)
+        out = np.empty(int(n.value), np.int32)
+        self._ck(self.lib.femb_boundary_dofs_get(self.h, _ptr(out)))
+        return out.astype(np.int64)
+
+    def dirichlet_apply(self, use_boundary_list=True, dof_offset=0, extra_dofs=None, values=None, penalty=1.0e60):
+        extra = _arr(extra_dofs, np.int64)
+        values = _arr(values, np.float64)
+        self._ck(self.lib.femb_dirichlet_apply(self.h, int(use_boundary_list), dof_offset, 0 if extra is None else extra.shape[0], _ptr(extra), _ptr(values), penalty))
+
+    def system_save(self):
+        self._ck(self.lib.femb_system_save(self.h))
+
+    def system_add_saved(self):
+        self._ck(self.lib.femb_system_add_saved(self.h))
+
+    def residual(self, x=None, zero_fixed=True, want_vector=False, n=None):
+        """-> ||A x - b||_2 (and the vector when want_vector)."""
+        x = _arr(x, np.float64)
+        res = np.empty(n, np.float64) if want_vector else None
+        nrm = _f64(0.0)
+        self._ck(self.lib.femb_residual(self.h, _ptr(x), int(zero_fixed), _ptr(res), C.byref(nrm)))
+        return (float(nrm.value), res) if want_vector else float(nrm.value)
 
     def quadrature_set(self, xref, w):
         xref, w = _arr(xref, np.float64), _arr(w, np.float64)

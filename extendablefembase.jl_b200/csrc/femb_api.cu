@@ -83,6 +83,7 @@ int32_t femb_destroy(femb_ctx* ctx) {
         femb_free(&e.reftensor);
     }
     femb_free_entities(ctx);
+    femb_free_system(ctx);
     femb_free(&ctx->coords);
     femb_free(&ctx->cellnodes);
     femb_free(&ctx->cellvol);

@@ -143,6 +143,18 @@ struct femb_ctx {
 
     FembEntities ent[2];
 
+    // Dirichlet data and the row-wise view of the pattern for A x - b (femb_system.cu)
+    int32_t* bdofs = nullptr;      // last femb_boundary_dofs result: sorted, 1-based, local to its space
+    int64_t nbdofs = 0;
+    int64_t* fixed = nullptr;      // rows fixed by the last femb_dirichlet_apply (0-based, matrix numbering)
+    int64_t nfixed = 0;
+    int64_t* csr_ptr = nullptr;    // nrows + 1
+    int32_t* csr_col = nullptr;    // nnz: column of each entry, rows contiguous
+    uint32_t* csr_slot = nullptr;  // nnz: its position in nzval
+    double* resvec = nullptr;      // nrows (+ 1 scratch)
+    double* saved_nzval = nullptr; // femb_system_save: Alin / blin of Example210:164-165
+    double* saved_b = nullptr;
+
     // colouring of cells (FEMB_SCATTER_COLORED)
     int ncolors = 0;
     int32_t* color_perm = nullptr;          // cells sorted by colour
@@ -245,6 +257,10 @@ void femb_free_space(FembSpace& s);
 // femb_grid.cu
 int femb_build_entities(femb_ctx* ctx, int kind);
 void femb_free_entities(femb_ctx* ctx);
+// femb_system.cu
+void femb_free_csr(femb_ctx* ctx);
+void femb_free_saved(femb_ctx* ctx);
+void femb_free_system(femb_ctx* ctx);
 // assemble.cu
 int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec);
 int femb_build_coloring(femb_ctx* ctx);

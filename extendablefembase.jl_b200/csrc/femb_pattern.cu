@@ -10,6 +10,11 @@
 #include "femb_internal.h"
 
 void femb_free_pattern(femb_ctx* ctx) {
+    femb_free_csr(ctx);
+    femb_free_saved(ctx);
+    femb_free(&ctx->resvec);
+    femb_free(&ctx->fixed);
+    ctx->nfixed = 0;
     femb_free(&ctx->colptr);
     femb_free(&ctx->rowval);
     femb_free(&ctx->nzval);

@@ -135,6 +135,26 @@ int32_t femb_space_set_from_pattern(femb_ctx* ctx, int32_t space_id, int32_t fam
                                     int64_t* coffset_out);
 int32_t femb_space_get_celldofs(femb_ctx* ctx, int32_t space_id, int32_t* celldofs);
 
+/* ---- after the assembly: Dirichlet penalisation and the residual, without a host round trip of A ---------
+ * femb_boundary_dofs: boundarydofs(FES) (dofmaps.jl:871-899; Example200:86, Example210:172) for a registered space
+ * from the device face enumeration: every dof attached to a face with one neighbour cell; segs = the dofmap pattern
+ * as in femb_space_set_from_pattern.  The list is sorted and unique (the reference returns BFaceDofs.colentries,
+ * which repeats shared dofs; its callers only loop over it), 1-based, local to the space.
+ * femb_dirichlet_apply: A[d,d] = penalty; b[d] = penalty * values[d] (values == NULL: 0) for d in
+ * (boundary list + dof_offset, when use_boundary_list) and the extra dofs (1-based, matrix numbering) —
+ * Example200:87-90, Example210:197-200 (penalty 1e60, the extra dof fixes one pressure value, Example210:173).
+ * femb_residual: res = A x - b (x == NULL: the vector of femb_vector_set(1, ..)), rows fixed by the last
+ * femb_dirichlet_apply zeroed when zero_fixed; norm_out = ||res||_2 (Example210:180-185, :204-209).  Row-wise
+ * sums in ascending column order, write-once: bit-reproducible. */
+int32_t femb_boundary_dofs(femb_ctx* ctx, int32_t space_id, int32_t nseg, const int32_t* segs, int64_t* n_out);
+int32_t femb_boundary_dofs_get(femb_ctx* ctx, int32_t* dofs);
+int32_t femb_dirichlet_apply(femb_ctx* ctx, int32_t use_boundary_list, int64_t dof_offset, int64_t n_extra,
+                             const int64_t* extra_dofs, const double* values_or_null, double penalty);
+int32_t femb_residual(femb_ctx* ctx, const double* x_or_null, int32_t zero_fixed, double* res_or_null, double* norm_out);
+/* Alin = deepcopy(A); blin = deepcopy(b) (Example210:164-165) and A += Alin; b += blin (Example210:192-193), on the device */
+int32_t femb_system_save(femb_ctx* ctx);
+int32_t femb_system_add_saved(femb_ctx* ctx);
+
 /* ---- QuadratureRule: qf.xref (dim x nqp), qf.w (nqp)   (quadrature.jl:38-42) ------------------ */
 int32_t femb_quadrature_set(femb_ctx* ctx, int32_t nqp, const double* xref, const double* w);
 

@@ -517,6 +517,16 @@ def test_example210_newton_converges():
     assert errs[1] < errs[0] / 4  # at least second-order decay of the nodal velocity error under refinement
 
 
+def test_example210_device_resident_loop_matches_host_loop():
+    """The Newton loop with penalisation, saved linear part and both residual norms on the device (femb_system.cu) takes the
+    same iterations to the same solution as the host loop"""
+    ex = _load_example("example210_lowlevel_navierstokes")
+    sol_h, nl_h, its_h, err_h = ex.main(nref=4)
+    sol_d, nl_d, its_d, err_d = ex.main(nref=4, device_loop=True)
+    assert its_d == its_h and nl_d < 1e-8
+    assert np.abs(sol_d.entries - sol_h.entries).max() <= 1e-9 * np.abs(sol_h.entries).max()
+
+
 # ---------------------------------------------------------------------------------------------
 # FEMB_SCATTER_COLORED: cell colouring, plain read-modify-write per colour, bit-reproducible
 # ---------------------------------------------------------------------------------------------
@@ -638,3 +648,80 @@ def test_device_dofmaps_assemble_like_host_dofmaps():
         res.append(S.ctx.matrix_get())
         S.ctx.close()
     assert np.array_equal(res[0], res[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# boundarydofs, Dirichlet penalisation and the residual A x - b on the device
+# ---------------------------------------------------------------------------------------------
+BDOF_CASES = [(lambda: fb.H1P1(1), 2), (lambda: fb.H1Pk(2, 2, 2), 2), (lambda: fb.H1P3(1, 2), 2), (lambda: fb.H1Pk(1, 2, 4), 2),
+              (lambda: fb.H1P1(1), 3), (lambda: fb.H1P2(1, 3), 3), (lambda: fb.H1P2(3, 3), 3), (lambda: fb.H1P3(1, 3), 3)]
+
+
+@pytest.mark.parametrize("mk,dim", BDOF_CASES)
+def test_device_boundarydofs_match_host(mk, dim):
+    from femb_b200.assembly import _register_space
+    from femb_b200.fespace import boundarydofs, parse_pattern
+
+    ft = mk()
+    grid = _shuffled(_grid2d(5) if dim == 2 else _grid3d(3), seed=4)
+    fes = fb.FESpace(ft, grid)
+    ctx = _lib.Context(0)
+    ctx.mesh_set(grid["Coordinates"], grid["CellNodes"], None)
+    for dev in (False, True):  # host-provided and device-generated CellDofs
+        _register_space(ctx, 0, fes, device_dofmap=dev)
+        got = ctx.boundary_dofs(0, parse_pattern(ft.get_dofmap_pattern(grid.geometry)))
+        assert np.array_equal(got, boundarydofs(fes))
+    ctx.close()
+
+
+def test_device_dirichlet_and_residual_match_host():
+    """Example200 (P2, 2-D): penalised system and residual of a random vector, device vs scipy on the downloaded matrix;
+    Example210 layout: extra pressure dof, boundary values."""
+    import scipy.sparse as sp
+    from femb_b200.assembly import _Session
+    from femb_b200.fespace import boundarydofs, parse_pattern
+
+    grid = _grid2d(9, True)
+    FESu, FESp = fb.FESpace(fb.H1Pk(2, 2, 2), grid), fb.FESpace(fb.H1Pk(1, 2, 1), grid)
+    n = FESu.ndofs + FESp.ndofs
+    S = _Session([FESu, FESp], fb.QuadratureRule(grid.geometry, 5))
+    ctx = S.ctx
+    egu, eiu, eip = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity"), S.evaluator(1, "Identity")
+    ctx.pattern_build([(0, 0), (0, 1), (1, 0)], [FESu.ndofs + 1])
+    rng = np.random.default_rng(2)
+    sol = rng.uniform(-1, 1, n)
+    ctx.vector_set(1, sol)
+    ctx.matrix_zero(); ctx.vector_zero()
+    ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, 1e-2, True, True, _lib.RHS_EX210, fb.Example210RHS(1e-2, 0.0).params())
+    colptr, rowval = ctx.pattern_get(n)
+    A0 = sp.csc_matrix((ctx.matrix_get(), rowval - 1, colptr - 1), shape=(n, n))
+    b0 = ctx.vector_get(n)
+    # residual without fixed rows
+    nrm, res = ctx.residual(None, zero_fixed=False, want_vector=True, n=n)
+    ref = A0 @ sol - b0
+    scale = np.abs(A0).max() * np.abs(sol).max()
+    assert np.abs(res - ref).max() <= 1e-12 * scale * 50
+    assert abs(nrm - np.linalg.norm(ref)) <= 1e-12 * np.linalg.norm(ref)
+    # Dirichlet rows: boundary dofs of the velocity space + one pressure dof, values from a vector
+    bd = ctx.boundary_dofs(0, parse_pattern(FESu.fetype.get_dofmap_pattern(grid.geometry)))
+    assert np.array_equal(bd, boundarydofs(FESu))
+    uinit = rng.uniform(-1, 1, n)
+    ctx.dirichlet_apply(True, 0, np.array([FESu.ndofs + 1]), uinit, 1.0e60)
+    A1 = sp.csc_matrix((ctx.matrix_get(), rowval - 1, colptr - 1), shape=(n, n)).tolil()
+    b1 = ctx.vector_get(n)
+    Ah, bh = A0.tolil(), b0.copy()
+    fixed = np.concatenate([bd, [FESu.ndofs + 1]]) - 1
+    for d in fixed:
+        Ah[d, d] = 1.0e60
+        bh[d] = 1.0e60 * uinit[d]
+    assert (abs(A1 - Ah)).max() == 0.0 and np.array_equal(b1, bh)
+    x2 = rng.uniform(-1, 1, n)
+    nrm2, res2 = ctx.residual(x2, zero_fixed=True, want_vector=True, n=n)
+    ref2 = Ah.tocsc() @ x2 - bh
+    ref2[fixed] = 0.0
+    assert np.abs(res2 - ref2).max() <= 1e-12 * scale * 50
+    assert abs(nrm2 - np.linalg.norm(ref2)) <= 1e-12 * np.linalg.norm(ref2)
+    # twice the same: bit-identical (write-once row sums)
+    nrm3, res3 = ctx.residual(x2, zero_fixed=True, want_vector=True, n=n)
+    assert nrm3 == nrm2 and np.array_equal(res3, res2)
+    ctx.close()

@@ -111,6 +111,20 @@ def c5_taylor_hood(n, steps, warmup):
         ms = timeit(step, ctx, steps, warmup)
         out.append({"config": f"C5 Example210 Taylor-Hood update_system! {label}, n={n}", "ncells": grid.ncells, "ndofs": FESu.ndofs + FESp.ndofs, "nnz": nnz,
                     "ms_per_step": ms, "cells_per_s": grid.ncells / (ms * 1e-3)})
+    # the steps after the assembly on the device: boundary dofs, 1e60 penalisation, residual norm
+    from femb_b200.fespace import parse_pattern
+
+    segs = parse_pattern(FESu.fetype.get_dofmap_pattern(grid.geometry))
+    t0 = time.perf_counter()
+    nb = ctx.boundary_dofs(0, segs, download=False)
+    ctx.sync()
+    t_bd = (time.perf_counter() - t0) * 1e3
+    pin = np.array([FESu.ndofs + 1])
+    ctx.residual(None, zero_fixed=True)  # builds the row-wise view once
+    ms_dir = timeit(lambda: ctx.dirichlet_apply(True, 0, pin, None, 1.0e60), ctx, steps, warmup)
+    ms_res = timeit(lambda: ctx.residual(None, zero_fixed=True), ctx, steps, warmup)
+    out.append({"config": f"C5 after-assembly steps on the device, n={n}", "boundary_dofs": nb, "boundary_dofs_ms_first_call": t_bd, "dirichlet_apply_ms": ms_dir,
+                "residual_norm_ms": ms_res, "nnz": nnz, "residual_GBps": (nnz * 16 + (FESu.ndofs + FESp.ndofs) * 24) / (ms_res * 1e-3) / 1e9})
     return out
 
 
