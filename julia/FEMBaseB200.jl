@@ -86,6 +86,90 @@ function space_set!(ctx::Context, id::Integer, FES::FESpace)
     end
 end
 
+# ---- grid components and dofmaps generated on the device (optional: skips the host instantiation of
+# xgrid[CellFaces] / xgrid[CellEdges] and fe_space[CellDofs], timed at Example200:55,59) ----------------------------
+const SEGCODE = Dict('n' => Int32(0), 'f' => Int32(1), 'e' => Int32(2), 'i' => Int32(3), 'c' => Int32(3))
+
+# "N1E1" -> Int32[type, each_component, q, ...]  (the parser of src/dofmaps.jl:284-301)
+function pattern_segments(pattern::String)
+    segs = Int32[]
+    for m in eachmatch(r"([NnFfEeIiCc])(\d+)", pattern)
+        c = m.captures[1][1]
+        append!(segs, (SEGCODE[lowercase(c)], Int32(isuppercase(c)), parse(Int32, m.captures[2])))
+    end
+    return segs
+end
+
+"""
+    grid_entities!(ctx, xgrid, kind) -> NamedTuple
+
+Face (kind = 0) or edge (kind = 1) enumeration of the mesh registered with `mesh_set!`, on the device; the result can be
+stored into `xgrid[CellFaces]`, `xgrid[FaceNodes]`, `xgrid[CellFaceSigns]`, `xgrid[CellFaceOrientations]`,
+`xgrid[FaceCells]` / `xgrid[CellEdges]`, `xgrid[EdgeNodes]`, `xgrid[CellEdgeSigns]`.
+"""
+function grid_entities!(ctx::Context, xgrid::ExtendableGrid, kind::Integer)
+    n = Ref{Int64}(0)
+    check(ctx, ccall((:femb_grid_entities, libfemb), Int32, (Ptr{Cvoid}, Int32, Ref{Int64}), ctx.h, kind, n))
+    dim = size(xgrid[Coordinates], 1)
+    ncells = num_cells(xgrid)
+    faces = kind == 0 || dim == 2
+    per = faces ? dim + 1 : 6
+    k = (faces && dim == 3) ? 3 : 2
+    cell_ent, ent_nodes, signs = zeros(Int32, per, ncells), zeros(Int32, k, n[]), zeros(Int32, per, ncells)
+    orient = faces ? zeros(Int32, per, ncells) : nothing
+    facecells = faces ? zeros(Int32, 2, n[]) : nothing
+    check(ctx, ccall((:femb_grid_entities_get, libfemb), Int32,
+        (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+        ctx.h, kind, cell_ent, ent_nodes, signs, faces ? orient : C_NULL, faces ? facecells : C_NULL))
+    return (; cell_ent, ent_nodes, signs, orient, facecells)
+end
+
+# fe_space[CellDofs] generated on the device from get_dofmap_pattern (src/dofmaps.jl:419-627); returns (ndofs, coffset)
+function space_set_from_pattern!(ctx::Context, id::Integer, FEType, EG)
+    segs = pattern_segments(ExtendableFEMBase.get_dofmap_pattern(FEType, CellDofs, EG))
+    ndofs, coffset = Ref{Int64}(0), Ref{Int64}(0)
+    GC.@preserve segs check(ctx, ccall((:femb_space_set_from_pattern, libfemb), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Int32, Int32, Int32, Ptr{Int32}, Ref{Int64}, Ref{Int64}),
+        ctx.h, id, family(FEType), get_ncomponents(FEType), get_ndofs(ON_CELLS, FEType, EG), get_ndofs_all(ON_CELLS, FEType, EG),
+        handler(FEType, EG), length(segs) ÷ 3, segs, ndofs, coffset))
+    return ndofs[], coffset[]
+end
+
+function celldofs(ctx::Context, id::Integer, nd::Integer, ncells::Integer)
+    out = zeros(Int32, nd, ncells)
+    check(ctx, ccall((:femb_space_get_celldofs, libfemb), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), ctx.h, id, out))
+    return out
+end
+
+# ---- the steps after the assembly, on the device (Example200:86-92, Example210:172-173,180-185,192-209) -------------
+# boundarydofs(FES) (src/dofmaps.jl:871-899), sorted and unique
+function boundarydofs(ctx::Context, id::Integer, FEType, EG)
+    segs = pattern_segments(ExtendableFEMBase.get_dofmap_pattern(FEType, CellDofs, EG))
+    n = Ref{Int64}(0)
+    GC.@preserve segs check(ctx, ccall((:femb_boundary_dofs, libfemb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ref{Int64}), ctx.h, id, length(segs) ÷ 3, segs, n))
+    dofs = zeros(Int32, n[])
+    check(ctx, ccall((:femb_boundary_dofs_get, libfemb), Int32, (Ptr{Cvoid}, Ptr{Int32}), ctx.h, dofs))
+    return dofs
+end
+
+# A[dof,dof] = penalty; b[dof] = penalty * values[dof] for the boundary dofs of the last boundarydofs call (+ offset) and `extra`
+function dirichlet!(ctx::Context; offset = 0, extra = Int64[], values = nothing, penalty = 1.0e60)
+    GC.@preserve extra values check(ctx, ccall((:femb_dirichlet_apply, libfemb), Int32,
+        (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Float64),
+        ctx.h, 1, offset, length(extra), extra, values === nothing ? C_NULL : pointer(values), penalty))
+end
+
+# norm(A * x - b) with the fixed rows zeroed (x = nothing: the vector of the last femb_vector_set(1, ..))
+function residual_norm(ctx::Context, x = nothing)
+    nrm = Ref{Float64}(0)
+    GC.@preserve x check(ctx, ccall((:femb_residual, libfemb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32, Ptr{Float64}, Ref{Float64}),
+        ctx.h, x === nothing ? C_NULL : pointer(x), 1, C_NULL, nrm))
+    return nrm[]
+end
+
+system_save!(ctx::Context) = check(ctx, ccall((:femb_system_save, libfemb), Int32, (Ptr{Cvoid},), ctx.h))            # Alin = deepcopy(A); blin = deepcopy(b)
+system_add_saved!(ctx::Context) = check(ctx, ccall((:femb_system_add_saved, libfemb), Int32, (Ptr{Cvoid},), ctx.h))  # A += Alin; b += blin
+
 function quadrature_set!(ctx::Context, qf::QuadratureRule)
     xref = reduce(hcat, qf.xref)                 # dim x nqp
     w = collect(Float64, qf.w)
