@@ -135,12 +135,15 @@ def solve_stokes_device(FES, teval=0.0, maxits=20):
     return sol, nlres, it
 
 
-def l2_errors(sol, FESu, FESp):
-    """nodal-point (vertex rule) L2 errors like compute_error (Example210:112-154), velocity only at the P2 nodes"""
-    pts = p2_nodal_points(FESu.xgrid)
-    ue = u_exact(pts)
-    uh = np.stack([sol.entries[: FESu.ndofs // 2], sol.entries[FESu.ndofs // 2: FESu.ndofs]], axis=1)
-    return float(np.sqrt(np.mean(np.sum((uh - ue) ** 2, axis=1))))
+def l2_errors(sol, FESu, FESp, order=2):
+    """Example210:88-96: subtract the integral mean of the pressure (compute_error(sol[2], nothing, order, 1)), then the
+    VertexRule l2 errors of velocity and pressure — compute_error runs on the device (femb_eval_error)."""
+    nu = FESu.ndofs
+    pmean = fb.compute_error(FESp, sol.entries[nu:], None, order, 1).sum()
+    sol.entries[nu:] -= pmean
+    err_u = float(np.sqrt(fb.compute_error(FESu, sol.entries[:nu], u_exact, 2).sum()))
+    err_p = float(np.sqrt(fb.compute_error(FESp, sol.entries[nu:], lambda x: p_exact(x)[..., None], 2).sum()))
+    return err_u, err_p
 
 
 def main(nref=5, order=2, device_loop=False):
@@ -148,8 +151,8 @@ def main(nref=5, order=2, device_loop=False):
     xgrid = fb.simplexgrid(X, X)
     FES = [fb.FESpace(fb.H1Pk(2, 2, order), xgrid, "velocity space"), fb.FESpace(fb.H1Pk(1, 2, order - 1), xgrid, "pressure space")]
     sol, nlres, its = (solve_stokes_device if device_loop else solve_stokes_lowlevel)(FES)
-    err = l2_errors(sol, *FES)
-    print(f"nodal l2 error velo = {err:.4e} after {its} Newton iterations")
+    err, err_p = l2_errors(sol, *FES, order=order)
+    print(f"l2 error velo = {err:.4e}, l2 error pressure = {err_p:.4e} after {its} Newton iterations")
     return sol, nlres, its, err
 
 

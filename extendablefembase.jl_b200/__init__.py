@@ -7,18 +7,18 @@ this package, and ``csrc/`` = hand-written sm_100a CUDA kernels behind the C ABI
 the repo root is the import shim).
 """
 from . import _lib
-from .assembly import AffineFunction, Example210RHS, assemble_hdiv_mixed, assemble_poisson, prepare_assembly
+from .assembly import AffineFunction, Example210RHS, assemble_hdiv_mixed, assemble_poisson, compute_error, prepare_assembly
 from .fedefs import H1P1, H1P2, H1P3, H1Pk, HDIVBDM1, HDIVRT0, L2P0
 from .feevaluator import Divergence, FEEvaluator, Gradient, Identity
 from .fematrix import ExtendableSparseMatrixCSC, FEMatrix, FEVector
 from .fespace import FESpace, boundarydofs
 from .grids import ExtendableGrid, grid_tetrahedron, grid_triangle, jitter, simplexgrid
-from .quadrature import QuadratureRule
+from .quadrature import QuadratureRule, VertexRule
 
 CellDofs = "CellDofs"
 
 __all__ = [
-    "AffineFunction", "Example210RHS", "assemble_hdiv_mixed", "assemble_poisson", "prepare_assembly",
+    "AffineFunction", "Example210RHS", "assemble_hdiv_mixed", "assemble_poisson", "compute_error", "prepare_assembly", "VertexRule",
     "H1P1", "H1P2", "H1P3", "H1Pk", "HDIVBDM1", "HDIVRT0", "L2P0",
     "Divergence", "FEEvaluator", "Gradient", "Identity",
     "ExtendableSparseMatrixCSC", "FEMatrix", "FEVector", "FESpace", "boundarydofs", "CellDofs",

@@ -43,6 +43,7 @@ SIGNATURES = {
     "femb_boundary_dofs_get": (_i32, [_p, _p]),
     "femb_dirichlet_apply": (_i32, [_p, _i32, _i64, _i64, _p, _p, _f64]),
     "femb_residual": (_i32, [_p, _p, _i32, _p, C.POINTER(_f64)]),
+    "femb_eval_error": (_i32, [_p, _i32, _p, _p, _i32, _p]),
     "femb_system_save": (_i32, [_p]),
     "femb_system_add_saved": (_i32, [_p]),
     "femb_quadrature_set": (_i32, [_p, _i32, _p, _p]),
@@ -221,6 +222,13 @@ class Context:
         extra = _arr(extra_dofs, np.int64)
         values = _arr(values, np.float64)
         self._ck(self.lib.femb_dirichlet_apply(self.h, int(use_boundary_list), dof_offset, 0 if extra is None else extra.shape[0], _ptr(extra), _ptr(values), penalty))
+
+    def eval_error(self, eid, coefficients, exact_qp, p, resultdim):
+        """compute_error: -> (ncells, resultdim) array of sum_qp (uh - u)^p |T| w_qp."""
+        coefficients, exact_qp = _arr(coefficients, np.float64), _arr(exact_qp, np.float64)
+        out = np.empty((self.ncells, resultdim), np.float64)
+        self._ck(self.lib.femb_eval_error(self.h, eid, _ptr(coefficients), _ptr(exact_qp), p, _ptr(out)))
+        return out
 
     def system_save(self):
         self._ck(self.lib.femb_system_save(self.h))

@@ -237,3 +237,29 @@ def assemble_hdiv_mixed(A: FEMatrix, FESv, FESq, *, device=0, scatter=None):
     ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
     ctx.matrix_add_to(Ae.nzval)
     return S
+
+
+# --------------------------------------------------------------------------------------
+# compute_error (Example210:110-154)
+# --------------------------------------------------------------------------------------
+def compute_error(fes, coefficients, u=None, order=None, p=2, *, operator=Identity, device=0):
+    """Drop-in for ``compute_error(uh::FEVectorBlock, u, order, p)``: ``error[cell, d] = sum_qp (uh_d - u_d)^p |T| w_qp`` over the
+    ``VertexRule`` of the given order (default: the polynomial order of the element), evaluated on the device.  ``u`` maps the
+    physical points ``x[..., dim]`` to values ``[..., ncomp]`` (or is None).  Returns ``(ncells, ncomp)`` (the bytes of Julia's
+    ``ncomp x ncells``)."""
+    from .quadrature import VertexRule
+
+    g = fes.xgrid.geometry
+    if order is None:
+        order = fes.fetype.get_polynomialorder(g)
+    qf = VertexRule(g, order)
+    S = _Session([fes], qf, device)
+    try:
+        ev = S.evaluator(0, operator)
+        exact = None
+        if u is not None:
+            x = S.ctx.qp_coords(len(qf))
+            exact = np.ascontiguousarray(np.asarray(u(x), dtype=np.float64).reshape(x.shape[0], len(qf), ev.resultdim))
+        return S.ctx.eval_error(ev._eid, np.asarray(coefficients, dtype=np.float64), exact, int(p), ev.resultdim)
+    finally:
+        S.ctx.close()

@@ -157,6 +157,74 @@ extern "C" int32_t femb_qp_coords(femb_ctx* ctx, double* out) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// compute_error (Example210_LowLevelNavierStokes.jl:110-154): error[d, cell] = sum_qp (uh_d(x_qp) - u_d(x_qp))^p |T| w_qp with
+// uh = eval_febe! of the coefficient vector through any registered evaluator (Identity: L^p error, Gradient: its seminorm)
+// ---------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_eval_error(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol, int64_t ncells,
+                             SpaceDev s, int op, int R, QuadDev q, const double* __restrict__ rv, const double* __restrict__ rd,
+                             const double* __restrict__ coef, const double* __restrict__ exact, int p, double* __restrict__ out) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cell >= ncells) return;
+    Geo<DIM> g;
+    load_geo<DIM>(coords, cellnodes, cellvol, cell, g);
+    double err[9];
+    for (int r = 0; r < R; r++) err[r] = 0.0;
+    for (int qp = 0; qp < q.nqp; qp++) {
+        double uh[9];
+        for (int r = 0; r < R; r++) uh[r] = 0.0;
+        for (int dof = 0; dof < s.nd; dof++) {
+            double v[9];
+            for (int r = 0; r < R; r++) v[r] = 0.0;
+            eval_op<DIM>(s, op, g, cell, dof, qp, rv, rd, v);
+            const double c = coef[s.celldofs[cell * s.nd + dof] - 1];
+            for (int r = 0; r < R; r++) uh[r] += c * v[r];
+        }
+        for (int r = 0; r < R; r++) {
+            const double diff = uh[r] - (exact ? exact[((size_t)cell * q.nqp + qp) * R + r] : 0.0);
+            double pw = 1.0;
+            for (int i = 0; i < p; i++) pw *= diff;
+            err[r] += pw * g.vol * q.w[qp];
+        }
+    }
+    for (int r = 0; r < R; r++) out[cell * R + r] = err[r];
+}
+
+extern "C" int32_t femb_eval_error(femb_ctx* ctx, int32_t id, const double* coefficients, const double* exact_qp, int32_t p, double* error_out) {
+    FEMB_CHECK_CTX(ctx);
+    FEMB_TRY(check_eval(ctx, id));
+    const FembEval& e = ctx->evals[id];
+    const FembSpace& s = ctx->spaces[e.space];
+    if (!coefficients || !error_out || p < 1 || p > 16 || e.resultdim > 9) return femb_fail(ctx, FEMB_ERR_ARG, "femb_eval_error: bad arguments");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->ncells == 0) return FEMB_OK;
+    const size_t nq = (size_t)ctx->ncells * e.nqp * e.resultdim;
+    double *dcoef = nullptr, *dexact = nullptr, *dout = nullptr;
+    int st = femb_alloc(ctx, &dcoef, (size_t)s.ndofs);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &dout, (size_t)ctx->ncells * e.resultdim);
+    if (st == FEMB_OK && exact_qp) st = femb_alloc(ctx, &dexact, nq);
+    if (st == FEMB_OK) st = femb_h2d(ctx, dcoef, coefficients, (size_t)s.ndofs);
+    if (st == FEMB_OK && exact_qp) st = femb_h2d(ctx, dexact, exact_qp, nq);
+    if (st == FEMB_OK) {
+        const unsigned grid = (unsigned)((ctx->ncells + 127) / 128);
+        const QuadDev q = quad_dev(e, ctx->dim);
+        if (ctx->dim == 2)
+            k_eval_error<2><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, space_dev(s), e.op, e.resultdim, q, e.refvals,
+                                                          e.refderivs, dcoef, dexact, p, dout);
+        else
+            k_eval_error<3><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, space_dev(s), e.op, e.resultdim, q, e.refvals,
+                                                          e.refderivs, dcoef, dexact, p, dout);
+        ctx->launches++;
+        st = femb_d2h(ctx, error_out, dout, (size_t)ctx->ncells * e.resultdim);
+        if (st == FEMB_OK) st = femb_sync(ctx);
+    }
+    femb_free(&dcoef);
+    femb_free(&dexact);
+    femb_free(&dout);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // generic cell-parallel bilinear form: CTA = CPB cells; cvals staged in shared memory
 // ---------------------------------------------------------------------------------------------------
 struct BilArgs {

@@ -36,6 +36,42 @@ class QuadratureRule:
         return f"QuadratureRule({self.geometry}, {self.name!r}, npoints={len(self)})"
 
 
+_TRI_EDGES = ((0, 1), (1, 2), (2, 0))
+_TET_EDGES = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
+_TET_FACES = ((0, 2, 1), (0, 1, 3), (1, 2, 3), (0, 3, 2))
+
+
+def VertexRule(geometry: str, order: int = 1) -> QuadratureRule:
+    """``VertexRule(EG, order)`` (/root/reference/src/quadrature.jl:103-138 triangle, :157-186 tetrahedron): the Lagrange
+    points of the given order with equal weights; the rule of ``compute_error`` (Example210:122)."""
+    from fractions import Fraction as Fr
+
+    d = 2 if geometry == "Triangle2D" else 3
+    if order == 0:
+        pts = [[Fr(1, d + 1)] * d]
+    else:
+        pts = [[Fr(0)] * d] + [[Fr(int(i == j)) for i in range(d)] for j in range(d)]
+    for a, b in (_TRI_EDGES if d == 2 else _TET_EDGES):
+        for j in range(1, order):
+            pts.append([Fr(j, order) * pts[b][i] + (1 - Fr(j, order)) * pts[a][i] for i in range(d)])
+    if d == 2:
+        interior = {3: [(1, 1)], 4: [(1, 1), (2, 1), (1, 2)], 5: [(1, 1), (3, 1), (1, 3), (2, 1), (2, 2), (1, 2)]}.get(order, [])
+        pts += [[Fr(x, order), Fr(y, order)] for x, y in interior]
+        if order > 5:
+            raise NotImplementedError("VertexRule for order > 5 on Triangle2D (quadrature.jl:133-135)")
+    else:
+        if order > 2:
+            for j in range(1, order - 1):
+                for k in range(1, order - 1):
+                    for f in _TET_FACES:
+                        pts.append([Fr(j, order) * pts[f[2]][i] + Fr(k, order) * pts[f[1]][i] + (1 - Fr(j, order) - Fr(k, order)) * pts[f[0]][i] for i in range(d)])
+        if order > 3:
+            raise NotImplementedError("VertexRule for order > 3 on Tetrahedron3D (quadrature.jl:181-183)")
+    xref = np.array([[float(c) for c in p] for p in pts])
+    w = np.full(len(pts), 1.0 / len(pts))
+    return QuadratureRule(geometry, xref=xref, w=w, name="vertex rule")
+
+
 def _triangle(order: int):
     # quadrature.jl:257-279
     if order <= 1:

@@ -151,6 +151,12 @@ int32_t femb_boundary_dofs_get(femb_ctx* ctx, int32_t* dofs);
 int32_t femb_dirichlet_apply(femb_ctx* ctx, int32_t use_boundary_list, int64_t dof_offset, int64_t n_extra,
                              const int64_t* extra_dofs, const double* values_or_null, double penalty);
 int32_t femb_residual(femb_ctx* ctx, const double* x_or_null, int32_t zero_fixed, double* res_or_null, double* norm_out);
+/* compute_error (Example210:110-154) through a registered evaluator (register it after femb_quadrature_set with the
+ * VertexRule, quadrature.jl:103-186): error_out[d, cell] = sum_qp (uh_d(x_qp) - exact_qp[d, qp, cell])^p |T| w_qp with
+ * uh = eval_febe! of `coefficients` (the ndofs values of the evaluator's space); exact_qp may be NULL (u = nothing).
+ * error_out: resultdim x ncells. */
+int32_t femb_eval_error(femb_ctx* ctx, int32_t eval_id, const double* coefficients, const double* exact_qp_or_null, int32_t p,
+                        double* error_out);
 /* Alin = deepcopy(A); blin = deepcopy(b) (Example210:164-165) and A += Alin; b += blin (Example210:192-193), on the device */
 int32_t femb_system_save(femb_ctx* ctx);
 int32_t femb_system_add_saved(femb_ctx* ctx);

@@ -74,6 +74,39 @@ def quadrature(geometry: str, order: int):
     raise ValueError(geometry)
 
 
+def vertex_rule(geometry: str, order: int = 1):
+    """VertexRule(EG, order) (quadrature.jl:103-138 triangle, :157-186 tetrahedron): Lagrange points, equal weights."""
+    d = DIM[geometry]
+    pts = [[1.0 / (d + 1)] * d] if order == 0 else [[0.0] * d] + [[float(i == j) for i in range(d)] for j in range(d)]
+    edges = [(0, 1), (1, 2), (2, 0)] if d == 2 else [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    for a, b in edges:  # quadrature.jl:110-115 / :165-170
+        for j in range(1, order):
+            pts.append([j / order * pts[b][i] + (1 - j / order) * pts[a][i] for i in range(d)])
+    if d == 2:  # :117-132
+        extra = {3: [(1, 1)], 4: [(1, 1), (2, 1), (1, 2)], 5: [(1, 1), (3, 1), (1, 3), (2, 1), (2, 2), (1, 2)]}.get(order, [])
+        pts += [[x / order, y / order] for x, y in extra]
+    elif order > 2:  # :172-179
+        faces = [(0, 2, 1), (0, 1, 3), (1, 2, 3), (0, 3, 2)]
+        for j in range(1, order - 1):
+            for k in range(1, order - 1):
+                for f in faces:
+                    pts.append([j / order * pts[f[2]][i] + k / order * pts[f[1]][i] + (1 - j / order - k / order) * pts[f[0]][i] for i in range(d)])
+    return np.array(pts), np.full(len(pts), 1.0 / len(pts))
+
+
+def compute_error(el, g, coords, cellnodes, cellvolumes, celldofs, uh, u, order, p=2, op="Identity", facesigns=None, edgesigns=None, orient=None):
+    """Example210_LowLevelNavierStokes.jl:110-154: error[cell, d] = sum_qp (uh_d(x_qp) - u_d(x_qp))^p |T| w_qp over the VertexRule."""
+    xref, w = vertex_rule(g, order)
+    cv = update_basis(el, op, g, xref, coords, cellnodes, facesigns, edgesigns, orient)  # [cell, r, dof, qp]
+    coef = np.asarray(uh)[celldofs - 1]  # [cell, dof]
+    uhq = np.einsum("crdq,cd->cqr", cv, coef)  # eval_febe! (:135)
+    if u is not None:
+        A, b, det, M = l2g(coords, cellnodes)
+        x = np.einsum("ckj,qj->cqk", A, xref) + b[:, None, :]  # eval_trafo! (:140)
+        uhq = uhq - np.asarray(u(x)).reshape(uhq.shape)
+    return np.einsum("cqr,q,c->cr", uhq ** p, w, cellvolumes)  # :146
+
+
 def _stroud(order: int):
     """quadrature.jl:631-665.  The reference gets the 1-D nodes from Golub-Welsch eigen-decompositions;
     here they come from scipy's Gauss-Legendre / Gauss-Jacobi(1,0) routines (same nodes, ascending)."""

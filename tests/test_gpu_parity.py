@@ -725,3 +725,34 @@ def test_device_dirichlet_and_residual_match_host():
     nrm3, res3 = ctx.residual(x2, zero_fixed=True, want_vector=True, n=n)
     assert nrm3 == nrm2 and np.array_equal(res3, res2)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# compute_error (Example210:110-154) on the device vs the oracle restatement
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mk,dim,op", [(lambda: fb.H1Pk(2, 2, 2), 2, "Identity"), (lambda: fb.H1Pk(1, 2, 1), 2, "Identity"), (lambda: fb.H1P3(1, 2), 2, "Gradient"),
+                                       (lambda: fb.H1P2(1, 3), 3, "Identity"), (lambda: fb.HDIVBDM1(3), 3, "Identity")])
+def test_compute_error_matches_oracle(mk, dim, op):
+    ft = mk()
+    grid = _grid2d(6, True) if dim == 2 else _grid3d(3, True)
+    fes = fb.FESpace(ft, grid)
+    rng = np.random.default_rng(8)
+    uh = rng.uniform(-1, 1, fes.ndofs)
+    el = _oracle_el(ft)
+    fs, es, ori = _signs(grid, ft)
+    R = {"Identity": ft.ncomponents if ft.family != "Hdiv" else dim, "Gradient": ft.ncomponents * dim}[op]
+
+    def u(x):
+        return np.stack([np.sin(3 * x[..., 0]) * (r + 1) + x[..., -1] ** 2 for r in range(R)], axis=-1)
+
+    for exact in (u, None):
+        got = fb.compute_error(fes, uh, exact, order=2, p=2, operator=op)
+        ref = orc.compute_error(el, grid.geometry, grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"], fes["CellDofs"], uh, exact, 2, 2, op, fs, es, ori)
+        assert got.shape == ref.shape == (grid.ncells, R)
+        assert np.abs(got - ref).max() <= RTOL * np.abs(ref).max()
+    # nodal interpolant of a quadratic in P2: zero error at the Lagrange points of order 2
+    if ft.family == "H1" and ft.order == 2 and ft.ncomponents == 1 and dim == 3:
+        pts = np.concatenate([grid["Coordinates"], 0.5 * (grid["Coordinates"][grid["EdgeNodes"][:, 0] - 1] + grid["Coordinates"][grid["EdgeNodes"][:, 1] - 1])])
+        quad = lambda x: (1 + x[..., 0] - 2 * x[..., 1] * x[..., 2] + x[..., 0] ** 2)[..., None]  # noqa: E731
+        err = fb.compute_error(fes, quad(pts)[:, 0], quad, order=2)
+        assert np.sqrt(err.sum()) < 1e-14

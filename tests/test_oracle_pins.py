@@ -402,3 +402,20 @@ def test_bdm1_orientation_codes():
             flux = el.basis("Tetrahedron3D", pts)[:, sub, :] @ n  # [q, 3]
             N = area * np.stack([fw @ flux, (fw * (fx[:, 0] - 1 / 3)) @ flux, (fw * (fx[:, 1] - 1 / 3)) @ flux])
             assert np.allclose(N @ np.diag([sign, -1.0, 1.0]), np.eye(3), atol=1e-12), (j, gn, code)
+
+
+def test_vertex_rule_points_and_host_mirror_agree():
+    """VertexRule (quadrature.jl:103-186): point counts = Lagrange nodes of the order, weights sum to 1, the vertices come first;
+    the host mirror builds the same table in exact rationals."""
+    import femb_b200 as fb
+
+    for g, d, counts in (("Triangle2D", 2, {0: 1, 1: 3, 2: 6, 3: 10, 4: 15, 5: 21}), ("Tetrahedron3D", 3, {0: 1, 1: 4, 2: 10, 3: 20})):
+        for order, n in counts.items():
+            xref, w = orc.vertex_rule(g, order)
+            assert xref.shape == (n, d) and abs(w.sum() - 1.0) < 1e-15
+            assert len({tuple(np.round(p, 12)) for p in xref}) == n  # distinct points
+            assert (xref >= -1e-15).all() and (xref.sum(axis=1) <= 1 + 1e-15).all()
+            qf = fb.VertexRule(g, order)
+            assert np.abs(qf.xref - xref).max() < 1e-15 and np.array_equal(qf.w, w)
+    # order 2 on the triangle: vertices then the midpoints of the edges (1,2), (2,3), (3,1)
+    assert np.allclose(orc.vertex_rule("Triangle2D", 2)[0][3:], [[0.5, 0.0], [0.5, 0.5], [0.0, 0.5]])
