@@ -44,6 +44,8 @@ SIGNATURES = {
     "femb_dirichlet_apply": (_i32, [_p, _i32, _i64, _i64, _p, _p, _f64]),
     "femb_residual": (_i32, [_p, _p, _i32, _p, C.POINTER(_f64)]),
     "femb_eval_error": (_i32, [_p, _i32, _p, _p, _i32, _p]),
+    "femb_block_matmul": (_i32, [_p, _i32, _i32, _p, _f64, _i32, _p]),
+    "femb_lrmatmul": (_i32, [_p, _p, _p, _p, _p, _f64, C.POINTER(_f64)]),
     "femb_system_save": (_i32, [_p]),
     "femb_system_add_saved": (_i32, [_p]),
     "femb_quadrature_set": (_i32, [_p, _i32, _p, _p]),
@@ -229,6 +231,20 @@ class Context:
         out = np.empty((self.ncells, resultdim), np.float64)
         self._ck(self.lib.femb_eval_error(self.h, eid, _ptr(coefficients), _ptr(exact_qp), p, _ptr(out)))
         return out
+
+    def block_matmul(self, a, b, brow=-1, bcol=-1, factor=1.0, transposed=False):
+        """addblock_matmul!(a, B[brow, bcol], b; factor, transposed): a (float64, contiguous) is updated in place."""
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+        b = _arr(b, np.float64)
+        self._ck(self.lib.femb_block_matmul(self.h, brow, bcol, _ptr(b), factor, int(transposed), _ptr(a)))
+        return a
+
+    def lrmatmul(self, a1, b1, a2=None, b2=None, factor=1.0):
+        """lrmatmul(a, A, b) / ldrdmatmul(a1, a2, A, b1, b2): (a1 - a2)' A (b1 - b2) * factor."""
+        a1, a2, b1, b2 = (_arr(v, np.float64) for v in (a1, a2, b1, b2))
+        out = _f64(0.0)
+        self._ck(self.lib.femb_lrmatmul(self.h, _ptr(a1), _ptr(a2), _ptr(b1), _ptr(b2), factor, C.byref(out)))
+        return float(out.value)
 
     def system_save(self):
         self._ck(self.lib.femb_system_save(self.h))

@@ -119,6 +119,54 @@ __global__ void k_add_inplace(double* __restrict__ y, const double* __restrict__
     if (i < n) y[i] += x[i];
 }
 
+// a[row - r0] += factor * sum_{col in [c0, c1)} A[row, col] b[col - c0]   (row-wise view, 8 lanes per row, fixed tree)
+__global__ void __launch_bounds__(256) k_block_matvec(const int64_t* __restrict__ ptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ slot,
+                                                      const double* __restrict__ nzval, const double* __restrict__ b, int64_t r0, int64_t r1, int64_t c0,
+                                                      int64_t c1, double factor, double* __restrict__ a) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t row = r0 + (t >> 3);
+    const int sub = (int)(t & 7);
+    double acc = 0.0;
+    if (row < r1) {
+        const int64_t e = ptr[row + 1];
+        for (int64_t q = ptr[row] + sub; q < e; q += 8) {
+            const int64_t c = col[q];
+            if (c >= c0 && c < c1) acc += nzval[slot[q]] * b[c - c0];
+        }
+    }
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+    if (row < r1 && sub == 0) a[row - r0] += factor * acc;
+}
+
+// transposed: a[col - c0] += factor * sum_{row in [r0, r1)} A[row, col] b[row - r0]   (CSC columns directly)
+// LR = 1: out[col - c0] = factor * (b1 - b2)[col] * sum_row A[row, col] (a1 - a2)[row]  (terms of lrmatmul / ldrdmatmul)
+template <int LR>
+__global__ void __launch_bounds__(256) k_block_matvec_t(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, const double* __restrict__ nzval,
+                                                        const double* __restrict__ b, const double* __restrict__ b2, const double* __restrict__ c1v,
+                                                        const double* __restrict__ c2v, int64_t r0, int64_t r1, int64_t c0, int64_t c1, double factor,
+                                                        double* __restrict__ a) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t cl = c0 + (t >> 3);
+    const int sub = (int)(t & 7);
+    double acc = 0.0;
+    if (cl < c1) {
+        const int64_t e = colptr[cl + 1] - 1;
+        for (int64_t q = colptr[cl] - 1 + sub; q < e; q += 8) {
+            const int64_t r = rowval[q] - 1;
+            if (r >= r0 && r < r1) acc += nzval[q] * (b[r - r0] - (LR && b2 ? b2[r - r0] : 0.0));
+        }
+    }
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+    acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+    if (cl < c1 && sub == 0) {
+        if (LR) a[cl - c0] = factor * acc * (c1v[cl - c0] - (c2v ? c2v[cl - c0] : 0.0));
+        else a[cl - c0] += factor * acc;
+    }
+}
+
 struct Square {
     __host__ __device__ double operator()(double v) const { return v * v; }
 };
@@ -331,6 +379,86 @@ int32_t femb_dirichlet_apply(femb_ctx* ctx, int32_t use_boundary_list, int64_t d
     if (nerr) return femb_fail(ctx, FEMB_ERR_PATTERN, "%d fixed dofs are out of range or have no diagonal entry in the pattern", nerr);
     ctx->nfixed = n;
     return FEMB_OK;
+}
+
+// block ranges of (brow, bcol) in the matrix layout; brow = bcol = -1: the whole matrix
+static int block_range(femb_ctx* ctx, int brow, int bcol, int64_t& r0, int64_t& r1, int64_t& c0, int64_t& c1) {
+    if (!ctx->nzval) return femb_fail(ctx, FEMB_ERR_ARG, "no pattern: femb_pattern_build / femb_pattern_adopt first");
+    if (brow == -1 && bcol == -1) {
+        r0 = c0 = 0; r1 = ctx->nrows; c1 = ctx->ncols;
+        return FEMB_OK;
+    }
+    if (brow < 0 || brow >= ctx->nrs || bcol < 0 || bcol >= ctx->ncs) return femb_fail(ctx, FEMB_ERR_ARG, "block (%d, %d) is outside the matrix layout", brow, bcol);
+    r0 = ctx->row_off[brow]; r1 = ctx->row_off[brow + 1];
+    c0 = ctx->col_off[bcol]; c1 = ctx->col_off[bcol + 1];
+    return FEMB_OK;
+}
+
+int32_t femb_block_matmul(femb_ctx* ctx, int32_t brow, int32_t bcol, const double* b, double factor, int32_t transposed, double* a) {
+    FEMB_CHECK_CTX(ctx);
+    int64_t r0, r1, c0, c1;
+    FEMB_TRY(block_range(ctx, brow, bcol, r0, r1, c0, c1));
+    if (!a || !b) return femb_fail(ctx, FEMB_ERR_ARG, "femb_block_matmul: NULL vector");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    const int64_t na = transposed ? c1 - c0 : r1 - r0, nb = transposed ? r1 - r0 : c1 - c0;
+    if (na == 0) return FEMB_OK;
+    if (!transposed) FEMB_TRY(build_csr(ctx));
+    double *da = nullptr, *db = nullptr;
+    int st = femb_alloc(ctx, &da, (size_t)na);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &db, (size_t)std::max<int64_t>(nb, 1));
+    if (st == FEMB_OK) st = femb_h2d(ctx, da, a, (size_t)na);
+    if (st == FEMB_OK && nb) st = femb_h2d(ctx, db, b, (size_t)nb);
+    if (st == FEMB_OK) {
+        const unsigned grid = (unsigned)((na * 8 + 255) / 256);
+        if (transposed)
+            k_block_matvec_t<0><<<grid, 256, 0, ctx->stream>>>(ctx->colptr, ctx->rowval, ctx->nzval, db, nullptr, nullptr, nullptr, r0, r1, c0, c1, factor, da);
+        else
+            k_block_matvec<<<grid, 256, 0, ctx->stream>>>(ctx->csr_ptr, ctx->csr_col, ctx->csr_slot, ctx->nzval, db, r0, r1, c0, c1, factor, da);
+        ctx->launches++;
+        st = femb_d2h(ctx, a, da, (size_t)na);
+        if (st == FEMB_OK) st = femb_sync(ctx);
+    }
+    femb_free(&da);
+    femb_free(&db);
+    return st;
+}
+
+int32_t femb_lrmatmul(femb_ctx* ctx, const double* a1, const double* a2, const double* b1, const double* b2, double factor, double* out) {
+    FEMB_CHECK_CTX(ctx);
+    int64_t r0, r1, c0, c1;
+    FEMB_TRY(block_range(ctx, -1, -1, r0, r1, c0, c1));
+    if (!a1 || !b1 || !out) return femb_fail(ctx, FEMB_ERR_ARG, "femb_lrmatmul: NULL argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    *out = 0.0;
+    if (c1 == 0 || r1 == 0) return FEMB_OK;
+    double *da1 = nullptr, *da2 = nullptr, *db1 = nullptr, *db2 = nullptr, *terms = nullptr;
+    void* tmp = nullptr;
+    int st = femb_alloc(ctx, &da1, (size_t)r1);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &db1, (size_t)c1);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &terms, (size_t)c1 + 1);
+    if (st == FEMB_OK && a2) st = femb_alloc(ctx, &da2, (size_t)r1);
+    if (st == FEMB_OK && b2) st = femb_alloc(ctx, &db2, (size_t)c1);
+    if (st == FEMB_OK) st = femb_h2d(ctx, da1, a1, (size_t)r1);
+    if (st == FEMB_OK) st = femb_h2d(ctx, db1, b1, (size_t)c1);
+    if (st == FEMB_OK && a2) st = femb_h2d(ctx, da2, a2, (size_t)r1);
+    if (st == FEMB_OK && b2) st = femb_h2d(ctx, db2, b2, (size_t)c1);
+    if (st == FEMB_OK) {
+        k_block_matvec_t<1><<<(unsigned)((c1 * 8 + 255) / 256), 256, 0, ctx->stream>>>(ctx->colptr, ctx->rowval, ctx->nzval, da1, da2, db1, db2, 0, r1, 0, c1, factor, terms);
+        ctx->launches += 2;
+        size_t tb = 0;
+        cudaError_t e = cub::DeviceReduce::Sum(nullptr, tb, terms, terms + c1, c1, ctx->stream);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp, std::max<size_t>(tb, 1));
+        if (e == cudaSuccess) e = cub::DeviceReduce::Sum(tmp, tb, terms, terms + c1, c1, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, terms + c1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) st = femb_fail(ctx, FEMB_ERR_CUDA, "femb_lrmatmul: %s", cudaGetErrorString(e));
+    }
+    femb_free(&da1); femb_free(&da2); femb_free(&db1); femb_free(&db2); femb_free(&terms);
+    if (tmp) cudaFree(tmp);
+    return st;
 }
 
 int32_t femb_system_save(femb_ctx* ctx) {

@@ -157,6 +157,14 @@ int32_t femb_residual(femb_ctx* ctx, const double* x_or_null, int32_t zero_fixed
  * error_out: resultdim x ncells. */
 int32_t femb_eval_error(femb_ctx* ctx, int32_t eval_id, const double* coefficients, const double* exact_qp_or_null, int32_t p,
                         double* error_out);
+/* addblock_matmul!(a, B, b; factor, transposed) (src/fematrix.jl:486-563): a += factor * B b (or B' b) for the block
+ * (brow, bcol) of the matrix layout, vectors in block-local numbering; brow = bcol = -1: the whole matrix (:570-602).
+ * femb_lrmatmul: lrmatmul / ldrdmatmul (src/fematrix.jl:607-637): (a1 - a2)' A (b1 - b2) * factor over the whole matrix
+ * (a2 / b2 may be NULL).  Row-wise / column-wise sums with a fixed reduction tree: bit-reproducible. */
+int32_t femb_block_matmul(femb_ctx* ctx, int32_t brow, int32_t bcol, const double* b, double factor, int32_t transposed,
+                          double* a_inout);
+int32_t femb_lrmatmul(femb_ctx* ctx, const double* a1, const double* a2_or_null, const double* b1, const double* b2_or_null,
+                      double factor, double* out);
 /* Alin = deepcopy(A); blin = deepcopy(b) (Example210:164-165) and A += Alin; b += blin (Example210:192-193), on the device */
 int32_t femb_system_save(femb_ctx* ctx);
 int32_t femb_system_add_saved(femb_ctx* ctx);

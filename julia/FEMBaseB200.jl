@@ -167,6 +167,29 @@ function residual_norm(ctx::Context, x = nothing)
     return nrm[]
 end
 
+# addblock_matmul!(a, B[brow, bcol], b; factor, transposed) (src/fematrix.jl:486-563), block numbers 0-based in the layout
+function block_matmul!(ctx::Context, a::Vector{Float64}, b::Vector{Float64}; brow = -1, bcol = -1, factor = 1.0, transposed = false)
+    GC.@preserve a b check(ctx, ccall((:femb_block_matmul, libfemb), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Float64, Int32, Ptr{Float64}),
+        ctx.h, brow, bcol, b, factor, transposed, a))
+    return a
+end
+
+# lrmatmul(a, A, b) / ldrdmatmul(a1, a2, A, b1, b2) (src/fematrix.jl:607-637)
+function lrmatmul(ctx::Context, a1, b1; a2 = nothing, b2 = nothing, factor = 1.0)
+    out = Ref{Float64}(0)
+    GC.@preserve a1 a2 b1 b2 check(ctx, ccall((:femb_lrmatmul, libfemb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}),
+        ctx.h, a1, a2 === nothing ? C_NULL : pointer(a2), b1, b2 === nothing ? C_NULL : pointer(b2), factor, out))
+    return out[]
+end
+
+# compute_error(uh, u, order, p) (Example210:110-154): exact = values of u at the quadrature points (resultdim x nqp x ncells) or nothing
+function eval_error(ctx::Context, eval_id::Integer, coefficients::Vector{Float64}, exact, p::Integer, resultdim::Integer, ncells::Integer)
+    err = zeros(Float64, resultdim, ncells)
+    GC.@preserve coefficients exact check(ctx, ccall((:femb_eval_error, libfemb), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}),
+        ctx.h, eval_id, coefficients, exact === nothing ? C_NULL : pointer(exact), p, err))
+    return err
+end
+
 system_save!(ctx::Context) = check(ctx, ccall((:femb_system_save, libfemb), Int32, (Ptr{Cvoid},), ctx.h))            # Alin = deepcopy(A); blin = deepcopy(b)
 system_add_saved!(ctx::Context) = check(ctx, ccall((:femb_system_add_saved, libfemb), Int32, (Ptr{Cvoid},), ctx.h))  # A += Alin; b += blin
 

@@ -756,3 +756,43 @@ def test_compute_error_matches_oracle(mk, dim, op):
         quad = lambda x: (1 + x[..., 0] - 2 * x[..., 1] * x[..., 2] + x[..., 0] ** 2)[..., None]  # noqa: E731
         err = fb.compute_error(fes, quad(pts)[:, 0], quad, order=2)
         assert np.sqrt(err.sum()) < 1e-14
+
+
+def test_block_matmul_and_lrmatmul_match_scipy():
+    """addblock_matmul! (fematrix.jl:486-563) per block / transposed / whole matrix, lrmatmul and ldrdmatmul (:607-637)"""
+    import scipy.sparse as sp
+    from femb_b200.assembly import _Session
+
+    grid = _grid2d(7, True)
+    FESu, FESp = fb.FESpace(fb.H1Pk(2, 2, 2), grid), fb.FESpace(fb.H1Pk(1, 2, 1), grid)
+    nu, npr = FESu.ndofs, FESp.ndofs
+    n = nu + npr
+    S = _Session([FESu, FESp], fb.QuadratureRule(grid.geometry, 5))
+    ctx = S.ctx
+    egu, eiu, eip = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity"), S.evaluator(1, "Identity")
+    ctx.pattern_build([(0, 0), (0, 1), (1, 0)], [nu + 1])
+    rng = np.random.default_rng(6)
+    ctx.vector_set(1, rng.uniform(-1, 1, n))
+    ctx.matrix_zero(); ctx.vector_zero()
+    ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, 1e-2, True, True, _lib.RHS_NONE, None)
+    colptr, rowval = ctx.pattern_get(n)
+    A = sp.csc_matrix((ctx.matrix_get(), rowval - 1, colptr - 1), shape=(n, n)).tocsr()
+    off = [0, nu, n]
+    scale = abs(A).max()
+    for br in (0, 1):
+        for bc in (0, 1):
+            B = A[off[br]:off[br + 1], off[bc]:off[bc + 1]]
+            for transposed in (False, True):
+                b = rng.uniform(-1, 1, B.shape[0] if transposed else B.shape[1])
+                a0 = rng.uniform(-1, 1, B.shape[1] if transposed else B.shape[0])
+                a = ctx.block_matmul(a0.copy(), b, br, bc, factor=-0.75, transposed=transposed)
+                ref = a0 - 0.75 * ((B.T @ b) if transposed else (B @ b))
+                assert np.abs(a - ref).max() <= 1e-12 * scale * 30
+    b, a0 = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    a = ctx.block_matmul(a0.copy(), b, factor=2.0)
+    assert np.abs(a - (a0 + 2.0 * (A @ b))).max() <= 1e-12 * scale * 60
+    a1, a2, b1, b2 = (rng.uniform(-1, 1, n) for _ in range(4))
+    assert abs(ctx.lrmatmul(a1, b1, factor=1.5) - 1.5 * (a1 @ (A @ b1))) <= 1e-12 * scale * n
+    assert abs(ctx.lrmatmul(a1, b1, a2, b2) - (a1 - a2) @ (A @ (b1 - b2))) <= 1e-12 * scale * n
+    assert ctx.lrmatmul(a1, b1, a2, b2) == ctx.lrmatmul(a1, b1, a2, b2)  # reproducible
+    ctx.close()
