@@ -68,7 +68,7 @@ def c3_p2_3d(m, steps, warmup, order=2, check=False):
     return res
 
 
-def c4_hdiv(m, steps, warmup, name):
+def c4_hdiv(m, steps, warmup, name, scatter=None):
     X = np.linspace(0, 1, m + 1)
     grid = fb.simplexgrid(X, X, X)
     ft = fb.HDIVRT0(3) if name == "RT0" else fb.HDIVBDM1(3)
@@ -78,6 +78,8 @@ def c4_hdiv(m, steps, warmup, name):
     ctx = S.ctx
     eid, ediv, eq = S.evaluator(0, "Identity"), S.evaluator(0, "Divergence"), S.evaluator(1, "Identity")
     nnz = ctx.pattern_build([(0, 0), (0, 1), (1, 0)])
+    if scatter is not None:
+        ctx.set_scatter(scatter)
 
     def step():
         ctx.matrix_zero()
@@ -85,7 +87,7 @@ def c4_hdiv(m, steps, warmup, name):
         ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
 
     ms = timeit(step, ctx, steps, warmup)
-    return {"config": f"C4 HDIV{name}{{3}} mass + (div v, q) vs L2P0, Kuhn m={m}", "ncells": grid.ncells, "ndofs": FESv.ndofs + FESq.ndofs, "nnz": nnz,
+    return {"config": f"C4 HDIV{name}{{3}} mass + (div v, q) vs L2P0, Kuhn m={m}" + ("" if scatter is None else f", scatter policy {scatter}"), "ncells": grid.ncells, "ndofs": FESv.ndofs + FESq.ndofs, "nnz": nnz,
             "ms_per_step": ms, "cells_per_s": grid.ncells / (ms * 1e-3)}
 
 
@@ -258,6 +260,7 @@ if __name__ == "__main__":
     ap.add_argument("--n5", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--scatter", type=int, default=None, help="C4: 0 atomic, 1 coloured, 2 gather (default policy of the library)")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     a = ap.parse_args()
@@ -268,8 +271,8 @@ if __name__ == "__main__":
         elif w == "c3p1":
             res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 1))
         elif w == "c4":
-            res.append(c4_hdiv(a.m4, a.steps, a.warmup, "RT0"))
-            res.append(c4_hdiv(a.m4, a.steps, a.warmup, "BDM1"))
+            res.append(c4_hdiv(a.m4, a.steps, a.warmup, "RT0", a.scatter))
+            res.append(c4_hdiv(a.m4, a.steps, a.warmup, "BDM1", a.scatter))
         elif w == "c5":
             res += c5_taylor_hood(a.n5, a.steps, a.warmup)
         elif w == "topo":
