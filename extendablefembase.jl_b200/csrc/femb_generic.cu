@@ -313,12 +313,14 @@ __global__ void __launch_bounds__(128) k_bilinear(BilArgs a) {
 // (compile-time NQ x R), the column-side values of the cell are staged once in shared memory; every thread then forms
 // its row of the local matrix (one LDS per FMA, no index arithmetic per entry) and scatters it.  Same arithmetic order
 // as k_bilinear / the reference loops: temp = sum_qp w_qp (sum_r row * col), value = (factor * temp) * |T|.
+#define FEMB_ROWS_PAD 2
 template <int DIM, int NQ, int R>
 __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Geo<DIM>* geo = reinterpret_cast<Geo<DIM>*>(smem_raw);
-    double* colv = reinterpret_cast<double*>(geo + a.cpb);  // [cl][qp * R + r][k]
+    double* colv = reinterpret_cast<double*>(geo + a.cpb);  // [cl][qp * R + r][k], cells FEMB_ROWS_PAD doubles apart in the banks
     const int ndr = a.rs.nd, ndc = a.cs.nd;
+    const int cstride = NQ * R * ndc + FEMB_ROWS_PAD;  // the lanes of different cells read different banks (broadcast per cell)
     const int64_t base = a.p0 + (int64_t)blockIdx.x * a.cpb;
     const int ncl = (int)min((int64_t)a.cpb, a.p1 - base);
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
         }
         if (a.same) {
 #pragma unroll
-            for (int i = 0; i < NQ * R; i++) colv[((size_t)cl * (NQ * R) + i) * ndc + j] = rv[i];
+            for (int i = 0; i < NQ * R; i++) colv[(size_t)cl * cstride + i * ndc + j] = rv[i];
         }
     }
     if (!a.same) {
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
             double v[9];
             eval_op<DIM>(a.cs, a.op_c, geo[c2], a.perm ? a.perm[base + c2] : base + c2, k, qp, a.rv_c, a.rd_c, v);
 #pragma unroll
-            for (int r = 0; r < R; r++) colv[((size_t)c2 * (NQ * R) + qp * R + r) * ndc + k] = v[r];
+            for (int r = 0; r < R; r++) colv[(size_t)c2 * cstride + (qp * R + r) * ndc + k] = v[r];
         }
     }
     __syncthreads();
@@ -356,9 +358,15 @@ __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
     const bool sym = a.flags & FEMB_BIL_SYMMETRIC_UPPER;
     const double vol = (a.flags & FEMB_BIL_NO_VOLUME) ? 1.0 : geo[cl].vol;
     const int per = ndr * ndc;
-    const double* cv = colv + (size_t)cl * (NQ * R) * ndc;
+    const double* cv = colv + (size_t)cl * cstride;
     const int32_t* sl = a.slots + cell * per + j * ndc;
-    for (int k = sym ? j : 0; k < ndc; k++) {
+    int32_t sk[4] = {0, 0, 0, 0};
+    const int kfirst = sym ? j : 0;
+    for (int k = kfirst; k < ndc; k++) {
+        if (((k - kfirst) & 3) == 0) {  // slots of the next four entries in flight together
+#pragma unroll
+            for (int i = 0; i < 4; i++) sk[i] = (k + i < ndc) ? __ldg(sl + k + i) : 0;
+        }
         double temp = 0.0;
 #pragma unroll
         for (int qp = 0; qp < NQ; qp++) {
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
         }
         const double val = sym ? temp * (a.factor * vol) : (a.factor * temp) * vol;
         if (sym && !(fabs(val) > a.drop_tol)) continue;
-        scatter_add(a.nzval, a.touched, a.errflag, __ldg(sl + k), val, a.atomic);
+        scatter_add(a.nzval, a.touched, a.errflag, sk[(k - kfirst) & 3], val, a.atomic);
         if (sym && k > j) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots + cell * per + k * ndc + j), val, a.atomic);
         if (a.slots_t) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots_t + cell * per + k * ndr + j), val, a.atomic);
     }
@@ -437,7 +445,7 @@ int launch_bilinear(femb_ctx* ctx, int er, int ec, int op_r, int op_c, int brow,
     if (rows && rs.nd <= 64) {
         kern = rows;
         cpb = std::max(1, 128 / rs.nd);
-        per_cell = (size_t)a.nqp * a.R * cs.nd * sizeof(double);
+        per_cell = ((size_t)a.nqp * a.R * cs.nd + FEMB_ROWS_PAD) * sizeof(double);
         cpb = (int)std::min<size_t>(cpb, (96 * 1024) / (per_cell + geo_bytes));
         a.cpb = cpb;
         smem = cpb * (per_cell + geo_bytes);
