@@ -434,8 +434,8 @@ extern "C" int32_t femb_pattern_get_slots(femb_ctx* ctx, int64_t n, const int64_
         if (slots[i] < 0 || slots[i] >= ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "slot out of range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int64_t *d_idx = nullptr, *d_out = nullptr;
-    FEMB_TRY(femb_alloc(ctx, &d_idx, (size_t)n));
-    int st = femb_alloc(ctx, &d_out, (size_t)n);
+    int st = femb_alloc(ctx, &d_idx, (size_t)n);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &d_out, (size_t)n);
     if (st == FEMB_OK) st = femb_h2d(ctx, d_idx, slots, (size_t)n);
     if (st == FEMB_OK) {
         k_gather_i64<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->rowval, d_idx, n, d_out);
@@ -676,9 +676,16 @@ int femb_build_gmap(femb_ctx* ctx) {
     const int64_t nslices = (s.ndofs + 31) / 32;
     int32_t* deg = nullptr;
     void* tmp = nullptr;
-    FEMB_TRY(femb_alloc(ctx, &deg, (size_t)nslices + 1));
-    FEMB_TRY(femb_alloc(ctx, &ctx->gslice_ptr, (size_t)nslices + 1));
-    CUDA_TRY(ctx, cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nslices + 1), ctx->stream));
+    {
+        int st = femb_alloc(ctx, &deg, (size_t)nslices + 1);
+        if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->gslice_ptr, (size_t)nslices + 1);
+        if (st == FEMB_OK && cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nslices + 1), ctx->stream) != cudaSuccess)
+            st = femb_fail(ctx, FEMB_ERR_CUDA, "femb_build_gmap: memset failed");
+        if (st != FEMB_OK) {
+            cudaFree(deg);
+            return st;
+        }
+    }
     k_slice_deg<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(s.adj_ptr, s.ndofs, nslices, deg);
     KERNEL_CHECK(ctx);
     // longest slice and total rows; if padding every slice to the longest costs < 10 % more rows, use that uniform
@@ -796,10 +803,18 @@ int femb_build_hmap(femb_ctx* ctx) {
     const int nwords = (s.nd + 3) / 4;
     int32_t *deg = nullptr, *clen = nullptr;
     void* tmp = nullptr;
-    FEMB_TRY(femb_alloc(ctx, &deg, (size_t)nslices + 1));
-    FEMB_TRY(femb_alloc(ctx, &clen, (size_t)nslices));
-    FEMB_TRY(femb_alloc(ctx, &ctx->hslice_ptr, (size_t)nslices + 1));
-    CUDA_TRY(ctx, cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nslices + 1), ctx->stream));
+    {
+        int st = femb_alloc(ctx, &deg, (size_t)nslices + 1);
+        if (st == FEMB_OK) st = femb_alloc(ctx, &clen, (size_t)nslices);
+        if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->hslice_ptr, (size_t)nslices + 1);
+        if (st == FEMB_OK && cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nslices + 1), ctx->stream) != cudaSuccess)
+            st = femb_fail(ctx, FEMB_ERR_CUDA, "femb_build_hmap: memset failed");
+        if (st != FEMB_OK) {
+            cudaFree(deg);
+            cudaFree(clen);
+            return st;
+        }
+    }
     k_slice_deg<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(s.adj_ptr, s.ndofs, nslices, deg);
     k_slice_collen<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(ctx->colptr, s.ndofs, nslices, clen);
     ctx->launches += 2;
