@@ -796,3 +796,30 @@ def test_block_matmul_and_lrmatmul_match_scipy():
     assert abs(ctx.lrmatmul(a1, b1, a2, b2) - (a1 - a2) @ (A @ (b1 - b2))) <= 1e-12 * scale * n
     assert ctx.lrmatmul(a1, b1, a2, b2) == ctx.lrmatmul(a1, b1, a2, b2)  # reproducible
     ctx.close()
+
+
+def test_device_topology_hand_derived_answers():
+    """The hand-derived tables of tests/test_grids.py (two triangles, two glued tetrahedra) straight from the device enumeration."""
+    from test_grids import hand_grids
+
+    for grid, hand in hand_grids():
+        dev = fb.ExtendableGrid(grid["Coordinates"], grid["CellNodes"], grid.geometry).instantiate_on_device()
+        for name, want in hand.items():
+            if name != "cellnodes":
+                assert np.array_equal(dev._c[name], want), name
+
+
+def test_compute_error_known_answers():
+    """uh = 1, u = nothing: error = |T| (VertexRule weights sum to 1, any p); P1 interpolant of a linear u: zero error;
+    integral mean: sum_cells error(p = 1) = integral of uh (Example210:88)."""
+    grid = _grid2d(5, True)
+    fes = fb.FESpace(fb.H1Pk(1, 2, 1), grid)
+    one = np.ones(fes.ndofs)
+    for p in (1, 2, 3):
+        err = fb.compute_error(fes, one, None, order=2, p=p)
+        assert np.abs(err[:, 0] - grid["CellVolumes"]).max() <= 1e-15
+    x = grid["Coordinates"]
+    lin = lambda y: (2.0 - 3.0 * y[..., 0] + 0.5 * y[..., 1])[..., None]  # noqa: E731
+    assert fb.compute_error(fes, lin(x)[:, 0], lin, order=3).sum() <= 1e-28
+    # integral of the P1 interpolant of x + y over the (jittered, but still unit) square = 1
+    assert abs(fb.compute_error(fes, x[:, 0] + x[:, 1], None, order=1, p=1).sum() - 1.0) <= 1e-13

@@ -33,3 +33,46 @@ def test_face_and_edge_counts_euler():
     assert g.nnodes - g.nedges + g.nfaces - g.ncells == 1
     g2 = fb.simplexgrid(X, X)
     assert g2.nnodes - g2.nfaces + g2.ncells == 1
+
+
+# hand-derived topology of the unit square split like simplexgrid (cells (1,2,4), (4,3,1)): first-appearance numbering,
+# FaceNodes in the creating cell's local order, +1 for the creator / -1 for the neighbour, FaceCells (creator, neighbour)
+HAND_SQUARE = dict(
+    cellnodes=np.array([[1, 2, 4], [4, 3, 1]], dtype=np.int32),
+    CellFaces=np.array([[1, 2, 3], [4, 5, 3]]), FaceNodes=np.array([[1, 2], [2, 4], [4, 1], [4, 3], [3, 1]]),
+    CellFaceSigns=np.array([[1, 1, 1], [1, 1, -1]]), FaceCells=np.array([[1, 0], [1, 0], [1, 2], [2, 0], [2, 0]]),
+    CellFaceOrientations=np.array([[1, 1, 1], [1, 1, 2]]),
+)
+# two positively oriented tetrahedra glued along the face {2,3,4}: cell 1 = (1,2,3,4), cell 2 = (2,3,4,5)
+HAND_TETS = dict(
+    cellnodes=np.array([[1, 2, 3, 4], [2, 3, 4, 5]], dtype=np.int32),
+    # local faces (1,3,2), (1,2,4), (2,3,4), (1,4,3):  cell 1 -> (1,3,2) (1,2,4) (2,3,4) (1,4,3);  cell 2 -> (2,4,3) (2,3,5) (3,4,5) (2,5,4)
+    CellFaces=np.array([[1, 2, 3, 4], [3, 5, 6, 7]]),
+    FaceNodes=np.array([[1, 3, 2], [1, 2, 4], [2, 3, 4], [1, 4, 3], [2, 3, 5], [3, 4, 5], [2, 5, 4]]),
+    CellFaceSigns=np.array([[1, 1, 1, 1], [-1, 1, 1, 1]]),
+    # the neighbour reads the glued face as (2,4,3) = (l1,l3,l2) of the global (2,3,4): orientation code 4 (hdiv_bdm1.jl:238-246)
+    CellFaceOrientations=np.array([[1, 1, 1, 1], [4, 1, 1, 1]]),
+    FaceCells=np.array([[1, 0], [1, 0], [1, 2], [1, 0], [2, 0], [2, 0], [2, 0]]),
+    # local edges (1,2) (1,3) (1,4) (2,3) (2,4) (3,4): cell 2 -> (2,3) (2,4) (2,5) (3,4) (3,5) (4,5)
+    CellEdges=np.array([[1, 2, 3, 4, 5, 6], [4, 5, 7, 6, 8, 9]]),
+    EdgeNodes=np.array([[1, 2], [1, 3], [1, 4], [2, 3], [2, 4], [3, 4], [2, 5], [3, 5], [4, 5]]),
+    CellEdgeSigns=np.array([[1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1]]),
+)
+
+
+def hand_grids():
+    sq = fb.ExtendableGrid(np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]), HAND_SQUARE["cellnodes"], "Triangle2D")
+    tc = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 1.0, 1.0]])
+    tets = fb.ExtendableGrid(tc, HAND_TETS["cellnodes"], "Tetrahedron3D")
+    return (sq, HAND_SQUARE), (tets, HAND_TETS)
+
+
+def test_hand_derived_topology_host():
+    for grid, hand in hand_grids():
+        for name, want in hand.items():
+            if name != "cellnodes":
+                assert np.array_equal(grid[name], want), name
+    tets = hand_grids()[1][0]
+    c = tets["Coordinates"][tets["CellNodes"] - 1]
+    det = np.linalg.det(np.transpose(c[:, 1:, :] - c[:, :1, :], (0, 2, 1)))
+    assert (det > 0).all()  # both cells positively oriented, as simplexgrid produces them
