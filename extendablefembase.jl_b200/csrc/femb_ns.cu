@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(128) k_convection2d(ConvArgs a) {
 // adv_j = u_h . grad psi_j the Newton terms of Example210:339-355 collapse to
 //     Aloc[(ck,k),(cj,j)] += w psi_k ( g[ck][cj] psi_j + delta(ck,cj) adv_j ),
 //     b[(c,j)]            += w |T| psi_j ( (jac . input)_c - value_c )          (Example210:358-363)
-// One thread per (cell, 6x6 block): 36 accumulators in registers, no shared-memory staging of cvals.
+// One thread per (cell, 6x6 block): 36 accumulators in registers, no shared-memory staging of cvals.  The kernel is
+// latency-bound at 2 CTAs / SM (180 registers); capping it at 168 (3 CTAs / SM, 24 bytes of spill) measured 2.38 vs 2.91 ms
+// on 2.1M cells, 128 registers (4 CTAs, 400 bytes of spill) 3.98 ms.
 struct Conv2Args {
     const double* coords;
     const int32_t* cellnodes;
@@ -132,7 +134,7 @@ struct Conv2Args {
 };
 
 template <int NDS>
-__global__ void __launch_bounds__(128) k_convection2d_blocks(const Conv2Args a) {
+__global__ void __launch_bounds__(128, 3) k_convection2d_blocks(const Conv2Args a) {
     __shared__ double tab[FEMB_MAX_QP][NDS][3];  // psi, dpsi/dxref_0, dpsi/dxref_1
     for (int i = threadIdx.x; i < a.nqp * NDS; i += blockDim.x) {
         const int q = i / NDS, d = i - q * NDS;
