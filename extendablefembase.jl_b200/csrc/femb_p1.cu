@@ -130,6 +130,9 @@ __device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, 
 //  * STAGE: the slice's gather-map entries (all visits) are copied to shared memory with cp.async (LDGSTS) at the very
 //    start, so the streamed part of the input arrives in ONE memory latency instead of one per visit and costs no
 //    registers; only the coordinate / volume loads of the next visit stay in a register pipeline.
+#ifndef FEMB_P1_STAGE16
+#define FEMB_P1_STAGE16 1
+#endif
 #ifndef FEMB_P1_MINB
 #define FEMB_P1_MINB 8  // resident CTAs per SM the 2-D gather kernel is compiled for (register cap 65536 / (128 * MINB))
 #endif
@@ -172,6 +175,24 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
     if (STAGE) {
         const unsigned sst = (unsigned)__cvta_generic_to_shared(acc + (size_t)(a.maxlen + 1) * nt) + ((tid >> 5) * 4u * (unsigned)a.maxrows * 32u + lane) * 4u;
         const unsigned pst = (unsigned)a.maxrows * 128u;  // plane stride in bytes
+#if FEMB_P1_STAGE16
+        // the rows of a slice are contiguous per plane (128 bytes each): the warp copies them in 16-byte pieces, 512 bytes per
+        // instruction, i.e. a quarter of the LDGSTS instructions of the per-lane 4-byte copies (the kernel is issue-bound)
+        {
+            const unsigned swarp = sst - lane * 4u;  // this warp's staging block
+            const uint32_t* gw0 = ga - lane;          // row0 of plane 0
+            const int nq = nrows * 8;                 // 16-byte pieces per plane
+            constexpr int NPL = NEED_CELL ? 4 : 3;
+#pragma unroll
+            for (int p = 0; p < NPL; p++)
+                for (int q = (int)lane; q < nq; q += 32)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(swarp + (unsigned)p * pst + (unsigned)q * 16u), "l"(gw0 + (size_t)p * gs + (size_t)q * 4)
+                                 : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();  // the pieces were copied by other lanes
+#else
         for (int r = 0; r < nrows; r++) {
             const uint32_t* g = ga + ((size_t)r << 5);
             const unsigned d = sst + (unsigned)r * 128u;
@@ -182,6 +203,7 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
         auto lds32 = [](unsigned addr) {
             unsigned v;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
