@@ -130,6 +130,12 @@ __device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, 
 //  * STAGE: the slice's gather-map entries (all visits) are copied to shared memory with cp.async (LDGSTS) at the very
 //    start, so the streamed part of the input arrives in ONE memory latency instead of one per visit and costs no
 //    registers; only the coordinate / volume loads of the next visit stay in a register pipeline.
+#ifndef FEMB_P1_OPAQUE
+#define FEMB_P1_OPAQUE 1
+#endif
+#ifndef FEMB_P1_UNROLL
+#define FEMB_P1_UNROLL 2
+#endif
 #ifndef FEMB_P1_STAGE16
 #define FEMB_P1_STAGE16 1
 #endif
@@ -163,7 +169,10 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
         len = (int)(a.colptr[c + 1] - 1 - base);
         self = __ldg(xy + c);
     }
-    const unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + tid * 8u;
+    unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + tid * 8u;
+#if FEMB_P1_OPAQUE
+    asm volatile("" : "+r"(sacc));  // keep the accumulator address in its register: re-deriving it costs six instructions per use
+#endif
     for (int i = 0; i < len; i++) sts64(sacc + i * (nt * 8u), 0.0);
     unsigned long long mask = 0ull;
     double bsum = 0.0, diag = 0.0;
@@ -216,6 +225,8 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
             pb1 = __ldg(xy + lds32(sst + pst));
             if (HAS_VOL) vol1 = __ldg(a.cellvol + lds32(sst + 3u * pst));
         }
+        constexpr int UNR = FEMB_P1_UNROLL;
+#pragma unroll UNR
         for (int r = 0; r < nrows; r++) {
             const unsigned d = sst + (unsigned)r * 128u;
             const unsigned w = lds32(d + 2u * pst);
