@@ -370,7 +370,9 @@ struct HArgs {
 // SPLIT = 1: one thread per column, 4 slices (warps) per CTA.  SPLIT = 4: one slice per CTA, the 4 warps share the
 // columns of the slice — warp w takes the visits r = w (mod 4), computes them in parallel and the shared-memory
 // accumulation is serialised in visit order between barriers, so the result is bit-identical to SPLIT = 1.
-template <int DIM, int ND, int NQ, int SPLIT>
+// FAST: no value filter (drop_tol <= 0), no slot tracking and a complete map (no missing positions): the accumulation is a
+// branch-free load / add / store per row instead of ~23 instructions of filter, tracking and error bookkeeping.
+template <int DIM, int ND, int NQ, int SPLIT, bool FAST>
 __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM, ND, NQ> tab) {
     constexpr unsigned ncol = 128 / SPLIT;  // columns per CTA
     constexpr int NW = (ND + 3) / 4;
@@ -488,7 +490,14 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
         }
 #pragma unroll 1
         for (int ph = 0; ph < SPLIT; ph++) {
-            if (on && (SPLIT == 1 || (int)warp == ph)) {
+            if (FAST && on && (SPLIT == 1 || (int)warp == ph)) {
+#pragma unroll
+                for (int j = 0; j < ND; j++) {
+                    const unsigned ad = sacc + ((words[j >> 2] >> (8 * (j & 3))) & 0xFFu) * (ncol * 8u);
+                    sts64(ad, lds64(ad) + v[j]);
+                }
+            }
+            if (!FAST && on && (SPLIT == 1 || (int)warp == ph)) {
 #pragma unroll
                 for (int j = 0; j < ND; j++) {
                     const unsigned pos = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
@@ -536,8 +545,9 @@ static int launch_h1_gather_t(femb_ctx* ctx, const FembEval& EG, const FembEval*
             tab.wphi[q][j] = EI ? EG.w[q] * EI->h_refvals[(size_t)q * s.nd_all + j] : 0.0;
         }
     }
-    auto kern1 = k_h1_gather<DIM, ND, NQ, 1>;
-    auto kern4 = k_h1_gather<DIM, ND, NQ, 4>;
+    const bool fast = ctx->hmap_complete && !a.touched && !(a.drop_tol > 0.0);
+    auto kern1 = fast ? k_h1_gather<DIM, ND, NQ, 1, true> : k_h1_gather<DIM, ND, NQ, 1, false>;
+    auto kern4 = fast ? k_h1_gather<DIM, ND, NQ, 4, true> : k_h1_gather<DIM, ND, NQ, 4, false>;
     size_t max1 = 0, max4 = 0;
     for (auto& r : ctx->hranges) {
         if (r.split == 4) max4 = std::max(max4, (size_t)std::max(1, r.maxlen) * 32 * sizeof(double));

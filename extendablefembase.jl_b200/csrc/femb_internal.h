@@ -126,6 +126,7 @@ struct femb_ctx {
     size_t hmap_stride = 0;
     int32_t* hslice_ptr = nullptr;
     int hmap_space = -1, hmap_words = 0;
+    bool hmap_complete = false;    // every (cell, row) of the map has a slot: the gather may skip its per-entry checks
     struct HRange { int64_t s0, s1; int maxlen; int split; };  // split: threads per column (1, or 4 for high-degree columns)
     std::vector<HRange> hranges;   // contiguous slice ranges with their longest CSC column (shared-memory sizing)
     double* cellrhs = nullptr;     // [cell][qp][comp]: factor w_q |T| f(x_q), pre-pass of the Identity rhs gather

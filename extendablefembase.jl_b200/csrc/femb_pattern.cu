@@ -759,7 +759,7 @@ __global__ void k_slice_collen(const int64_t* __restrict__ colptr, int64_t ndofs
 
 __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices, int nd, int nwords,
                        const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
-                       const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hmap, size_t stride) {
+                       const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hmap, size_t stride, int32_t* __restrict__ nmissing) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nslices * 32) return;
     const int64_t slice = c >> 5;
@@ -779,6 +779,7 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
             for (int j = 0; j < nd; j++) {
                 int64_t p = find_slot(colptr, rowval, c, (int64_t)celldofs[(int64_t)cell * nd + j]);
                 uint32_t pos = (p < 0) ? 0xFFu : (uint32_t)(p - base);
+                if (p < 0) atomicAdd(nmissing, 1);  // rows without a slot (compressed / adopted patterns): the gather must check
                 words[j >> 2] = (words[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (pos << (8 * (j & 3)));
             }
         }
@@ -877,9 +878,17 @@ int femb_build_hmap(femb_ctx* ctx) {
     ctx->hmap_stride = (size_t)rows * 32;
     ctx->hmap_words = nwords;
     FEMB_TRY(femb_alloc(ctx, &ctx->hmap, ctx->hmap_stride * (2 + nwords)));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
     k_hmap<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.nd, nwords, s.celldofs, ctx->colptr, ctx->rowval,
-                                                                            ctx->hslice_ptr, ctx->hmap, ctx->hmap_stride);
+                                                                            ctx->hslice_ptr, ctx->hmap, ctx->hmap_stride, ctx->errflag);
     KERNEL_CHECK(ctx);
+    {
+        int32_t nmiss = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&nmiss, ctx->errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
+        ctx->hmap_complete = nmiss == 0;
+    }
     ctx->hmap_space = sid;
     return FEMB_OK;
 }
