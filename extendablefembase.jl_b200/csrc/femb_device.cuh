@@ -153,7 +153,9 @@ __device__ __forceinline__ double coef_of(const SpaceDev& s, int64_t cell, int d
 // ---- stage 2: update_basis! for one (dof, qp) ------------------------------------------------------
 // refvals  [qp][nd_all][ncomp]; refderivs [qp][nd_all][ncomp][DIM]
 // out[r], r < resultdim.  Accumulation order follows the reference loops.
-template <int DIM>
+// RT > 0: the caller knows the result length at compile time (k_bilinear_rows): every index into `out` is then static
+// and the array lives in registers instead of local memory.
+template <int DIM, int RT = 0>
 __device__ __forceinline__ void eval_op(const SpaceDev& s, int op, const Geo<DIM>& g, int64_t cell, int dof, int qp,
                                         const double* __restrict__ refvals, const double* __restrict__ refderivs,
                                         double* out) {
@@ -162,9 +164,26 @@ __device__ __forceinline__ void eval_op(const SpaceDev& s, int op, const Geo<DIM
     if (s.family != FEMB_FAMILY_HDIV) {
         if (op == FEMB_OP_IDENTITY) {  // feevaluator_h1.jl:2-14
             const double* v = refvals + ((size_t)qp * s.nd_all + sub) * nc;
-            for (int k = 0; k < nc; k++) out[k] = v[k];
+            if (RT > 0) {
+#pragma unroll
+                for (int k = 0; k < RT; k++) out[k] = v[k];
+            } else {
+                for (int k = 0; k < nc; k++) out[k] = v[k];
+            }
         } else if (op == FEMB_OP_GRADIENT) {  // feevaluator_h1.jl:61-74
             const double* d = refderivs + ((size_t)qp * s.nd_all + sub) * nc * DIM;
+            if (RT > 0) {
+#pragma unroll
+                for (int c = 0; c < RT / DIM; c++) {
+#pragma unroll
+                    for (int k = 0; k < DIM; k++) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int j = 0; j < DIM; j++) a += g.M[k][j] * d[c * DIM + j];
+                        out[k + DIM * c] = a;
+                    }
+                }
+            } else
             for (int c = 0; c < nc; c++) {
 #pragma unroll
                 for (int k = 0; k < DIM; k++) {
@@ -203,7 +222,7 @@ __device__ __forceinline__ void eval_op(const SpaceDev& s, int op, const Geo<DIM
                 double a = 0.0;
 #pragma unroll
                 for (int l = 0; l < DIM; l++) a += g.A[k][l] * v[l];
-                out[k] = a * (cf / g.det);
+                if (RT == 0 || k < RT) out[k] = a * (cf / g.det);
             }
         } else if (op == FEMB_OP_DIVERGENCE) {  // feevaluator_hdiv.jl:66-83
             const double* d = refderivs + ((size_t)qp * s.nd_all + sub) * DIM * DIM;

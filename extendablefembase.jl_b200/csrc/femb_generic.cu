@@ -333,8 +333,8 @@ __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
     if (active) {
 #pragma unroll
         for (int qp = 0; qp < NQ; qp++) {
-            double v[9];
-            eval_op<DIM>(a.rs, a.op_r, geo[cl], cell, j, qp, a.rv_r, a.rd_r, v);
+            double v[R];
+            eval_op<DIM, R>(a.rs, a.op_r, geo[cl], cell, j, qp, a.rv_r, a.rd_r, v);
 #pragma unroll
             for (int r = 0; r < R; r++) rv[qp * R + r] = v[r];
         }
@@ -347,8 +347,8 @@ __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
         for (int i = tid; i < ncl * NQ * ndc; i += nt) {
             const int c2 = i / (NQ * ndc), rem = i - c2 * (NQ * ndc);
             const int qp = rem / ndc, k = rem - qp * ndc;
-            double v[9];
-            eval_op<DIM>(a.cs, a.op_c, geo[c2], a.perm ? a.perm[base + c2] : base + c2, k, qp, a.rv_c, a.rd_c, v);
+            double v[R];
+            eval_op<DIM, R>(a.cs, a.op_c, geo[c2], a.perm ? a.perm[base + c2] : base + c2, k, qp, a.rv_c, a.rd_c, v);
 #pragma unroll
             for (int r = 0; r < R; r++) colv[(size_t)c2 * cstride + (qp * R + r) * ndc + k] = v[r];
         }
@@ -360,26 +360,31 @@ __global__ void __launch_bounds__(128) k_bilinear_rows(BilArgs a) {
     const int per = ndr * ndc;
     const double* cv = colv + (size_t)cl * cstride;
     const int32_t* sl = a.slots + cell * per + j * ndc;
-    int32_t sk[4] = {0, 0, 0, 0};
     const int kfirst = sym ? j : 0;
-    for (int k = kfirst; k < ndc; k++) {
-        if (((k - kfirst) & 3) == 0) {  // slots of the next four entries in flight together
+    for (int k0 = kfirst; k0 < ndc; k0 += 4) {
+        int32_t sk[4];  // slots of the next four entries in flight together (static indices: registers)
 #pragma unroll
-            for (int i = 0; i < 4; i++) sk[i] = (k + i < ndc) ? __ldg(sl + k + i) : 0;
+        for (int i = 0; i < 4; i++) sk[i] = (k0 + i < ndc) ? __ldg(sl + k0 + i) : 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = k0 + i;
+            if (k < ndc) {
+                double temp = 0.0;
+#pragma unroll
+                for (int qp = 0; qp < NQ; qp++) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) d += rv[qp * R + r] * cv[(qp * R + r) * ndc + k];
+                    temp += a.w[qp] * d;
+                }
+                const double val = sym ? temp * (a.factor * vol) : (a.factor * temp) * vol;
+                if (!sym || fabs(val) > a.drop_tol) {
+                    scatter_add(a.nzval, a.touched, a.errflag, sk[i], val, a.atomic);
+                    if (sym && k > j) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots + cell * per + k * ndc + j), val, a.atomic);
+                    if (a.slots_t) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots_t + cell * per + k * ndr + j), val, a.atomic);
+                }
+            }
         }
-        double temp = 0.0;
-#pragma unroll
-        for (int qp = 0; qp < NQ; qp++) {
-            double d = 0.0;
-#pragma unroll
-            for (int r = 0; r < R; r++) d += rv[qp * R + r] * cv[(qp * R + r) * ndc + k];
-            temp += a.w[qp] * d;
-        }
-        const double val = sym ? temp * (a.factor * vol) : (a.factor * temp) * vol;
-        if (sym && !(fabs(val) > a.drop_tol)) continue;
-        scatter_add(a.nzval, a.touched, a.errflag, sk[(k - kfirst) & 3], val, a.atomic);
-        if (sym && k > j) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots + cell * per + k * ndc + j), val, a.atomic);
-        if (a.slots_t) scatter_add(a.nzval, a.touched, a.errflag, __ldg(a.slots_t + cell * per + k * ndr + j), val, a.atomic);
     }
 }
 
