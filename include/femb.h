@@ -80,7 +80,9 @@ enum {
 enum {
     FEMB_SCATTER_ATOMIC = 0,   /* red.global.add.f64 (fastest; summation order not fixed)            */
     FEMB_SCATTER_COLORED = 1,  /* cell colouring, plain read-modify-write per colour (bit-reproducible) */
-    FEMB_SCATTER_GATHER = 2    /* owner-computes column gather, write-once (bit-reproducible; P1 only) */
+    FEMB_SCATTER_GATHER = 2    /* default: owner-computes column gather, write-once, bit-reproducible, where a gather
+                                * kernel exists (scalar H1 P1 and P2 stiffness + rhs of femb_assemble_poisson, every
+                                * linear form); the other bilinear forms use the atomic scatter under this policy  */
 };
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
