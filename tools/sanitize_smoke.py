@@ -42,4 +42,26 @@ for ft in (fb.HDIVRT0(3), fb.HDIVBDM1(3), fb.HDIVRT0(2), fb.HDIVBDM1(2)):
     A = fb.FEMatrix([FESv, FESq])
     fb.assemble_hdiv_mixed(A, FESv, FESq)
     print(ft, A.entries.nnz)
+# coloured scatter, device topology / dofmaps, boundary dofs, penalisation, residual, block products, compute_error
+for ft in (fb.HDIVBDM1(3), fb.H1P3(1, 3)):
+    FESv, FESq = fb.FESpace(ft, g3), fb.FESpace(fb.L2P0(1), g3)
+    A = fb.FEMatrix([FESv, FESq])
+    fb.assemble_hdiv_mixed(A, FESv, FESq, scatter=_lib.SCATTER_COLORED) if ft.family == "Hdiv" else None
+for g in (g2, g3):
+    dev = fb.ExtendableGrid(g["Coordinates"], g["CellNodes"], g.geometry).instantiate_on_device()
+    print("entities", g.geometry, dev["FaceNodes"].shape[0], dev["EdgeNodes"].shape[0])
+from femb_b200.fespace import parse_pattern
+fes = fb.FESpace(fb.H1P2(1, 3), g3)
+S = _Session([fes], fb.QuadratureRule(g3.geometry, 2), device_dofmaps=True)
+eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+S.ctx.pattern_build([(0, 0)])
+S.ctx.matrix_zero(); S.ctx.vector_zero()
+S.ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, rhs3.params(), 0.0)
+nb = S.ctx.boundary_dofs(0, parse_pattern(fes.fetype.get_dofmap_pattern(g3.geometry)), download=False)
+S.ctx.dirichlet_apply(True, 0, None, None, 1.0e60)
+x = np.random.default_rng(1).uniform(-1, 1, fes.ndofs)
+print("residual", nb, S.ctx.residual(x, zero_fixed=True), S.ctx.lrmatmul(x, x))
+S.ctx.block_matmul(np.zeros(fes.ndofs), x, 0, 0, transposed=True)
+S.ctx.system_save(); S.ctx.system_add_saved()
+print("compute_error", float(fb.compute_error(fes, x, None, order=2).sum()))
 print("done")
