@@ -76,3 +76,24 @@ def test_hand_derived_topology_host():
     c = tets["Coordinates"][tets["CellNodes"] - 1]
     det = np.linalg.det(np.transpose(c[:, 1:, :] - c[:, :1, :], (0, 2, 1)))
     assert (det > 0).all()  # both cells positively oriented, as simplexgrid produces them
+
+
+def test_hand_derived_boundarydofs():
+    """boundarydofs (dofmaps.jl:871-899) on the two-triangle square: all four nodes; of the five faces only the diagonal
+    (face 3) is interior.  P2: nodes + boundary faces; vector-valued: the same per component, shifted by coffset."""
+    from femb_b200.fespace import boundarydofs
+
+    sq = hand_grids()[0][0]
+    assert boundarydofs(fb.FESpace(fb.H1Pk(1, 2, 1), sq)).tolist() == [1, 2, 3, 4]
+    assert boundarydofs(fb.FESpace(fb.H1Pk(1, 2, 2), sq)).tolist() == [1, 2, 3, 4, 4 + 1, 4 + 2, 4 + 4, 4 + 5]
+    fes2 = fb.FESpace(fb.H1Pk(2, 2, 2), sq)
+    assert fes2.coffset == 9
+    assert boundarydofs(fes2).tolist() == [1, 2, 3, 4, 5, 6, 8, 9] + [9 + d for d in (1, 2, 3, 4, 5, 6, 8, 9)]
+    # P3: two dofs per face (F2) and one interior dof per cell (I1): ndofs = 4 + 2*5 + 2
+    fes3 = fb.FESpace(fb.H1Pk(1, 2, 3), sq)
+    assert fes3.ndofs == 16
+    want = [1, 2, 3, 4] + sorted(4 + f + m * 5 for f in (1, 2, 4, 5) for m in (0, 1))
+    assert boundarydofs(fes3).tolist() == want
+    # two glued tetrahedra: every node and every edge lies on the boundary, only the glued face is interior
+    tets = hand_grids()[1][0]
+    assert boundarydofs(fb.FESpace(fb.H1P2(1, 3), tets)).tolist() == list(range(1, 5 + 9 + 1))
