@@ -803,3 +803,53 @@ def interpolate_hdiv(el: Element, g, coords, facenodes, u):
     for m in range(nmom):
         res[m * nf:(m + 1) * nf] = out[m::nmom]
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# grid topology ([EXT E1] recollection of ExtendableGrids): the literal loop over cells and
+# local entities, numbering faces / edges in order of first appearance.  Small meshes only (pure Python).
+# ---------------------------------------------------------------------------------------------
+LOCAL_FACES = {TRI: [(0, 1), (1, 2), (2, 0)], TET: [(0, 2, 1), (0, 1, 3), (1, 2, 3), (0, 3, 2)]}
+LOCAL_EDGES = {TRI: [(0, 1), (1, 2), (2, 0)], TET: [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]}
+
+
+def enumerate_entities(g, cellnodes, kind="faces"):
+    """-> dict(cell_entities [ncells, k] 1-based, entity_nodes [n, m] in the creating cell's local order, signs, and for
+    faces: facecells [n, 2] (creator, neighbour or 0), orientations (1 creator sequence; 2: (l3,l2,l1), 3: (l2,l1,l3),
+    4: (l1,l3,l2) of the global face, hdiv_bdm1.jl:238-246; triangles: 1 creator / 2 neighbour))."""
+    table = LOCAL_FACES[g] if kind == "faces" else LOCAL_EDGES[g]
+    ids, nodes, first_cell = {}, [], []
+    nc = len(cellnodes)
+    ce = np.zeros((nc, len(table)), dtype=np.int64)
+    sg = np.zeros_like(ce)
+    ori = np.zeros_like(ce)
+    fc = []
+    for c in range(nc):
+        for l, loc in enumerate(table):
+            tup = tuple(int(cellnodes[c][i]) for i in loc)
+            key = tuple(sorted(tup))
+            created = key not in ids
+            if created:
+                ids[key] = len(nodes)
+                nodes.append(tup)
+                fc.append([c + 1, 0])
+            e = ids[key]
+            ce[c, l] = e + 1
+            glob = nodes[e]
+            if kind == "faces":
+                sg[c, l] = 1 if created else -1
+                if not created:
+                    fc[e][1] = c + 1
+                if len(tup) == 2:
+                    ori[c, l] = 1 if created else 2
+                else:
+                    l1, l2, l3 = tup
+                    ori[c, l] = {(l1, l2, l3): 1, (l3, l2, l1): 2, (l2, l1, l3): 3, (l1, l3, l2): 4}.get(glob, 0)
+            else:
+                sg[c, l] = 1 if tup[0] == glob[0] else -1
+    out = {"cell_entities": ce, "entity_nodes": np.array(nodes, dtype=np.int64), "signs": sg}
+    if kind == "faces":
+        out["facecells"] = np.array(fc, dtype=np.int64)
+        out["orientations"] = ori
+    return out
+

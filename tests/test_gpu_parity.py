@@ -823,3 +823,15 @@ def test_compute_error_known_answers():
     assert fb.compute_error(fes, lin(x)[:, 0], lin, order=3).sum() <= 1e-28
     # integral of the P1 interpolant of x + y over the (jittered, but still unit) square = 1
     assert abs(fb.compute_error(fes, x[:, 0] + x[:, 1], None, order=1, p=1).sum() - 1.0) <= 1e-13
+
+
+def test_device_topology_matches_the_oracle_loop():
+    """device face / edge enumeration against the literal first-appearance loop of oracle/femb_oracle.py (bit-exact)"""
+    for grid in (_shuffled(_grid2d(4), seed=21), _shuffled(_grid3d(3), seed=22)):
+        dev = fb.ExtendableGrid(grid["Coordinates"], grid["CellNodes"], grid.geometry).instantiate_on_device()
+        f = orc.enumerate_entities(grid.geometry, grid["CellNodes"], "faces")
+        e = orc.enumerate_entities(grid.geometry, grid["CellNodes"], "edges")
+        for name, want in (("CellFaces", f["cell_entities"]), ("FaceNodes", f["entity_nodes"]), ("CellFaceSigns", f["signs"]),
+                           ("FaceCells", f["facecells"]), ("CellFaceOrientations", f["orientations"]), ("CellEdges", e["cell_entities"]),
+                           ("EdgeNodes", e["entity_nodes"]), ("CellEdgeSigns", e["signs"])):
+            assert np.array_equal(dev._c[name], want), name

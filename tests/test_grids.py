@@ -97,3 +97,25 @@ def test_hand_derived_boundarydofs():
     # two glued tetrahedra: every node and every edge lies on the boundary, only the glued face is interior
     tets = hand_grids()[1][0]
     assert boundarydofs(fb.FESpace(fb.H1P2(1, 3), tets)).tolist() == list(range(1, 5 + 9 + 1))
+
+
+def test_host_topology_matches_the_oracle_loop():
+    """grids.py (sort-based, vectorised) against the literal first-appearance loop of the oracle on shuffled meshes"""
+    import femb_oracle as orc
+
+    rng = np.random.default_rng(12)
+    X = np.linspace(0, 1, 5)
+    for grid in (fb.simplexgrid(X, X), fb.simplexgrid(X[:4], X[:4], X[:4])):
+        cn = grid["CellNodes"][rng.permutation(grid.ncells)]
+        g = fb.ExtendableGrid(grid["Coordinates"], cn, grid.geometry)
+        f = orc.enumerate_entities(g.geometry, cn, "faces")
+        assert np.array_equal(g["CellFaces"], f["cell_entities"]) and np.array_equal(g["FaceNodes"], f["entity_nodes"])
+        assert np.array_equal(g["CellFaceSigns"], f["signs"]) and np.array_equal(g["FaceCells"], f["facecells"])
+        assert np.array_equal(g["CellFaceOrientations"], f["orientations"]) and (f["orientations"] > 0).all()
+        e = orc.enumerate_entities(g.geometry, cn, "edges")
+        assert np.array_equal(g["CellEdges"], e["cell_entities"]) and np.array_equal(g["EdgeNodes"], e["entity_nodes"])
+        assert np.array_equal(g["CellEdgeSigns"], e["signs"])
+    for grid, hand in hand_grids():
+        f = orc.enumerate_entities(grid.geometry, hand["cellnodes"], "faces")
+        assert np.array_equal(f["cell_entities"], hand["CellFaces"]) and np.array_equal(f["entity_nodes"], hand["FaceNodes"])
+        assert np.array_equal(f["orientations"], hand["CellFaceOrientations"])
