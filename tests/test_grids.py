@@ -119,3 +119,20 @@ def test_host_topology_matches_the_oracle_loop():
         f = orc.enumerate_entities(grid.geometry, hand["cellnodes"], "faces")
         assert np.array_equal(f["cell_entities"], hand["CellFaces"]) and np.array_equal(f["entity_nodes"], hand["FaceNodes"])
         assert np.array_equal(f["orientations"], hand["CellFaceOrientations"])
+
+
+def test_boundarydofs_geometric_criterion():
+    """Independent check of boundarydofs: on the unit square / cube a P2 dof is a boundary dof iff its Lagrange point
+    (node or edge midpoint) lies on the boundary of the domain."""
+    from femb_b200.fespace import boundarydofs
+
+    X = np.linspace(0, 1, 5)
+    for grid in (fb.simplexgrid(X, X), fb.simplexgrid(X[:4] / X[3], X[:4] / X[3], X[:4] / X[3])):
+        c = grid["Coordinates"]
+        en = grid["EdgeNodes"]
+        pts = np.concatenate([c, 0.5 * (c[en[:, 0] - 1] + c[en[:, 1] - 1])])
+        on_bnd = ((np.abs(pts) < 1e-14) | (np.abs(pts - 1.0) < 1e-14)).any(axis=1)
+        ft = fb.H1Pk(1, 2, 2) if grid.dim == 2 else fb.H1P2(1, 3)
+        fes = fb.FESpace(ft, grid)
+        assert fes.ndofs == pts.shape[0]
+        assert np.array_equal(boundarydofs(fes), np.nonzero(on_bnd)[0] + 1)
