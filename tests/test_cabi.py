@@ -51,3 +51,38 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+\S*oracle|femb_oracle|oracle/", src, flags=re.M), f"{f} uses the oracle"
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+
+    exe = str(tmp_path / "c_abi_poisson")
+    pkg = os.path.join(ROOT, "extendablefembase.jl_b200")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_poisson.c"),
+           "-L", pkg, "-lfemb", "-Wl,-rpath," + pkg, "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True)
+    return subprocess.run([exe], capture_output=True, text=True)
+
+
+def test_plain_c_caller_compiles_against_the_header(libfemb, tmp_path):
+    """examples/c_abi_poisson.c uses nothing but include/femb.h and libfemb.so (no torch, no Python); without a GPU it
+    reports the library's error and exits with its 'no device' code."""
+    import torch
+
+    r = _build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+    else:
+        assert r.returncode == 77 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_known_answer(libfemb, tmp_path):
+    """the two-triangle unit square through the C ABI from C: SURVEY.md Appendix C values, hypotenuse entries filtered"""
+    r = _build_c_example(tmp_path)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "nnz = 12"
+    vals = {l.split("=")[0].strip(): float(l.split("=")[1]) for l in lines[1:13]}
+    assert vals["A[1,1]"] == 1.0 and vals["A[2,1]"] == -0.5 and vals["A[4,4]"] == 1.0 and "A[4,1]" not in vals and "A[1,4]" not in vals
+    assert lines[13].split() == ["b", "=", "0.0000", "0.0556", "-0.0556", "0.0000"]
