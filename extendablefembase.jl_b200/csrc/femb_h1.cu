@@ -313,6 +313,10 @@ __device__ __forceinline__ void ldg256(const double* p, double& a, double& b, do
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // coefficient record of one cell (k_cell_coef): Kc[0..5], |T| f(x_q) at [6, 6 + NQ)
 template <int DIM, int KP, int NQ>
 __device__ __forceinline__ void load_coef(const double* __restrict__ cc, bool has_rhs, double (&kc)[KP], double (&f)[NQ]) {
@@ -346,14 +350,20 @@ __device__ __forceinline__ void load_coef(const double* __restrict__ cc, bool ha
 
 template <int DIM, int ND, int NQ>
 struct HTab {
-    double D[NQ][DIM][ND];  // reference gradients d phi_j / d xref_a at xref_q
-    double wphi[NQ][ND];    // w_q phi_k(xref_q)
-    double w[NQ];
+    double D[NQ][DIM][ND];   // reference gradients d phi_j / d xref_a at xref_q (row side: uniform operands)
+    double wD[NQ][DIM][ND];  // w_q D (column side: read with the per-lane local index k)
+    double wphi[NQ][ND];     // w_q phi_k(xref_q)
+    double L4[NQ][DIM + 1];  // P2 only: 4 lambda_i(xref_q), the barycentric coordinates of the quadrature points
 };
+
+#ifndef FEMB_H1_KTAB_SMEM
+#define FEMB_H1_KTAB_SMEM 0
+#endif
 
 struct HArgs {
     const double* coef;
     const int32_t* hslice_ptr;
+    const uint8_t* hslice_zero;
     const uint32_t* hmap;
     size_t hstride;
     const int64_t* colptr;
@@ -367,24 +377,54 @@ struct HArgs {
     int64_t slice_begin, slice_end;
 };
 
+// local edges of the P2 dofs DIM+1 .. (ExtendableGrids local edge / face numbering, h1_p2.jl): vertices (a, b), a < b
+template <int DIM>
+__device__ __host__ constexpr int p2_edge_a(int e) {
+    return DIM == 2 ? (e == 0 ? 0 : (e == 1 ? 1 : 0)) : (e < 3 ? 0 : (e < 5 ? 1 : 2));
+}
+template <int DIM>
+__device__ __host__ constexpr int p2_edge_b(int e) {
+    return DIM == 2 ? (e == 0 ? 1 : 2) : (e < 3 ? e + 1 : (e == 3 ? 2 : 3));
+}
+
 // SPLIT = 1: one thread per column, 4 slices (warps) per CTA.  SPLIT = 4: one slice per CTA, the 4 warps share the
 // columns of the slice — warp w takes the visits r = w (mod 4), computes them in parallel and the shared-memory
-// accumulation is serialised in visit order between barriers, so the result is bit-identical to SPLIT = 1.
-// FAST: no value filter (drop_tol <= 0), no slot tracking and a complete map (no missing positions): the accumulation is a
-// branch-free load / add / store per row instead of ~23 instructions of filter, tracking and error bookkeeping.
-template <int DIM, int ND, int NQ, int SPLIT, bool FAST>
-__global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM, ND, NQ> tab) {
+// accumulation is serialised in visit order between barriers (same sums in the same order as one thread per column).
+// FAST: no value filter (drop_tol <= 0), no slot tracking and a complete map (no missing positions): the accumulation is
+// branch-free, uses the map's first-touch flags (store instead of add: no zeroed accumulator, fewer shared-memory reads)
+// and, with one thread per column, reads the accumulator rows of a visit before the FP64 work and sums on top of them.
+// What bounds this kernel is the L1 data pipe (ncu: l1tex wavefronts 74-76 %): one wavefront per 32-byte sector of a
+// scattered access, two per 64-bit shared-memory access of a warp — so the design minimises those: 256-bit loads of the
+// coefficient record, 256-bit stores of the finished column, k and the flags packed into the position words.
+template <int DIM, int ND, int NQ, int SPLIT, bool FAST, bool P2S>
+__global__ void __launch_bounds__(128, 4) k_h1_gather(const HArgs a, const HTab<DIM, ND, NQ> tab) {
     constexpr unsigned ncol = 128 / SPLIT;  // columns per CTA
     constexpr int NW = (ND + 3) / 4;
     constexpr int KP = (DIM == 2) ? 3 : 6;
+    constexpr unsigned PAD = 0xFFFFFFFFu;
     extern __shared__ double acc[];  // [maxlen of the range][ncol]
     __shared__ double bpart[SPLIT == 1 ? 1 : 4][32];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#if FEMB_H1_KTAB_SMEM
+    constexpr int KT_N = (NQ * DIM + NQ + 1) & ~1;  // column-side table row: w_q D_q[b][k] (NQ * DIM), w_q phi_k(x_q) (NQ)
+    constexpr int KT_STRIDE = KT_N + 2;             // 16-byte aligned rows that start in different banks
+    __shared__ __align__(16) double ktab[ND * KT_STRIDE];
+    for (int i = tid; i < ND * KT_N; i += 128) {
+        const int kk = i / KT_N, e = i % KT_N;
+        double val = 0.0;
+        if (e < NQ * DIM) val = tab.wD[e / DIM][e % DIM][kk];
+        else if (e < NQ * DIM + NQ) val = tab.wphi[e - NQ * DIM][kk];
+        ktab[kk * KT_STRIDE + e] = val;
+    }
+    __syncthreads();  // (before any early exit)
+    const unsigned stab = (unsigned)__cvta_generic_to_shared(ktab);
+#endif
     const int64_t slice = a.slice_begin + (SPLIT == 1 ? (int64_t)blockIdx.x * 4 + warp : (int64_t)blockIdx.x);
     if (SPLIT == 1 && slice >= a.slice_end) return;  // (SPLIT == 4: the grid is exact)
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.hslice_ptr + slice), nrows = __ldg(a.hslice_ptr + slice + 1) - row0;
+    const bool zero_first = !FAST || __ldg(a.hslice_zero + slice) != 0;
     int64_t base = 0;
     int len = 0;
     if (valid) {
@@ -392,8 +432,11 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
         len = (int)(a.colptr[c + 1] - 1 - base);
     }
     const unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + (SPLIT == 1 ? tid : lane) * 8u;
-    for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) sts64(sacc + i * (ncol * 8u), 0.0);
+    if (zero_first) {
+        for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) sts64(sacc + i * (ncol * 8u), 0.0);
+    }
     if (SPLIT > 1) __syncthreads();
+    const unsigned fmask = zero_first ? 0u : 0xFFFFFFFFu;  // zeroed accumulators: every visit adds
     double bsum = 0.0;
     unsigned err = 0u;
     const int niter = (nrows + SPLIT - 1) / SPLIT;
@@ -401,22 +444,20 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
     // flight while the current visit is computed (padding entries point at cell 0: their loads stay in bounds)
     const int rfirst = (SPLIT == 1) ? 0 : (int)warp;
     const uint32_t* __restrict__ hbase = a.hmap + ((size_t)row0 << 5) + lane;
-    unsigned k1 = 0xFFFFFFFFu, cell1 = 0u, k2 = 0xFFFFFFFFu, cell2 = 0u, w1[NW], w2[NW];
+    unsigned cell1 = 0u, cell2 = 0u, w1[NW], w2[NW];
 #pragma unroll
-    for (int wd = 0; wd < NW; wd++) w1[wd] = w2[wd] = 0xFFFFFFFFu;
+    for (int wd = 0; wd < NW; wd++) w1[wd] = w2[wd] = PAD;
     if (rfirst < nrows) {
         const uint32_t* hp = hbase + ((size_t)rfirst << 5);
-        k1 = __ldg(hp + a.hstride);
         cell1 = __ldg(hp);
 #pragma unroll
-        for (int wd = 0; wd < NW; wd++) w1[wd] = __ldg(hp + (2 + wd) * a.hstride);
+        for (int wd = 0; wd < NW; wd++) w1[wd] = __ldg(hp + (1 + wd) * a.hstride);
     }
     if (rfirst + SPLIT < nrows) {
         const uint32_t* hp = hbase + ((size_t)(rfirst + SPLIT) << 5);
-        k2 = __ldg(hp + a.hstride);
         cell2 = __ldg(hp);
 #pragma unroll
-        for (int wd = 0; wd < NW; wd++) w2[wd] = __ldg(hp + (2 + wd) * a.hstride);
+        for (int wd = 0; wd < NW; wd++) w2[wd] = __ldg(hp + (1 + wd) * a.hstride);
     }
     double kc1[KP], f1[NQ];
     {
@@ -426,30 +467,45 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
     }
     for (int it = 0; it < niter; it++) {
         const int r = it * SPLIT + rfirst;
-        const unsigned k = k1;
-        const bool on = k != 0xFFFFFFFFu;
         double v[ND], kc[KP], fq[NQ];
         unsigned words[NW];
 #pragma unroll
         for (int wd = 0; wd < NW; wd++) words[wd] = w1[wd];
+        const unsigned k = (words[NW - 1] >> 16) & 0xFu;
+        const unsigned first = (words[NW - 1] >> 20) & fmask;
+        const bool on = k != 0xFu;
 #pragma unroll
         for (int i = 0; i < KP; i++) kc[i] = kc1[i];
 #pragma unroll
         for (int qp = 0; qp < NQ; qp++) fq[qp] = f1[qp];
         // rotate the pipeline
-        k1 = k2; cell1 = cell2;
+        cell1 = cell2;
 #pragma unroll
         for (int wd = 0; wd < NW; wd++) w1[wd] = w2[wd];
         if (r + 2 * SPLIT < nrows) {
             const uint32_t* hp = hbase + ((size_t)(r + 2 * SPLIT) << 5);
-            k2 = __ldg(hp + a.hstride);
             cell2 = __ldg(hp);
 #pragma unroll
-            for (int wd = 0; wd < NW; wd++) w2[wd] = __ldg(hp + (2 + wd) * a.hstride);
+            for (int wd = 0; wd < NW; wd++) w2[wd] = __ldg(hp + (1 + wd) * a.hstride);
         } else {
-            k2 = 0xFFFFFFFFu; cell2 = 0u;
+            cell2 = 0u;
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) w2[wd] = PAD;
         }
         load_coef<DIM, KP, NQ>(a.coef + (size_t)cell1 * FEMB_COEF_STRIDE, a.has_rhs != 0, kc1, f1);
+        constexpr bool HOIST = FAST && SPLIT == 1;
+        unsigned ad[ND];
+        if (FAST) {
+#pragma unroll
+            for (int j = 0; j < ND; j++) ad[j] = sacc + ((words[j >> 2] >> (8 * (j & 3))) & 0xFFu) * (ncol * 8u);
+        }
+        if (HOIST && on) {
+#pragma unroll
+            for (int j = 0; j < ND; j++) v[j] = lds64_unless(ad[j], (first >> j) & 1u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < ND; j++) v[j] = 0.0;
+        }
         if (on) {
             double Km[DIM][DIM];  // symmetric Kmat from the coefficient order (00, 11, [22,] 01, [02, 12])
             if (DIM == 2) {
@@ -458,61 +514,134 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
                 Km[0][0] = kc[0]; Km[1][1] = kc[1]; Km[2][2] = kc[2];
                 Km[0][1] = Km[1][0] = kc[3]; Km[0][2] = Km[2][0] = kc[4]; Km[1][2] = Km[2][1] = kc[5];
             }
+#if FEMB_H1_KTAB_SMEM
+            double g[KT_N];
+            {
+                const unsigned ka = stab + k * (KT_STRIDE * 8u);
+#pragma unroll
+                for (int i = 0; i < KT_N; i += 2) lds128(ka + i * 8u, g[i], g[i + 1]);
+            }
+#endif
             double h[NQ][DIM];
 #pragma unroll
             for (int qp = 0; qp < NQ; qp++) {
                 double dk[DIM];
 #pragma unroll
-                for (int b = 0; b < DIM; b++) dk[b] = tab.D[qp][b][k];  // per-lane k: indexed constant-bank load
+#if FEMB_H1_KTAB_SMEM
+                for (int b = 0; b < DIM; b++) dk[b] = g[qp * DIM + b];
+#else
+                for (int b = 0; b < DIM; b++) dk[b] = tab.wD[qp][b][k];  // per-lane k: indexed constant-bank load
+#endif
 #pragma unroll
                 for (int aa = 0; aa < DIM; aa++) {
                     double s2 = 0.0;
 #pragma unroll
                     for (int b = 0; b < DIM; b++) s2 += Km[aa][b] * dk[b];
-                    h[qp][aa] = s2 * tab.w[qp];
+                    h[qp][aa] = s2;
                 }
             }
+            if (P2S) {
+                // P2 row side in barycentric form (verified against the evaluator's table at launch): with L = 4 lambda(x_q),
+                // s_q = sum_a h[q][a], H[a] = sum_q h[q][a]:  vertex 0: -sum_q L_0 s_q + sum_a H[a];  vertex i: sum_q L_i
+                // h[q][i-1] - H[i-1];  edge (0,b): sum_q L_0 h[q][b-1] - L_b s_q;  edge (a,b): sum_q L_a h[q][b-1] + L_b h[q][a-1]
+                // — 16 uniform table values instead of 120, and 0.6 of the FMAs of the dense product
+                double sq[NQ], H[DIM];
 #pragma unroll
-            for (int j = 0; j < ND; j++) {
-                double vj = 0.0;
+                for (int aa = 0; aa < DIM; aa++) H[aa] = 0.0;
 #pragma unroll
-                for (int qp = 0; qp < NQ; qp++)
+                for (int qp = 0; qp < NQ; qp++) {
+                    double t = h[qp][0];
 #pragma unroll
-                    for (int aa = 0; aa < DIM; aa++) vj += tab.D[qp][aa][j] * h[qp][aa];
-                v[j] = vj;
+                    for (int aa = 1; aa < DIM; aa++) t += h[qp][aa];
+                    sq[qp] = t;
+#pragma unroll
+                    for (int aa = 0; aa < DIM; aa++) H[aa] += h[qp][aa];
+                }
+                {
+                    double t = v[0];
+#pragma unroll
+                    for (int aa = 0; aa < DIM; aa++) t += H[aa];
+#pragma unroll
+                    for (int qp = 0; qp < NQ; qp++) t -= tab.L4[qp][0] * sq[qp];
+                    v[0] = t;
+                }
+#pragma unroll
+                for (int i = 1; i <= DIM; i++) {
+                    double t = v[i] - H[i - 1];
+#pragma unroll
+                    for (int qp = 0; qp < NQ; qp++) t += tab.L4[qp][i] * h[qp][i - 1];
+                    v[i] = t;
+                }
+#pragma unroll
+                for (int e = 0; e < ND - DIM - 1; e++) {
+                    const int ea = p2_edge_a<DIM>(e), eb = p2_edge_b<DIM>(e);
+                    double t = v[DIM + 1 + e];
+#pragma unroll
+                    for (int qp = 0; qp < NQ; qp++) {
+                        if (ea == 0) {
+                            t += tab.L4[qp][0] * h[qp][eb - 1];
+                            t -= tab.L4[qp][eb] * sq[qp];
+                        } else {
+                            t += tab.L4[qp][ea] * h[qp][eb - 1];
+                            t += tab.L4[qp][eb] * h[qp][ea - 1];
+                        }
+                    }
+                    v[DIM + 1 + e] = t;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < ND; j++) {
+                    double vj = v[j];
+#pragma unroll
+                    for (int qp = 0; qp < NQ; qp++)
+#pragma unroll
+                        for (int aa = 0; aa < DIM; aa++) vj += tab.D[qp][aa][j] * h[qp][aa];
+                    v[j] = vj;
+                }
             }
             if (a.has_rhs) {
                 double t = 0.0;
 #pragma unroll
+#if FEMB_H1_KTAB_SMEM
+                for (int qp = 0; qp < NQ; qp++) t += g[NQ * DIM + qp] * fq[qp];
+#else
                 for (int qp = 0; qp < NQ; qp++) t += tab.wphi[qp][k] * fq[qp];
+#endif
                 bsum += t;
             }
         }
-#pragma unroll 1
-        for (int ph = 0; ph < SPLIT; ph++) {
-            if (FAST && on && (SPLIT == 1 || (int)warp == ph)) {
+        if (HOIST) {
+            if (on) {
 #pragma unroll
-                for (int j = 0; j < ND; j++) {
-                    const unsigned ad = sacc + ((words[j >> 2] >> (8 * (j & 3))) & 0xFFu) * (ncol * 8u);
-                    sts64(ad, lds64(ad) + v[j]);
-                }
+                for (int j = 0; j < ND; j++) sts64(ad[j], v[j]);
             }
-            if (!FAST && on && (SPLIT == 1 || (int)warp == ph)) {
+        } else {
+#pragma unroll 1
+            for (int ph = 0; ph < SPLIT; ph++) {
+                if (FAST && on && (SPLIT == 1 || (int)warp == ph)) {
+                    double o[ND];
 #pragma unroll
-                for (int j = 0; j < ND; j++) {
-                    const unsigned pos = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                    if (fabs(v[j]) > a.drop_tol) {
-                        if (pos == 0xFFu) {
-                            err = 1u;
-                        } else {
-                            const unsigned ad = sacc + pos * (ncol * 8u);
-                            sts64(ad, lds64(ad) + v[j]);
-                            if (a.touched) a.touched[base + pos] = 1;
+                    for (int j = 0; j < ND; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
+#pragma unroll
+                    for (int j = 0; j < ND; j++) sts64(ad[j], o[j] + v[j]);
+                }
+                if (!FAST && on && (SPLIT == 1 || (int)warp == ph)) {
+#pragma unroll
+                    for (int j = 0; j < ND; j++) {
+                        const unsigned pos = (words[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                        if (fabs(v[j]) > a.drop_tol) {
+                            if (pos == 0xFFu) {
+                                err = 1u;
+                            } else {
+                                const unsigned adr = sacc + pos * (ncol * 8u);
+                                sts64(adr, lds64(adr) + v[j]);
+                                if (a.touched) a.touched[base + pos] = 1;
+                            }
                         }
                     }
                 }
+                if (SPLIT > 1) __syncthreads();
             }
-            if (SPLIT > 1) __syncthreads();
         }
     }
     if (err) atomicAdd(a.errflag, 1);
@@ -523,10 +652,34 @@ __global__ void __launch_bounds__(128) k_h1_gather(const HArgs a, const HTab<DIM
     }
     if (!valid) return;
     double* out = a.nzval + base;
-    if (a.acc_A) {
-        for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) out[i] += lds64(sacc + i * (ncol * 8u));
-    } else {
-        for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) out[i] = lds64(sacc + i * (ncol * 8u));
+    {
+        // write-out: a lane owns the contiguous entries of its column, so it stores them as whole 32-byte sectors
+        // (st.global.v4.f64) between a scalar head and tail — a quarter of the store wavefronts of 8-byte stores, and
+        // no partially written sectors for L2 to merge.
+        const int w0 = (SPLIT == 1 ? 0 : (int)warp);
+        const int head = min(len, (int)((4 - (base & 3)) & 3));
+        const int ng = (len - head) >> 2;
+        const int tail0 = head + 4 * ng;
+        for (int i = w0; i < head; i += SPLIT) {
+            const double t = lds64(sacc + i * (ncol * 8u));
+            out[i] = a.acc_A ? out[i] + t : t;
+        }
+        for (int i = tail0 + w0; i < len; i += SPLIT) {
+            const double t = lds64(sacc + i * (ncol * 8u));
+            out[i] = a.acc_A ? out[i] + t : t;
+        }
+        for (int g = w0; g < ng; g += SPLIT) {
+            const int i = head + 4 * g;
+            double t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) t[u] = lds64(sacc + (i + u) * (ncol * 8u));
+            if (a.acc_A) {
+                double o0, o1, o2, o3;
+                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o0), "=d"(o1), "=d"(o2), "=d"(o3) : "l"(out + i));
+                t[0] += o0; t[1] += o1; t[2] += o2; t[3] += o3;
+            }
+            stg256(out + i, t[0], t[1], t[2], t[3]);
+        }
     }
     if (a.has_rhs && (SPLIT == 1 || warp == 0)) {
         if (a.acc_b) a.bvec[c] += bsum;
@@ -539,15 +692,45 @@ static int launch_h1_gather_t(femb_ctx* ctx, const FembEval& EG, const FembEval*
     const FembSpace& s = ctx->spaces[EG.space];
     HTab<DIM, ND, NQ> tab;
     for (int q = 0; q < NQ; q++) {
-        tab.w[q] = EG.w[q];
         for (int j = 0; j < ND; j++) {
-            for (int d = 0; d < DIM; d++) tab.D[q][d][j] = EG.h_refderivs[((size_t)q * s.nd_all + j) * DIM + d];
+            for (int d = 0; d < DIM; d++) {
+                tab.D[q][d][j] = EG.h_refderivs[((size_t)q * s.nd_all + j) * DIM + d];
+                tab.wD[q][d][j] = EG.w[q] * tab.D[q][d][j];
+            }
             tab.wphi[q][j] = EI ? EG.w[q] * EI->h_refvals[(size_t)q * s.nd_all + j] : 0.0;
         }
     }
+    // P2 in barycentric form: L4 from the quadrature points, accepted only if it reproduces the evaluator's table
+    bool p2s = ND == (DIM + 1) * (DIM + 2) / 2;
+    if (p2s) {
+        for (int q = 0; q < NQ; q++) {
+            double l0 = 1.0;
+            for (int d = 0; d < DIM; d++) {
+                tab.L4[q][d + 1] = 4.0 * EG.xref[q * DIM + d];
+                l0 -= EG.xref[q * DIM + d];
+            }
+            tab.L4[q][0] = 4.0 * l0;
+        }
+        for (int q = 0; q < NQ && p2s; q++)
+            for (int d = 0; d < DIM && p2s; d++)
+                for (int j = 0; j < ND && p2s; j++) {
+                    double ref;  // d phi_j / d xref_d at x_q from the barycentric formulas
+                    if (j == 0) ref = -(tab.L4[q][0] - 1.0);
+                    else if (j <= DIM) ref = (j - 1 == d) ? tab.L4[q][j] - 1.0 : 0.0;
+                    else {
+                        const int ea = DIM == 2 ? p2_edge_a<2>(j - DIM - 1) : p2_edge_a<3>(j - DIM - 1), eb = DIM == 2 ? p2_edge_b<2>(j - DIM - 1) : p2_edge_b<3>(j - DIM - 1);
+                        if (ea == 0) ref = ((eb - 1 == d) ? tab.L4[q][0] : 0.0) - tab.L4[q][eb];
+                        else ref = ((eb - 1 == d) ? tab.L4[q][ea] : 0.0) + ((ea - 1 == d) ? tab.L4[q][eb] : 0.0);
+                    }
+                    if (fabs(ref - tab.D[q][d][j]) > 1e-13 * (1.0 + fabs(ref))) p2s = false;
+                }
+    }
+    if (!p2s)
+        for (int q = 0; q < NQ; q++)
+            for (int i = 0; i <= DIM; i++) tab.L4[q][i] = 0.0;
     const bool fast = ctx->hmap_complete && !a.touched && !(a.drop_tol > 0.0);
-    auto kern1 = fast ? k_h1_gather<DIM, ND, NQ, 1, true> : k_h1_gather<DIM, ND, NQ, 1, false>;
-    auto kern4 = fast ? k_h1_gather<DIM, ND, NQ, 4, true> : k_h1_gather<DIM, ND, NQ, 4, false>;
+    auto kern1 = fast ? (p2s ? k_h1_gather<DIM, ND, NQ, 1, true, true> : k_h1_gather<DIM, ND, NQ, 1, true, false>) : k_h1_gather<DIM, ND, NQ, 1, false, false>;
+    auto kern4 = fast ? (p2s ? k_h1_gather<DIM, ND, NQ, 4, true, true> : k_h1_gather<DIM, ND, NQ, 4, true, false>) : k_h1_gather<DIM, ND, NQ, 4, false, false>;
     size_t max1 = 0, max4 = 0;
     for (auto& r : ctx->hranges) {
         if (r.split == 4) max4 = std::max(max4, (size_t)std::max(1, r.maxlen) * 32 * sizeof(double));
@@ -598,7 +781,7 @@ int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     else k_cell_coef<3><<<gridc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, ctx->cellcoef);
     KERNEL_CHECK(ctx);
     HArgs a;
-    a.coef = ctx->cellcoef; a.hslice_ptr = ctx->hslice_ptr; a.hmap = ctx->hmap; a.hstride = ctx->hmap_stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
+    a.coef = ctx->cellcoef; a.hslice_ptr = ctx->hslice_ptr; a.hslice_zero = ctx->hslice_zero; a.hmap = ctx->hmap; a.hstride = ctx->hmap_stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag; a.drop_tol = drop_tol;
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;

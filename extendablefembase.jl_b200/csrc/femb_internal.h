@@ -120,11 +120,12 @@ struct femb_ctx {
     int gmap_maxrows = 0;            // longest slice (rows) = largest number of cells around a dof
     int gmap_space = -1;
     // general scalar-H1 gather map (P2, ...; femb_pattern.cu): sliced ELL over (dof, adjacent cell) pairs, SoA planes
-    // 0 = cell, 1 = local index k of the dof in that cell, 2.. = positions of the cell's local rows in the dof's CSC
-    // column packed 4 x 8 bit per word (0xFF = not in the pattern)
+    // 0 = cell, 1.. = positions of the cell's local rows in the dof's CSC column packed 4 x 8 bit per word (0xFF = not
+    // in the pattern); the spare bytes of the last word carry the local index k of the dof and the first-touch flags
     uint32_t* hmap = nullptr;
     size_t hmap_stride = 0;
     int32_t* hslice_ptr = nullptr;
+    uint8_t* hslice_zero = nullptr;  // per slice: some column has positions without a local contribution (zero the accumulators)
     int hmap_space = -1, hmap_words = 0;
     bool hmap_complete = false;    // every (cell, row) of the map has a slot: the gather may skip its per-entry checks
     struct HRange { int64_t s0, s1; int maxlen; int split; };  // split: threads per column (1, or 4 for high-degree columns)

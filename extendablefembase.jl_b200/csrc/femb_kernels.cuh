@@ -31,6 +31,15 @@ __device__ __forceinline__ double lds64(unsigned addr) {
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
+// 0.0 when `skip` is set, else the shared-memory value (predicated load: no branch, no wavefront for skipped lanes)
+__device__ __forceinline__ double lds64_unless(unsigned addr, unsigned skip) {
+    double v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@!p ld.shared.f64 %0, [%1];\n\t}" : "=d"(v) : "r"(addr), "r"(skip));
+    return v;
+}
+__device__ __forceinline__ void lds128(unsigned addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
 __device__ __forceinline__ void sts64(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
 // femb_generic.cu

@@ -27,6 +27,7 @@ void femb_free_pattern(femb_ctx* ctx) {
     ctx->chunk_n = 0;
     femb_free(&ctx->hmap);
     femb_free(&ctx->hslice_ptr);
+    femb_free(&ctx->hslice_zero);
     femb_free(&ctx->cellcoef);
     ctx->hmap_stride = 0;
     ctx->hmap_space = -1;
@@ -757,9 +758,16 @@ __global__ void k_slice_collen(const int64_t* __restrict__ colptr, int64_t ndofs
     maxlen[s] = m;
 }
 
+// Map entry of (column c, e-th adjacent cell), planes [row][lane]: plane 0 = cell, planes 1 .. nwords = positions of the
+// cell's local rows inside CSC column c, 8 bits each (0xFF = not in the pattern).  The two spare bytes of the last word hold
+// the local index k of c in the cell (bits 16-19, 0xF = padding entry) and one "first touch" flag per local row (bit 20 + j:
+// no earlier visit of this column wrote that position, so the gather stores instead of adding and needs no zeroed
+// accumulator).  needs_zero[slice] = 1 when a column of the slice has positions no cell contributes to (halo rows of a
+// partitioned mesh, extra diagonal entries): those slices zero their accumulators first.
 __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices, int nd, int nwords,
                        const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
-                       const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hmap, size_t stride, int32_t* __restrict__ nmissing) {
+                       const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hmap, size_t stride, int32_t* __restrict__ nmissing,
+                       uint8_t* __restrict__ needs_zero) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nslices * 32) return;
     const int64_t slice = c >> 5;
@@ -768,9 +776,12 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
     const int e0 = c < ndofs ? adj_ptr[c] : 0;
     const int deg = c < ndofs ? adj_ptr[c + 1] - e0 : 0;
     const int64_t base = c < ndofs ? colptr[c] - 1 : 0;
+    const int len = c < ndofs ? (int)(colptr[c + 1] - 1 - base) : 0;
+    uint32_t seen[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // positions written by earlier visits (max_collen <= 254)
+    int nseen = 0;
     for (int r = 0; r < nrows; r++) {
         const size_t idx = ((size_t)(row0 + r) << 5) + lane;
-        uint32_t cell = 0, k = FEMB_GMAP_INVALID;
+        uint32_t cell = 0, k = 0xFu, first = 0u;
         uint32_t words[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         if (r < deg) {
             uint32_t a = adj[e0 + r];
@@ -780,18 +791,25 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
                 int64_t p = find_slot(colptr, rowval, c, (int64_t)celldofs[(int64_t)cell * nd + j]);
                 uint32_t pos = (p < 0) ? 0xFFu : (uint32_t)(p - base);
                 if (p < 0) atomicAdd(nmissing, 1);  // rows without a slot (compressed / adopted patterns): the gather must check
+                else if (!((seen[pos >> 5] >> (pos & 31)) & 1u)) {
+                    seen[pos >> 5] |= 1u << (pos & 31);
+                    first |= 1u << j;
+                    nseen++;
+                }
                 words[j >> 2] = (words[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (pos << (8 * (j & 3)));
             }
         }
+        words[nwords - 1] = (words[nwords - 1] & 0xFFFFu) | (k << 16) | (first << 20);
         hmap[idx] = cell;
-        hmap[stride + idx] = k;
-        for (int wd = 0; wd < nwords; wd++) hmap[(2 + wd) * stride + idx] = words[wd];
+        for (int wd = 0; wd < nwords; wd++) hmap[(1 + wd) * stride + idx] = words[wd];
     }
+    if (nseen < len) needs_zero[slice] = 1;
 }
 
 int femb_build_hmap(femb_ctx* ctx) {
     femb_free(&ctx->hmap);
     femb_free(&ctx->hslice_ptr);
+    femb_free(&ctx->hslice_zero);
     ctx->hmap_stride = 0;
     ctx->hmap_space = -1;
     ctx->hranges.clear();
@@ -799,7 +817,8 @@ int femb_build_hmap(femb_ctx* ctx) {
     if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
     const int sid = ctx->row_spaces[0];
     const FembSpace& s = ctx->spaces[sid];
-    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd > 16 || ctx->max_collen > 254) return FEMB_OK;
+    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd > 12 || ctx->max_collen > 254) return FEMB_OK;
+    if ((s.nd & 3) != 1 && (s.nd & 3) != 2) return FEMB_OK;  // the last position word must have two spare bytes (k + first-touch flags)
     const int64_t nslices = (s.ndofs + 31) / 32;
     const int nwords = (s.nd + 3) / 4;
     int32_t *deg = nullptr, *clen = nullptr;
@@ -877,10 +896,12 @@ int femb_build_hmap(femb_ctx* ctx) {
     ctx->hranges = rg;
     ctx->hmap_stride = (size_t)rows * 32;
     ctx->hmap_words = nwords;
-    FEMB_TRY(femb_alloc(ctx, &ctx->hmap, ctx->hmap_stride * (2 + nwords)));
+    FEMB_TRY(femb_alloc(ctx, &ctx->hmap, ctx->hmap_stride * (1 + nwords)));
+    FEMB_TRY(femb_alloc(ctx, &ctx->hslice_zero, (size_t)nslices));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hslice_zero, 0, (size_t)nslices, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
     k_hmap<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.nd, nwords, s.celldofs, ctx->colptr, ctx->rowval,
-                                                                            ctx->hslice_ptr, ctx->hmap, ctx->hmap_stride, ctx->errflag);
+                                                                            ctx->hslice_ptr, ctx->hmap, ctx->hmap_stride, ctx->errflag, ctx->hslice_zero);
     KERNEL_CHECK(ctx);
     {
         int32_t nmiss = 0;
