@@ -51,8 +51,8 @@ int32_t femb_create(int32_t device, femb_ctx** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev2)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev3)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&ctx->errflag, sizeof(int32_t))) != cudaSuccess ||
-        (e = cudaMemset(ctx->errflag, 0, sizeof(int32_t))) != cudaSuccess) {
+        (e = cudaMalloc((void**)&ctx->errflag, 4 * sizeof(int32_t))) != cudaSuccess ||  // [0] missing slots, [1] femb_dirichlet_apply, [2] connectivity compare
+        (e = cudaMemset(ctx->errflag, 0, 4 * sizeof(int32_t))) != cudaSuccess) {
         g_err = cudaGetErrorString(e);
         delete ctx;
         return FEMB_ERR_CUDA;
@@ -86,8 +86,11 @@ int32_t femb_destroy(femb_ctx* ctx) {
     femb_free_system(ctx);
     femb_free(&ctx->coords);
     femb_free(&ctx->cellnodes);
+    femb_free(&ctx->cellnodes_tmp);
     femb_free(&ctx->cellvol);
     femb_free(&ctx->cellrhs);
+    femb_free(&ctx->bvec);
+    femb_free(&ctx->sol);
     femb_free(&ctx->errflag);
     femb_free(&ctx->color_perm);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -129,6 +132,37 @@ int32_t femb_host_unregister(femb_ctx* ctx, void* ptr) {
     return FEMB_OK;
 }
 
+}  // extern "C" (reopened below)
+
+// flag = 1 if the two index arrays differ anywhere (grid-stride, one atomic per CTA that saw a difference)
+__global__ void k_differs_i32(const int32_t* __restrict__ a, const int32_t* __restrict__ b, size_t n, int32_t* __restrict__ flag) {
+    bool d = false;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d |= a[i] != b[i];
+    if (__syncthreads_or(d) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// uploads `cellnodes` into the scratch copy on `stream` and compares it with the registered connectivity there; the
+// result is read with femb_cellnodes_differ after the stream has been synchronised
+int femb_cellnodes_compare_async(femb_ctx* ctx, const int32_t* cellnodes, cudaStream_t stream) {
+    const size_t n = (size_t)ctx->ncells * ctx->nnpc;
+    if (!ctx->cellnodes_tmp) FEMB_TRY(femb_alloc(ctx, &ctx->cellnodes_tmp, n));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag + 2, 0, sizeof(int32_t), stream));
+    if (n == 0) return FEMB_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellnodes_tmp, cellnodes, sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+    k_differs_i32<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, stream>>>(ctx->cellnodes, ctx->cellnodes_tmp, n, ctx->errflag + 2);
+    KERNEL_CHECK(ctx);
+    return FEMB_OK;
+}
+
+int femb_cellnodes_differ(femb_ctx* ctx, bool* differ) {
+    int32_t f = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&f, ctx->errflag + 2, sizeof(f), cudaMemcpyDeviceToHost));
+    *differ = f != 0;
+    return FEMB_OK;
+}
+
+extern "C" {
+
 int32_t femb_mesh_set(femb_ctx* ctx, int32_t dim, int64_t nnodes, const double* coords, int32_t nnpc, int64_t ncells,
                       const int32_t* cellnodes, const double* cellvolumes) {
     FEMB_CHECK_CTX(ctx);
@@ -137,22 +171,37 @@ int32_t femb_mesh_set(femb_ctx* ctx, int32_t dim, int64_t nnodes, const double* 
     if (!coords || !cellnodes || nnodes <= 0 || ncells < 0) return femb_fail(ctx, FEMB_ERR_ARG, "femb_mesh_set: bad arguments");
     if (ncells * (int64_t)32 >= ((int64_t)1 << 32)) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "ncells too large for 32-bit adjacency packing");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    bool same_shape = (ctx->dim == dim && ctx->nnodes == nnodes && ctx->ncells == ncells);
-    if (!same_shape) {
+    bool same_shape = (ctx->dim == dim && ctx->nnodes == nnodes && ctx->ncells == ncells && ctx->cellnodes);
+    bool same_topology = false;
+    if (same_shape) {
+        // equal counts do not mean equal connectivity (edge flips, renumbering): everything derived from CellNodes — the
+        // pattern, the gather maps, the dof adjacency, the entities — is kept only if the new array is identical
+        FEMB_TRY(femb_cellnodes_compare_async(ctx, cellnodes, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        bool differ = true;
+        FEMB_TRY(femb_cellnodes_differ(ctx, &differ));
+        same_topology = !differ;
+    }
+    if (!same_topology) {
         // a new mesh invalidates everything derived from it
         femb_free_pattern(ctx);
         for (auto& s : ctx->spaces) femb_free_space(s);
         femb_free_entities(ctx);
-        FEMB_TRY(femb_alloc(ctx, &ctx->coords, (size_t)nnodes * dim));
-        FEMB_TRY(femb_alloc(ctx, &ctx->cellnodes, (size_t)ncells * nnpc));
-        femb_free(&ctx->cellvol);
+        if (same_shape) {  // the scratch copy already holds the new connectivity
+            std::swap(ctx->cellnodes, ctx->cellnodes_tmp);
+        } else {
+            FEMB_TRY(femb_alloc(ctx, &ctx->coords, (size_t)nnodes * dim));
+            FEMB_TRY(femb_alloc(ctx, &ctx->cellnodes, (size_t)ncells * nnpc));
+            femb_free(&ctx->cellvol);
+        }
     }
+    femb_free(&ctx->cellnodes_tmp);
     ctx->dim = dim;
     ctx->nnpc = nnpc;
     ctx->nnodes = nnodes;
     ctx->ncells = ncells;
     FEMB_TRY(femb_h2d(ctx, ctx->coords, coords, (size_t)nnodes * dim));
-    FEMB_TRY(femb_h2d(ctx, ctx->cellnodes, cellnodes, (size_t)ncells * nnpc));
+    if (!same_shape) FEMB_TRY(femb_h2d(ctx, ctx->cellnodes, cellnodes, (size_t)ncells * nnpc));
     if (cellvolumes) {
         if (!ctx->cellvol) FEMB_TRY(femb_alloc(ctx, &ctx->cellvol, (size_t)ncells));
         FEMB_TRY(femb_h2d(ctx, ctx->cellvol, cellvolumes, (size_t)ncells));
@@ -279,6 +328,7 @@ int32_t femb_matrix_layout(femb_ctx* ctx, int32_t nr, const int32_t* rows, int32
     ctx->ncs = nc;
     ctx->nrows = ctx->row_off[nr];
     ctx->ncols = ctx->col_off[nc];
+    if (resized) ctx->extra_entries.clear();  // their keys were encoded against the old row count
     if (resized || !ctx->bvec) {
         femb_free_pattern(ctx);
         FEMB_TRY(femb_alloc(ctx, &ctx->bvec, (size_t)ctx->nrows));
@@ -292,6 +342,7 @@ int32_t femb_matrix_layout(femb_ctx* ctx, int32_t nr, const int32_t* rows, int32
 int32_t femb_matrix_zero(femb_ctx* ctx) {
     FEMB_CHECK_CTX(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->dirty_A = false;
     ctx->zero_pending_A = true;  // applied lazily (femb_flush_zero) or skipped by write-once kernels
     if (ctx->touched) CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 0, ctx->nnz, ctx->stream));
     return FEMB_OK;
@@ -300,6 +351,7 @@ int32_t femb_matrix_zero(femb_ctx* ctx) {
 int32_t femb_vector_zero(femb_ctx* ctx) {
     FEMB_CHECK_CTX(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->dirty_b = false;
     ctx->zero_pending_b = true;
     return FEMB_OK;
 }
@@ -369,6 +421,7 @@ int32_t femb_vector_set(femb_ctx* ctx, int32_t which, const double* v) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (which == 0) {
         ctx->zero_pending_b = false;
+        ctx->dirty_b = true;
         FEMB_TRY(femb_h2d(ctx, ctx->bvec, v, (size_t)ctx->nrows));
     }
     else FEMB_TRY(femb_h2d(ctx, ctx->sol, v, (size_t)ctx->ncols));

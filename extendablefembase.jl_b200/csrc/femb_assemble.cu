@@ -15,6 +15,25 @@ extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, 
     RhsDev rhs;
     double* dev_f = nullptr;
     FEMB_TRY(make_rhs(ctx, rhs_kind, data, ctx->spaces[EG.space].ncomp, EG.nqp, rhs, &dev_f));
+    const bool fused = ctx->fused_exchange && ctx->comm && !ctx->peers.empty() && ctx->stream_x;
+    if (fused) {
+        // the exchange sends the whole ghost slot / entry: accumulating over several assemblies would re-send earlier sums
+        if (ctx->dirty_A || ctx->dirty_b) {
+            cudaFree(dev_f);
+            return femb_fail(ctx, FEMB_ERR_ARG, "fused exchange: call femb_matrix_zero and femb_vector_zero before each femb_assemble_poisson");
+        }
+        if (ctx->exchange_nnz != ctx->nnz) {
+            cudaFree(dev_f);
+            return femb_fail(ctx, FEMB_ERR_ARG, "fused exchange: the exchange plan was built for another pattern");
+        }
+        if (rhs_kind == FEMB_RHS_NONE) {  // no rhs is assembled: the vector part of the plan must not carry stale values
+            int zs = femb_flush_zero(ctx, false, true);
+            if (zs != FEMB_OK) { cudaFree(dev_f); return zs; }
+        }
+    }
+    ctx->exchange_done = false;
+    ctx->dirty_A = true;
+    if (rhs_kind != FEMB_RHS_NONE) ctx->dirty_b = true;
     int st = femb_timer_begin(ctx);
     if (st == FEMB_OK) {
         if (ctx->scatter == FEMB_SCATTER_GATHER && ctx->gmap && ctx->gmap_space == EG.space && (!ctx->touched || ctx->max_collen <= 64) &&
@@ -28,6 +47,11 @@ extern "C" int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eg, int32_t ei, 
                 st = launch_bilinear(ctx, eg, eg, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, FEMB_BIL_SYMMETRIC_UPPER, drop_tol);
             if (st == FEMB_OK && rhs_kind != FEMB_RHS_NONE) st = launch_linear(ctx, ei, 0, 1.0, rhs);
         }
+    }
+    if (st == FEMB_OK && fused && !ctx->exchange_done) {
+        // dispatch paths without an overlapped exchange (general H1 gather, tensor-core, generic kernels): same result, sequential
+        st = femb_flush_zero(ctx, true, true);
+        if (st == FEMB_OK) st = femb_exchange_on(ctx, ctx->stream);
     }
     if (st == FEMB_OK) st = femb_timer_end(ctx);
     cudaFree(dev_f);

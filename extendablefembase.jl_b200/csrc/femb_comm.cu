@@ -34,14 +34,17 @@ NcclApi g_nccl;
 
 bool load_nccl() {
     if (g_nccl.handle) return true;
-    const char* names[] = {getenv("FEMB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    // FEMB_NCCL_LIB, when set, is the only candidate (a wrong path must fail, not silently bind another NCCL)
+    const char* env = getenv("FEMB_NCCL_LIB");
+    const char* names[] = {env, env ? nullptr : "libnccl.so.2", env ? nullptr : "libnccl.so"};
     for (const char* n : names) {
         if (!n) continue;
         g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (g_nccl.handle) break;
     }
     if (!g_nccl.handle) {
-        g_nccl.err = std::string("cannot dlopen libnccl.so.2 (set FEMB_NCCL_LIB): ") + (dlerror() ? dlerror() : "");
+        const char* e = dlerror();  // one call: dlerror() clears the pending message
+        g_nccl.err = std::string("cannot dlopen libnccl.so.2 (set FEMB_NCCL_LIB): ") + (e ? e : "");
         return false;
     }
 #define BIND(field, sym)                                                      \
@@ -88,7 +91,10 @@ __global__ void k_unpack_add(double* __restrict__ dst, const int64_t* __restrict
     }
 }
 
-void free_exchange(femb_ctx* ctx) {
+}  // namespace
+
+// drops the exchange plan (the slot lists refer to one particular pattern: called whenever nnz / the slots change)
+void femb_free_exchange(femb_ctx* ctx) {
     femb_free(&ctx->send_slots);
     femb_free(&ctx->recv_slots);
     femb_free(&ctx->send_b);
@@ -96,10 +102,14 @@ void free_exchange(femb_ctx* ctx) {
     femb_free(&ctx->sendbuf);
     femb_free(&ctx->recvbuf);
     ctx->peers.clear();
+    ctx->send_ptr.clear();
+    ctx->recv_ptr.clear();
+    ctx->sendb_ptr.clear();
+    ctx->recvb_ptr.clear();
     ctx->nsend = ctx->nrecv = ctx->nsendb = ctx->nrecvb = 0;
+    ctx->xdof_send_lo = ctx->xdof_recv_lo = 0;
+    ctx->xdof_send_hi = ctx->xdof_recv_hi = -1;
 }
-
-}  // namespace
 
 int femb_exchange_on(femb_ctx* ctx, cudaStream_t stream) {
     const int np = (int)ctx->peers.size();
@@ -174,51 +184,68 @@ int32_t femb_comm_set_exchange(femb_ctx* ctx, int32_t npeers, const int32_t* pee
     if (npeers < 0 || (npeers && (!peers || !send_ptr || !recv_ptr || !sendb_ptr || !recvb_ptr)))
         return femb_fail(ctx, FEMB_ERR_ARG, "femb_comm_set_exchange: bad arguments");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    free_exchange(ctx);
-    if (npeers == 0) return FEMB_OK;
+    // everything is validated on locals first; the context only changes once every list has been checked and copied
+    if (npeers == 0) {
+        femb_free_exchange(ctx);
+        return FEMB_OK;
+    }
     for (int p = 0; p < npeers; p++) {
         if (peers[p] < 0 || peers[p] >= ctx->nranks || peers[p] == ctx->rank) return femb_fail(ctx, FEMB_ERR_ARG, "peer %d is not a valid remote rank", peers[p]);
         if (p && peers[p] <= peers[p - 1]) return femb_fail(ctx, FEMB_ERR_ARG, "peers must be ascending (fixed summation order)");
+    }
+    const int64_t* ptrs[4] = {send_ptr, recv_ptr, sendb_ptr, recvb_ptr};
+    for (const int64_t* q : ptrs) {
+        if (q[0] != 0) return femb_fail(ctx, FEMB_ERR_ARG, "femb_comm_set_exchange: pointer arrays must start at 0");
+        for (int p = 0; p < npeers; p++)
+            if (q[p + 1] < q[p]) return femb_fail(ctx, FEMB_ERR_ARG, "femb_comm_set_exchange: pointer arrays must be non-decreasing");
+    }
+    const int64_t nsend = send_ptr[npeers], nrecv = recv_ptr[npeers], nsendb = sendb_ptr[npeers], nrecvb = recvb_ptr[npeers];
+    if ((nsend && !send_slots) || (nrecv && !recv_slots) || (nsendb && !send_b) || (nrecvb && !recv_b))
+        return femb_fail(ctx, FEMB_ERR_ARG, "femb_comm_set_exchange: a slot list is NULL but its count is not zero");
+    if ((nsend || nrecv) && !ctx->nzval) return femb_fail(ctx, FEMB_ERR_ARG, "femb_comm_set_exchange: build or adopt the pattern first");
+    // range checks on the host (the lists are O(interface))
+    for (int64_t i = 0; i < nsend; i++)
+        if (send_slots[i] < 0 || send_slots[i] >= ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "send slot out of range");
+    for (int64_t i = 0; i < nrecv; i++)
+        if (recv_slots[i] < 0 || recv_slots[i] >= ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "recv slot out of range");
+    for (int64_t i = 0; i < nsendb; i++)
+        if (send_b[i] < 0 || send_b[i] >= ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "send vector index out of range");
+    for (int64_t i = 0; i < nrecvb; i++)
+        if (recv_b[i] < 0 || recv_b[i] >= ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "recv vector index out of range");
+    femb_free_exchange(ctx);
+    int st = femb_alloc(ctx, &ctx->send_slots, (size_t)nsend);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->recv_slots, (size_t)nrecv);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->send_b, (size_t)nsendb);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->recv_b, (size_t)nrecvb);
+    if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->sendbuf, (size_t)(nsend + nsendb));
+    if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->recvbuf, (size_t)(nrecv + nrecvb));
+    if (st == FEMB_OK) st = femb_h2d(ctx, ctx->send_slots, send_slots, (size_t)nsend);
+    if (st == FEMB_OK) st = femb_h2d(ctx, ctx->recv_slots, recv_slots, (size_t)nrecv);
+    if (st == FEMB_OK) st = femb_h2d(ctx, ctx->send_b, send_b, (size_t)nsendb);
+    if (st == FEMB_OK) st = femb_h2d(ctx, ctx->recv_b, recv_b, (size_t)nrecvb);
+    if (st == FEMB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = femb_fail(ctx, FEMB_ERR_CUDA, "femb_comm_set_exchange: copy failed");
+    if (st != FEMB_OK) {
+        femb_free_exchange(ctx);  // no half-installed plan
+        return st;
     }
     ctx->peers.assign(peers, peers + npeers);
     ctx->send_ptr.assign(send_ptr, send_ptr + npeers + 1);
     ctx->recv_ptr.assign(recv_ptr, recv_ptr + npeers + 1);
     ctx->sendb_ptr.assign(sendb_ptr, sendb_ptr + npeers + 1);
     ctx->recvb_ptr.assign(recvb_ptr, recvb_ptr + npeers + 1);
-    ctx->nsend = send_ptr[npeers];
-    ctx->nrecv = recv_ptr[npeers];
-    ctx->nsendb = sendb_ptr[npeers];
-    ctx->nrecvb = recvb_ptr[npeers];
-    // range checks on the host (the lists are O(interface))
-    for (int64_t i = 0; i < ctx->nsend; i++)
-        if (send_slots[i] < 0 || send_slots[i] >= ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "send slot out of range");
-    for (int64_t i = 0; i < ctx->nrecv; i++)
-        if (recv_slots[i] < 0 || recv_slots[i] >= ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "recv slot out of range");
-    for (int64_t i = 0; i < ctx->nsendb; i++)
-        if (send_b[i] < 0 || send_b[i] >= ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "send vector index out of range");
-    for (int64_t i = 0; i < ctx->nrecvb; i++)
-        if (recv_b[i] < 0 || recv_b[i] >= ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "recv vector index out of range");
-    ctx->xdof_send_lo = ctx->xdof_recv_lo = 0;
-    ctx->xdof_send_hi = ctx->xdof_recv_hi = -1;
-    if (ctx->nsendb) {
-        ctx->xdof_send_lo = *std::min_element(send_b, send_b + ctx->nsendb);
-        ctx->xdof_send_hi = *std::max_element(send_b, send_b + ctx->nsendb);
+    ctx->nsend = nsend;
+    ctx->nrecv = nrecv;
+    ctx->nsendb = nsendb;
+    ctx->nrecvb = nrecvb;
+    if (nsendb) {
+        ctx->xdof_send_lo = *std::min_element(send_b, send_b + nsendb);
+        ctx->xdof_send_hi = *std::max_element(send_b, send_b + nsendb);
     }
-    if (ctx->nrecvb) {
-        ctx->xdof_recv_lo = *std::min_element(recv_b, recv_b + ctx->nrecvb);
-        ctx->xdof_recv_hi = *std::max_element(recv_b, recv_b + ctx->nrecvb);
+    if (nrecvb) {
+        ctx->xdof_recv_lo = *std::min_element(recv_b, recv_b + nrecvb);
+        ctx->xdof_recv_hi = *std::max_element(recv_b, recv_b + nrecvb);
     }
-    FEMB_TRY(femb_alloc(ctx, &ctx->send_slots, (size_t)ctx->nsend));
-    FEMB_TRY(femb_alloc(ctx, &ctx->recv_slots, (size_t)ctx->nrecv));
-    FEMB_TRY(femb_alloc(ctx, &ctx->send_b, (size_t)ctx->nsendb));
-    FEMB_TRY(femb_alloc(ctx, &ctx->recv_b, (size_t)ctx->nrecvb));
-    FEMB_TRY(femb_alloc(ctx, &ctx->sendbuf, (size_t)(ctx->nsend + ctx->nsendb)));
-    FEMB_TRY(femb_alloc(ctx, &ctx->recvbuf, (size_t)(ctx->nrecv + ctx->nrecvb)));
-    FEMB_TRY(femb_h2d(ctx, ctx->send_slots, send_slots, (size_t)ctx->nsend));
-    FEMB_TRY(femb_h2d(ctx, ctx->recv_slots, recv_slots, (size_t)ctx->nrecv));
-    FEMB_TRY(femb_h2d(ctx, ctx->send_b, send_b, (size_t)ctx->nsendb));
-    FEMB_TRY(femb_h2d(ctx, ctx->recv_b, recv_b, (size_t)ctx->nrecvb));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->exchange_nnz = ctx->nnz;
     return FEMB_OK;
 }
 
@@ -227,6 +254,7 @@ int32_t femb_exchange(femb_ctx* ctx) {
     if (!ctx->comm) return femb_fail(ctx, FEMB_ERR_ARG, "femb_exchange: femb_comm_init has not been called");
     if (ctx->peers.empty()) return FEMB_OK;
     if (!ctx->nzval || !ctx->bvec) return femb_fail(ctx, FEMB_ERR_ARG, "femb_exchange: no matrix / vector");
+    if (ctx->exchange_nnz != ctx->nnz) return femb_fail(ctx, FEMB_ERR_ARG, "femb_exchange: the exchange plan was built for another pattern");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     FEMB_TRY(femb_flush_zero(ctx, true, true));
     FEMB_TRY(femb_timer_begin(ctx));
@@ -250,7 +278,7 @@ int32_t femb_set_fused_exchange(femb_ctx* ctx, int32_t enable) {
 
 int32_t femb_comm_destroy(femb_ctx* ctx) {
     FEMB_CHECK_CTX(ctx);
-    free_exchange(ctx);
+    femb_free_exchange(ctx);
     if (ctx->stream_x) {
         cudaStreamDestroy(ctx->stream_x);
         cudaEventDestroy(ctx->ev_x0);

@@ -652,6 +652,7 @@ extern "C" int32_t femb_assemble_bilinear(femb_ctx* ctx, int32_t er, int32_t ec,
     FEMB_TRY(check_eval(ctx, ec));
     FEMB_TRY(require_pattern(ctx));
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->dirty_A = true;
     FEMB_TRY(femb_timer_begin(ctx));
     FEMB_TRY(launch_bilinear(ctx, er, ec, ctx->evals[er].op, ctx->evals[ec].op, brow, bcol, factor, flags, drop_tol));
     return femb_timer_end(ctx);
@@ -665,6 +666,7 @@ extern "C" int32_t femb_assemble_linear(femb_ctx* ctx, int32_t ev, int32_t brow,
     RhsDev rhs;
     double* dev_f = nullptr;
     FEMB_TRY(make_rhs(ctx, rhs_kind, data, ctx->evals[ev].resultdim, ctx->evals[ev].nqp, rhs, &dev_f));
+    ctx->dirty_b = true;
     int st = femb_timer_begin(ctx);
     if (st == FEMB_OK && rhs_kind != FEMB_RHS_NONE) st = launch_linear(ctx, ev, brow, factor, rhs);
     if (st == FEMB_OK) st = femb_timer_end(ctx);

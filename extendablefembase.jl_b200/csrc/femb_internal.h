@@ -85,6 +85,7 @@ struct femb_ctx {
     int64_t nnodes = 0, ncells = 0;
     double* coords = nullptr;     // dim x nnodes
     int32_t* cellnodes = nullptr; // nnpc x ncells
+    int32_t* cellnodes_tmp = nullptr;  // scratch copy for the "is the connectivity unchanged" compare
     double* cellvol = nullptr;    // ncells or null
 
     FembSpace spaces[FEMB_MAX_SPACES];
@@ -137,6 +138,7 @@ struct femb_ctx {
     double* nzval = nullptr;      // nnz
     bool zero_pending_A = false;  // femb_matrix_zero is lazy: write-once kernels skip the memset
     bool zero_pending_b = false;
+    bool dirty_A = false, dirty_b = false;  // something was assembled / set since the last femb_matrix_zero / femb_vector_zero
     uint8_t* touched = nullptr;   // nnz (only when tracking)
     bool track = false;
     double* bvec = nullptr;       // nrows
@@ -181,8 +183,10 @@ struct femb_ctx {
     double* sendbuf = nullptr;      // [matrix part | vector part] per peer, contiguous
     double* recvbuf = nullptr;
     int64_t nsend = 0, nrecv = 0, nsendb = 0, nrecvb = 0;
+    int64_t exchange_nnz = -1;      // nnz of the pattern the plan was validated against
     // fused (overlapped) exchange: dof ranges that must be assembled before the exchange may start
     bool fused_exchange = false;
+    bool exchange_done = false;     // set by the assembly path that performed the (overlapped) exchange itself
     int64_t xdof_send_lo = 0, xdof_send_hi = -1, xdof_recv_lo = 0, xdof_recv_hi = -1;  // [lo, hi] of send_b / recv_b
     cudaStream_t stream_x = nullptr;
     cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
@@ -248,6 +252,9 @@ static inline int femb_d2h(femb_ctx* ctx, T* dst, const T* src, size_t n) {
     return FEMB_OK;
 }
 
+// femb_api.cu
+int femb_cellnodes_compare_async(femb_ctx* ctx, const int32_t* cellnodes, cudaStream_t stream);
+int femb_cellnodes_differ(femb_ctx* ctx, bool* differ);
 // pattern.cu
 int femb_build_adjacency(femb_ctx* ctx, int space_id);
 int femb_build_slotmaps(femb_ctx* ctx);
@@ -270,3 +277,4 @@ int femb_timer_begin(femb_ctx* ctx);
 int femb_timer_end(femb_ctx* ctx);
 // comm.cu: pack -> NCCL send/recv -> add on `stream` (no timing, no lazy-zero flush)
 int femb_exchange_on(femb_ctx* ctx, cudaStream_t stream);
+void femb_free_exchange(femb_ctx* ctx);

@@ -240,6 +240,7 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
     RhsDev rhs;
     double* dev_f = nullptr;
     FEMB_TRY(make_rhs(ctx, linear ? rhs_kind : FEMB_RHS_NONE, data, 2, EG.nqp, rhs, &dev_f));
+    ctx->dirty_A = ctx->dirty_b = true;
     int st = femb_timer_begin(ctx);
     if (st == FEMB_OK && linear) {
         // Aloc[k,j] = mu * sum_qp w <grad_j, grad_k>, then * |T|                 (Example210:284-290,368)

@@ -627,10 +627,13 @@ int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
             }
             FEMB_TRY(launch_p1_slices(ctx, L, pos, L.nslices, ctx->stream));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x1, 0));
+            ctx->exchange_done = true;
             return FEMB_OK;
         }
         FEMB_TRY(launch_p1_slices(ctx, L, 0, L.nslices, ctx->stream));  // interface too large to be worth splitting
-        return femb_exchange_on(ctx, ctx->stream);
+        FEMB_TRY(femb_exchange_on(ctx, ctx->stream));
+        ctx->exchange_done = true;
+        return FEMB_OK;
     }
     return launch_p1_slices(ctx, L, 0, L.nslices, ctx->stream);
 }
@@ -761,13 +764,23 @@ extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coords + hi_n * dim, coords + hi_n * dim, sizeof(double) * (ctx->nnodes - hi_n) * dim, cudaMemcpyHostToDevice, ctx->stream_h2d));
     if (cellvol && ctx->ncells > hi_c)
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellvol + hi_c, cellvol + hi_c, sizeof(double) * (ctx->ncells - hi_c), cudaMemcpyHostToDevice, ctx->stream_h2d));
-    if (cellnodes)  // NULL: topology unchanged since femb_mesh_set (it is what the reused pattern was built from)
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellnodes, cellnodes, sizeof(int32_t) * ctx->ncells * ctx->nnpc, cudaMemcpyHostToDevice, ctx->stream_h2d));
-    int st = femb_timer_end(ctx);
+    // cellnodes != NULL: the caller is not sure the connectivity is the registered one.  The numeric phase never reads it
+    // (the gather map of the symbolic phase is the topology), so it is uploaded behind the geometry and compared on the
+    // device: a difference means the result above belongs to the OLD topology -> FEMB_ERR_ARG, the caller must
+    // femb_mesh_set + rebuild the pattern.  NULL = connectivity declared unchanged (geometry-only step).
+    int st = FEMB_OK;
+    if (cellnodes) st = femb_cellnodes_compare_async(ctx, cellnodes, ctx->stream_h2d);
+    if (st == FEMB_OK) st = femb_timer_end(ctx);
     cudaError_t e1 = cudaStreamSynchronize(ctx->stream_h2d), e2 = cudaStreamSynchronize(ctx->stream_d2h);
     cudaFree(dev_f);
     if (st != FEMB_OK) return st;
     CUDA_TRY(ctx, e1);
     CUDA_TRY(ctx, e2);
+    if (cellnodes) {
+        bool differ = false;
+        FEMB_TRY(femb_cellnodes_differ(ctx, &differ));
+        if (differ)
+            return femb_fail(ctx, FEMB_ERR_ARG, "femb_assemble_poisson_host: cellnodes differs from the connectivity the pattern was built from; call femb_mesh_set and rebuild the pattern");
+    }
     return femb_sync(ctx);
 }

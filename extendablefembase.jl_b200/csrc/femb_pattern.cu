@@ -12,6 +12,7 @@
 void femb_free_pattern(femb_ctx* ctx) {
     femb_free_csr(ctx);
     femb_free_saved(ctx);
+    femb_free_exchange(ctx);
     femb_free(&ctx->resvec);
     femb_free(&ctx->fixed);
     ctx->nfixed = 0;
@@ -533,6 +534,14 @@ extern "C" int32_t femb_pattern_compress(femb_ctx* ctx, int64_t* nnz_out) {
     ctx->rowval = rv2;
     ctx->nzval = nz2;
     ctx->nnz = nnz2;
+    // everything keyed on the old slot numbering goes: the row-wise view, the saved linear part, the fixed rows, the
+    // exchange plan (the caller re-installs it for the new pattern) and the colouring-independent chunk table
+    femb_free_csr(ctx);
+    femb_free_saved(ctx);
+    femb_free(&ctx->fixed);
+    ctx->nfixed = 0;
+    femb_free_exchange(ctx);
+    ctx->chunk_n = 0;
     FEMB_TRY(femb_alloc(ctx, &ctx->touched, (size_t)nnz2));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 1, nnz2, ctx->stream));
     FEMB_TRY(femb_build_gmap(ctx));

@@ -364,11 +364,12 @@ int32_t femb_dirichlet_apply(femb_ctx* ctx, int32_t use_boundary_list, int64_t d
     int32_t nerr = 0;
     if (rc == FEMB_OK) {
         const unsigned grid = (unsigned)((n + 255) / 256);
-        e = cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream);
+        // its own flag word: pending "no slot" errors of the assemblies ([0]) stay for femb_sync to report
+        e = cudaMemsetAsync(ctx->errflag + 1, 0, sizeof(int32_t), ctx->stream);
         k_fixed_list<<<grid, 256, 0, ctx->stream>>>(ctx->bdofs, nb, dof_offset, d_extra, n_extra, ctx->fixed);
-        k_dirichlet<<<grid, 256, 0, ctx->stream>>>(ctx->fixed, n, ctx->colptr, ctx->rowval, ctx->nzval, ctx->bvec, d_values, penalty, ctx->nrows, ctx->errflag);
+        k_dirichlet<<<grid, 256, 0, ctx->stream>>>(ctx->fixed, n, ctx->colptr, ctx->rowval, ctx->nzval, ctx->bvec, d_values, penalty, ctx->nrows, ctx->errflag + 1);
         ctx->launches += 2;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&nerr, ctx->errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&nerr, ctx->errflag + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
     }

@@ -98,7 +98,11 @@ int32_t femb_host_unregister(femb_ctx* ctx, void* ptr);
 /* ---- stage-1 inputs: xgrid[Coordinates], xgrid[CellNodes], xgrid[CellVolumes] ----------------
  * (ExtendableGrids components read at Example200:107,114; Example210:227-228; feevaluator.jl:94-97)
  * coords: dim x nnodes Float64; cellnodes: nnpc x ncells Int32 1-based; cellvolumes: ncells or NULL
- * (NULL: |T| = |det A|/dim! is computed on the device). */
+ * (NULL: |T| = |det A|/dim! is computed on the device).
+ * A call with the same dim / nnodes / ncells compares the new CellNodes with the registered one on the device: if it is
+ * identical only the geometry is replaced and everything derived from the connectivity (spaces, pattern, gather maps,
+ * grid entities) stays valid — the steady state of a moving-mesh loop; if it differs anywhere (edge flips,
+ * renumbering) the call behaves like a new mesh: spaces, pattern and entities are dropped and must be registered again. */
 int32_t femb_mesh_set(femb_ctx* ctx, int32_t dim, int64_t nnodes, const double* coords, int32_t nnpc,
                       int64_t ncells, const int32_t* cellnodes, const double* cellvolumes_or_null);
 
@@ -246,8 +250,11 @@ int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id,
  * and download of the finished nzval / b ranges overlap.  Equivalent to femb_mesh_set (same shapes: the symbolic
  * phase is reused) + femb_matrix_zero + femb_vector_zero + femb_assemble_poisson + femb_matrix_get +
  * femb_vector_get, bit for bit.  Scalar P1 with rhs_kind NONE / AFFINE; pin the host arrays with
- * femb_host_register for the copies to overlap.  cellvol must be given iff the registered mesh has volumes;
- * cellnodes may be NULL (connectivity unchanged — the numeric phase reads the geometry only). */
+ * femb_host_register for the copies to overlap.  cellvol must be given iff the registered mesh has volumes.
+ * cellnodes = NULL declares the connectivity unchanged (the numeric phase reads the geometry only: the fast, default way
+ * to call this).  cellnodes != NULL is uploaded behind the geometry and compared with the registered connectivity on
+ * the device; if it differs the call returns FEMB_ERR_ARG (the buffers then hold the matrix of the OLD topology and must
+ * be discarded): call femb_mesh_set and rebuild the pattern. */
 int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id, double mu, int32_t rhs_kind, const double* params,
                                    double drop_tol, const double* coords, const int32_t* cellnodes, const double* cellvolumes_or_null,
                                    double* nzval_out, double* b_out, int32_t nchunks);
@@ -289,9 +296,13 @@ int32_t femb_comm_set_exchange(femb_ctx* ctx, int32_t npeers, const int32_t* pee
 /* pack -> ncclSend/ncclRecv (one group) -> add in ascending peer order (reproducible).  Received non-zero matrix
  * values also mark their slot as touched (femb_pattern_compress).  Sent ghost entries are left in place. */
 int32_t femb_exchange(femb_ctx* ctx);
-/* enable = 1: femb_assemble_poisson (scalar P1 gather path) performs the exchange itself, overlapped with the bulk of
- * the assembly: the slices holding ghost and owned-interface columns are launched first, the pack / NCCL / add
- * sequence runs on a second stream while the remaining columns are assembled.  Do not call femb_exchange then. */
+/* enable = 1: femb_assemble_poisson performs the exchange itself.  On the scalar P1 gather path it is overlapped with
+ * the bulk of the assembly: the slices holding ghost and owned-interface columns are launched first, the pack / NCCL /
+ * add sequence runs on a second stream while the remaining columns are assembled; every other dispatch path runs the
+ * same exchange right after its kernels.  Do not call femb_exchange then.  Each such assembly must start from
+ * femb_matrix_zero + femb_vector_zero (the whole ghost entry is sent: FEMB_ERR_ARG otherwise); without an rhs the
+ * vector part of the plan carries zeros.  The plan must have been installed for the current pattern
+ * (femb_pattern_build / _adopt / _compress drop it). */
 int32_t femb_set_fused_exchange(femb_ctx* ctx, int32_t enable);
 int32_t femb_comm_destroy(femb_ctx* ctx);
 

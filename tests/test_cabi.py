@@ -86,3 +86,24 @@ def test_plain_c_caller_known_answer(libfemb, tmp_path):
     vals = {l.split("=")[0].strip(): float(l.split("=")[1]) for l in lines[1:13]}
     assert vals["A[1,1]"] == 1.0 and vals["A[2,1]"] == -0.5 and vals["A[4,4]"] == 1.0 and "A[4,1]" not in vals and "A[1,4]" not in vals
     assert lines[13].split() == ["b", "=", "0.0000", "0.0556", "-0.0556", "0.0000"]
+
+
+def test_missing_nccl_is_a_status_not_a_crash(tmp_path):
+    """without a loadable libnccl, femb_comm_unique_id must return FEMB_ERR_NCCL (5) — in a fresh process,
+    because a process that already dlopen'ed NCCL keeps it."""
+    import subprocess
+    import sys
+
+    from femb_b200 import _lib
+
+    code = (
+        "import ctypes, sys\n"
+        f"lib = ctypes.CDLL({_lib.LIBPATH!r})\n"
+        "buf = ctypes.create_string_buffer(128)\n"
+        "lib.femb_comm_unique_id.restype = ctypes.c_int32\n"
+        "print(lib.femb_comm_unique_id(buf))\n"
+    )
+    env = dict(os.environ, FEMB_NCCL_LIB=str(tmp_path / "no_such_libnccl.so"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "5"

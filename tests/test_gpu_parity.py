@@ -835,3 +835,160 @@ def test_device_topology_matches_the_oracle_loop():
                            ("FaceCells", f["facecells"]), ("CellFaceOrientations", f["orientations"]), ("CellEdges", e["cell_entities"]),
                            ("EdgeNodes", e["entity_nodes"]), ("CellEdgeSigns", e["signs"])):
             assert np.array_equal(dev._c[name], want), name
+
+
+# ---------------------------------------------------------------------------------------------
+# sizes that reach the code paths only big meshes take (VERDICT r01 "what's weak" 1): several launch ranges, SPLIT-4
+# vertex columns, first-touch accumulators, multi-CTA grids of the generic kernels — against the oracle, not identities
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,jit,device_dofmaps", [(64, False, True), (48, False, True), (24, True, False)])
+def test_midsize_p2_3d_against_c_oracle(m, jit, device_dofmaps):
+    """BASELINE.json configs[2] (H1P2{1,3} stiffness + rhs on the Kuhn mesh) at m = 48 (663,552 tets, ndofs 912,673): device
+    result against the C restatement of the reference loop on the device's pattern; the pattern itself must take every
+    reference contribution (miss == 0) and hold no slot the reference never writes."""
+    import oracle_c
+    from femb_b200.assembly import _Session
+
+    grid = _grid3d(m, jit)
+    if device_dofmaps:
+        grid.instantiate_on_device(0, components=("edges",))
+    fes = fb.FESpace(fb.H1P2(1, 3), grid)
+    qf = fb.QuadratureRule(grid.geometry, 2)
+    S = _Session([fes], qf, device_dofmaps=device_dofmaps)
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    nnz = ctx.pattern_build([(0, 0)])
+    p = np.array([0.25, 1.0, -1.0, 0.5])
+    mu = 1.3
+    ctx.matrix_zero()
+    ctx.vector_zero()
+    ctx.assemble_poisson(eg._eid, ei._eid, mu, _lib.RHS_AFFINE, p, 0.0)
+    nz, b = ctx.matrix_get(), ctx.vector_get(fes.ndofs)
+    colptr, rowval = ctx.pattern_get(fes.ndofs)
+    cd = np.ascontiguousarray(ctx.space_get_celldofs(0, 10) if device_dofmaps else fes["CellDofs"])
+    el = _oracle_el(fb.H1P2(1, 3))
+    xref, w = orc.quadrature("Tetrahedron3D", 2)
+    vals, der = el.tabulate("Tetrahedron3D", xref)
+    nz2, b2 = np.zeros(nnz), np.zeros(fes.ndofs)
+    miss = oracle_c.example200(grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"], cd, w, xref, vals[:, :, 0], der[:, :, 0, :], mu, p, 0.0, colptr, rowval,
+                               nz2, b2, oracle_c.max_threads())
+    assert miss == 0
+    scale = np.abs(nz2).max()
+    assert np.abs(nz - nz2).max() <= RTOL * scale
+    assert np.abs(b - b2).max() <= RTOL * np.abs(b2).max()
+    # structural pattern = union of dofs x dofs: every slot gets at least one contribution; a second assembly adds up
+    ctx.assemble_poisson(eg._eid, ei._eid, mu, _lib.RHS_AFFINE, p, 0.0)
+    assert np.abs(ctx.matrix_get() - 2 * nz).max() <= 4 * RTOL * scale
+    cols = np.repeat(np.arange(fes.ndofs, dtype=np.int64), np.diff(colptr))
+    assert np.abs(np.bincount(cols, weights=nz, minlength=fes.ndofs)).max() <= 1e-12 * scale  # 1^T A = 0
+
+
+@pytest.mark.parametrize("name,n,scatter", [("HDIVRT0", 32, None), ("HDIVBDM1", 24, None), ("HDIVRT0", 20, _lib.SCATTER_COLORED)])
+def test_midsize_hdiv_3d_against_oracle(name, n, scatter):
+    """BASELINE.json configs[3] at m = 32 / 24 (196,608 / 82,944 tets): mass + (div v, q) blocks against the numpy oracle."""
+    from femb_b200.assembly import _Session
+
+    grid = _grid3d(n, True)
+    g = grid.geometry
+    ft = {"HDIVRT0": fb.HDIVRT0, "HDIVBDM1": fb.HDIVBDM1}[name](3)
+    FESv, FESq = fb.FESpace(ft, grid), fb.FESpace(fb.L2P0(1), grid)
+    qf = fb.QuadratureRule(g, 2)
+    S = _Session([FESv, FESq], qf)
+    ctx = S.ctx
+    eid, ediv, eq = S.evaluator(0, "Identity"), S.evaluator(0, "Divergence"), S.evaluator(1, "Identity")
+    nnz = ctx.pattern_build([(0, 0), (0, 1), (1, 0)])
+    if scatter is not None:
+        ctx.set_scatter(scatter)
+    ctx.matrix_zero()
+    ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
+    ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
+    ctx.sync()
+    nz = ctx.matrix_get()
+    nall = FESv.ndofs + FESq.ndofs
+    cp, rv = ctx.pattern_get(nall)
+    el, elq = _oracle_el(ft), orc.Element("L2P0", 1)
+    xref, w = orc.quadrature(g, 2)
+    args = (g, xref, grid["Coordinates"], grid["CellNodes"], grid["CellFaceSigns"], None, grid["CellFaceOrientations"])
+    V = orc.update_basis(el, "Identity", *args)
+    D = orc.update_basis(el, "Divergence", *args)
+    Q = orc.update_basis(elq, "Identity", *args)
+    vol = grid["CellVolumes"]
+    M = orc.bilinear_local(V, V, w, vol)
+    B = orc.bilinear_local(D, Q, w, vol)
+    I1, J1, V1 = orc.block_triplets(M, FESv["CellDofs"], FESv["CellDofs"])
+    I2, J2, V2 = orc.block_triplets(B, FESv["CellDofs"], FESq["CellDofs"], 0, FESv.ndofs)
+    colptr, rowval, nzval = orc.flush_csc(nall, nall, np.concatenate([I1, I2, J2]), np.concatenate([J1, J2, I2]), np.concatenate([V1, V2, V2]))
+    assert nnz == rowval.shape[0] and np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    assert np.abs(nz - nzval).max() <= RTOL * max(np.abs(M).max(), np.abs(B).max())
+
+
+def test_midsize_example210_against_oracle():
+    """BASELINE.json configs[4] at n = 256 (131,072 triangles, 592k dofs): update_system!(true, true) against the numpy oracle."""
+    n = 256
+    grid = _grid2d(n, True)
+    FESu, FESp = fb.FESpace(fb.H1Pk(2, 2, 2), grid), fb.FESpace(fb.H1Pk(1, 2, 1), grid)
+    mu = 1.0e-2
+    sol = fb.FEVector([FESu, FESp])
+    sol.entries[:] = np.random.default_rng(5).uniform(-1, 1, sol.entries.shape[0])
+    A, b = fb.FEMatrix([FESu, FESp]), fb.FEVector([FESu, FESp])
+    upd = fb.prepare_assembly(A, b, FESu, FESp, sol, mu=mu)
+    upd(True, True)
+    coords = grid["Coordinates"]
+    c2, r2, v2, b2 = orc.example210_assemble(coords, grid["CellNodes"], grid["CellVolumes"], FESu["CellDofs"], FESp["CellDofs"], FESu.ndofs, FESp.ndofs,
+                                             sol.entries, mu, 0.0, True, True)
+    import scipy.sparse as sp
+
+    n_all = FESu.ndofs + FESp.ndofs
+    want = sp.csc_matrix((v2, r2 - 1, c2 - 1), shape=(n_all,) * 2)
+    E = A.entries
+    D = (E.to_scipy() - want).tocoo()
+    assert np.abs(D.data).max() <= RTOL * np.abs(v2).max()
+    # pattern: the oracle's entries plus the pinned pressure diagonal, nothing else
+    P = sp.csc_matrix((np.ones_like(v2), r2 - 1, c2 - 1), shape=(n_all,) * 2).tolil()
+    P[FESu.ndofs, FESu.ndofs] = 1
+    P = P.tocsc()
+    P.sort_indices()
+    assert np.array_equal(E.colptr - 1, P.indptr) and np.array_equal(E.rowval - 1, P.indices)
+    assert np.abs(b.entries - b2).max() <= RTOL * np.abs(b2).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# connectivity guard (ADVICE r01): equal counts are not equal topology
+# ---------------------------------------------------------------------------------------------
+def test_changed_connectivity_is_detected():
+    from femb_b200.assembly import _Session
+
+    grid = _grid2d(24, True)
+    fes = fb.FESpace(fb.H1P1(1), grid)
+    S = _Session([fes], fb.QuadratureRule(grid.geometry, 0))
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    nnz = ctx.pattern_build([(0, 0)])
+    p = np.array([0.3, 1.0, -1.0])
+    coords, cn, vol = grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"]
+    nz, b = np.empty(nnz), np.empty(fes.ndofs)
+    # unchanged connectivity, passed or declared (NULL): fine
+    ctx.assemble_poisson_host(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0, coords, cn, vol, nz, b, 4)
+    nz0 = nz.copy()
+    ctx.assemble_poisson_host(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0, coords, None, vol, nz, b, 4)
+    assert np.array_equal(nz, nz0)
+    # an edge flip between the two triangles of one quad: same counts, different topology
+    cn2 = cn.copy()
+    quad = np.unique(cn2[:2])
+    assert quad.shape[0] == 4
+    a, c = np.intersect1d(cn2[0], cn2[1])  # the shared edge
+    o0, o1 = np.setdiff1d(cn2[0], [a, c])[0], np.setdiff1d(cn2[1], [a, c])[0]
+    cn2[0], cn2[1] = [a, o0, o1], [c, o1, o0]
+    with pytest.raises(_lib.FembError) as ei_:
+        ctx.assemble_poisson_host(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0, coords, cn2, vol, nz, b, 4)
+    assert ei_.value.status == 1 and "connectivity" in str(ei_.value)
+    # femb_mesh_set with the same counts: identical connectivity keeps the symbolic phase ...
+    ctx.mesh_set(coords, cn, vol)
+    ctx.matrix_zero()
+    ctx.vector_zero()
+    ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0)
+    assert np.array_equal(ctx.matrix_get(), nz0)
+    # ... a changed one drops spaces and pattern: assembling without registering them again is an error, not a stale matrix
+    ctx.mesh_set(coords, cn2, vol)
+    with pytest.raises(_lib.FembError):
+        ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0)
