@@ -224,11 +224,12 @@ def exchange_plan(part: LocalPart, colptr, rowval, sent_by_all: list, fetch=None
     return ExchangePlan(np.asarray(peers, dtype=np.int32), i64(sp), cat(ss), i64(rp), cat(rs), i64(sbp), cat(sb), i64(rbp), cat(rb))
 
 
-def slab_partition_3d(m: int, rank: int, nranks: int, layers: int | None = None, order: int = 2):
+def slab_partition_3d(m: int, rank: int, nranks: int, layers: int | None = None, order: int = 2, device: int | None = None):
     """Rank `rank`'s z-slab of the Kuhn-split cube grid (m x m quads per layer, `layers` cube layers per rank, default m)
     with the dofs of H1P1 / H1P2{1,3}: nodes, then (order 2) edges, local numbering of the local grid.  Global dof ids:
     node id, or NN + min_node * NN + max_node for an edge (unique, not dense).  Dofs lying entirely in the bottom plane
-    of a slab are owned by the rank below.  Halo dofs are discovered from the peers (add_halo).  -> (LocalPart, grid)"""
+    of a slab are owned by the rank below.  Halo dofs are discovered from the peers (add_halo).  `device`: enumerate the
+    edges on that GPU (femb_grid_entities) instead of in numpy.  -> (LocalPart, grid)"""
     from .grids import simplexgrid
 
     L = m if layers is None else layers
@@ -236,6 +237,8 @@ def slab_partition_3d(m: int, rank: int, nranks: int, layers: int | None = None,
     X = np.linspace(0.0, 1.0, m + 1)
     Z = np.arange(z0, z0 + L + 1) / float(m)
     grid = simplexgrid(X, X, Z)
+    if device is not None and order == 2:
+        grid.instantiate_on_device(device, components=("edges",))  # xgrid[EdgeNodes] from the device enumeration, not the numpy one
     nxy = (m + 1) * (m + 1)
     NN = nxy * (nranks * L + 1)
     gnode = np.arange(grid.nnodes, dtype=np.int64) + z0 * nxy  # local lexicographic numbering is the global one shifted
