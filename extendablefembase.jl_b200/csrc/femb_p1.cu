@@ -60,7 +60,6 @@ template <bool TRACK, int RHS, bool HAS_VOL, int NQP>
 __device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, const double2 self, const double2 pa, const double2 pb, const double volr,
                                          const P1Tab2& tab, const RhsDev& rhs, const double drop_tol, const double mu_wsum, const unsigned sacc,
                                          double& diag, unsigned& dpos, unsigned& err, unsigned long long& mask, double& bsum) {
-    constexpr unsigned nt = 128;
     const unsigned k = w & 3u;
     const double uax = pb.x - self.x, uay = pb.y - self.y;
     const double ubx = self.x - pa.x, uby = self.y - pa.y;
@@ -82,12 +81,12 @@ __device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, 
         dpos = ps;
     }
     if (ka && pA != 0xFFu) {
-        const unsigned ad = sacc + pA * (nt * 8u);
+        const unsigned ad = sacc + pA * 8u;
         sts64(ad, lds64(ad) + va);
         if (TRACK) mask |= 1ull << (pA & 63u);
     }
     if (kb && pB != 0xFFu) {
-        const unsigned ad = sacc + pB * (nt * 8u);
+        const unsigned ad = sacc + pB * 8u;
         sts64(ad, lds64(ad) + vb);
         if (TRACK) mask |= 1ull << (pB & 63u);
     }
@@ -144,12 +143,16 @@ __device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, 
 #endif
 template <bool TRACK, int RHS, bool HAS_VOL, int NQP, bool STAGE, int MINB = FEMB_P1_MINB>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
 __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
-    constexpr unsigned nt = 128;
     constexpr bool NEED_CELL = HAS_VOL || RHS == FEMB_RHS_QPVALUES;
-    extern __shared__ double acc[];  // [maxlen + 1][128], then (STAGE) u32 [4 warps][4 planes][maxrows][32]
-    const unsigned tid = threadIdx.x, lane = tid & 31u;
-    const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + (tid >> 5);
+    constexpr int NPL = NEED_CELL ? 4 : 3;  // gather-map planes this variant reads
+    // dynamic shared memory: [4 mbarriers | pad to 128 B][4 warps x flat accumulators (maxlen * 32 + 2 doubles)][(STAGE) u32 [4 warps][4 planes][maxrows][32]]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + warp;
     if (slice >= a.slice_end) return;  // whole warp out of range
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned accw = ((unsigned)a.maxlen * 32u + 2u) * 8u;  // bytes of one warp's accumulator block
+    const unsigned wacc = smem0 + 128u + warp * accw;
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     int row0, nrows;
@@ -160,6 +163,28 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
         row0 = __ldg(a.gslice_ptr + slice);
         nrows = __ldg(a.gslice_ptr + slice + 1) - row0;
     }
+    const uint32_t* __restrict__ ga = a.gmap + ((size_t)row0 << 5) + lane;
+    const size_t gs = a.gstride;
+    // STAGE: the slice's gather-map entries (all visits, NPL planes of nrows x 128 bytes, each contiguous in global memory)
+    // come in as NPL bulk copies (cp.async.bulk, SASS UBLKCP) issued by ONE lane and signalled on a per-warp mbarrier: no
+    // per-lane copy instructions, no L1 wavefronts, one memory latency for all visits — and they fly while the warp
+    // reads colptr / its own coordinates and clears the accumulators.
+    const unsigned mbar = smem0 + warp * 8u;
+    const unsigned sstw = smem0 + 128u + 4u * accw + warp * (4u * (unsigned)a.maxrows * 128u);  // this warp's staging block
+    const unsigned pst = (unsigned)a.maxrows * 128u;                                              // plane stride in bytes
+    if (STAGE && nrows > 0) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const unsigned bytes = (unsigned)nrows * 128u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * NPL) : "memory");
+#pragma unroll
+            for (int p = 0; p < NPL; p++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst),
+                             "l"(ga + (size_t)p * gs), "r"(bytes), "r"(mbar)
+                             : "memory");
+        }
+    }
     const double2* __restrict__ xy = reinterpret_cast<const double2*>(a.coords);
     int64_t base = 0;
     int len = 0;
@@ -169,50 +194,35 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
         len = (int)(a.colptr[c + 1] - 1 - base);
         self = __ldg(xy + c);
     }
-    unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + tid * 8u;
+    // The 32 columns of the slice are one contiguous range [base0, base0 + total) of nzval: the accumulators mirror it
+    // (element i of the range at wacc + (i + par) * 8, par = parity of base0 so that 16-byte aligned global runs are 16-byte
+    // aligned in shared memory).  Lanes with the same position in equally long columns hit different banks (odd column
+    // lengths; two lanes per 8-byte bank pair = the minimum of a 64-bit access), and the finished range leaves with ONE bulk
+    // store instead of `len` strided 8-byte stores per lane (one L1 wavefront per lane and entry before).
+    const int nvalid = (int)min((int64_t)32, a.ndofs - slice * 32);
+    const int64_t base0 = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const int64_t endl = __shfl_sync(0xFFFFFFFFu, base + len, nvalid - 1);
+    const int total = (int)(endl - base0);
+    const unsigned par = (unsigned)(base0 & 1);
+    if (!valid) base = base0;
+    unsigned sacc = wacc + ((unsigned)(base - base0) + par) * 8u;
 #if FEMB_P1_OPAQUE
     asm volatile("" : "+r"(sacc));  // keep the accumulator address in its register: re-deriving it costs six instructions per use
 #endif
-    for (int i = 0; i < len; i++) sts64(sacc + i * (nt * 8u), 0.0);
+    for (int i = (int)lane; i < total + 2; i += 32) sts64(wacc + (unsigned)i * 8u, 0.0);
+    __syncwarp();
     unsigned long long mask = 0ull;
     double bsum = 0.0, diag = 0.0;
     unsigned err = 0u, dpos = 0xFFu;
     const double drop_tol = a.drop_tol, mu_wsum = tab.mu_wsum;
 
-    const uint32_t* __restrict__ ga = a.gmap + ((size_t)row0 << 5) + lane;
-    const size_t gs = a.gstride;
     if (STAGE) {
-        const unsigned sst = (unsigned)__cvta_generic_to_shared(acc + (size_t)(a.maxlen + 1) * nt) + ((tid >> 5) * 4u * (unsigned)a.maxrows * 32u + lane) * 4u;
-        const unsigned pst = (unsigned)a.maxrows * 128u;  // plane stride in bytes
-#if FEMB_P1_STAGE16
-        // the rows of a slice are contiguous per plane (128 bytes each): the warp copies them in 16-byte pieces, 512 bytes per
-        // instruction, i.e. a quarter of the LDGSTS instructions of the per-lane 4-byte copies (the kernel is issue-bound)
-        {
-            const unsigned swarp = sst - lane * 4u;  // this warp's staging block
-            const uint32_t* gw0 = ga - lane;          // row0 of plane 0
-            const int nq = nrows * 8;                 // 16-byte pieces per plane
-            constexpr int NPL = NEED_CELL ? 4 : 3;
-#pragma unroll
-            for (int p = 0; p < NPL; p++)
-                for (int q = (int)lane; q < nq; q += 32)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(swarp + (unsigned)p * pst + (unsigned)q * 16u), "l"(gw0 + (size_t)p * gs + (size_t)q * 4)
-                                 : "memory");
+        const unsigned sst = sstw + lane * 4u;
+        if (nrows > 0) {  // wait for the bulk copies (phase 0 of the barrier)
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();  // the pieces were copied by other lanes
-#else
-        for (int r = 0; r < nrows; r++) {
-            const uint32_t* g = ga + ((size_t)r << 5);
-            const unsigned d = sst + (unsigned)r * 128u;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(g) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + pst), "l"(g + gs) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 2u * pst), "l"(g + 2 * gs) : "memory");
-            if (NEED_CELL) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 3u * pst), "l"(g + 3 * gs) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
         auto lds32 = [](unsigned addr) {
             unsigned v;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -294,18 +304,31 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
         p1_visit<TRACK, RHS, HAS_VOL, NQP>(w, cell, self, pa, pb, volr, tab, rhs, drop_tol, mu_wsum, sacc, diag, dpos, err, mask, bsum);
     }
     }
-    if (!valid) return;
-    if (err) atomicAdd(a.errflag, 1);
-    if (dpos != 0xFFu) {
-        sts64(sacc + dpos * (nt * 8u), diag);  // the diagonal row received no shared-memory update
+    if (valid && err) atomicAdd(a.errflag, 1);
+    if (valid && dpos != 0xFFu) {
+        sts64(sacc + dpos * 8u, diag);  // the diagonal row received no shared-memory update
         if (TRACK) mask |= 1ull << (dpos & 63u);
     }
-    double* out = a.nzval + base;
+    double* out0 = a.nzval + base0;
     if (a.acc_A) {
-        for (int i = 0; i < len; i++) out[i] += lds64(sacc + i * (nt * 8u));
-    } else {
-        for (int i = 0; i < len; i++) out[i] = lds64(sacc + i * (nt * 8u));
+        __syncwarp();
+        for (int i = (int)lane; i < total; i += 32) out0[i] += lds64(wacc + ((unsigned)i + par) * 8u);  // coalesced
+    } else if (total > 0) {
+        // one bulk store of the 16-byte aligned part of the range (cp.async.bulk.global.shared::cta, SASS UBLKCP), scalar head / tail
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+            const int head = (int)par, body = (total - head) & ~1;
+            if (head) out0[0] = lds64(wacc + 8u);
+            if (head + body < total) out0[total - 1] = lds64(wacc + ((unsigned)(total - 1) + par) * 8u);
+            if (body > 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out0 + head), "r"(wacc + 2u * par * 8u), "r"((unsigned)body * 8u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must stay alive until it has been read
+            }
+        }
     }
+    if (!valid) return;
     if (TRACK) {
         for (int i = 0; i < len; i++)
             if ((mask >> i) & 1ull) a.touched[base + i] = 1;
@@ -537,7 +560,7 @@ static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const Rhs
                 t2.t[k][q][2] = lam[others[k][0]];
                 t2.t[k][q][3] = lam[others[k][1]];
             }
-        L.smem = (size_t)(a.maxlen + 1) * 128 * sizeof(double);
+        L.smem = 128 + 4 * ((size_t)a.maxlen * 32 + 2) * sizeof(double);  // mbarriers + per-warp flat accumulators
         // staged variant: + u32 [4 warps][4 planes][maxrows][32] for the slice's gather-map entries
         static const int stage_env = getenv("FEMB_P1_STAGE") ? atoi(getenv("FEMB_P1_STAGE")) : 1;
         a.maxrows = (stage_env && ctx->gmap_maxrows > 0 && ctx->gmap_maxrows <= 12) ? ctx->gmap_maxrows : 0;
