@@ -29,6 +29,21 @@ def p2_nodal_points(xgrid):
     return np.concatenate([c, 0.5 * (c[fn[:, 0] - 1] + c[fn[:, 1] - 1])])
 
 
+def p2_interpolate(xgrid, u, teval):
+    """interpolate!(u_init[1], u!; time) of the reference for H1Pk{2,2,2} on the host (vectorised): node values and edge dofs
+    that preserve the edge mean (MomentInterpolator of order 0: (mean - (u(a) + u(b)) / 6) * 3/2, 3-point Gauss rule) —
+    the same operator femb_interpolate applies on the device.  -> (npoints, 2)"""
+    from femb_b200.quadrature import gauss_jacobi_01
+
+    c, fn = xgrid["Coordinates"], xgrid["FaceNodes"]
+    a, b = c[np.minimum(fn[:, 0], fn[:, 1]) - 1], c[np.maximum(fn[:, 0], fn[:, 1]) - 1]
+    un = u(c, teval)
+    ua, ub = u(a, teval), u(b, teval)
+    qx, qw = gauss_jacobi_01(3)
+    mean = sum(w * u(a + x * (b - a), teval) for x, w in zip(qx, qw))
+    return np.concatenate([un, (mean - (ua + ub) / 6.0) * 1.5])
+
+
 def solve_stokes_lowlevel(FES, teval=0.0, maxits=20):
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
@@ -40,8 +55,7 @@ def solve_stokes_lowlevel(FES, teval=0.0, maxits=20):
     Alin, blin = A.entries.nzval.copy(), b.entries.copy()  # keep the linear part (Example210:164-165)
     # boundary data: nodal interpolation of the exact velocity (Example210:168-173)
     u_init = np.zeros_like(sol.entries)
-    pts = p2_nodal_points(FESu.xgrid)
-    ue = u_exact(pts, teval)
+    ue = p2_interpolate(FESu.xgrid, u_exact, teval)
     u_init[: FESu.ndofs] = np.concatenate([ue[:, 0], ue[:, 1]])
     fixed = np.concatenate([fb.boundarydofs(FESu), [FESu.ndofs + 1]])  # + one pressure dof
     E = A.entries
@@ -99,11 +113,17 @@ def solve_stokes_device(FES, teval=0.0, maxits=20):
     ctx.system_save()
     E = A.entries
     n = E.shape[0]
+    segs = parse_pattern(FESu.fetype.get_dofmap_pattern(FESu.xgrid.geometry))
+    nb = ctx.boundary_dofs(0, segs, download=False)
+    fx = np.concatenate([ctx.boundary_dofs(0, segs), [FESu.ndofs + 1]]) - 1
+    # boundary data: interpolate!(u_init[1], u!; time) restricted to the boundary dofs, ON THE DEVICE (femb_interpolate: node
+    # values + edge-mean preserving edge dofs with the reference's 3-point Gauss rule); it stays there for dirichlet_apply,
+    # the copy is only what the host solve below eliminates with
+    from femb_b200.quadrature import gauss_jacobi_01
+
+    qx, qw = gauss_jacobi_01(3)
     u_init = np.zeros(n)
-    ue = u_exact(p2_nodal_points(FESu.xgrid), teval)
-    u_init[: FESu.ndofs] = np.concatenate([ue[:, 0], ue[:, 1]])
-    nb = ctx.boundary_dofs(0, parse_pattern(FESu.fetype.get_dofmap_pattern(FESu.xgrid.geometry)), download=False)
-    fx = np.concatenate([ctx.boundary_dofs(0, parse_pattern(FESu.fetype.get_dofmap_pattern(FESu.xgrid.geometry))), [FESu.ndofs + 1]]) - 1
+    u_init[: FESu.ndofs] = ctx.interpolate(0, segs, FESu.ndofs, _lib.FUNC_EX210_U, np.array([MU, teval]), qx, qw, only_boundary=True)
     assert fx.shape[0] == nb + 1
     free = np.setdiff1d(np.arange(n), fx)
     pin = np.array([FESu.ndofs + 1])
@@ -118,7 +138,7 @@ def solve_stokes_device(FES, teval=0.0, maxits=20):
         x[free] = spla.spsolve(M[free][:, free].tocsc(), rhs[free] - M[free][:, fx] @ x[fx])
         return x
 
-    ctx.dirichlet_apply(True, 0, pin, u_init, 1.0e60)  # also registers the fixed rows the residuals skip
+    ctx.dirichlet_apply(True, 0, pin, None, 1.0e60)  # device-resident boundary data; also registers the fixed rows the residuals skip
     nlres = np.inf
     for it in range(1, maxits + 1):
         sol.entries[:] = host_solve()
@@ -127,7 +147,7 @@ def solve_stokes_device(FES, teval=0.0, maxits=20):
         ctx.vector_zero()
         ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, MU, False, True, _lib.RHS_NONE, None)
         ctx.system_add_saved()
-        ctx.dirichlet_apply(True, 0, pin, u_init, 1.0e60)
+        ctx.dirichlet_apply(True, 0, pin, None, 1.0e60)
         nlres = ctx.residual(None, zero_fixed=True)
         print(f"ITERATION {it}: linear residual = {linres:.3e}, nonlinear residual = {nlres:.3e}")
         if nlres < max(1.0e-12, 20 * linres):

@@ -17,6 +17,7 @@ LIBPATH = os.environ.get("FEMB_LIB") or os.path.join(HERE, "libfemb.so")  # FEMB
 FAMILY = {"H1": 0, "Hdiv": 1, "L2": 2}
 OP_IDENTITY, OP_GRADIENT, OP_DIVERGENCE = 0, 1, 2
 RHS_NONE, RHS_AFFINE, RHS_QPVALUES, RHS_EX210 = 0, 1, 2, 3
+FUNC_AFFINE, FUNC_EX210_U = 1, 2
 BIL_TRANSPOSE_COPY, BIL_SYMMETRIC_UPPER, BIL_NO_VOLUME = 1, 2, 4
 SCATTER_ATOMIC, SCATTER_COLORED, SCATTER_GATHER = 0, 1, 2
 ENTITY_FACES, ENTITY_EDGES = 0, 1
@@ -42,6 +43,7 @@ SIGNATURES = {
     "femb_boundary_dofs": (_i32, [_p, _i32, _i32, _p, C.POINTER(_i64)]),
     "femb_boundary_dofs_get": (_i32, [_p, _p]),
     "femb_dirichlet_apply": (_i32, [_p, _i32, _i64, _i64, _p, _p, _f64]),
+    "femb_interpolate": (_i32, [_p, _i32, _i32, _p, _i64, _i32, _p, _i32, _p, _p, _i32, _p]),
     "femb_residual": (_i32, [_p, _p, _i32, _p, C.POINTER(_f64)]),
     "femb_eval_error": (_i32, [_p, _i32, _p, _p, _i32, _p]),
     "femb_block_matmul": (_i32, [_p, _i32, _i32, _p, _f64, _i32, _p]),
@@ -224,6 +226,18 @@ class Context:
         extra = _arr(extra_dofs, np.int64)
         values = _arr(values, np.float64)
         self._ck(self.lib.femb_dirichlet_apply(self.h, int(use_boundary_list), dof_offset, 0 if extra is None else extra.shape[0], _ptr(extra), _ptr(values), penalty))
+
+    def interpolate(self, sid, segs, ndofs, func_kind, params, qx=None, qw=None, only_boundary=False, dof_offset=0, download=True):
+        """interpolate!(target, FES, u) for nodal H1 spaces (node dofs + at most one dof per edge) on the device; the result
+        stays there as the boundary data of dirichlet_apply(values=None).  qx/qw: rule on [0,1] for the edge means
+        (None: midpoint values).  func_kind: FUNC_AFFINE / FUNC_EX210_U."""
+        flat = np.array([[self._SEG_CODE[t], int(each), q] for t, each, q in segs], dtype=np.int32)
+        params = _arr(params, np.float64)
+        qx, qw = _arr(qx, np.float64), _arr(qw, np.float64)
+        out = np.empty(ndofs, np.float64) if download else None
+        self._ck(self.lib.femb_interpolate(self.h, sid, flat.shape[0], _ptr(flat), dof_offset, func_kind, _ptr(params), 0 if qx is None else qx.shape[0],
+                                           _ptr(qx), _ptr(qw), int(only_boundary), _ptr(out)))
+        return out
 
     def eval_error(self, eid, coefficients, exact_qp, p, resultdim):
         """compute_error: -> (ncells, resultdim) array of sum_qp (uh - u)^p |T| w_qp."""

@@ -328,7 +328,10 @@ int32_t femb_matrix_layout(femb_ctx* ctx, int32_t nr, const int32_t* rows, int32
     ctx->ncs = nc;
     ctx->nrows = ctx->row_off[nr];
     ctx->ncols = ctx->col_off[nc];
-    if (resized) ctx->extra_entries.clear();  // their keys were encoded against the old row count
+    if (resized) {
+        ctx->extra_entries.clear();  // their keys were encoded against the old row count
+        femb_free(&ctx->dirval);      // boundary data in the old numbering
+    }
     if (resized || !ctx->bvec) {
         femb_free_pattern(ctx);
         FEMB_TRY(femb_alloc(ctx, &ctx->bvec, (size_t)ctx->nrows));

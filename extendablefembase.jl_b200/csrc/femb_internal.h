@@ -156,6 +156,7 @@ struct femb_ctx {
     int32_t* csr_col = nullptr;    // nnz: column of each entry, rows contiguous
     uint32_t* csr_slot = nullptr;  // nnz: its position in nzval
     double* resvec = nullptr;      // nrows (+ 1 scratch)
+    double* dirval = nullptr;      // nrows: boundary data of femb_interpolate (used by femb_dirichlet_apply when values == NULL)
     double* saved_nzval = nullptr; // femb_system_save: Alin / blin of Example210:164-165
     double* saved_b = nullptr;
 

@@ -235,7 +235,110 @@ void femb_free_system(femb_ctx* ctx) {
     femb_free(&ctx->bdofs);
     femb_free(&ctx->fixed);
     femb_free(&ctx->resvec);
+    femb_free(&ctx->dirval);
     ctx->nbdofs = ctx->nfixed = 0;
+}
+
+// ---- interpolate!(target, FES, u) for nodal H1 spaces with node dofs and at most one dof per edge (H1P1, H1P2, H1Pk order <= 2) ----
+// node dofs: point evaluation (NodalInterpolator, interpolators.jl:93-127); edge dofs: the edge mean is preserved
+// (MomentInterpolator of order 0, h1_p2.jl:47-76 / interpolators.jl:330-460): with mean(phi_vertex) = 1/6 and
+// mean(phi_edge) = 2/3 on the reference edge, value = (mean_e(u) - (u(a) + u(b)) / 6) * 3/2, mean_e(u) by the caller's
+// rule on [0,1] (the reference: Gauss rule of order 2 * order_FE).  nq = 0: the value at the edge midpoint instead.
+__constant__ int8_t d_tri_faces[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+__constant__ int8_t d_tet_edges[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+
+struct InterpFunc {
+    int kind, ncomp;
+    double p[16];  // FEMB_FUNC_AFFINE: per component c0, g_1..g_dim;  FEMB_FUNC_EX210_U: {mu, t}
+};
+struct InterpArgs {
+    const double* coords;
+    const int32_t* cellnodes;
+    const int32_t* celldofs;
+    int64_t ncells;
+    int nd, nds, nnpc, nedge;      // local dofs (all components), per component, nodes per cell, edge dofs per component
+    int nq;
+    double qx[16], qw[16];
+    const uint8_t* only;           // per dof of the space: 1 = write (NULL: all)
+    double* target;                // + dof_offset already applied
+};
+
+template <int DIM>
+__device__ __forceinline__ void interp_eval(const InterpFunc& f, const double* x, double* u) {
+    if (f.kind == FEMB_FUNC_EX210_U) {  // Example210:51-57
+        const double pi = 3.14159265358979323846;
+        const double e = exp(-8.0 * pi * pi * f.p[0] * f.p[1]);
+        u[0] = e * sin(2.0 * pi * x[0]) * sin(2.0 * pi * x[1]);
+        u[1] = e * cos(2.0 * pi * x[0]) * cos(2.0 * pi * x[1]);
+    } else {
+        for (int c = 0; c < f.ncomp; c++) {
+            double s = f.p[c * (DIM + 1)];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) s += f.p[c * (DIM + 1) + 1 + d] * x[d];
+            u[c] = s;
+        }
+    }
+}
+
+template <int DIM>
+__global__ void k_interpolate(const InterpArgs a, const InterpFunc f) {
+    const int per = a.nnpc + a.nedge;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= a.ncells * per) return;
+    const int64_t cell = t / per;
+    const int l = (int)(t - cell * per);
+    // skip early when none of the component dofs is selected
+    if (a.only) {
+        bool any = false;
+        for (int c = 0; c < f.ncomp; c++) any = any || a.only[a.celldofs[cell * a.nd + c * a.nds + l] - 1];
+        if (!any) return;
+    }
+    double u[3] = {0.0, 0.0, 0.0};
+    if (l < a.nnpc) {
+        const int64_t n = a.cellnodes[cell * a.nnpc + l] - 1;
+        double x[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) x[d] = a.coords[n * DIM + d];
+        interp_eval<DIM>(f, x, u);
+    } else {
+        const int e = l - a.nnpc;
+        const int i0 = DIM == 2 ? d_tri_faces[e][0] : d_tet_edges[e][0], i1 = DIM == 2 ? d_tri_faces[e][1] : d_tet_edges[e][1];
+        int64_t na = a.cellnodes[cell * a.nnpc + i0] - 1, nb = a.cellnodes[cell * a.nnpc + i1] - 1;
+        if (na > nb) {  // orient by the global node ids: every cell sharing the edge computes bit-identical values
+            const int64_t tmp = na; na = nb; nb = tmp;
+        }
+        double xa[DIM], xb[DIM], x[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            xa[d] = a.coords[na * DIM + d];
+            xb[d] = a.coords[nb * DIM + d];
+        }
+        if (a.nq == 0) {
+#pragma unroll
+            for (int d = 0; d < DIM; d++) x[d] = 0.5 * (xa[d] + xb[d]);
+            interp_eval<DIM>(f, x, u);
+        } else {
+            double ua[3], ub[3], m[3] = {0.0, 0.0, 0.0}, v[3];
+            interp_eval<DIM>(f, xa, ua);
+            interp_eval<DIM>(f, xb, ub);
+            for (int q = 0; q < a.nq; q++) {
+#pragma unroll
+                for (int d = 0; d < DIM; d++) x[d] = xa[d] + a.qx[q] * (xb[d] - xa[d]);
+                interp_eval<DIM>(f, x, v);
+                for (int c = 0; c < f.ncomp; c++) m[c] += a.qw[q] * v[c];
+            }
+            for (int c = 0; c < f.ncomp; c++) u[c] = (m[c] - (ua[c] + ub[c]) * (1.0 / 6.0)) * 1.5;
+        }
+    }
+    for (int c = 0; c < f.ncomp; c++) {
+        const int64_t dof = (int64_t)a.celldofs[cell * a.nd + c * a.nds + l] - 1;
+        if (!a.only || a.only[dof]) a.target[dof] = u[c];
+    }
+}
+
+__global__ void k_flag_list(const int32_t* __restrict__ list, int64_t n, uint8_t* __restrict__ flags) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) flags[list[i] - 1] = 1;
 }
 
 extern "C" {
@@ -336,6 +439,74 @@ int32_t femb_boundary_dofs_get(femb_ctx* ctx, int32_t* dofs) {
     return FEMB_OK;
 }
 
+int32_t femb_interpolate(femb_ctx* ctx, int32_t id, int32_t nseg, const int32_t* segs, int64_t dof_offset, int32_t func_kind, const double* params,
+                         int32_t nq, const double* qx, const double* qw, int32_t only_boundary, double* target_or_null) {
+    FEMB_CHECK_CTX(ctx);
+    if (id < 0 || id >= FEMB_MAX_SPACES || !ctx->spaces[id].set) return femb_fail(ctx, FEMB_ERR_ARG, "unknown space");
+    const FembSpace& s = ctx->spaces[id];
+    if (!ctx->bvec) return femb_fail(ctx, FEMB_ERR_ARG, "femb_matrix_layout must precede femb_interpolate");
+    if (s.family != FEMB_FAMILY_H1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd % s.ncomp)
+        return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "femb_interpolate covers nodal H1 spaces without per-cell handlers");
+    if (nq < 0 || nq > 16 || (nq && (!qx || !qw)) || !params) return femb_fail(ctx, FEMB_ERR_ARG, "femb_interpolate: bad rule / parameters");
+    if (dof_offset < 0 || dof_offset + s.ndofs > ctx->nrows) return femb_fail(ctx, FEMB_ERR_ARG, "femb_interpolate: dof_offset outside the layout");
+    const int dim = ctx->dim, nnpc = dim + 1, nel = dim == 2 ? 3 : 6, nds = s.nd / s.ncomp;
+    // the dofmap pattern must be: one dof per node, optionally one dof per edge (2-D: faces), every component the same
+    bool nodes = false, edges = false;
+    for (int g = 0; g < nseg; g++) {
+        const int type = segs[3 * g], each = segs[3 * g + 1], q = segs[3 * g + 2];
+        if (!each || q != 1) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "femb_interpolate: pattern segment %d is not one dof per entity and component", g);
+        if (type == 0 && !nodes && !edges) nodes = true;
+        else if (((type == 1 && dim == 2) || (type == 2 && dim == 3)) && nodes && !edges) edges = true;
+        else return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "femb_interpolate: only node dofs followed by one dof per edge are supported");
+    }
+    if (!nodes || nds != nnpc + (edges ? nel : 0)) return femb_fail(ctx, FEMB_ERR_ARG, "femb_interpolate: pattern does not match the registered space");
+    InterpFunc f;
+    f.kind = func_kind;
+    f.ncomp = s.ncomp;
+    for (double& v : f.p) v = 0.0;
+    if (func_kind == FEMB_FUNC_AFFINE) {
+        for (int i = 0; i < s.ncomp * (dim + 1); i++) f.p[i] = params[i];
+    } else if (func_kind == FEMB_FUNC_EX210_U) {
+        if (dim != 2 || s.ncomp != 2) return femb_fail(ctx, FEMB_ERR_ARG, "FEMB_FUNC_EX210_U is the 2-D two-component u! of Example210");
+        f.p[0] = params[0];
+        f.p[1] = params[1];
+    } else {
+        return femb_fail(ctx, FEMB_ERR_ARG, "unknown function kind %d", func_kind);
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->dirval) {
+        FEMB_TRY(femb_alloc(ctx, &ctx->dirval, (size_t)ctx->nrows));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->dirval, 0, sizeof(double) * ctx->nrows, ctx->stream));
+    }
+    uint8_t* only = nullptr;
+    if (only_boundary) {
+        if (!ctx->bdofs) return femb_fail(ctx, FEMB_ERR_ARG, "femb_boundary_dofs must precede femb_interpolate(only_boundary)");
+        FEMB_TRY(femb_alloc(ctx, &only, (size_t)s.ndofs));
+        cudaMemsetAsync(only, 0, (size_t)s.ndofs, ctx->stream);
+        if (ctx->nbdofs) k_flag_list<<<(unsigned)((ctx->nbdofs + 255) / 256), 256, 0, ctx->stream>>>(ctx->bdofs, ctx->nbdofs, only);
+        ctx->launches++;
+    }
+    InterpArgs a;
+    a.coords = ctx->coords; a.cellnodes = ctx->cellnodes; a.celldofs = s.celldofs; a.ncells = ctx->ncells;
+    a.nd = s.nd; a.nds = nds; a.nnpc = nnpc; a.nedge = edges ? nel : 0; a.nq = nq;
+    for (int q = 0; q < nq; q++) { a.qx[q] = qx[q]; a.qw[q] = qw[q]; }
+    a.only = only;
+    a.target = ctx->dirval + dof_offset;
+    const int64_t nt = ctx->ncells * (nnpc + a.nedge);
+    cudaError_t e = cudaSuccess;
+    if (nt) {
+        if (dim == 2) k_interpolate<2><<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(a, f);
+        else k_interpolate<3><<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(a, f);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    int st = e == cudaSuccess ? FEMB_OK : femb_fail(ctx, FEMB_ERR_CUDA, "femb_interpolate: %s", cudaGetErrorString(e));
+    if (st == FEMB_OK && target_or_null) st = femb_d2h(ctx, target_or_null, ctx->dirval + dof_offset, (size_t)s.ndofs);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && st == FEMB_OK) st = femb_fail(ctx, FEMB_ERR_CUDA, "femb_interpolate: synchronize failed");
+    femb_free(&only);
+    return st;
+}
+
 int32_t femb_dirichlet_apply(femb_ctx* ctx, int32_t use_boundary_list, int64_t dof_offset, int64_t n_extra, const int64_t* extra_dofs,
                              const double* values, double penalty) {
     FEMB_CHECK_CTX(ctx);
@@ -367,7 +538,9 @@ int32_t femb_dirichlet_apply(femb_ctx* ctx, int32_t use_boundary_list, int64_t d
         // its own flag word: pending "no slot" errors of the assemblies ([0]) stay for femb_sync to report
         e = cudaMemsetAsync(ctx->errflag + 1, 0, sizeof(int32_t), ctx->stream);
         k_fixed_list<<<grid, 256, 0, ctx->stream>>>(ctx->bdofs, nb, dof_offset, d_extra, n_extra, ctx->fixed);
-        k_dirichlet<<<grid, 256, 0, ctx->stream>>>(ctx->fixed, n, ctx->colptr, ctx->rowval, ctx->nzval, ctx->bvec, d_values, penalty, ctx->nrows, ctx->errflag + 1);
+        // values == NULL: the device-resident boundary data of femb_interpolate (zeros if none was interpolated)
+        k_dirichlet<<<grid, 256, 0, ctx->stream>>>(ctx->fixed, n, ctx->colptr, ctx->rowval, ctx->nzval, ctx->bvec, d_values ? d_values : ctx->dirval, penalty, ctx->nrows,
+                                                  ctx->errflag + 1);
         ctx->launches += 2;
         if (e == cudaSuccess) e = cudaMemcpyAsync(&nerr, ctx->errflag + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

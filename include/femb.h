@@ -146,7 +146,8 @@ int32_t femb_space_get_celldofs(femb_ctx* ctx, int32_t space_id, int32_t* celldo
  * from the device face enumeration: every dof attached to a face with one neighbour cell; segs = the dofmap pattern
  * as in femb_space_set_from_pattern.  The list is sorted and unique (the reference returns BFaceDofs.colentries,
  * which repeats shared dofs; its callers only loop over it), 1-based, local to the space.
- * femb_dirichlet_apply: A[d,d] = penalty; b[d] = penalty * values[d] (values == NULL: 0) for d in
+ * femb_dirichlet_apply: A[d,d] = penalty; b[d] = penalty * values[d] (values == NULL: the device-resident boundary data of
+ * femb_interpolate, zeros if there is none) for d in
  * (boundary list + dof_offset, when use_boundary_list) and the extra dofs (1-based, matrix numbering) —
  * Example200:87-90, Example210:197-200 (penalty 1e60, the extra dof fixes one pressure value, Example210:173).
  * femb_residual: res = A x - b (x == NULL: the vector of femb_vector_set(1, ..)), rows fixed by the last
@@ -156,6 +157,20 @@ int32_t femb_boundary_dofs(femb_ctx* ctx, int32_t space_id, int32_t nseg, const 
 int32_t femb_boundary_dofs_get(femb_ctx* ctx, int32_t* dofs);
 int32_t femb_dirichlet_apply(femb_ctx* ctx, int32_t use_boundary_list, int64_t dof_offset, int64_t n_extra,
                              const int64_t* extra_dofs, const double* values_or_null, double penalty);
+/* interpolate!(u_init[1], u!; time) (Example210:168-173) on the device, for nodal H1 spaces whose dofmap pattern is one
+ * dof per node and, optionally, one dof per edge (2-D: face) and component — H1P1, H1P2, H1Pk of order <= 2, any number
+ * of components.  Node dofs: point evaluation (NodalInterpolator, src/interpolators.jl:93-127).  Edge dofs: the edge mean
+ * is preserved (MomentInterpolator of order 0, src/fedefs/h1_p2.jl:47-76, src/interpolators.jl:137-460):
+ * value = (mean_e(u) - (u(a) + u(b)) / 6) * 3/2 with mean_e by the rule (qx in [0,1], qw, nq points) the caller passes —
+ * the reference uses its Gauss rule of order 2 * order_FE (src/quadrature.jl:214-233, :609-628); nq = 0 evaluates at the
+ * edge midpoint instead.  func_kind / params: FEMB_FUNC_AFFINE (per component c0, g_1..g_dim), FEMB_FUNC_EX210_U {mu, t}
+ * (the exact velocity u! of Example210:51-57).  only_boundary: only the dofs of the last femb_boundary_dofs are written.
+ * The result is kept on the device as the boundary-data vector (matrix numbering: dof_offset + dof, zero elsewhere) that
+ * femb_dirichlet_apply uses when its values argument is NULL — no host round trip of u_init; target_or_null (ndofs of the
+ * space) receives a copy.  Edges are oriented by their global node ids: the result is bit-reproducible. */
+enum { FEMB_FUNC_AFFINE = 1, FEMB_FUNC_EX210_U = 2 };
+int32_t femb_interpolate(femb_ctx* ctx, int32_t space_id, int32_t nseg, const int32_t* segs, int64_t dof_offset, int32_t func_kind,
+                         const double* params, int32_t nq, const double* qx, const double* qw, int32_t only_boundary, double* target_or_null);
 int32_t femb_residual(femb_ctx* ctx, const double* x_or_null, int32_t zero_fixed, double* res_or_null, double* norm_out);
 /* compute_error (Example210:110-154) through a registered evaluator (register it after femb_quadrature_set with the
  * VertexRule, quadrature.jl:103-186): error_out[d, cell] = sum_qp (uh_d(x_qp) - exact_qp[d, qp, cell])^p |T| w_qp with

@@ -152,7 +152,23 @@ function boundarydofs(ctx::Context, id::Integer, FEType, EG)
     return dofs
 end
 
-# A[dof,dof] = penalty; b[dof] = penalty * values[dof] for the boundary dofs of the last boundarydofs call (+ offset) and `extra`
+# interpolate!(u_init[1], u!; time) on the device (node values + edge-mean preserving edge dofs); kind = :affine (params per
+# component c0, g...) or :ex210_u (params [mu, t]); the result stays on the device as the boundary data of dirichlet!(values = nothing)
+function interpolate_device!(ctx::Context, id::Integer, FES; kind = :ex210_u, params = Float64[], only_boundary = true, offset = 0, quadorder = 4)
+    FEType = eltype(FES)
+    EG = FES.xgrid[UniqueCellGeometries][1]
+    segs = pattern_segments(ExtendableFEMBase.get_dofmap_pattern(FEType, CellDofs, EG))
+    qf = QuadratureRule{Float64, Edge1D}(quadorder)
+    qx = Float64[x[1] for x in qf.xref]
+    qw = Vector{Float64}(qf.w)
+    target = zeros(Float64, FES.ndofs)
+    GC.@preserve segs params qx qw target check(ctx, ccall((:femb_interpolate, libfemb), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int64, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}),
+        ctx.h, id, length(segs) ÷ 3, segs, offset, kind == :affine ? 1 : 2, params, length(qw), qx, qw, only_boundary ? 1 : 0, target))
+    return target
+end
+
+# A[dof,dof] = penalty; b[dof] = penalty * values[dof] (values = nothing: the device-resident data of interpolate_device!) for the boundary dofs of the last boundarydofs call (+ offset) and `extra`
 function dirichlet!(ctx::Context; offset = 0, extra = Int64[], values = nothing, penalty = 1.0e60)
     GC.@preserve extra values check(ctx, ccall((:femb_dirichlet_apply, libfemb), Int32,
         (Ptr{Cvoid}, Int32, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Float64),

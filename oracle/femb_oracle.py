@@ -853,3 +853,45 @@ def enumerate_entities(g, cellnodes, kind="faces"):
         out["orientations"] = ori
     return out
 
+
+
+# ---------------------------------------------------------------------------------------------
+# interpolate!(target, FES, u) for H1P1 / H1P2 / H1Pk{.,.,<=2}   (Example210:168-173)
+#   nodes:  NodalInterpolator, /root/reference/src/interpolators.jl:93-127  (point evaluation, components coffset apart)
+#   edges:  MomentInterpolator(FES, ON_EDGES | ON_FACES) with order 0, /root/reference/src/fedefs/h1_p2.jl:47-76,
+#           /root/reference/src/interpolators.jl:137-460: the interior dof of the edge is set so that the edge mean of u is
+#           preserved; MOMxBASIS = means of the P2 edge basis (1/6, 1/6, 2/3), moments integrated with the Edge1D rule of
+#           order 2 * order_FE (quadrature.jl:214-233 -> generic Gauss rule, :609-628), vertex contributions subtracted.
+# ---------------------------------------------------------------------------------------------
+def gauss_rule_edge(order: int):
+    """QuadratureRule{T, Edge1D}(order) for order > 2: get_generic_quadrature_Gauss (quadrature.jl:609-628)."""
+    ngpts = order // 2 + 1
+    k = np.arange(1, ngpts, dtype=np.float64)
+    gamma = k / np.sqrt(4.0 * k * k - 1.0)
+    vals, vecs = np.linalg.eigh(np.diag(gamma, 1) + np.diag(gamma, -1))
+    return 0.5 * vals + 0.5, 0.5 * (2.0 * vecs[0, :] ** 2)
+
+
+def interpolate_h1_nodal_edge(coords, edgenodes, u, ncomp, order_fe=2, bonus_quadorder=0):
+    """-> target of length ncomp * (nnodes + nedges) (component-blocked, nodes then edges per component), literal loops."""
+    nn = coords.shape[0]
+    ne = 0 if edgenodes is None else edgenodes.shape[0]
+    coffset = nn + ne
+    target = np.zeros(ncomp * coffset)
+    for j in range(nn):  # interpolators.jl:111-124
+        r = np.atleast_1d(u(coords[j]))
+        for k in range(ncomp):
+            target[j + k * coffset] = r[k]
+    if ne:
+        qx, qw = gauss_rule_edge(2 * order_fe + bonus_quadorder)
+        mom_vertex, mom_interior = 1.0 / 6.0, 2.0 / 3.0  # MOMxBASIS of the P2 basis on the reference edge against the constant
+        for e in range(ne):
+            a, b = edgenodes[e, 0] - 1, edgenodes[e, 1] - 1
+            f_mom = np.zeros(ncomp)
+            for q in range(qx.shape[0]):  # eval_trafo! on the edge: x = x_a + xref (x_b - x_a)
+                x = coords[a] + qx[q] * (coords[b] - coords[a])
+                f_mom += qw[q] * np.atleast_1d(u(x))
+            for k in range(ncomp):  # subtract the exterior (vertex) dofs, solve the 1 x 1 interior system
+                f = f_mom[k] - mom_vertex * (target[a + k * coffset] + target[b + k * coffset])
+                target[nn + e + k * coffset] = f / mom_interior
+    return target

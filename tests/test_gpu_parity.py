@@ -992,3 +992,53 @@ def test_changed_connectivity_is_detected():
     ctx.mesh_set(coords, cn2, vol)
     with pytest.raises(_lib.FembError):
         ctx.assemble_poisson(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# interpolate!(u_init[1], u!) on the device (node values + edge-mean preserving edge dofs)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,ncomp,kind", [(2, 2, "ex210"), (2, 1, "affine"), (3, 1, "affine"), (3, 3, "affine")])
+def test_device_interpolation_matches_oracle(dim, ncomp, kind):
+    from femb_b200.assembly import _Session
+    from femb_b200.fespace import parse_pattern
+
+    grid = _grid2d(9, True) if dim == 2 else _grid3d(4, True)
+    ft = fb.H1Pk(ncomp, 2, 2) if dim == 2 else fb.H1P2(ncomp, 3)
+    fes = fb.FESpace(ft, grid)
+    S = _Session([fes], fb.QuadratureRule(grid.geometry, 2))
+    ctx = S.ctx
+    segs = parse_pattern(ft.get_dofmap_pattern(grid.geometry))
+    edgenodes = grid["FaceNodes"] if dim == 2 else grid["EdgeNodes"]
+    mu, t = 1.0e-2, 0.3
+    if kind == "ex210":
+        e = np.exp(-8 * np.pi**2 * mu * t)
+        u = lambda x: np.array([e * np.sin(2 * np.pi * x[0]) * np.sin(2 * np.pi * x[1]), e * np.cos(2 * np.pi * x[0]) * np.cos(2 * np.pi * x[1])])  # noqa: E731
+        fk, params = _lib.FUNC_EX210_U, np.array([mu, t])
+    else:
+        rng = np.random.default_rng(4)
+        c0, g = rng.uniform(-1, 1, ncomp), rng.uniform(-1, 1, (ncomp, dim))
+        u = lambda x: c0 + g @ x  # noqa: E731
+        fk, params = _lib.FUNC_AFFINE, np.concatenate([np.concatenate([[c0[c]], g[c]]) for c in range(ncomp)])
+    want = orc.interpolate_h1_nodal_edge(grid["Coordinates"], edgenodes, u, ncomp)
+    qx, qw = orc.gauss_rule_edge(4)
+    got = ctx.interpolate(0, segs, fes.ndofs, fk, params, qx, qw)
+    assert np.abs(got - want).max() <= RTOL * np.abs(want).max()
+    if kind == "affine":  # the P2 interpolant of an affine function is the function: edge dofs = midpoint values
+        mid = ctx.interpolate(0, segs, fes.ndofs, fk, params)
+        assert np.abs(mid - want).max() <= 1e-14
+    # boundary dofs only: everything else keeps its value (zero), and dirichlet_apply(values=None) uses the device vector
+    bd = ctx.boundary_dofs(0, segs)
+    ctx.pattern_build([(0, 0)])
+    S2 = _Session([fes], fb.QuadratureRule(grid.geometry, 2))
+    c2 = S2.ctx
+    c2.pattern_build([(0, 0)])
+    c2.boundary_dofs(0, segs, download=False)
+    only = c2.interpolate(0, segs, fes.ndofs, fk, params, qx, qw, only_boundary=True)
+    ref = np.zeros_like(want)
+    ref[bd - 1] = want[bd - 1]
+    assert np.abs(only - ref).max() <= RTOL * np.abs(want).max()
+    c2.matrix_zero()
+    c2.vector_zero()
+    c2.dirichlet_apply(True, 0, None, None, 1.0e60)
+    b = c2.vector_get(fes.ndofs)
+    assert np.abs(b * 1.0e-60 - ref).max() <= RTOL * max(np.abs(want).max(), 1.0)
