@@ -688,13 +688,14 @@ __global__ void __launch_bounds__(128, 4) k_h1_gather(const HArgs a, const HTab<
 }
 
 template <int DIM, int ND, int NQ>
-static int launch_h1_gather_t(femb_ctx* ctx, const FembEval& EG, const FembEval* EI, HArgs a) {
+static int launch_h1_gather_t(femb_ctx* ctx, const FembHMap& H, const FembEval& EG, const FembEval* EI, HArgs a) {
     const FembSpace& s = ctx->spaces[EG.space];
+    const int nc = s.ncomp;  // component-blocked vector spaces: the scalar basis is component 0 of the first ND functions
     HTab<DIM, ND, NQ> tab;
     for (int q = 0; q < NQ; q++) {
         for (int j = 0; j < ND; j++) {
             for (int d = 0; d < DIM; d++) {
-                tab.D[q][d][j] = EG.h_refderivs[((size_t)q * s.nd_all + j) * DIM + d];
+                tab.D[q][d][j] = EG.h_refderivs[((size_t)q * s.nd_all + j) * nc * DIM + d];
                 tab.wD[q][d][j] = EG.w[q] * tab.D[q][d][j];
             }
             tab.wphi[q][j] = EI ? EG.w[q] * EI->h_refvals[(size_t)q * s.nd_all + j] : 0.0;
@@ -728,11 +729,11 @@ static int launch_h1_gather_t(femb_ctx* ctx, const FembEval& EG, const FembEval*
     if (!p2s)
         for (int q = 0; q < NQ; q++)
             for (int i = 0; i <= DIM; i++) tab.L4[q][i] = 0.0;
-    const bool fast = ctx->hmap_complete && !a.touched && !(a.drop_tol > 0.0);
+    const bool fast = H.complete && !a.touched && !(a.drop_tol > 0.0);
     auto kern1 = fast ? (p2s ? k_h1_gather<DIM, ND, NQ, 1, true, true> : k_h1_gather<DIM, ND, NQ, 1, true, false>) : k_h1_gather<DIM, ND, NQ, 1, false, false>;
     auto kern4 = fast ? (p2s ? k_h1_gather<DIM, ND, NQ, 4, true, true> : k_h1_gather<DIM, ND, NQ, 4, true, false>) : k_h1_gather<DIM, ND, NQ, 4, false, false>;
     size_t max1 = 0, max4 = 0;
-    for (auto& r : ctx->hranges) {
+    for (auto& r : H.ranges) {
         if (r.split == 4) max4 = std::max(max4, (size_t)std::max(1, r.maxlen) * 32 * sizeof(double));
         else max1 = std::max(max1, (size_t)std::max(1, r.maxlen) * 128 * sizeof(double));
     }
@@ -746,7 +747,7 @@ static int launch_h1_gather_t(femb_ctx* ctx, const FembEval& EG, const FembEval*
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max4));
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
-    for (auto& r : ctx->hranges) {
+    for (auto& r : H.ranges) {
         if (r.s1 <= r.s0) continue;
         a.slice_begin = r.s0;
         a.slice_end = r.s1;
@@ -766,7 +767,8 @@ static int launch_h1_gather_t(femb_ctx* ctx, const FembEval& EG, const FembEval*
 int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
-    if (!ctx->hmap || ctx->hmap_space != EG.space || EG.nqp > 10) return FEMB_ERR_UNSUPPORTED;
+    const FembHMap& H = ctx->hm;
+    if (!H.map || H.space != EG.space || EG.nqp > 10 || s.ncomp != 1) return FEMB_ERR_UNSUPPORTED;
     if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return FEMB_ERR_UNSUPPORTED;
     if (EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * ctx->dim) return FEMB_ERR_UNSUPPORTED;
     const FembEval* EI = rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr;
@@ -781,7 +783,7 @@ int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     else k_cell_coef<3><<<gridc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, ctx->cellcoef);
     KERNEL_CHECK(ctx);
     HArgs a;
-    a.coef = ctx->cellcoef; a.hslice_ptr = ctx->hslice_ptr; a.hslice_zero = ctx->hslice_zero; a.hmap = ctx->hmap; a.hstride = ctx->hmap_stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
+    a.coef = ctx->cellcoef; a.hslice_ptr = H.slice_ptr; a.hslice_zero = H.slice_zero; a.hmap = H.map; a.hstride = H.stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag; a.drop_tol = drop_tol;
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
@@ -789,6 +791,47 @@ int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     a.slice_begin = a.slice_end = 0;
     ctx->zero_pending_A = false;
     if (a.has_rhs) ctx->zero_pending_b = false;
-    if (key == 20603) return launch_h1_gather_t<2, 6, 3>(ctx, EG, EI, a);
-    return launch_h1_gather_t<3, 10, 4>(ctx, EG, EI, a);
+    if (key == 20603) return launch_h1_gather_t<2, 6, 3>(ctx, H, EG, EI, a);
+    return launch_h1_gather_t<3, 10, 4>(ctx, H, EG, EI, a);
+}
+
+// mu (grad u, grad v) of a component-blocked vector-valued P2 space in block (0,0) of a multi-space layout (the Laplacian of
+// Example210:284-290,368): every component is the scalar P2 stiffness, the cross-component entries are exact zeros.  Owner-
+// computes by column like the scalar case (write-once per launch, bit-reproducible); the columns also hold rows of other
+// blocks, so the result is ADDED to nzval (the lazy zero is flushed first).  FEMB_ERR_UNSUPPORTED when not covered.
+int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu) {
+    const FembEval& EG = ctx->evals[eg];
+    const FembSpace& s = ctx->spaces[EG.space];
+    if (s.ncomp < 2 || ctx->touched || EG.nqp > 10) return FEMB_ERR_UNSUPPORTED;
+    if (EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * s.ncomp * ctx->dim) return FEMB_ERR_UNSUPPORTED;
+    const int nds = s.nd / s.ncomp;
+    const int key = ctx->dim * 10000 + nds * 100 + EG.nqp;
+    if (key != 20603 && key != 20609 && key != 31004) return FEMB_ERR_UNSUPPORTED;
+    int st = femb_build_hmap_vec(ctx);
+    if (st != FEMB_OK) return st;
+    const FembHMap& H = ctx->hm_vec;
+    if (H.space != EG.space) return FEMB_ERR_UNSUPPORTED;
+    if (!ctx->cellcoef) FEMB_TRY(femb_alloc(ctx, &ctx->cellcoef, (size_t)ctx->ncells * FEMB_COEF_STRIDE));
+    if (ctx->ncells == 0) return FEMB_OK;
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    RhsDev norhs;
+    norhs.kind = FEMB_RHS_NONE;
+    norhs.ncomp = 1;
+    norhs.fvals = nullptr;
+    QuadDev q = quad_dev(EG, ctx->dim);
+    const unsigned gridc = (unsigned)((ctx->ncells + 127) / 128);
+    if (ctx->dim == 2) k_cell_coef<2><<<gridc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, norhs, q, ctx->cellcoef);
+    else k_cell_coef<3><<<gridc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, norhs, q, ctx->cellcoef);
+    KERNEL_CHECK(ctx);
+    HArgs a;
+    a.coef = ctx->cellcoef; a.hslice_ptr = H.slice_ptr; a.hslice_zero = H.slice_zero; a.hmap = H.map; a.hstride = H.stride;
+    a.colptr = ctx->colptr + H.col_off; a.ndofs = s.ndofs;
+    a.nzval = ctx->nzval; a.touched = nullptr; a.bvec = nullptr; a.errflag = ctx->errflag; a.drop_tol = 0.0;
+    a.acc_A = 1;
+    a.acc_b = 1;
+    a.has_rhs = 0;
+    a.slice_begin = a.slice_end = 0;
+    if (key == 20603) return launch_h1_gather_t<2, 6, 3>(ctx, H, EG, nullptr, a);
+    if (key == 20609) return launch_h1_gather_t<2, 6, 9>(ctx, H, EG, nullptr, a);
+    return launch_h1_gather_t<3, 10, 4>(ctx, H, EG, nullptr, a);
 }

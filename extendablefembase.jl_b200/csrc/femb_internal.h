@@ -59,6 +59,21 @@ struct FembEval {
     double w[FEMB_MAX_QP];
 };
 
+// H1 gather map: sliced ELL over (column dof, adjacent cell) pairs, SoA planes [row][lane]: plane 0 = cell, planes 1.. = positions
+// of the cell's local rows in the dof's CSC column packed 4 x 8 bit per word (0xFF = not in the pattern); the spare bytes of the
+// last word carry the local index k of the dof (within its component) and the first-touch flags
+struct FembHMap {
+    uint32_t* map = nullptr;
+    size_t stride = 0;
+    int32_t* slice_ptr = nullptr;
+    uint8_t* slice_zero = nullptr;  // per slice: some column has positions without a local contribution (zero the accumulators)
+    int space = -1, words = 0;
+    int64_t col_off = 0;            // first column of the block in the matrix
+    bool complete = false;          // every (cell, row) of the map has a slot: the gather may skip its per-entry checks
+    struct Range { int64_t s0, s1; int maxlen; int split; };  // split: threads per column (1, or 4 for high-degree columns)
+    std::vector<Range> ranges;      // contiguous slice ranges with their longest CSC column (shared-memory sizing)
+};
+
 struct FembBlock {
     int brow = 0, bcol = 0;       // indices into layout row/col space lists
     int32_t* slots = nullptr;     // device [ncells][ndr][ndc] -> 0-based nz index, -1 = absent
@@ -120,17 +135,9 @@ struct femb_ctx {
     bool gmap_uniform = false;       // every slice padded to gmap_maxrows rows (row0 = slice * maxrows, no indirection)
     int gmap_maxrows = 0;            // longest slice (rows) = largest number of cells around a dof
     int gmap_space = -1;
-    // general scalar-H1 gather map (P2, ...; femb_pattern.cu): sliced ELL over (dof, adjacent cell) pairs, SoA planes
-    // 0 = cell, 1.. = positions of the cell's local rows in the dof's CSC column packed 4 x 8 bit per word (0xFF = not
-    // in the pattern); the spare bytes of the last word carry the local index k of the dof and the first-touch flags
-    uint32_t* hmap = nullptr;
-    size_t hmap_stride = 0;
-    int32_t* hslice_ptr = nullptr;
-    uint8_t* hslice_zero = nullptr;  // per slice: some column has positions without a local contribution (zero the accumulators)
-    int hmap_space = -1, hmap_words = 0;
-    bool hmap_complete = false;    // every (cell, row) of the map has a slot: the gather may skip its per-entry checks
-    struct HRange { int64_t s0, s1; int maxlen; int split; };  // split: threads per column (1, or 4 for high-degree columns)
-    std::vector<HRange> hranges;   // contiguous slice ranges with their longest CSC column (shared-memory sizing)
+    // general H1 gather maps (P2, ...; femb_pattern.cu): hm = the single scalar block of a one-space layout (Example200), hm_vec = the
+    // component-diagonal part of block (0,0) of a vector-valued space in a multi-space layout (Example210's Laplacian)
+    FembHMap hm, hm_vec;
     double* cellrhs = nullptr;     // [cell][qp][comp]: factor w_q |T| f(x_q), pre-pass of the Identity rhs gather
     size_t cellrhs_n = 0;
     double* cellcoef = nullptr;    // [cell][FEMB_COEF_STRIDE]: Kc (3 / 6) then |T| f(x_q) per quadrature point (pre-pass of the gather)
@@ -261,6 +268,8 @@ int femb_build_adjacency(femb_ctx* ctx, int space_id);
 int femb_build_slotmaps(femb_ctx* ctx);
 int femb_build_gmap(femb_ctx* ctx);
 int femb_build_hmap(femb_ctx* ctx);
+int femb_build_hmap_vec(femb_ctx* ctx);  // lazy: component-diagonal map of block (0,0) of a vector-valued H1 space
+void femb_free_hmap(FembHMap& H);
 #define FEMB_COEF_STRIDE 16  // doubles per cell in femb_ctx::cellcoef (6 + up to 10 quadrature points)
 void femb_free_pattern(femb_ctx* ctx);
 void femb_free_space(FembSpace& s);

@@ -56,3 +56,4 @@ int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
 // femb_h1.cu (both return FEMB_ERR_UNSUPPORTED, without an error message, when the path does not cover the space)
 int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_tol);
 int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol);
+int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu);

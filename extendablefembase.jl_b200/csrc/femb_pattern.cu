@@ -26,13 +26,9 @@ void femb_free_pattern(femb_ctx* ctx) {
     ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
     ctx->chunk_n = 0;
-    femb_free(&ctx->hmap);
-    femb_free(&ctx->hslice_ptr);
-    femb_free(&ctx->hslice_zero);
+    femb_free_hmap(ctx->hm);
+    femb_free_hmap(ctx->hm_vec);
     femb_free(&ctx->cellcoef);
-    ctx->hmap_stride = 0;
-    ctx->hmap_space = -1;
-    ctx->hranges.clear();
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
     ctx->nnz = 0;
@@ -772,9 +768,11 @@ __global__ void k_slice_collen(const int64_t* __restrict__ colptr, int64_t ndofs
 // the local index k of c in the cell (bits 16-19, 0xF = padding entry) and one "first touch" flag per local row (bit 20 + j:
 // no earlier visit of this column wrote that position, so the gather stores instead of adding and needs no zeroed
 // accumulator).  needs_zero[slice] = 1 when a column of the slice has positions no cell contributes to (halo rows of a
-// partitioned mesh, extra diagonal entries): those slices zero their accumulators first.
-__global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices, int nd, int nwords,
-                       const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval,
+// partitioned mesh, extra diagonal entries, rows of other components / blocks): those slices zero their accumulators first.
+// Vector-valued (component-blocked) spaces: nd = ncomp * nds; the rows of a visit are the nds dofs of the column's own
+// component, k is the index within the component; row_off / col_off place the block in the matrix.
+__global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices, int nd, int nds, int nwords,
+                       const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int64_t row_off, int64_t col_off,
                        const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hmap, size_t stride, int32_t* __restrict__ nmissing,
                        uint8_t* __restrict__ needs_zero) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -784,8 +782,9 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
     const int row0 = slice_ptr[slice], nrows = slice_ptr[slice + 1] - row0;
     const int e0 = c < ndofs ? adj_ptr[c] : 0;
     const int deg = c < ndofs ? adj_ptr[c + 1] - e0 : 0;
-    const int64_t base = c < ndofs ? colptr[c] - 1 : 0;
-    const int len = c < ndofs ? (int)(colptr[c + 1] - 1 - base) : 0;
+    const int64_t gc = col_off + c;
+    const int64_t base = c < ndofs ? colptr[gc] - 1 : 0;
+    const int len = c < ndofs ? (int)(colptr[gc + 1] - 1 - base) : 0;
     uint32_t seen[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // positions written by earlier visits (max_collen <= 254)
     int nseen = 0;
     for (int r = 0; r < nrows; r++) {
@@ -795,9 +794,11 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
         if (r < deg) {
             uint32_t a = adj[e0 + r];
             cell = a / (uint32_t)nd;
-            k = a - cell * (uint32_t)nd;
-            for (int j = 0; j < nd; j++) {
-                int64_t p = find_slot(colptr, rowval, c, (int64_t)celldofs[(int64_t)cell * nd + j]);
+            const uint32_t kf = a - cell * (uint32_t)nd;
+            const uint32_t comp = kf / (uint32_t)nds;
+            k = kf - comp * (uint32_t)nds;
+            for (int j = 0; j < nds; j++) {
+                int64_t p = find_slot(colptr, rowval, gc, row_off + (int64_t)celldofs[(int64_t)cell * nd + comp * nds + j]);
                 uint32_t pos = (p < 0) ? 0xFFu : (uint32_t)(p - base);
                 if (p < 0) atomicAdd(nmissing, 1);  // rows without a slot (compressed / adopted patterns): the gather must check
                 else if (!((seen[pos >> 5] >> (pos & 31)) & 1u)) {
@@ -815,27 +816,27 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
     if (nseen < len) needs_zero[slice] = 1;
 }
 
-int femb_build_hmap(femb_ctx* ctx) {
-    femb_free(&ctx->hmap);
-    femb_free(&ctx->hslice_ptr);
-    femb_free(&ctx->hslice_zero);
-    ctx->hmap_stride = 0;
-    ctx->hmap_space = -1;
-    ctx->hranges.clear();
-    if (ctx->gmap_space >= 0) return FEMB_OK;  // scalar P1 has its own map
-    if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
-    const int sid = ctx->row_spaces[0];
+void femb_free_hmap(FembHMap& H) {
+    femb_free(&H.map);
+    femb_free(&H.slice_ptr);
+    femb_free(&H.slice_zero);
+    H.stride = 0;
+    H.space = -1;
+    H.ranges.clear();
+}
+
+// builds the map of the (component-diagonal part of the) square block of space `sid` whose rows / columns start at row_off / col_off
+static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off, int64_t col_off) {
     const FembSpace& s = ctx->spaces[sid];
-    if (s.family != FEMB_FAMILY_H1 || s.ncomp != 1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd > 12 || ctx->max_collen > 254) return FEMB_OK;
-    if ((s.nd & 3) != 1 && (s.nd & 3) != 2) return FEMB_OK;  // the last position word must have two spare bytes (k + first-touch flags)
+    const int nds = s.nd / s.ncomp;
     const int64_t nslices = (s.ndofs + 31) / 32;
-    const int nwords = (s.nd + 3) / 4;
+    const int nwords = (nds + 3) / 4;
     int32_t *deg = nullptr, *clen = nullptr;
     void* tmp = nullptr;
     {
         int st = femb_alloc(ctx, &deg, (size_t)nslices + 1);
         if (st == FEMB_OK) st = femb_alloc(ctx, &clen, (size_t)nslices);
-        if (st == FEMB_OK) st = femb_alloc(ctx, &ctx->hslice_ptr, (size_t)nslices + 1);
+        if (st == FEMB_OK) st = femb_alloc(ctx, &H.slice_ptr, (size_t)nslices + 1);
         if (st == FEMB_OK && cudaMemsetAsync(deg, 0, sizeof(int32_t) * (nslices + 1), ctx->stream) != cudaSuccess)
             st = femb_fail(ctx, FEMB_ERR_CUDA, "femb_build_hmap: memset failed");
         if (st != FEMB_OK) {
@@ -845,15 +846,15 @@ int femb_build_hmap(femb_ctx* ctx) {
         }
     }
     k_slice_deg<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(s.adj_ptr, s.ndofs, nslices, deg);
-    k_slice_collen<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(ctx->colptr, s.ndofs, nslices, clen);
+    k_slice_collen<<<(unsigned)((nslices + 127) / 128), 128, 0, ctx->stream>>>(ctx->colptr + col_off, s.ndofs, nslices, clen);
     ctx->launches += 2;
     size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, ctx->hslice_ptr, nslices + 1, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, H.slice_ptr, nslices + 1, ctx->stream);
     cudaError_t e = cudaMalloc(&tmp, tb);
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, deg, ctx->hslice_ptr, nslices + 1, ctx->stream);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, deg, H.slice_ptr, nslices + 1, ctx->stream);
     int32_t rows = 0;
     std::vector<int32_t> h_clen((size_t)nslices);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&rows, ctx->hslice_ptr + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&rows, H.slice_ptr + nslices, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_clen.data(), clen, sizeof(int32_t) * nslices, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(tmp);
@@ -863,7 +864,7 @@ int femb_build_hmap(femb_ctx* ctx) {
     CUDA_TRY(ctx, e);
     // contiguous slice ranges of similar column length (shared memory per thread = maxlen doubles): runs of equal
     // class ceil(len / 32), short runs (< 1/64 of the slices) merged into their predecessor, at most 16 ranges
-    std::vector<femb_ctx::HRange> rg;
+    std::vector<FembHMap::Range> rg;
     const int64_t minrun = std::max<int64_t>(512, nslices / 64);
     for (int64_t sl = 0; sl < nslices; sl++) {
         const int cls = (h_clen[sl] + 31) / 32;
@@ -888,7 +889,7 @@ int femb_build_hmap(femb_ctx* ctx) {
     // columns with many adjacent cells (vertex dofs of P2 tetrahedra: ~24) are split over 4 threads
     {
         std::vector<int32_t> h_ptr((size_t)nslices + 1);
-        CUDA_TRY(ctx, cudaMemcpy(h_ptr.data(), ctx->hslice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost));
+        CUDA_TRY(ctx, cudaMemcpy(h_ptr.data(), H.slice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost));
         for (auto& r : rg) r.split = ((double)(h_ptr[r.s1] - h_ptr[r.s0]) / (double)(r.s1 - r.s0) >= 12.0) ? 4 : 1;
         // neighbours with the same split whose merged accumulator block stays small (<= 24 KB per CTA) become one launch
         for (size_t i = 0; i + 1 < rg.size();) {
@@ -902,25 +903,56 @@ int femb_build_hmap(femb_ctx* ctx) {
             }
         }
     }
-    ctx->hranges = rg;
-    ctx->hmap_stride = (size_t)rows * 32;
-    ctx->hmap_words = nwords;
-    FEMB_TRY(femb_alloc(ctx, &ctx->hmap, ctx->hmap_stride * (1 + nwords)));
-    FEMB_TRY(femb_alloc(ctx, &ctx->hslice_zero, (size_t)nslices));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hslice_zero, 0, (size_t)nslices, ctx->stream));
+    H.ranges = rg;
+    H.stride = (size_t)rows * 32;
+    H.words = nwords;
+    H.col_off = col_off;
+    FEMB_TRY(femb_alloc(ctx, &H.map, H.stride * (1 + nwords)));
+    FEMB_TRY(femb_alloc(ctx, &H.slice_zero, (size_t)nslices));
+    CUDA_TRY(ctx, cudaMemsetAsync(H.slice_zero, 0, (size_t)nslices, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
-    k_hmap<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.nd, nwords, s.celldofs, ctx->colptr, ctx->rowval,
-                                                                            ctx->hslice_ptr, ctx->hmap, ctx->hmap_stride, ctx->errflag, ctx->hslice_zero);
+    k_hmap<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.nd, nds, nwords, s.celldofs, ctx->colptr, ctx->rowval,
+                                                                            row_off, col_off, H.slice_ptr, H.map, H.stride, ctx->errflag, H.slice_zero);
     KERNEL_CHECK(ctx);
     {
         int32_t nmiss = 0;
         CUDA_TRY(ctx, cudaMemcpyAsync(&nmiss, ctx->errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
-        ctx->hmap_complete = nmiss == 0;
+        H.complete = nmiss == 0;
     }
-    ctx->hmap_space = sid;
+    H.space = sid;
     return FEMB_OK;
+}
+
+static bool hmap_space_ok(const femb_ctx* ctx, const FembSpace& s) {
+    if (s.family != FEMB_FAMILY_H1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd % s.ncomp || ctx->max_collen > 254) return false;
+    const int nds = s.nd / s.ncomp;
+    return nds <= 12 && ((nds & 3) == 1 || (nds & 3) == 2);  // the last position word must have two spare bytes (k + first-touch flags)
+}
+
+int femb_build_hmap(femb_ctx* ctx) {
+    femb_free_hmap(ctx->hm);
+    femb_free_hmap(ctx->hm_vec);
+    if (ctx->gmap_space >= 0) return FEMB_OK;  // scalar P1 has its own map
+    if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
+    const int sid = ctx->row_spaces[0];
+    const FembSpace& s = ctx->spaces[sid];
+    if (s.ncomp != 1 || !hmap_space_ok(ctx, s)) return FEMB_OK;
+    return build_hmap_into(ctx, ctx->hm, sid, 0, 0);
+}
+
+// lazy: the (u,u) block of FEMatrix([FES_u, ...]) with a component-blocked vector-valued H1 space FES_u (Example210's Laplacian)
+int femb_build_hmap_vec(femb_ctx* ctx) {
+    if (ctx->hm_vec.map) return FEMB_OK;
+    if (ctx->nrs < 1 || ctx->ncs < 1 || ctx->row_spaces[0] != ctx->col_spaces[0]) return FEMB_ERR_UNSUPPORTED;
+    bool have = false;
+    for (auto& b : ctx->blocks) have = have || (b.brow == 0 && b.bcol == 0);
+    const int sid = ctx->row_spaces[0];
+    const FembSpace& s = ctx->spaces[sid];
+    if (!have || !hmap_space_ok(ctx, s)) return FEMB_ERR_UNSUPPORTED;
+    FEMB_TRY(femb_build_adjacency(ctx, sid));
+    return build_hmap_into(ctx, ctx->hm_vec, sid, ctx->row_off[0], ctx->col_off[0]);
 }
 
 // ---------------------------------------------------------------------------------------------------
