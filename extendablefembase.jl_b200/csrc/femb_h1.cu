@@ -767,6 +767,12 @@ static int launch_h1_gather_t(femb_ctx* ctx, const FembHMap& H, const FembEval& 
 int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
+    {
+        // P2 on tetrahedra without value filter / slot tracking: closed-form kernel (femb_p2.cu)
+        const int st = launch_p2_gather(ctx, eg, ei, mu, rhs, drop_tol);
+        if (st != FEMB_ERR_UNSUPPORTED) return st;
+    }
+    FEMB_TRY(femb_hmap_set_canon(ctx, ctx->hm, false));
     const FembHMap& H = ctx->hm;
     if (!H.map || H.space != EG.space || EG.nqp > 10 || s.ncomp != 1) return FEMB_ERR_UNSUPPORTED;
     if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return FEMB_ERR_UNSUPPORTED;

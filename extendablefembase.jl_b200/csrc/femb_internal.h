@@ -70,8 +70,10 @@ struct FembHMap {
     int space = -1, words = 0;
     int64_t col_off = 0;            // first column of the block in the matrix
     bool complete = false;          // every (cell, row) of the map has a slot: the gather may skip its per-entry checks
-    struct Range { int64_t s0, s1; int maxlen; int split; };  // split: threads per column (1, or 4 for high-degree columns)
+    bool canon = false;             // positions / first-touch flags of every entry are in P2 role order (femb_p2.cu) instead of local dof order
+    struct Range { int64_t s0, s1; int maxlen; int split; int mode = 2; int maxrows = 0; };  // split: threads per column (1, or 4 for high-degree columns)
     std::vector<Range> ranges;      // contiguous slice ranges with their longest CSC column (shared-memory sizing)
+    std::vector<Range> cranges;     // femb_p2.cu: `ranges` cut where the kind of dof changes (mode 0 = vertex dofs, 1 = edge dofs, 2 = both)
 };
 
 struct FembBlock {
@@ -140,6 +142,7 @@ struct femb_ctx {
     FembHMap hm, hm_vec;
     double* cellrhs = nullptr;     // [cell][qp][comp]: factor w_q |T| f(x_q), pre-pass of the Identity rhs gather
     size_t cellrhs_n = 0;
+    double* p2rec = nullptr;       // [cell][28]: per-cell record of the closed-form P2 gather (femb_p2.cu)
     double* cellcoef = nullptr;    // [cell][FEMB_COEF_STRIDE]: Kc (3 / 6) then |T| f(x_q) per quadrature point (pre-pass of the gather)
 
     double* nzval = nullptr;      // nnz
@@ -270,6 +273,8 @@ int femb_build_gmap(femb_ctx* ctx);
 int femb_build_hmap(femb_ctx* ctx);
 int femb_build_hmap_vec(femb_ctx* ctx);  // lazy: component-diagonal map of block (0,0) of a vector-valued H1 space
 void femb_free_hmap(FembHMap& H);
+int femb_hmap_set_canon(femb_ctx* ctx, FembHMap& H, bool canon);  // permutes the map entries in place between local dof order and P2 role order
+void femb_p2_role_perm(uint8_t perm[12][12]);                      // femb_p2.cu: perm[k][role] = local dof
 #define FEMB_COEF_STRIDE 16  // doubles per cell in femb_ctx::cellcoef (6 + up to 10 quadrature points)
 void femb_free_pattern(femb_ctx* ctx);
 void femb_free_space(FembSpace& s);

@@ -1,0 +1,602 @@
+// Scalar H1P2 on tetrahedra (C3 of BASELINE.json: Example200's assemble! with H1P2{1,3}) as an owner-computes gather in
+// closed form.  With constant mu on an affine cell the quadrature sum of Example200:139-146 collapses to the reference-tensor
+// contraction  A_jk = sum_ab G_ab T_ab[j,k],  G_ab = mu |T| grad(lambda_a).grad(lambda_b)  (the P1 stiffness of the cell), and
+// for P2 (phi_i = lambda_i (2 lambda_i - 1), phi_ij = 4 lambda_i lambda_j, src/fedefs/h1_p2.jl) T is so sparse that a column
+// of the local matrix needs 3 (vertex dof) or 5 (edge dof) of the six G_ab and 15-40 flops instead of the ~220 of the
+// quadrature form.  The constants are exact integrals; the launcher accepts the closed form only if it reproduces the
+// evaluator's own quadrature tables for every local column (else the general kernel of femb_h1.cu runs).
+//
+// What this buys (ncu of the general kernel: L1 data pipe 72 %, long-scoreboard stalls at 16 warps / SM, 124 registers):
+//  * a vertex-column visit reads ONE 32-byte sector (G_k. and the local rhs entry) instead of a 96-byte record,
+//  * no quadrature tables, no h_q intermediates: ~70 registers, twice the resident warps,
+//  * the gather map is put into "role order" (self / other vertices / incident edges / opposite edges) once, so the numeric
+//    kernel has no per-lane indexing except one select chain over the local edge number.
+#include <cstdlib>
+
+#include "femb_kernels.cuh"
+
+namespace {
+
+#ifndef P2_MINB
+#define P2_MINB 4
+#endif
+#ifndef P2_DEPTH
+#define P2_DEPTH 1
+#endif
+#ifndef P2_DEPTH0
+#define P2_DEPTH0 2
+#endif
+#ifndef P2_MINB0
+#define P2_MINB0 4
+#endif
+
+constexpr int P2_REC = 32;  // doubles per cell (28 used; the vertex part and the edge part are one aligned 128-byte line each): 4 vertex sectors [G_k,o1 G_k,o2 G_k,o3 bl_k], [G01 G02 G03 G12] [G13 G23 bl4 bl5] [bl6 bl7 bl8 bl9]
+
+struct P2Const {
+    double alpha, beta, gd, go, mus, mud;
+};
+
+struct P2Wphi {
+    double v[FEMB_COEF_STRIDE - 6][10];  // w_q phi_j(xref_q)
+};
+
+struct P2Args {
+    const double* rec;
+    const int32_t* slice_ptr;
+    const uint8_t* slice_zero;
+    const uint32_t* map;
+    size_t stride;
+    const int64_t* colptr;
+    int64_t ndofs;
+    double* nzval;
+    double* bvec;
+    int acc_A, acc_b, has_rhs;
+    int64_t slice_begin, slice_end;
+    int maxlen, maxrows;  // of the launch range: longest CSC column, most visits of a slice (shared-memory layout)
+    P2Const c;
+};
+
+// local edge (a, b), a < b, of a tetrahedron -> 0..5 (ExtendableGrids local edge numbering, as femb_h1.cu p2_edge_a/b)
+constexpr int edge_of(int a, int b) { return a == 0 ? b - 1 : (a == 1 ? b + 1 : 5); }
+
+// role order of the rows of local column k (host + symbolic phase): vertex k -> [k, o1, o2, o3, (k o1), (k o2), (k o3),
+// (o1 o2), (o1 o3), (o2 o3)] with o ascending; edge (i j), others k < l -> [i, j, k, l, (ij), (ik), (il), (jk), (jl), (kl)]
+void p2_role_perm(uint8_t perm[10][10]) {
+    auto E = [](int a, int b) { return 4 + (a < b ? edge_of(a, b) : edge_of(b, a)); };
+    for (int k = 0; k < 4; k++) {
+        int o[3], n = 0;
+        for (int v = 0; v < 4; v++)
+            if (v != k) o[n++] = v;
+        const int r[10] = {k, o[0], o[1], o[2], E(k, o[0]), E(k, o[1]), E(k, o[2]), E(o[0], o[1]), E(o[0], o[2]), E(o[1], o[2])};
+        for (int i = 0; i < 10; i++) perm[k][i] = (uint8_t)r[i];
+    }
+    const int ea[6] = {0, 0, 0, 1, 1, 2}, eb[6] = {1, 2, 3, 2, 3, 3};
+    for (int e = 0; e < 6; e++) {
+        const int i = ea[e], j = eb[e];
+        int o[2], n = 0;
+        for (int v = 0; v < 4; v++)
+            if (v != i && v != j) o[n++] = v;
+        const int r[10] = {i, j, o[0], o[1], E(i, j), E(i, o[0]), E(i, o[1]), E(j, o[0]), E(j, o[1]), E(o[0], o[1])};
+        for (int t = 0; t < 10; t++) perm[4 + e][t] = (uint8_t)r[t];
+    }
+}
+
+// the ten entries of local column k in role order from the six off-diagonal G (order 01 02 03 12 13 23): host mirror of the
+// device formulas, used by the launch-time check against the quadrature tables
+void p2_column_closed(const P2Const& c, const double G6[6], int k, double v[10]) {
+    auto G = [&](int a, int b) { return G6[a < b ? edge_of(a, b) : edge_of(b, a)]; };
+    if (k < 4) {
+        int o[3], n = 0;
+        for (int t = 0; t < 4; t++)
+            if (t != k) o[n++] = t;
+        const double g1 = G(k, o[0]), g2 = G(k, o[1]), g3 = G(k, o[2]), gkk = -((g1 + g2) + g3);
+        v[0] = c.alpha * gkk;
+        v[1] = c.beta * g1; v[2] = c.beta * g2; v[3] = c.beta * g3;
+        v[4] = c.gd * g1 + c.go * gkk; v[5] = c.gd * g2 + c.go * gkk; v[6] = c.gd * g3 + c.go * gkk;
+        v[7] = c.go * (g1 + g2); v[8] = c.go * (g1 + g3); v[9] = c.go * (g2 + g3);
+    } else {
+        const int ea[6] = {0, 0, 0, 1, 1, 2}, eb[6] = {1, 2, 3, 2, 3, 3};
+        const int i = ea[k - 4], j = eb[k - 4];
+        int o[2], n = 0;
+        for (int t = 0; t < 4; t++)
+            if (t != i && t != j) o[n++] = t;
+        const double g0 = G(i, j), g1 = G(i, o[0]), g2 = G(i, o[1]), g3 = G(j, o[0]), g4 = G(j, o[1]);
+        const double gii = -((g0 + g1) + g2), gjj = -((g0 + g3) + g4);
+        v[0] = c.gd * g0 + c.go * gii; v[1] = c.gd * g0 + c.go * gjj;
+        v[2] = c.go * (g1 + g3); v[3] = c.go * (g2 + g4);
+        v[4] = c.mus * (gii + gjj) + 2.0 * c.mud * g0;
+        v[5] = c.mus * g3 - c.mud * g2; v[6] = c.mus * g4 - c.mud * g1;
+        v[7] = c.mus * g1 - c.mud * g4; v[8] = c.mus * g2 - c.mud * g3;
+        v[9] = c.mud * ((g1 + g2) + (g3 + g4));
+    }
+}
+
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cell pre-pass: G (six off-diagonals of mu |T| grad lambda_a . grad lambda_b) and the local rhs vector, laid out so that
+// a vertex-column visit needs one 32-byte sector and an edge-column visit two or three
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_cell_p2rec(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
+                                                    int64_t ncells, double mu, RhsDev rhs, QuadDev q, P2Wphi wp, double* __restrict__ out) {
+    __shared__ double tile[128][P2_REC + 1];  // staged so that the records leave the SM coalesced
+    const int64_t cell0 = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t cell = cell0 + threadIdx.x;
+    if (cell < ncells) {
+        double x[4][3];
+        load_nodes<3>(coords, cellnodes, cell, x);
+        double A[3][3], C[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) A[d][i] = x[i + 1][d] - x[0][d];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int ra = (r + 1) % 3, rb = (r + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
+                C[r][j] = A[ra][ja] * A[rb][jb] - A[ra][jb] * A[rb][ja];
+            }
+        const double det = A[0][0] * C[0][0] + A[0][1] * C[0][1] + A[0][2] * C[0][2];
+        const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * (1.0 / 6.0);
+        const double sc = (mu * vol) / (det * det);
+        // K_pr = mu |T| grad lambda_{p+1} . grad lambda_{r+1}  (the columns of the cofactor matrix over det)
+        double K[3][3];
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int r = p; r < 3; r++) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) s += C[k][p] * C[k][r];
+                K[p][r] = K[r][p] = s * sc;
+            }
+        const double G01 = -((K[0][0] + K[0][1]) + K[0][2]), G02 = -((K[0][1] + K[1][1]) + K[1][2]), G03 = -((K[0][2] + K[1][2]) + K[2][2]);
+        const double G12 = K[0][1], G13 = K[0][2], G23 = K[1][2];
+        double bl[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) bl[j] = 0.0;
+        if (rhs.kind != FEMB_RHS_NONE) {
+            for (int qp = 0; qp < q.nqp; qp++) {
+                double f;
+                if (rhs.kind == FEMB_RHS_AFFINE) {  // f(x_qp), x_qp = A xref_qp + x_1
+                    f = rhs.p[0];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        double sx = x[0][d];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) sx += A[d][i] * q.xref[qp * 3 + i];
+                        f += rhs.p[1 + d] * sx;
+                    }
+                } else {
+                    f = __ldg(rhs.fvals + (size_t)cell * q.nqp + qp);
+                }
+                f *= vol;
+#pragma unroll
+                for (int j = 0; j < 10; j++) bl[j] += wp.v[qp][j] * f;
+            }
+        }
+        double* o = tile[threadIdx.x];
+        o[0] = G01; o[1] = G02; o[2] = G03; o[3] = bl[0];
+        o[4] = G01; o[5] = G12; o[6] = G13; o[7] = bl[1];
+        o[8] = G02; o[9] = G12; o[10] = G23; o[11] = bl[2];
+        o[12] = G03; o[13] = G13; o[14] = G23; o[15] = bl[3];
+        o[16] = G01; o[17] = G02; o[18] = G03; o[19] = G12;
+        o[20] = G13; o[21] = G23; o[22] = bl[4]; o[23] = bl[5];
+        o[24] = bl[6]; o[25] = bl[7]; o[26] = bl[8]; o[27] = bl[9];
+        o[28] = o[29] = o[30] = o[31] = 0.0;
+    }
+    __syncthreads();
+    const int64_t nloc = min((int64_t)128, ncells - cell0);
+    double* dst = out + cell0 * P2_REC;
+    for (int i = threadIdx.x; i < nloc * P2_REC; i += 128) dst[i] = tile[i / P2_REC][i % P2_REC];
+}
+
+// record pieces of a visit, loaded one visit ahead.  MODE 0: slices of vertex dofs only (r[0..3] = the dof's sector), MODE 1:
+// edge dofs only (r[0..7] = the six G + bl4 bl5, r[8] = bl_k for k >= 6), MODE 2: any.  The wide loads are unconditional
+// (padding entries point at cell 0): a conditionally written destination would need a copy that waits for the load.
+template <int MODE>
+__device__ __forceinline__ void p2_load_rec(const double* __restrict__ rec, unsigned cell, unsigned k, int has_rhs, double (&r)[9]) {
+#ifdef P2_DBG_REC
+    cell &= 1023u;  // timing experiment: every record load hits the cache
+#endif
+    const double* p = rec + (size_t)cell * P2_REC;
+    if (MODE == 0) {
+        ldg256(p + 4u * (k & 3u), r[0], r[1], r[2], r[3]);
+    } else {
+        ldg256(p + ((MODE == 2 && k < 4u) ? 4u * k : 16u), r[0], r[1], r[2], r[3]);
+        ldg256(p + 20, r[4], r[5], r[6], r[7]);
+        if (has_rhs && k - 6u < 4u) r[8] = __ldg(p + 18 + k);
+    }
+}
+
+// the ten entries of the visit's local column in role order (p2_column_closed) and the local rhs entry
+template <int MODE>
+__device__ __forceinline__ double p2_column(const P2Const& c, unsigned k, const double (&r)[9], double (&v)[10]) {
+    if (MODE == 0 || (MODE == 2 && k < 4u)) {
+        const double g1 = r[0], g2 = r[1], g3 = r[2], gkk = -((g1 + g2) + g3);
+        v[0] = c.alpha * gkk;
+        v[1] = c.beta * g1; v[2] = c.beta * g2; v[3] = c.beta * g3;
+        v[4] = c.gd * g1 + c.go * gkk; v[5] = c.gd * g2 + c.go * gkk; v[6] = c.gd * g3 + c.go * gkk;
+        v[7] = c.go * (g1 + g2); v[8] = c.go * (g1 + g3); v[9] = c.go * (g2 + g3);
+        return r[3];
+    }
+    // edge e = (i j), others k < l: G_ij G_ik G_il G_jk G_jl picked from (01 02 03 12 13 23) = r[0..5] by select chains
+    // (selp: the local edge number differs from lane to lane, branches would serialise the warp)
+    const unsigned e = k - 4u;
+    double g0, g1, g2, g3, g4, bl;
+    asm("{\n\t.reg .pred p0, p1, p2, p3, p4, p5, po, l2, l3;\n\t.reg .f64 t0, t1, t2, t3;\n\t"
+        "setp.eq.u32 p0, %6, 0;\n\tsetp.eq.u32 p1, %6, 1;\n\tsetp.eq.u32 p2, %6, 2;\n\tsetp.eq.u32 p3, %6, 3;\n\tsetp.eq.u32 p4, %6, 4;\n\tsetp.eq.u32 p5, %6, 5;\n\t"
+        "setp.lt.u32 l2, %6, 2;\n\tsetp.lt.u32 l3, %6, 3;\n\tor.pred po, p0, p5;\n\t"
+        "selp.f64 t0, %8, %9, p1;\n\tselp.f64 t0, %7, t0, p0;\n\tselp.f64 t1, %11, %12, p4;\n\tselp.f64 t1, %10, t1, p3;\n\tselp.f64 %0, t0, t1, l3;\n\t"
+        "selp.f64 %1, %8, %7, po;\n\tselp.f64 %4, %11, %12, po;\n\t"
+        "selp.f64 t2, %11, %10, p3;\n\tselp.f64 t2, %8, t2, p2;\n\tselp.f64 %2, %9, t2, l2;\n\t"
+        "selp.f64 t3, %8, %9, p3;\n\tselp.f64 t3, %11, t3, p2;\n\tselp.f64 %3, %10, t3, l2;\n\t"
+        "selp.f64 t0, %14, %15, p1;\n\tselp.f64 %5, %13, t0, p0;\n\t}"
+        : "=d"(g0), "=d"(g1), "=d"(g2), "=d"(g3), "=d"(g4), "=d"(bl)
+        : "r"(e), "d"(r[0]), "d"(r[1]), "d"(r[2]), "d"(r[3]), "d"(r[4]), "d"(r[5]), "d"(r[6]), "d"(r[7]), "d"(r[8]));
+    const double gii = -((g0 + g1) + g2), gjj = -((g0 + g3) + g4);
+    v[0] = c.gd * g0 + c.go * gii; v[1] = c.gd * g0 + c.go * gjj;
+    v[2] = c.go * (g1 + g3); v[3] = c.go * (g2 + g4);
+    v[4] = c.mus * (gii + gjj) + 2.0 * c.mud * g0;
+    v[5] = c.mus * g3 - c.mud * g2; v[6] = c.mus * g4 - c.mud * g1;
+    v[7] = c.mus * g1 - c.mud * g4; v[8] = c.mus * g2 - c.mud * g3;
+    v[9] = c.mud * ((g1 + g2) + (g3 + g4));
+    return bl;
+}
+
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// one visit: compute with the record in `cur` (loaded DEPTH visits ago), then start the load of the record of the visit
+// DEPTH visits ahead into the same registers (the caller unrolls over a ring of DEPTH buffers: no register copies).  The
+// map entries of all visits sit in shared memory (sst: this lane's column of the staged planes, pst: plane stride).
+template <int SPLIT, int MODE, int DEPTH>
+__device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[9], int r, int nrows, unsigned sst, unsigned pst, unsigned sacc, unsigned fmask, unsigned warp,
+                                         double& bsum) {
+    constexpr unsigned ncol = 128 / SPLIT;
+    const unsigned ra = sst + (unsigned)r * 128u;
+    const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst), wc = lds32(ra + 3u * pst);
+    const unsigned k = (wc >> 16) & 0xFu;
+    const unsigned first = (wc >> 20) & fmask;
+    const bool on = k != 0xFu;
+    double v[10];
+    unsigned ad[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+        const unsigned w = j < 4 ? wa : (j < 8 ? wb : wc);
+        ad[j] = sacc + ((w >> (8 * (j & 3))) & 0xFFu) * (ncol * 8u);
+    }
+    if (on) {
+        const double bl = p2_column<MODE>(a.c, k, cur, v);
+        if (a.has_rhs) bsum += bl;
+    }
+    if (r + DEPTH * SPLIT < nrows) {  // (uniform in the warp)
+        const unsigned rn = ra + (unsigned)(DEPTH * SPLIT) * 128u;
+        p2_load_rec<MODE>(a.rec, lds32(rn), (lds32(rn + 3u * pst) >> 16) & 0xFu, a.has_rhs, cur);
+    }
+#ifdef P2_DBG_NOACC
+    if (on) {  // timing experiment: no shared-memory accumulation
+        double t = 0.0;
+#pragma unroll
+        for (int j = 0; j < 10; j++) t += v[j];
+        bsum += t;
+        if (t == 123.456) sts64(ad[0], t);
+    }
+    return;
+#endif
+    if (SPLIT == 1) {
+        if (on) {
+            double o[10];
+#pragma unroll
+            for (int j = 0; j < 10; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
+#pragma unroll
+            for (int j = 0; j < 10; j++) sts64(ad[j], o[j] + v[j]);
+        }
+    } else {
+#pragma unroll 1
+        for (int ph = 0; ph < SPLIT; ph++) {
+            if (on && (int)warp == ph) {
+                double o[10];
+#pragma unroll
+                for (int j = 0; j < 10; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
+#pragma unroll
+                for (int j = 0; j < 10; j++) sts64(ad[j], o[j] + v[j]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// SPLIT = 1: one thread per column, 4 slices (warps) per CTA.  SPLIT = 4: one slice per CTA, warp w takes the visits
+// r = w (mod 4) and the shared-memory accumulation is serialised in visit order between barriers (same sums in the same
+// order as one thread per column).  Requires a complete map in role order, no value filter, no slot tracking.
+// Latency plan (the visit chain map entry -> record -> accumulate is what bounds this kernel, not a throughput): the slice's
+// whole map comes in with four bulk copies (cp.async.bulk + mbarrier, one memory latency for all visits), then every
+// record the slice will read is prefetched into L2 at once, and the visit loop loads records one visit ahead.
+// dynamic shared memory: [4 mbarriers | pad to 128 B][acc: maxlen x ncol doubles][map planes: (4 warps x) 4 x maxrows x 128 B]
+template <int SPLIT, int MODE>
+__global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gather(const P2Args a) {
+    constexpr unsigned ncol = 128 / SPLIT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double bpart[SPLIT == 1 ? 1 : 4][32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int64_t slice = a.slice_begin + (SPLIT == 1 ? (int64_t)blockIdx.x * 4 + warp : (int64_t)blockIdx.x);
+    if (SPLIT == 1 && slice >= a.slice_end) return;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned pst = (unsigned)a.maxrows * 128u;
+    const unsigned mbar = smem0 + (SPLIT == 1 ? warp : 0u) * 8u;
+    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * (ncol * 8u) + (SPLIT == 1 ? warp * 4u * pst : 0u);
+    const int64_t c = slice * 32 + lane;
+    const bool valid = c < a.ndofs;
+    const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
+    if (nrows > 0 && (SPLIT == 1 ? lane == 0 : tid == 0)) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)nrows * 128u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * 4u) : "memory");
+        const uint32_t* g = a.map + ((size_t)row0 << 5);
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst), "l"(g + (size_t)p * a.stride),
+                         "r"(bytes), "r"(mbar)
+                         : "memory");
+    }
+    const bool zero_first = __ldg(a.slice_zero + slice) != 0;
+    int64_t base = 0;
+    int len = 0;
+    if (valid) {
+        base = a.colptr[c] - 1;
+        len = (int)(a.colptr[c + 1] - 1 - base);
+    }
+    const unsigned sacc = smem0 + 128u + (SPLIT == 1 ? tid : lane) * 8u;
+    if (zero_first) {
+        for (int i = (SPLIT == 1 ? 0 : (int)warp); i < len; i += SPLIT) sts64(sacc + i * (ncol * 8u), 0.0);
+    }
+    if (SPLIT > 1) __syncthreads();
+    else __syncwarp();
+    const unsigned fmask = zero_first ? 0u : 0xFFFFFFFFu;  // zeroed accumulators: every visit adds
+    double bsum = 0.0;
+    const int niter = (nrows + SPLIT - 1) / SPLIT;
+    const int rfirst = (SPLIT == 1) ? 0 : (int)warp;
+    const unsigned sst = sstw + lane * 4u;
+    if (nrows > 0) {  // wait for the bulk copies (phase 0 of the barrier)
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+    }
+#ifndef P2_NO_PREFETCH
+    for (int r = rfirst + SPLIT; r < nrows; r += SPLIT) {  // every record of this lane's later visits -> L2, now
+        const unsigned k = (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu;
+        const double* p = a.rec + (size_t)lds32(sst + (unsigned)r * 128u) * P2_REC;
+        if (MODE == 0 || (MODE == 2 && k < 4u)) {
+            prefetch_l2(p + 4u * (k & 3u));
+        } else if (k != 0xFu) {
+            prefetch_l2(p + 16);
+            prefetch_l2(p + 20);
+            if (a.has_rhs && k >= 6u) prefetch_l2(p + 24);
+        }
+    }
+#endif
+    constexpr int DEPTH = MODE == 0 ? P2_DEPTH0 : P2_DEPTH;  // records in flight per lane (a vertex-dof record is 4 doubles, an edge-dof record 9)
+    double rec[DEPTH][9];
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) rec[u][i] = 0.0;
+        const int r = rfirst + u * SPLIT;
+        if (r < nrows) p2_load_rec<MODE>(a.rec, lds32(sst + (unsigned)r * 128u), (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu, a.has_rhs, rec[u]);
+    }
+    for (int it = 0; it < niter; it += DEPTH) {
+#pragma unroll
+        for (int u = 0; u < DEPTH; u++) {
+            if (u == 0 || it + u < niter) {  // (uniform in the CTA)
+                const int r = (it + u) * SPLIT + rfirst;
+                // (SPLIT = 4: a warp whose row index is past nrows only takes part in the barriers)
+                if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, sacc, fmask, warp, bsum);
+                else {
+#pragma unroll 1
+                    for (int ph = 0; ph < SPLIT; ph++) __syncthreads();
+                }
+            }
+        }
+    }
+    if (SPLIT > 1) {
+        bpart[warp][lane] = bsum;
+        __syncthreads();
+        bsum = ((bpart[0][lane] + bpart[1][lane]) + bpart[2][lane]) + bpart[3][lane];
+    }
+#ifdef P2_DBG_NOSTORE
+    if (bsum != 123.456) return;  // timing experiment: no write-out
+#endif
+    if (!valid) return;
+    double* out = a.nzval + base;
+    {
+        // write-out: a lane owns the contiguous entries of its column and stores them as whole 32-byte sectors between a
+        // scalar head and tail
+        const int w0 = (SPLIT == 1 ? 0 : (int)warp);
+        const int head = min(len, (int)((4 - (base & 3)) & 3));
+        const int ng = (len - head) >> 2;
+        const int tail0 = head + 4 * ng;
+        for (int i = w0; i < head; i += SPLIT) {
+            const double t = lds64(sacc + i * (ncol * 8u));
+            out[i] = a.acc_A ? out[i] + t : t;
+        }
+        for (int i = tail0 + w0; i < len; i += SPLIT) {
+            const double t = lds64(sacc + i * (ncol * 8u));
+            out[i] = a.acc_A ? out[i] + t : t;
+        }
+        for (int g = w0; g < ng; g += SPLIT) {
+            const int i = head + 4 * g;
+            double t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) t[u] = lds64(sacc + (i + u) * (ncol * 8u));
+            if (a.acc_A) {
+                double o0, o1, o2, o3;
+                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o0), "=d"(o1), "=d"(o2), "=d"(o3) : "l"(out + i));
+                t[0] += o0; t[1] += o1; t[2] += o2; t[3] += o3;
+            }
+            stg256(out + i, t[0], t[1], t[2], t[3]);
+        }
+    }
+    if (a.has_rhs && (SPLIT == 1 || warp == 0)) {
+        if (a.acc_b) a.bvec[c] += bsum;
+        else a.bvec[c] = bsum;
+    }
+}
+
+// per slice: bit 0 = holds vertex-dof visits, bit 1 = holds edge-dof visits (one warp per slice)
+__global__ void k_p2_slice_class(const uint32_t* __restrict__ kwords, const int32_t* __restrict__ slice_ptr, int64_t nslices, uint8_t* __restrict__ cls) {
+    const int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (slice >= nslices) return;
+    const int row0 = slice_ptr[slice], nrows = slice_ptr[slice + 1] - row0;
+    unsigned bits = 0u;
+    for (int r = 0; r < nrows; r++) {
+        const unsigned k = (kwords[((size_t)(row0 + r) << 5) + lane] >> 16) & 0xFu;
+        bits |= k < 4u ? 1u : (k < 10u ? 2u : 0u);
+    }
+    bits = __reduce_or_sync(0xFFFFFFFFu, bits);
+    if (lane == 0) cls[slice] = (uint8_t)bits;
+}
+
+}  // namespace
+
+// role permutation of the gather map (femb_pattern.cu applies it in place)
+void femb_p2_role_perm(uint8_t perm[12][12]) {
+    uint8_t p[10][10];
+    p2_role_perm(p);
+    for (int k = 0; k < 12; k++)
+        for (int r = 0; r < 12; r++) perm[k][r] = (k < 10 && r < 10) ? p[k][r] : (uint8_t)r;
+}
+
+// returns FEMB_ERR_UNSUPPORTED (no error message) when the closed form does not cover the space / rule / policy
+int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
+    static const bool enabled = [] { const char* e = getenv("FEMB_P2_CLOSED"); return !(e && e[0] == '0'); }();
+    if (!enabled) return FEMB_ERR_UNSUPPORTED;
+    const FembEval& EG = ctx->evals[eg];
+    const FembSpace& s = ctx->spaces[EG.space];
+    FembHMap& H = ctx->hm;
+    if (ctx->dim != 3 || s.nd != 10 || s.ncomp != 1 || !H.map || H.space != EG.space || !H.complete || ctx->touched || drop_tol > 0.0) return FEMB_ERR_UNSUPPORTED;
+    if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * 3) return FEMB_ERR_UNSUPPORTED;
+    if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return FEMB_ERR_UNSUPPORTED;
+    const FembEval* EI = rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr;
+    if (EI && EI->h_refvals.size() != (size_t)EG.nqp * s.nd_all) return FEMB_ERR_UNSUPPORTED;
+    // exact integrals of the P2 shape-function products on a tetrahedron (int lambda_a lambda_b = |T| / 20, int lambda_a^2 = |T| / 10)
+    const P2Const cst = {0.6, -0.2, 0.6, -0.2, 1.6, 0.8};
+    {
+        // accept the closed form only if it reproduces  sum_q w_q D_q[:,j]^T K D_q[:,k]  of the evaluator's tables (Example200:139-146)
+        const double K[3][3] = {{1.3, -0.21, 0.17}, {-0.21, 0.9, 0.33}, {0.17, 0.33, 1.1}};
+        const double G6[6] = {-((K[0][0] + K[0][1]) + K[0][2]), -((K[0][1] + K[1][1]) + K[1][2]), -((K[0][2] + K[1][2]) + K[2][2]), K[0][1], K[0][2], K[1][2]};
+        uint8_t perm[10][10];
+        p2_role_perm(perm);
+        for (int k = 0; k < 10; k++) {
+            double v[10];
+            p2_column_closed(cst, G6, k, v);
+            for (int r = 0; r < 10; r++) {
+                const int j = perm[k][r];
+                double ref = 0.0;
+                for (int q = 0; q < EG.nqp; q++)
+                    for (int aa = 0; aa < 3; aa++)
+                        for (int b = 0; b < 3; b++)
+                            ref += EG.w[q] * EG.h_refderivs[((size_t)q * s.nd_all + j) * 3 + aa] * K[aa][b] * EG.h_refderivs[((size_t)q * s.nd_all + k) * 3 + b];
+                if (fabs(ref - v[r]) > 1e-13) return FEMB_ERR_UNSUPPORTED;
+            }
+        }
+    }
+    if (!ctx->p2rec) FEMB_TRY(femb_alloc(ctx, &ctx->p2rec, (size_t)ctx->ncells * P2_REC));
+    if (ctx->ncells == 0) return FEMB_OK;
+    FEMB_TRY(femb_hmap_set_canon(ctx, H, true));
+    P2Wphi wp;
+    for (int q = 0; q < FEMB_COEF_STRIDE - 6; q++)
+        for (int j = 0; j < 10; j++) wp.v[q][j] = (EI && q < EG.nqp) ? EG.w[q] * EI->h_refvals[(size_t)q * s.nd_all + j] : 0.0;
+    QuadDev q = quad_dev(EG, 3);
+    k_cell_p2rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec);
+    KERNEL_CHECK(ctx);
+    P2Args a;
+    a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
+    a.nzval = ctx->nzval; a.bvec = ctx->bvec;
+    a.acc_A = ctx->zero_pending_A ? 0 : 1;
+    a.acc_b = ctx->zero_pending_b ? 0 : 1;
+    a.has_rhs = rhs.kind != FEMB_RHS_NONE;
+    a.slice_begin = a.slice_end = 0;
+    a.c = cst;
+    ctx->zero_pending_A = false;
+    if (a.has_rhs) ctx->zero_pending_b = false;
+    if (H.cranges.empty()) {
+        // cut the launch ranges where the kind of dof changes (vertex dofs | the slice that holds both | edge dofs): the
+        // kernels are specialised per kind (MODE), which keeps the vertex-dof kernel at one 32-byte record load per visit
+        const int64_t nslices = (s.ndofs + 31) / 32;
+        uint8_t* d_cls = nullptr;
+        FEMB_TRY(femb_alloc(ctx, &d_cls, (size_t)nslices));
+        k_p2_slice_class<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(H.map + 3 * H.stride, H.slice_ptr, nslices, d_cls);
+        ctx->launches++;
+        std::vector<uint8_t> cls((size_t)nslices);
+        cudaError_t e = cudaMemcpyAsync(cls.data(), d_cls, (size_t)nslices, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        femb_free(&d_cls);
+        CUDA_TRY(ctx, e);
+        std::vector<int32_t> hptr((size_t)nslices + 1);
+        CUDA_TRY(ctx, cudaMemcpy(hptr.data(), H.slice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost));
+        auto kind = [&](int64_t sl) { return cls[sl] == 1 ? 0 : (cls[sl] == 2 ? 1 : 2); };
+        std::vector<FembHMap::Range> out;
+        for (auto& r : H.ranges) {
+            for (int64_t sl = r.s0; sl < r.s1;) {
+                const int mode = kind(sl);
+                int64_t e1 = sl + 1;
+                while (e1 < r.s1 && kind(e1) == mode) e1++;
+                FembHMap::Range c = r;
+                c.s0 = sl; c.s1 = e1; c.mode = mode;
+                out.push_back(c);
+                sl = e1;
+            }
+        }
+        if (out.size() > 64) {  // dof kinds interleaved: one launch per original range with the general variant
+            out = H.ranges;
+            for (auto& c : out) c.mode = 2;
+        }
+        for (auto& c : out) {
+            c.maxrows = 1;
+            for (int64_t sl = c.s0; sl < c.s1; sl++) c.maxrows = std::max(c.maxrows, hptr[sl + 1] - hptr[sl]);
+        }
+        H.cranges = out;
+    }
+    {
+        const void* kern[2][3] = {{(const void*)k_p2_gather<1, 0>, (const void*)k_p2_gather<1, 1>, (const void*)k_p2_gather<1, 2>},
+                                  {(const void*)k_p2_gather<4, 0>, (const void*)k_p2_gather<4, 1>, (const void*)k_p2_gather<4, 2>}};
+        auto smem_of = [](const FembHMap::Range& r) {
+            const size_t ncol = r.split == 4 ? 32 : 128, nstage = r.split == 4 ? 1 : 4;
+            return 128 + (size_t)std::max(1, r.maxlen) * ncol * sizeof(double) + nstage * 4 * (size_t)r.maxrows * 128;
+        };
+        size_t need[2][3] = {{0, 0, 0}, {0, 0, 0}};
+        for (auto& r : H.cranges) need[r.split == 4][r.mode] = std::max(need[r.split == 4][r.mode], smem_of(r));
+        for (int sp = 0; sp < 2; sp++)
+            for (int m = 0; m < 3; m++) {
+                if (need[sp][m] > 200 * 1024) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "P2 gather: columns too long for the shared-memory accumulators");
+                if (!need[sp][m]) continue;
+                CUDA_TRY(ctx, cudaFuncSetAttribute(kern[sp][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[sp][m]));
+                CUDA_TRY(ctx, cudaFuncSetAttribute(kern[sp][m], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
+        for (auto& r : H.cranges) {
+            if (r.s1 <= r.s0) continue;
+            a.slice_begin = r.s0;
+            a.slice_end = r.s1;
+            a.maxlen = std::max(1, r.maxlen);
+            a.maxrows = r.maxrows;
+            void* params[1] = {(void*)&a};
+            const unsigned grid = r.split == 4 ? (unsigned)(r.s1 - r.s0) : (unsigned)((r.s1 - r.s0 + 3) / 4);
+            CUDA_TRY(ctx, cudaLaunchKernel(kern[r.split == 4][r.mode], dim3(grid), dim3(128), params, smem_of(r), ctx->stream));
+            KERNEL_CHECK(ctx);
+        }
+    }
+    return FEMB_OK;
+}

@@ -29,6 +29,7 @@ void femb_free_pattern(femb_ctx* ctx) {
     femb_free_hmap(ctx->hm);
     femb_free_hmap(ctx->hm_vec);
     femb_free(&ctx->cellcoef);
+    femb_free(&ctx->p2rec);
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
     ctx->nnz = 0;
@@ -822,7 +823,49 @@ void femb_free_hmap(FembHMap& H) {
     femb_free(&H.slice_zero);
     H.stride = 0;
     H.space = -1;
+    H.canon = false;
     H.ranges.clear();
+    H.cranges.clear();
+}
+
+// in-place permutation of the position bytes and first-touch flags of every map entry: role order <-> local dof order
+struct HPerm {
+    uint8_t p[12][12];
+};
+__global__ void k_hmap_canon(uint32_t* __restrict__ hmap, size_t stride, int nds, int nwords, HPerm perm, int inverse) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= stride) return;
+    uint32_t w[3] = {0u, 0u, 0u}, o[3] = {0u, 0u, 0u};
+    for (int wd = 0; wd < nwords; wd++) w[wd] = hmap[(1 + wd) * stride + idx];
+    const uint32_t k = (w[nwords - 1] >> 16) & 0xFu;
+    if (k == 0xFu) return;  // padding entry
+    const uint32_t first = w[nwords - 1] >> 20;
+    uint32_t nfirst = 0u;
+    for (int wd = 0; wd < nwords; wd++) o[wd] = w[wd];
+    for (int r = 0; r < nds; r++) {
+        const int j = perm.p[k][r];
+        const int src = inverse ? r : j, dst = inverse ? j : r;
+        const uint32_t b = (w[src >> 2] >> (8 * (src & 3))) & 0xFFu;
+        o[dst >> 2] = (o[dst >> 2] & ~(0xFFu << (8 * (dst & 3)))) | (b << (8 * (dst & 3)));
+        nfirst |= ((first >> src) & 1u) << dst;
+    }
+    o[nwords - 1] = (o[nwords - 1] & 0xFFFFu) | (k << 16) | (nfirst << 20);
+    for (int wd = 0; wd < nwords; wd++) hmap[(1 + wd) * stride + idx] = o[wd];
+}
+
+int femb_hmap_set_canon(femb_ctx* ctx, FembHMap& H, bool canon) {
+    if (!H.map || H.canon == canon) return FEMB_OK;
+    const FembSpace& s = ctx->spaces[H.space];
+    const int nds = s.nd / s.ncomp;
+    if (nds != 10 || H.words != 3) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "role order exists for P2 on tetrahedra only");
+    HPerm perm;
+    femb_p2_role_perm(perm.p);
+    if (H.stride) {
+        k_hmap_canon<<<(unsigned)((H.stride + 255) / 256), 256, 0, ctx->stream>>>(H.map, H.stride, nds, H.words, perm, canon ? 0 : 1);
+        KERNEL_CHECK(ctx);
+    }
+    H.canon = canon;
+    return FEMB_OK;
 }
 
 // builds the map of the (component-diagonal part of the) square block of space `sid` whose rows / columns start at row_off / col_off

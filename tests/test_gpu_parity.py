@@ -1042,3 +1042,38 @@ def test_device_interpolation_matches_oracle(dim, ncomp, kind):
     c2.dirichlet_apply(True, 0, None, None, 1.0e60)
     b = c2.vector_get(fes.ndofs)
     assert np.abs(b * 1.0e-60 - ref).max() <= RTOL * max(np.abs(want).max(), 1.0)
+
+
+def test_p2_3d_closed_form_and_quadrature_kernels_agree():
+    """H1P2{1,3}: the closed-form gather (femb_p2.cu; gather map in role order) and the general quadrature gather
+    (femb_h1.cu; local dof order — taken when the 1e-15 value filter of Example200:150 is on) run on the SAME context one
+    after the other; the map is re-ordered in place between them and both match the oracle."""
+    from femb_b200.assembly import _Session
+
+    grid = _grid3d(7, True)
+    fes = fb.FESpace(fb.H1P2(1, 3), grid)
+    qf = fb.QuadratureRule(grid.geometry, 2)
+    S = _Session([fes], qf)
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    ctx.pattern_build([(0, 0)])
+    p = np.array([0.25, 1.0, -1.0, 0.5])
+    rhs = fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]])
+    colptr, rowval, nzref, bref = orc.example200_assemble(_oracle_el(fb.H1P2(1, 3)), grid.geometry, grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"],
+                                                           fes["CellDofs"], fes.ndofs, 0.7, rhs)
+    cp, rv = ctx.pattern_get(fes.ndofs)
+    ref = {(int(r), c): v for c in range(fes.ndofs) for r, v in zip(rowval[colptr[c] - 1:colptr[c + 1] - 1], nzref[colptr[c] - 1:colptr[c + 1] - 1])}
+    scale = np.abs(nzref).max()
+    results = []
+    for drop_tol in (0.0, 1.0e-15, 0.0, -1.0):
+        ctx.matrix_zero()
+        ctx.vector_zero()
+        ctx.assemble_poisson(eg._eid, ei._eid, 0.7, _lib.RHS_AFFINE, p, drop_tol)
+        nz, b = ctx.matrix_get(), ctx.vector_get(fes.ndofs)
+        results.append(nz)
+        assert np.abs(b - bref).max() <= RTOL * np.abs(bref).max()
+        for c in range(0, fes.ndofs, 3):
+            for r, v in zip(rv[cp[c] - 1:cp[c + 1] - 1], nz[cp[c] - 1:cp[c + 1] - 1]):
+                assert abs(v - ref.get((int(r), c), 0.0)) <= RTOL * scale
+    assert np.array_equal(results[0], results[2])  # bit-reproducible across the re-ordering of the map
+    assert np.abs(results[0] - results[1]).max() <= RTOL * scale
