@@ -30,7 +30,9 @@ namespace {
 #define P2_MINB0 4
 #endif
 
-constexpr int P2_REC = 32;  // doubles per cell (28 used; the vertex part and the edge part are one aligned 128-byte line each): 4 vertex sectors [G_k,o1 G_k,o2 G_k,o3 bl_k], [G01 G02 G03 G12] [G13 G23 bl4 bl5] [bl6 bl7 bl8 bl9]
+// doubles per cell (the vertex part and the edge part are one aligned 128-byte line each): 4 vertex sectors [G_k,o1 G_k,o2 G_k,o3 bl_k],
+// then [G01 G02 G03 G12] and three sectors [G13 G23 bl_a bl_b], (a b) = (4 5) (6 7) (8 9): edge dof 4 + e reads sectors 4 and 5 + e / 2
+constexpr int P2_REC = 32;
 
 struct P2Const {
     double alpha, beta, gd, go, mus, mud;
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(128) k_cell_p2rec(const double* __restrict__ c
         o[12] = G03; o[13] = G13; o[14] = G23; o[15] = bl[3];
         o[16] = G01; o[17] = G02; o[18] = G03; o[19] = G12;
         o[20] = G13; o[21] = G23; o[22] = bl[4]; o[23] = bl[5];
-        o[24] = bl[6]; o[25] = bl[7]; o[26] = bl[8]; o[27] = bl[9];
-        o[28] = o[29] = o[30] = o[31] = 0.0;
+        o[24] = G13; o[25] = G23; o[26] = bl[6]; o[27] = bl[7];
+        o[28] = G13; o[29] = G23; o[30] = bl[8]; o[31] = bl[9];
     }
     __syncthreads();
     const int64_t nloc = min((int64_t)128, ncells - cell0);
@@ -198,10 +200,10 @@ __global__ void __launch_bounds__(128) k_cell_p2rec(const double* __restrict__ c
 }
 
 // record pieces of a visit, loaded one visit ahead.  MODE 0: slices of vertex dofs only (r[0..3] = the dof's sector), MODE 1:
-// edge dofs only (r[0..7] = the six G + bl4 bl5, r[8] = bl_k for k >= 6), MODE 2: any.  The wide loads are unconditional
+// edge dofs only (r[0..5] = the six G, r[6 + (k & 1)] = bl_k), MODE 2: any.  The wide loads are unconditional
 // (padding entries point at cell 0): a conditionally written destination would need a copy that waits for the load.
 template <int MODE>
-__device__ __forceinline__ void p2_load_rec(const double* __restrict__ rec, unsigned cell, unsigned k, int has_rhs, double (&r)[9]) {
+__device__ __forceinline__ void p2_load_rec(const double* __restrict__ rec, unsigned cell, unsigned k, int has_rhs, double (&r)[8]) {
 #ifdef P2_DBG_REC
     cell &= 1023u;  // timing experiment: every record load hits the cache
 #endif
@@ -210,14 +212,13 @@ __device__ __forceinline__ void p2_load_rec(const double* __restrict__ rec, unsi
         ldg256(p + 4u * (k & 3u), r[0], r[1], r[2], r[3]);
     } else {
         ldg256(p + ((MODE == 2 && k < 4u) ? 4u * k : 16u), r[0], r[1], r[2], r[3]);
-        ldg256(p + 20, r[4], r[5], r[6], r[7]);
-        if (has_rhs && k - 6u < 4u) r[8] = __ldg(p + 18 + k);
+        ldg256(p + 20 + 4u * min(((k - 4u) >> 1) & 3u, 2u), r[4], r[5], r[6], r[7]);
     }
 }
 
 // the ten entries of the visit's local column in role order (p2_column_closed) and the local rhs entry
 template <int MODE>
-__device__ __forceinline__ double p2_column(const P2Const& c, unsigned k, const double (&r)[9], double (&v)[10]) {
+__device__ __forceinline__ double p2_column(const P2Const& c, unsigned k, const double (&r)[8], double (&v)[10]) {
     if (MODE == 0 || (MODE == 2 && k < 4u)) {
         const double g1 = r[0], g2 = r[1], g3 = r[2], gkk = -((g1 + g2) + g3);
         v[0] = c.alpha * gkk;
@@ -230,16 +231,16 @@ __device__ __forceinline__ double p2_column(const P2Const& c, unsigned k, const 
     // (selp: the local edge number differs from lane to lane, branches would serialise the warp)
     const unsigned e = k - 4u;
     double g0, g1, g2, g3, g4, bl;
-    asm("{\n\t.reg .pred p0, p1, p2, p3, p4, p5, po, l2, l3;\n\t.reg .f64 t0, t1, t2, t3;\n\t"
+    asm("{\n\t.reg .pred p0, p1, p2, p3, p4, p5, po, l2, l3;\n\t.reg .f64 t0, t1, t2, t3;\n\t.reg .b32 tq;\n\t"
         "setp.eq.u32 p0, %6, 0;\n\tsetp.eq.u32 p1, %6, 1;\n\tsetp.eq.u32 p2, %6, 2;\n\tsetp.eq.u32 p3, %6, 3;\n\tsetp.eq.u32 p4, %6, 4;\n\tsetp.eq.u32 p5, %6, 5;\n\t"
         "setp.lt.u32 l2, %6, 2;\n\tsetp.lt.u32 l3, %6, 3;\n\tor.pred po, p0, p5;\n\t"
         "selp.f64 t0, %8, %9, p1;\n\tselp.f64 t0, %7, t0, p0;\n\tselp.f64 t1, %11, %12, p4;\n\tselp.f64 t1, %10, t1, p3;\n\tselp.f64 %0, t0, t1, l3;\n\t"
         "selp.f64 %1, %8, %7, po;\n\tselp.f64 %4, %11, %12, po;\n\t"
         "selp.f64 t2, %11, %10, p3;\n\tselp.f64 t2, %8, t2, p2;\n\tselp.f64 %2, %9, t2, l2;\n\t"
         "selp.f64 t3, %8, %9, p3;\n\tselp.f64 t3, %11, t3, p2;\n\tselp.f64 %3, %10, t3, l2;\n\t"
-        "selp.f64 t0, %14, %15, p1;\n\tselp.f64 %5, %13, t0, p0;\n\t}"
+        "and.b32 tq, %6, 1;\n\tsetp.ne.u32 p1, tq, 0;\n\tselp.f64 %5, %14, %13, p1;\n\t}"
         : "=d"(g0), "=d"(g1), "=d"(g2), "=d"(g3), "=d"(g4), "=d"(bl)
-        : "r"(e), "d"(r[0]), "d"(r[1]), "d"(r[2]), "d"(r[3]), "d"(r[4]), "d"(r[5]), "d"(r[6]), "d"(r[7]), "d"(r[8]));
+        : "r"(e), "d"(r[0]), "d"(r[1]), "d"(r[2]), "d"(r[3]), "d"(r[4]), "d"(r[5]), "d"(r[6]), "d"(r[7]));
     const double gii = -((g0 + g1) + g2), gjj = -((g0 + g3) + g4);
     v[0] = c.gd * g0 + c.go * gii; v[1] = c.gd * g0 + c.go * gjj;
     v[2] = c.go * (g1 + g3); v[3] = c.go * (g2 + g4);
@@ -261,8 +262,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // DEPTH visits ahead into the same registers (the caller unrolls over a ring of DEPTH buffers: no register copies).  The
 // map entries of all visits sit in shared memory (sst: this lane's column of the staged planes, pst: plane stride).
 template <int SPLIT, int MODE, int DEPTH>
-__device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[9], int r, int nrows, unsigned sst, unsigned pst, unsigned sacc, unsigned fmask, unsigned warp,
-                                         double& bsum) {
+__device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int r, int nrows, unsigned sst, unsigned pst, unsigned sacc, unsigned fmask, unsigned warp,
+                                         double& bsum, double (&racc)[3], unsigned (&rad)[3]) {
     constexpr unsigned ncol = 128 / SPLIT;
     const unsigned ra = sst + (unsigned)r * 128u;
     const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst), wc = lds32(ra + 3u * pst);
@@ -294,7 +295,26 @@ __device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[9], int 
     }
     return;
 #endif
-    if (SPLIT == 1) {
+    if (SPLIT == 1 && MODE == 1) {
+        // edge column (i j): the rows of its two vertices and its own row get a contribution from EVERY visit -> they are
+        // summed in registers (lower / higher global row: the CSC positions are ascending in the row, so comparing them
+        // orders the endpoints) and stored once after the last visit; seven accumulations per visit go through shared memory
+        if (on) {
+            const bool sw = ad[0] > ad[1];
+            racc[0] += sw ? v[1] : v[0];
+            racc[1] += sw ? v[0] : v[1];
+            racc[2] += v[4];
+            rad[0] = sw ? ad[1] : ad[0];
+            rad[1] = sw ? ad[0] : ad[1];
+            rad[2] = ad[4];
+            constexpr int J[7] = {2, 3, 5, 6, 7, 8, 9};
+            double o[7];
+#pragma unroll
+            for (int t = 0; t < 7; t++) o[t] = lds64_unless(ad[J[t]], (first >> J[t]) & 1u);
+#pragma unroll
+            for (int t = 0; t < 7; t++) sts64(ad[J[t]], o[t] + v[J[t]]);
+        }
+    } else if (SPLIT == 1) {
         if (on) {
             double o[10];
 #pragma unroll
@@ -382,33 +402,38 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
             prefetch_l2(p + 4u * (k & 3u));
         } else if (k != 0xFu) {
             prefetch_l2(p + 16);
-            prefetch_l2(p + 20);
-            if (a.has_rhs && k >= 6u) prefetch_l2(p + 24);
+            prefetch_l2(p + 20 + 4u * min(((k - 4u) >> 1) & 3u, 2u));
         }
     }
 #endif
     constexpr int DEPTH = MODE == 0 ? P2_DEPTH0 : P2_DEPTH;  // records in flight per lane (a vertex-dof record is 4 doubles, an edge-dof record 9)
-    double rec[DEPTH][9];
+    double rec[DEPTH][8];
 #pragma unroll
     for (int u = 0; u < DEPTH; u++) {
 #pragma unroll
-        for (int i = 0; i < 9; i++) rec[u][i] = 0.0;
+        for (int i = 0; i < 8; i++) rec[u][i] = 0.0;
         const int r = rfirst + u * SPLIT;
         if (r < nrows) p2_load_rec<MODE>(a.rec, lds32(sst + (unsigned)r * 128u), (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu, a.has_rhs, rec[u]);
     }
+    double racc[3] = {0.0, 0.0, 0.0};
+    unsigned rad[3] = {0u, 0u, 0u};
     for (int it = 0; it < niter; it += DEPTH) {
 #pragma unroll
         for (int u = 0; u < DEPTH; u++) {
             if (u == 0 || it + u < niter) {  // (uniform in the CTA)
                 const int r = (it + u) * SPLIT + rfirst;
                 // (SPLIT = 4: a warp whose row index is past nrows only takes part in the barriers)
-                if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, sacc, fmask, warp, bsum);
+                if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, sacc, fmask, warp, bsum, racc, rad);
                 else {
 #pragma unroll 1
                     for (int ph = 0; ph < SPLIT; ph++) __syncthreads();
                 }
             }
         }
+    }
+    if (SPLIT == 1 && MODE == 1 && rad[2] != 0u) {  // (a column with at least one visit)
+#pragma unroll
+        for (int t = 0; t < 3; t++) sts64(rad[t], racc[t]);
     }
     if (SPLIT > 1) {
         bpart[warp][lane] = bsum;
