@@ -416,7 +416,7 @@ def leg_c3(D, args, m):
                                   f"= {grid.ncells} per GPU", "ndofs_local": int(fes.ndofs), "nnz_local": int(nnz), "exchange_bytes_rank0": int(xbytes),
                       "l2": "far larger than L2 (%.1f GB/step)" % (bpc * grid.ncells / 1e9)},
            "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4), "kernel_ms": round(kms, 4),
-                        "algorithmic_bytes_per_cell": round(bpc, 1), "peak_source": src, "kernel": "k_cell_coef + k_h1_gather (vertex / edge column ranges)",
+                        "algorithmic_bytes_per_cell": round(bpc, 1), "peak_source": src, "kernel": "k_cell_p2rec + k_p2_gather (closed-form P2, vertex / edge column ranges)",
                         "traffic": None},
            "roofline_fp64": {"bound": "fp64", "achieved": round(tfl, 2), "peak": f64, "unit": "TFLOP/s", "frac": round(tfl / f64, 4),
                              "flops_per_cell": FLOPS_C3, "peak_source": "tools/fp64_peak.cu (DFMA), profiles/r01_fp64_peak.json"}}

@@ -443,28 +443,41 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
 #ifdef P2_DBG_NOSTORE
     if (bsum != 123.456) return;  // timing experiment: no write-out
 #endif
+    // write-out.  The 32 columns of the slice are one contiguous range of nzval; every aligned 32-byte sector of it is
+    // stored by exactly one lane (st.global.v4.f64): the lane whose column holds the sector's first entry — it reads the
+    // entries that belong to the next column from that column's accumulators.  Only the head of the slice's first column
+    // and the tail of its last one are scalar stores (the neighbouring slice owns the rest of those sectors).
+    if (SPLIT == 1) __syncwarp();  // (SPLIT = 4: the barrier above)
+    const int len_next = __shfl_down_sync(0xFFFFFFFFu, len, 1);
+    const int len_prev = __shfl_up_sync(0xFFFFFFFFu, len, 1);
     if (!valid) return;
     double* out = a.nzval + base;
     {
-        // write-out: a lane owns the contiguous entries of its column and stores them as whole 32-byte sectors between a
-        // scalar head and tail
         const int w0 = (SPLIT == 1 ? 0 : (int)warp);
-        const int head = min(len, (int)((4 - (base & 3)) & 3));
-        const int ng = (len - head) >> 2;
-        const int tail0 = head + 4 * ng;
-        for (int i = w0; i < head; i += SPLIT) {
-            const double t = lds64(sacc + i * (ncol * 8u));
-            out[i] = a.acc_A ? out[i] + t : t;
+        const int head = min(len, (int)((4 - (base & 3)) & 3));  // entries before the first sector that starts in this column
+        // the previous lane stores the head when it has a column of its own that ends where this one begins (a straddling
+        // sector) and this column holds all the sector's remaining entries
+        const bool head_by_prev = lane > 0 && len_prev > 0 && head > 0 && len >= head;
+        if (!head_by_prev && w0 == 0) {
+            for (int i = 0; i < head; i++) {
+                const double t = lds64(sacc + i * (ncol * 8u));
+                out[i] = a.acc_A ? out[i] + t : t;
+            }
         }
-        for (int i = tail0 + w0; i < len; i += SPLIT) {
-            const double t = lds64(sacc + i * (ncol * 8u));
-            out[i] = a.acc_A ? out[i] + t : t;
-        }
-        for (int g = w0; g < ng; g += SPLIT) {
+        const int nsec = (len - head + 3) >> 2;  // sectors that start in this column (the last one may straddle)
+        for (int g = w0; g < nsec; g += SPLIT) {
             const int i = head + 4 * g;
+            const int own = min(4, len - i);  // entries of the sector in this column
+            if (own < 4 && !(lane < 31 && len_next >= 4 - own)) {  // nobody to complete the sector with: scalar tail
+                for (int u = 0; u < own; u++) {
+                    const double t = lds64(sacc + (i + u) * (ncol * 8u));
+                    out[i + u] = a.acc_A ? out[i + u] + t : t;
+                }
+                continue;
+            }
             double t[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) t[u] = lds64(sacc + (i + u) * (ncol * 8u));
+            for (int u = 0; u < 4; u++) t[u] = lds64(u < own ? sacc + (i + u) * (ncol * 8u) : sacc + 8u + (u - own) * (ncol * 8u));
             if (a.acc_A) {
                 double o0, o1, o2, o3;
                 asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o0), "=d"(o1), "=d"(o2), "=d"(o3) : "l"(out + i));
