@@ -809,12 +809,18 @@ int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu) {
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
     if (s.ncomp < 2 || ctx->touched || EG.nqp > 10) return FEMB_ERR_UNSUPPORTED;
+    {
+        // P2 on triangles: closed-form kernel (femb_p2.cu)
+        const int st2 = launch_p2_gather_vec(ctx, eg, mu);
+        if (st2 != FEMB_ERR_UNSUPPORTED) return st2;
+    }
     if (EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * s.ncomp * ctx->dim) return FEMB_ERR_UNSUPPORTED;
     const int nds = s.nd / s.ncomp;
     const int key = ctx->dim * 10000 + nds * 100 + EG.nqp;
     if (key != 20603 && key != 20609 && key != 31004) return FEMB_ERR_UNSUPPORTED;
     int st = femb_build_hmap_vec(ctx);
     if (st != FEMB_OK) return st;
+    FEMB_TRY(femb_hmap_set_canon(ctx, ctx->hm_vec, false));
     const FembHMap& H = ctx->hm_vec;
     if (H.space != EG.space) return FEMB_ERR_UNSUPPORTED;
     if (!ctx->cellcoef) FEMB_TRY(femb_alloc(ctx, &ctx->cellcoef, (size_t)ctx->ncells * FEMB_COEF_STRIDE));

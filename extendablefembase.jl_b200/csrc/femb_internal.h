@@ -274,7 +274,7 @@ int femb_build_hmap(femb_ctx* ctx);
 int femb_build_hmap_vec(femb_ctx* ctx);  // lazy: component-diagonal map of block (0,0) of a vector-valued H1 space
 void femb_free_hmap(FembHMap& H);
 int femb_hmap_set_canon(femb_ctx* ctx, FembHMap& H, bool canon);  // permutes the map entries in place between local dof order and P2 role order
-void femb_p2_role_perm(uint8_t perm[12][12]);                      // femb_p2.cu: perm[k][role] = local dof
+void femb_p2_role_perm(uint8_t perm[12][12], int dim);             // femb_p2.cu: perm[k][role] = local dof
 #define FEMB_COEF_STRIDE 16  // doubles per cell in femb_ctx::cellcoef (6 + up to 10 quadrature points)
 void femb_free_pattern(femb_ctx* ctx);
 void femb_free_space(FembSpace& s);

@@ -59,3 +59,4 @@ int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
 int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu);
 // femb_p2.cu (FEMB_ERR_UNSUPPORTED, without an error message, when the closed form does not apply)
 int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol);
+int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu);

@@ -15,6 +15,15 @@
 
 #include "femb_kernels.cuh"
 
+#include <cstdio>
+// FEMB_P2_DEBUG=1: say why the closed-form path declined (it falls back silently otherwise)
+static int p2_unsupported(int line) {
+    static const bool dbg = [] { const char* e = getenv("FEMB_P2_DEBUG"); return e && e[0] == '1'; }();
+    if (dbg) fprintf(stderr, "femb_p2.cu:%d: closed-form P2 path not taken\n", line);
+    return FEMB_ERR_UNSUPPORTED;
+}
+#define P2_UNSUPPORTED p2_unsupported(__LINE__)
+
 namespace {
 
 #ifndef P2_MINB
@@ -507,28 +516,390 @@ __global__ void k_p2_slice_class(const uint32_t* __restrict__ kwords, const int3
     if (lane == 0) cls[slice] = (uint8_t)bits;
 }
 
+// ===================================================================================================
+// P2 on triangles (scalar, or one component of a component-blocked vector space: the Laplacian of Example210:284-290,368).
+// Same construction with three G (01 02 12): every visit — vertex or edge dof — needs ONE 32-byte sector that the pre-pass
+// writes in role order (vertex k: [G_k,o1 G_k,o2 bl_k -], edge (i j), other k: [G_ij G_ik G_jk bl]), so the numeric kernel has
+// no selects at all.  Local edges (h1_p2.jl / ExtendableGrids): e0 = (0 1), e1 = (1 2), e2 = (0 2).
+// ===================================================================================================
+constexpr int P2_REC2 = 24;  // doubles per cell: six sectors
+
+constexpr int edge_of2(int a, int b) { return a == 0 ? (b == 1 ? 0 : 2) : 1; }
+
+void p2_role_perm2(uint8_t perm[6][6]) {
+    auto E = [](int a, int b) { return 3 + (a < b ? edge_of2(a, b) : edge_of2(b, a)); };
+    for (int k = 0; k < 3; k++) {
+        const int o1 = k == 0 ? 1 : 0, o2 = k == 2 ? 1 : 2;
+        const int r[6] = {k, o1, o2, E(k, o1), E(k, o2), E(o1, o2)};
+        for (int i = 0; i < 6; i++) perm[k][i] = (uint8_t)r[i];
+    }
+    const int ea[3] = {0, 1, 0}, eb[3] = {1, 2, 2};
+    for (int e = 0; e < 3; e++) {
+        const int i = ea[e], j = eb[e], k = 3 - i - j;
+        const int r[6] = {i, j, k, E(i, j), E(i, k), E(j, k)};
+        for (int t = 0; t < 6; t++) perm[3 + e][t] = (uint8_t)r[t];
+    }
+}
+
+// host mirror of the device formulas (launch-time check against the quadrature tables); G3 by local edge = (G01 G12 G02)
+void p2_column_closed2(const P2Const& c, const double G3[3], int k, double v[6]) {
+    auto G = [&](int a, int b) { return G3[a < b ? edge_of2(a, b) : edge_of2(b, a)]; };
+    if (k < 3) {
+        const int o1 = k == 0 ? 1 : 0, o2 = k == 2 ? 1 : 2;
+        const double g1 = G(k, o1), g2 = G(k, o2), gkk = -(g1 + g2);
+        v[0] = c.alpha * gkk;
+        v[1] = c.beta * g1; v[2] = c.beta * g2;
+        v[3] = c.gd * g1 + c.go * gkk; v[4] = c.gd * g2 + c.go * gkk;
+        v[5] = c.go * (g1 + g2);
+    } else {
+        const int ea[3] = {0, 1, 0}, eb[3] = {1, 2, 2};
+        const int i = ea[k - 3], j = eb[k - 3], o = 3 - i - j;
+        const double g0 = G(i, j), g1 = G(i, o), g3 = G(j, o), gii = -(g0 + g1), gjj = -(g0 + g3);
+        v[0] = c.gd * g0 + c.go * gii; v[1] = c.gd * g0 + c.go * gjj;
+        v[2] = c.go * (g1 + g3);
+        v[3] = c.mus * (gii + gjj) + 2.0 * c.mud * g0;
+        v[4] = c.mus * g3; v[5] = c.mus * g1;
+    }
+}
+
+struct P2Wphi2 {
+    double v[FEMB_COEF_STRIDE - 6][6];
+};
+
+__global__ void __launch_bounds__(128) k_cell_p2rec2d(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
+                                                      int64_t ncells, double mu, RhsDev rhs, QuadDev q, P2Wphi2 wp, double* __restrict__ out) {
+    __shared__ double tile[128][P2_REC2 + 1];
+    const int64_t cell0 = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t cell = cell0 + threadIdx.x;
+    if (cell < ncells) {
+        double x[3][2];
+        load_nodes<2>(coords, cellnodes, cell, x);
+        const double a00 = x[1][0] - x[0][0], a01 = x[2][0] - x[0][0], a10 = x[1][1] - x[0][1], a11 = x[2][1] - x[0][1];
+        const double det = a00 * a11 - a01 * a10;
+        const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * 0.5;
+        const double sc = (mu * vol) / (det * det);
+        // det * grad lambda_1 = (a11, -a01), det * grad lambda_2 = (-a10, a00)
+        const double K00 = (a11 * a11 + a01 * a01) * sc, K11 = (a10 * a10 + a00 * a00) * sc, K01 = -(a11 * a10 + a01 * a00) * sc;
+        const double G01 = -(K00 + K01), G02 = -(K01 + K11), G12 = K01;
+        double bl[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) bl[j] = 0.0;
+        if (rhs.kind != FEMB_RHS_NONE) {
+            for (int qp = 0; qp < q.nqp; qp++) {
+                double f;
+                if (rhs.kind == FEMB_RHS_AFFINE) {
+                    const double px = x[0][0] + a00 * q.xref[qp * 2] + a01 * q.xref[qp * 2 + 1], py = x[0][1] + a10 * q.xref[qp * 2] + a11 * q.xref[qp * 2 + 1];
+                    f = rhs.p[0] + rhs.p[1] * px + rhs.p[2] * py;
+                } else {
+                    f = __ldg(rhs.fvals + (size_t)cell * q.nqp + qp);
+                }
+                f *= vol;
+#pragma unroll
+                for (int j = 0; j < 6; j++) bl[j] += wp.v[qp][j] * f;
+            }
+        }
+        double* o = tile[threadIdx.x];
+        o[0] = G01; o[1] = G02; o[2] = bl[0]; o[3] = 0.0;
+        o[4] = G01; o[5] = G12; o[6] = bl[1]; o[7] = 0.0;
+        o[8] = G02; o[9] = G12; o[10] = bl[2]; o[11] = 0.0;
+        o[12] = G01; o[13] = G02; o[14] = G12; o[15] = bl[3];  // e0 = (0 1), other 2
+        o[16] = G12; o[17] = G01; o[18] = G02; o[19] = bl[4];  // e1 = (1 2), other 0
+        o[20] = G02; o[21] = G01; o[22] = G12; o[23] = bl[5];  // e2 = (0 2), other 1
+    }
+    __syncthreads();
+    const int64_t nloc = min((int64_t)128, ncells - cell0);
+    double* dst = out + cell0 * P2_REC2;
+    for (int i = threadIdx.x; i < nloc * P2_REC2; i += 128) dst[i] = tile[i / P2_REC2][i % P2_REC2];
+}
+
+// one thread per column, 4 slices (warps) per CTA; map planes (cell, 2 position words) staged by bulk copies; records one
+// visit ahead; the rows of an edge column that every visit touches (its two vertices, itself) are summed in registers.
+// dynamic shared memory: [4 mbarriers | pad to 128 B][acc: maxlen x 128 doubles][4 warps x 3 planes x maxrows x 128 B]
+__global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= a.slice_end) return;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned pst = (unsigned)a.maxrows * 128u;
+    const unsigned mbar = smem0 + warp * 8u;
+    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * 1024u + warp * 3u * pst;
+    const int64_t c = slice * 32 + lane;
+    const bool valid = c < a.ndofs;
+    const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
+    if (nrows > 0 && lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)nrows * 128u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * 3u) : "memory");
+        const uint32_t* g = a.map + ((size_t)row0 << 5);
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst), "l"(g + (size_t)p * a.stride),
+                         "r"(bytes), "r"(mbar)
+                         : "memory");
+    }
+    const bool zero_first = __ldg(a.slice_zero + slice) != 0;
+    int64_t base = 0;
+    int len = 0;
+    if (valid) {
+        base = a.colptr[c] - 1;
+        len = (int)(a.colptr[c + 1] - 1 - base);
+    }
+    const unsigned sacc = smem0 + 128u + tid * 8u;
+    if (zero_first) {
+        for (int i = 0; i < len; i++) sts64(sacc + i * 1024u, 0.0);
+    }
+    __syncwarp();
+    const unsigned fmask = zero_first ? 0u : 0xFFFFFFFFu;
+    double bsum = 0.0;
+    const unsigned sst = sstw + lane * 4u;
+    if (nrows > 0) {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+    }
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    if (nrows > 0) ldg256(a.rec + (size_t)lds32(sst) * P2_REC2 + 4u * min((lds32(sst + 2u * pst) >> 16) & 0xFu, 5u), r0, r1, r2, r3);
+    double racc[3] = {0.0, 0.0, 0.0};
+    unsigned rad[3] = {0u, 0u, 0u};
+    for (int r = 0; r < nrows; r++) {
+        const unsigned ra = sst + (unsigned)r * 128u;
+        const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst);
+        const unsigned k = (wb >> 16) & 0xFu;
+        const unsigned first = (wb >> 20) & fmask;
+        const double c0 = r0, c1 = r1, c2 = r2, c3 = r3;
+        if (r + 1 < nrows) ldg256(a.rec + (size_t)lds32(ra + 128u) * P2_REC2 + 4u * min((lds32(ra + 128u + 2u * pst) >> 16) & 0xFu, 5u), r0, r1, r2, r3);
+        if (k == 0xFu) continue;
+        unsigned ad[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) ad[j] = sacc + (((j < 4 ? wa : wb) >> (8 * (j & 3))) & 0xFFu) * 1024u;
+        double v[6];
+        if (k < 3u) {  // vertex dof: (G_k,o1 G_k,o2 bl_k)
+            const double gkk = -(c0 + c1);
+            v[0] = a.c.alpha * gkk;
+            v[1] = a.c.beta * c0; v[2] = a.c.beta * c1;
+            v[3] = a.c.gd * c0 + a.c.go * gkk; v[4] = a.c.gd * c1 + a.c.go * gkk;
+            v[5] = a.c.go * (c0 + c1);
+            if (a.has_rhs) bsum += c2;
+            double o[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
+#pragma unroll
+            for (int j = 0; j < 6; j++) sts64(ad[j], o[j] + v[j]);
+        } else {  // edge dof (i j), other vertex k: (G_ij G_ik G_jk bl)
+            const double gii = -(c0 + c1), gjj = -(c0 + c2);
+            v[0] = a.c.gd * c0 + a.c.go * gii; v[1] = a.c.gd * c0 + a.c.go * gjj;
+            v[2] = a.c.go * (c1 + c2);
+            v[3] = a.c.mus * (gii + gjj) + 2.0 * a.c.mud * c0;
+            v[4] = a.c.mus * c2; v[5] = a.c.mus * c1;
+            if (a.has_rhs) bsum += c3;
+            const bool sw = ad[0] > ad[1];  // CSC positions ascend with the row: orders the two endpoints globally
+            racc[0] += sw ? v[1] : v[0];
+            racc[1] += sw ? v[0] : v[1];
+            racc[2] += v[3];
+            rad[0] = sw ? ad[1] : ad[0];
+            rad[1] = sw ? ad[0] : ad[1];
+            rad[2] = ad[3];
+            constexpr int J[3] = {2, 4, 5};
+            double o[3];
+#pragma unroll
+            for (int t = 0; t < 3; t++) o[t] = lds64_unless(ad[J[t]], (first >> J[t]) & 1u);
+#pragma unroll
+            for (int t = 0; t < 3; t++) sts64(ad[J[t]], o[t] + v[J[t]]);
+        }
+    }
+    if (rad[2] != 0u) {
+#pragma unroll
+        for (int t = 0; t < 3; t++) sts64(rad[t], racc[t]);
+    }
+    __syncwarp();
+    const int len_next = __shfl_down_sync(0xFFFFFFFFu, len, 1);
+    const int len_prev = __shfl_up_sync(0xFFFFFFFFu, len, 1);
+    if (!valid) return;
+    double* out = a.nzval + base;
+    {
+        // every aligned 32-byte sector of the slice's nzval range is stored by the lane whose column holds its first entry
+        const int head = min(len, (int)((4 - (base & 3)) & 3));
+        const bool head_by_prev = lane > 0 && len_prev > 0 && head > 0 && len >= head;
+        if (!head_by_prev) {
+            for (int i = 0; i < head; i++) {
+                const double t = lds64(sacc + i * 1024u);
+                out[i] = a.acc_A ? out[i] + t : t;
+            }
+        }
+        const int nsec = (len - head + 3) >> 2;
+        for (int g = 0; g < nsec; g++) {
+            const int i = head + 4 * g;
+            const int own = min(4, len - i);
+            if (own < 4 && !(lane < 31 && len_next >= 4 - own)) {
+                for (int u = 0; u < own; u++) {
+                    const double t = lds64(sacc + (i + u) * 1024u);
+                    out[i + u] = a.acc_A ? out[i + u] + t : t;
+                }
+                continue;
+            }
+            double t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) t[u] = lds64(u < own ? sacc + (i + u) * 1024u : sacc + 8u + (u - own) * 1024u);
+            if (a.acc_A) {
+                double o0, o1, o2, o3;
+                asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o0), "=d"(o1), "=d"(o2), "=d"(o3) : "l"(out + i));
+                t[0] += o0; t[1] += o1; t[2] += o2; t[3] += o3;
+            }
+            stg256(out + i, t[0], t[1], t[2], t[3]);
+        }
+    }
+    if (a.has_rhs) {
+        if (a.acc_b) a.bvec[c] += bsum;
+        else a.bvec[c] = bsum;
+    }
+}
+
 }  // namespace
 
 // role permutation of the gather map (femb_pattern.cu applies it in place)
-void femb_p2_role_perm(uint8_t perm[12][12]) {
-    uint8_t p[10][10];
-    p2_role_perm(p);
+void femb_p2_role_perm(uint8_t perm[12][12], int dim) {
     for (int k = 0; k < 12; k++)
-        for (int r = 0; r < 12; r++) perm[k][r] = (k < 10 && r < 10) ? p[k][r] : (uint8_t)r;
+        for (int r = 0; r < 12; r++) perm[k][r] = (uint8_t)r;
+    if (dim == 3) {
+        uint8_t p[10][10];
+        p2_role_perm(p);
+        for (int k = 0; k < 10; k++)
+            for (int r = 0; r < 10; r++) perm[k][r] = p[k][r];
+    } else {
+        uint8_t p[6][6];
+        p2_role_perm2(p);
+        for (int k = 0; k < 6; k++)
+            for (int r = 0; r < 6; r++) perm[k][r] = p[k][r];
+    }
+}
+
+// P2 on triangles: H = the scalar map (Example200) or the component-diagonal map of a vector space (Example210's Laplacian:
+// EI = nullptr, the result is added to nzval).  FEMB_ERR_UNSUPPORTED (no message) when the closed form does not apply.
+static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, const FembEval* EI, double mu, const RhsDev& rhs, bool vec) {
+    const FembSpace& s = ctx->spaces[EG.space];
+    const int nc = s.ncomp;
+    if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * nc * 2) return P2_UNSUPPORTED;
+    if (EI && EI->h_refvals.size() != (size_t)EG.nqp * s.nd_all * nc) return P2_UNSUPPORTED;
+    for (auto& r : H.ranges)
+        if (r.split != 1) return P2_UNSUPPORTED;
+    // exact integrals on a triangle: int lambda_a lambda_b = |T| / 12, int lambda_a^2 = |T| / 6
+    const P2Const cst = {1.0, -1.0 / 3.0, 4.0 / 3.0, 0.0, 8.0 / 3.0, 4.0 / 3.0};
+    {
+        const double K[2][2] = {{1.3, -0.21}, {-0.21, 0.9}};
+        const double G3[3] = {-(K[0][0] + K[0][1]), K[0][1], -(K[0][1] + K[1][1])};  // by local edge: (0 1), (1 2), (0 2)
+        uint8_t perm[6][6];
+        p2_role_perm2(perm);
+        auto D = [&](int q, int j, int d) { return EG.h_refderivs[((size_t)q * s.nd_all + j) * nc * 2 + d]; };  // component 0 of the first 6 functions
+        for (int k = 0; k < 6; k++) {
+            double v[6];
+            p2_column_closed2(cst, G3, k, v);
+            for (int r = 0; r < 6; r++) {
+                const int j = perm[k][r];
+                double ref = 0.0;
+                for (int q = 0; q < EG.nqp; q++)
+                    for (int aa = 0; aa < 2; aa++)
+                        for (int b = 0; b < 2; b++) ref += EG.w[q] * D(q, j, aa) * K[aa][b] * D(q, k, b);
+                if (fabs(ref - v[r]) > 5e-12) {
+                    if (getenv("FEMB_P2_DEBUG")) fprintf(stderr, "2-D check: k=%d r=%d j=%d ref=%.17g closed=%.17g nqp=%d nd_all=%d nc=%d\n", k, r, j, ref, v[r], EG.nqp, s.nd_all, nc);
+                    return P2_UNSUPPORTED;
+                }
+            }
+        }
+    }
+    if (!ctx->p2rec) FEMB_TRY(femb_alloc(ctx, &ctx->p2rec, (size_t)ctx->ncells * P2_REC));
+    if (ctx->ncells == 0) return FEMB_OK;
+    FEMB_TRY(femb_hmap_set_canon(ctx, H, true));
+    if (H.cranges.empty()) {
+        const int64_t nslices = (s.ndofs + 31) / 32;
+        std::vector<int32_t> hptr((size_t)nslices + 1);
+        CUDA_TRY(ctx, cudaMemcpyAsync(hptr.data(), H.slice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<FembHMap::Range> out = H.ranges;
+        for (auto& c : out) {
+            c.maxrows = 1;
+            for (int64_t sl = c.s0; sl < c.s1; sl++) c.maxrows = std::max(c.maxrows, hptr[sl + 1] - hptr[sl]);
+        }
+        H.cranges = out;
+    }
+    auto smem_of = [](const FembHMap::Range& r) { return 128 + (size_t)std::max(1, r.maxlen) * 1024 + 4 * 3 * (size_t)r.maxrows * 128; };
+    size_t need = 0;
+    for (auto& r : H.cranges) need = std::max(need, smem_of(r));
+    if (need > 200 * 1024) return P2_UNSUPPORTED;
+    P2Wphi2 wp;
+    for (int q = 0; q < FEMB_COEF_STRIDE - 6; q++)
+        for (int j = 0; j < 6; j++) wp.v[q][j] = (EI && q < EG.nqp) ? EG.w[q] * EI->h_refvals[((size_t)q * s.nd_all + j) * nc] : 0.0;
+    QuadDev q = quad_dev(EG, 2);
+    k_cell_p2rec2d<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec);
+    KERNEL_CHECK(ctx);
+    P2Args a;
+    a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr + H.col_off; a.ndofs = s.ndofs;
+    a.nzval = ctx->nzval; a.bvec = ctx->bvec;
+    a.has_rhs = (!vec && rhs.kind != FEMB_RHS_NONE) ? 1 : 0;
+    if (vec) {
+        a.acc_A = a.acc_b = 1;  // the columns also hold rows of other blocks: add (the caller flushed the lazy zero)
+    } else {
+        a.acc_A = ctx->zero_pending_A ? 0 : 1;
+        a.acc_b = ctx->zero_pending_b ? 0 : 1;
+        ctx->zero_pending_A = false;
+        if (a.has_rhs) ctx->zero_pending_b = false;
+    }
+    a.slice_begin = a.slice_end = 0;
+    a.c = cst;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_p2_gather2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_p2_gather2d, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (auto& r : H.cranges) {
+        if (r.s1 <= r.s0) continue;
+        a.slice_begin = r.s0;
+        a.slice_end = r.s1;
+        a.maxlen = std::max(1, r.maxlen);
+        a.maxrows = r.maxrows;
+        k_p2_gather2d<<<(unsigned)((r.s1 - r.s0 + 3) / 4), 128, smem_of(r), ctx->stream>>>(a);
+        KERNEL_CHECK(ctx);
+    }
+    return FEMB_OK;
+}
+
+static bool p2_closed_enabled() {
+    static const bool enabled = [] { const char* e = getenv("FEMB_P2_CLOSED"); return !(e && e[0] == '0'); }();
+    return enabled;
+}
+
+// mu (grad u, grad v) of a component-blocked vector-valued P2 space on triangles in block (0,0) (Example210's Laplacian), added to nzval
+int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu) {
+    if (!p2_closed_enabled()) return P2_UNSUPPORTED;
+    const FembEval& EG = ctx->evals[eg];
+    const FembSpace& s = ctx->spaces[EG.space];
+    if (ctx->dim != 2 || s.ncomp < 2 || s.nd != 6 * s.ncomp || ctx->touched) return P2_UNSUPPORTED;
+    int st = femb_build_hmap_vec(ctx);
+    if (st != FEMB_OK) return st;
+    FembHMap& H = ctx->hm_vec;
+    if (H.space != EG.space || !H.complete) return P2_UNSUPPORTED;
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    RhsDev norhs;
+    norhs.kind = FEMB_RHS_NONE;
+    norhs.ncomp = 1;
+    norhs.fvals = nullptr;
+    return launch_p2_gather2d(ctx, H, EG, nullptr, mu, norhs, true);
 }
 
 // returns FEMB_ERR_UNSUPPORTED (no error message) when the closed form does not cover the space / rule / policy
 int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
-    static const bool enabled = [] { const char* e = getenv("FEMB_P2_CLOSED"); return !(e && e[0] == '0'); }();
-    if (!enabled) return FEMB_ERR_UNSUPPORTED;
+    if (!p2_closed_enabled()) return P2_UNSUPPORTED;
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
     FembHMap& H = ctx->hm;
-    if (ctx->dim != 3 || s.nd != 10 || s.ncomp != 1 || !H.map || H.space != EG.space || !H.complete || ctx->touched || drop_tol > 0.0) return FEMB_ERR_UNSUPPORTED;
-    if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * 3) return FEMB_ERR_UNSUPPORTED;
-    if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return FEMB_ERR_UNSUPPORTED;
+    if (ctx->dim == 2) {
+        if (s.nd != 6 || s.ncomp != 1 || !H.map || H.space != EG.space || !H.complete || ctx->touched || drop_tol > 0.0) return P2_UNSUPPORTED;
+        if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return P2_UNSUPPORTED;
+        return launch_p2_gather2d(ctx, H, EG, rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr, mu, rhs, false);
+    }
+    if (ctx->dim != 3 || s.nd != 10 || s.ncomp != 1 || !H.map || H.space != EG.space || !H.complete || ctx->touched || drop_tol > 0.0) return P2_UNSUPPORTED;
+    if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * 3) return P2_UNSUPPORTED;
+    if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return P2_UNSUPPORTED;
     const FembEval* EI = rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr;
-    if (EI && EI->h_refvals.size() != (size_t)EG.nqp * s.nd_all) return FEMB_ERR_UNSUPPORTED;
+    if (EI && EI->h_refvals.size() != (size_t)EG.nqp * s.nd_all) return P2_UNSUPPORTED;
     // exact integrals of the P2 shape-function products on a tetrahedron (int lambda_a lambda_b = |T| / 20, int lambda_a^2 = |T| / 10)
     const P2Const cst = {0.6, -0.2, 0.6, -0.2, 1.6, 0.8};
     {
@@ -547,7 +918,7 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
                     for (int aa = 0; aa < 3; aa++)
                         for (int b = 0; b < 3; b++)
                             ref += EG.w[q] * EG.h_refderivs[((size_t)q * s.nd_all + j) * 3 + aa] * K[aa][b] * EG.h_refderivs[((size_t)q * s.nd_all + k) * 3 + b];
-                if (fabs(ref - v[r]) > 1e-13) return FEMB_ERR_UNSUPPORTED;
+                if (fabs(ref - v[r]) > 5e-12) return P2_UNSUPPORTED;  // (rules from an eigen-solver carry ~1e-14 in points and weights)
             }
         }
     }

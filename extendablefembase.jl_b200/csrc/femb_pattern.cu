@@ -857,9 +857,10 @@ int femb_hmap_set_canon(femb_ctx* ctx, FembHMap& H, bool canon) {
     if (!H.map || H.canon == canon) return FEMB_OK;
     const FembSpace& s = ctx->spaces[H.space];
     const int nds = s.nd / s.ncomp;
-    if (nds != 10 || H.words != 3) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "role order exists for P2 on tetrahedra only");
+    if (!((ctx->dim == 3 && nds == 10 && H.words == 3) || (ctx->dim == 2 && nds == 6 && H.words == 2)))
+        return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "role order exists for P2 on triangles / tetrahedra only");
     HPerm perm;
-    femb_p2_role_perm(perm.p);
+    femb_p2_role_perm(perm.p, ctx->dim);
     if (H.stride) {
         k_hmap_canon<<<(unsigned)((H.stride + 255) / 256), 256, 0, ctx->stream>>>(H.map, H.stride, nds, H.words, perm, canon ? 0 : 1);
         KERNEL_CHECK(ctx);

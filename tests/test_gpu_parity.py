@@ -1044,22 +1044,23 @@ def test_device_interpolation_matches_oracle(dim, ncomp, kind):
     assert np.abs(b * 1.0e-60 - ref).max() <= RTOL * max(np.abs(want).max(), 1.0)
 
 
-def test_p2_3d_closed_form_and_quadrature_kernels_agree():
-    """H1P2{1,3}: the closed-form gather (femb_p2.cu; gather map in role order) and the general quadrature gather
+@pytest.mark.parametrize("dim", [3, 2])
+def test_p2_closed_form_and_quadrature_kernels_agree(dim):
+    """H1P2{1,3} / H1P2{1,2}: the closed-form gather (femb_p2.cu; gather map in role order) and the general quadrature gather
     (femb_h1.cu; local dof order — taken when the 1e-15 value filter of Example200:150 is on) run on the SAME context one
     after the other; the map is re-ordered in place between them and both match the oracle."""
     from femb_b200.assembly import _Session
 
-    grid = _grid3d(7, True)
-    fes = fb.FESpace(fb.H1P2(1, 3), grid)
+    grid = _grid3d(7, True) if dim == 3 else _grid2d(37, True)
+    fes = fb.FESpace(fb.H1P2(1, dim), grid)
     qf = fb.QuadratureRule(grid.geometry, 2)
     S = _Session([fes], qf)
     ctx = S.ctx
     eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
     ctx.pattern_build([(0, 0)])
-    p = np.array([0.25, 1.0, -1.0, 0.5])
-    rhs = fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]])
-    colptr, rowval, nzref, bref = orc.example200_assemble(_oracle_el(fb.H1P2(1, 3)), grid.geometry, grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"],
+    p = np.array([0.25, 1.0, -1.0, 0.5][:dim + 1])
+    rhs = fb.AffineFunction([0.25], [[1.0, -1.0, 0.5][:dim]])
+    colptr, rowval, nzref, bref = orc.example200_assemble(_oracle_el(fb.H1P2(1, dim)), grid.geometry, grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"],
                                                            fes["CellDofs"], fes.ndofs, 0.7, rhs)
     cp, rv = ctx.pattern_get(fes.ndofs)
     ref = {(int(r), c): v for c in range(fes.ndofs) for r, v in zip(rowval[colptr[c] - 1:colptr[c + 1] - 1], nzref[colptr[c] - 1:colptr[c + 1] - 1])}

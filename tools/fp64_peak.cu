@@ -1,4 +1,4 @@
-// FP64 FMA throughput of the vector pipe ("FP64 = to be measured by the build"): 8 independent DFMA chains per
+// FP64 throughput of the vector pipe (DFMA) and of the tensor pipe (DMMA) ("FP64 = to be measured by the build"): 8 independent DFMA chains per
 // thread, 8 resident warps per scheduler.  nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/fp64_peak.cu -o tools/fp64_peak
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -16,6 +16,25 @@ __global__ void __launch_bounds__(1024) k_dfma(double* out, double a, double b, 
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; i++) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// FP64 tensor pipe: mma.sync.aligned.m8n8k4.row.col.f64 (SASS DMMA), 8 independent accumulator fragments per warp,
+// register-resident operands: 8 x 8 x 4 x 2 = 512 flops per warp instruction
+__global__ void __launch_bounds__(1024) k_dmma(double* out, double a, double b, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -39,7 +58,19 @@ int main() {
         if (rep > 0 && ms < best) best = ms;
     }
     const double flops = 2.0 * 32.0 * iters * (double)blocks * threads;
-    printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp64_fma_tflops\": %.2f, \"ms\": %.3f, \"how\": \"8 independent DFMA chains per thread, 2 x 1024 threads per SM, best of 4\"}\n",
-           p.name, p.multiProcessorCount, flops / (best * 1e-3) / 1e12, best);
+    float bestm = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        k_dmma<<<blocks, threads>>>(out, 1e-3, 1e-3, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < bestm) bestm = ms;
+    }
+    const double flops_mma = 512.0 * 32.0 * iters * (double)blocks * (threads / 32);
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp64_fma_tflops\": %.2f, \"ms\": %.3f, \"fp64_dmma_tflops\": %.2f, \"ms_dmma\": %.3f, "
+           "\"how\": \"8 independent DFMA chains per thread resp. 8 independent mma.sync.m8n8k4.f64 accumulator fragments per warp, 2 x 1024 threads per SM, best of 4\"}\n",
+           p.name, p.multiProcessorCount, flops / (best * 1e-3) / 1e12, best, flops_mma / (bestm * 1e-3) / 1e12, bestm);
     return 0;
 }
