@@ -367,6 +367,7 @@ struct HArgs {
     const uint32_t* hmap;
     size_t hstride;
     const int64_t* colptr;
+    const int32_t *sub0, *sublen;
     int64_t ndofs;
     double* nzval;
     uint8_t* touched;
@@ -430,6 +431,10 @@ __global__ void __launch_bounds__(128, 4) k_h1_gather(const HArgs a, const HTab<
     if (valid) {
         base = a.colptr[c] - 1;
         len = (int)(a.colptr[c + 1] - 1 - base);
+        if (a.sub0) {  // vector maps: the block's run of the column
+            base += a.sub0[c];
+            len = a.sublen[c];
+        }
     }
     const unsigned sacc = (unsigned)__cvta_generic_to_shared(acc) + (SPLIT == 1 ? tid : lane) * 8u;
     if (zero_first) {
@@ -789,7 +794,7 @@ int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     else k_cell_coef<3><<<gridc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, ctx->cellcoef);
     KERNEL_CHECK(ctx);
     HArgs a;
-    a.coef = ctx->cellcoef; a.hslice_ptr = H.slice_ptr; a.hslice_zero = H.slice_zero; a.hmap = H.map; a.hstride = H.stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
+    a.coef = ctx->cellcoef; a.hslice_ptr = H.slice_ptr; a.hslice_zero = H.slice_zero; a.hmap = H.map; a.hstride = H.stride; a.colptr = ctx->colptr; a.sub0 = a.sublen = nullptr; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag; a.drop_tol = drop_tol;
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
@@ -837,7 +842,7 @@ int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu) {
     KERNEL_CHECK(ctx);
     HArgs a;
     a.coef = ctx->cellcoef; a.hslice_ptr = H.slice_ptr; a.hslice_zero = H.slice_zero; a.hmap = H.map; a.hstride = H.stride;
-    a.colptr = ctx->colptr + H.col_off; a.ndofs = s.ndofs;
+    a.colptr = ctx->colptr + H.col_off; a.sub0 = H.sub0; a.sublen = H.sublen; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.touched = nullptr; a.bvec = nullptr; a.errflag = ctx->errflag; a.drop_tol = 0.0;
     a.acc_A = 1;
     a.acc_b = 1;

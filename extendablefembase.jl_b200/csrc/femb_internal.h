@@ -66,10 +66,12 @@ struct FembHMap {
     uint32_t* map = nullptr;
     size_t stride = 0;
     int32_t* slice_ptr = nullptr;
+    int32_t *sub0 = nullptr, *sublen = nullptr;  // vector maps: the run [sub0, sub0 + sublen) of each column that belongs to the block (positions are relative to it)
     uint8_t* slice_zero = nullptr;  // per slice: some column has positions without a local contribution (zero the accumulators)
     int space = -1, words = 0;
     int64_t col_off = 0;            // first column of the block in the matrix
     bool complete = false;          // every (cell, row) of the map has a slot: the gather may skip its per-entry checks
+    int twins = 1;                  // vector maps: number of components whose blocks are copies of each other (1 = not established)
     bool canon = false;             // positions / first-touch flags of every entry are in P2 role order (femb_p2.cu) instead of local dof order
     struct Range { int64_t s0, s1; int maxlen; int split; int mode = 2; int maxrows = 0; };  // split: threads per column (1, or 4 for high-degree columns)
     std::vector<Range> ranges;      // contiguous slice ranges with their longest CSC column (shared-memory sizing)

@@ -58,11 +58,13 @@ struct P2Args {
     const uint32_t* map;
     size_t stride;
     const int64_t* colptr;
+    const int32_t *sub0, *sublen;
     int64_t ndofs;
     double* nzval;
     double* bvec;
     int acc_A, acc_b, has_rhs;
     int64_t slice_begin, slice_end;
+    int twins;            // 2-D vector maps: the columns c, c + ndofs, ... (one per component) receive the same values
     int maxlen, maxrows;  // of the launch range: longest CSC column, most visits of a slice (shared-memory layout)
     P2Const c;
 };
@@ -386,6 +388,10 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
     if (valid) {
         base = a.colptr[c] - 1;
         len = (int)(a.colptr[c + 1] - 1 - base);
+        if (a.sub0) {  // vector maps: the block's run of the column
+            base += a.sub0[c];
+            len = a.sublen[c];
+        }
     }
     const unsigned sacc = smem0 + 128u + (SPLIT == 1 ? tid : lane) * 8u;
     if (zero_first) {
@@ -645,6 +651,10 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
     if (valid) {
         base = a.colptr[c] - 1;
         len = (int)(a.colptr[c + 1] - 1 - base);
+        if (a.sub0) {  // vector maps: the block's run of the column
+            base += a.sub0[c];
+            len = a.sublen[c];
+        }
     }
     const unsigned sacc = smem0 + 128u + tid * 8u;
     if (zero_first) {
@@ -717,11 +727,13 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
     const int len_next = __shfl_down_sync(0xFFFFFFFFu, len, 1);
     const int len_prev = __shfl_up_sync(0xFFFFFFFFu, len, 1);
     if (!valid) return;
-    double* out = a.nzval + base;
-    {
+    for (int comp = 0; comp < a.twins; comp++) {
+        if (comp > 0) base = a.colptr[c + comp * a.ndofs] - 1 + a.sub0[c + comp * a.ndofs];  // (twins: vector maps only)
+        double* out = a.nzval + base;
         // every aligned 32-byte sector of the slice's nzval range is stored by the lane whose column holds its first entry
         const int head = min(len, (int)((4 - (base & 3)) & 3));
-        const bool head_by_prev = lane > 0 && len_prev > 0 && head > 0 && len >= head;
+        const bool contiguous = a.sub0 == nullptr;  // (vector maps: the runs of neighbouring columns do not touch)
+        const bool head_by_prev = contiguous && lane > 0 && len_prev > 0 && head > 0 && len >= head;
         if (!head_by_prev) {
             for (int i = 0; i < head; i++) {
                 const double t = lds64(sacc + i * 1024u);
@@ -732,7 +744,7 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
         for (int g = 0; g < nsec; g++) {
             const int i = head + 4 * g;
             const int own = min(4, len - i);
-            if (own < 4 && !(lane < 31 && len_next >= 4 - own)) {
+            if (own < 4 && !(contiguous && lane < 31 && len_next >= 4 - own)) {
                 for (int u = 0; u < own; u++) {
                     const double t = lds64(sacc + (i + u) * 1024u);
                     out[i + u] = a.acc_A ? out[i + u] + t : t;
@@ -777,7 +789,7 @@ void femb_p2_role_perm(uint8_t perm[12][12], int dim) {
 
 // P2 on triangles: H = the scalar map (Example200) or the component-diagonal map of a vector space (Example210's Laplacian:
 // EI = nullptr, the result is added to nzval).  FEMB_ERR_UNSUPPORTED (no message) when the closed form does not apply.
-static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, const FembEval* EI, double mu, const RhsDev& rhs, bool vec) {
+static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, const FembEval* EI, double mu, const RhsDev& rhs, bool vec, bool vec_fresh = false) {
     const FembSpace& s = ctx->spaces[EG.space];
     const int nc = s.ncomp;
     if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * nc * 2) return P2_UNSUPPORTED;
@@ -834,11 +846,12 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
     k_cell_p2rec2d<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec);
     KERNEL_CHECK(ctx);
     P2Args a;
-    a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr + H.col_off; a.ndofs = s.ndofs;
+    a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr + H.col_off; a.sub0 = H.sub0; a.sublen = H.sublen; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.bvec = ctx->bvec;
     a.has_rhs = (!vec && rhs.kind != FEMB_RHS_NONE) ? 1 : 0;
     if (vec) {
-        a.acc_A = a.acc_b = 1;  // the columns also hold rows of other blocks: add (the caller flushed the lazy zero)
+        a.acc_A = vec_fresh ? 0 : 1;  // the columns also hold rows of other blocks: the caller flushed the lazy zero, only the block's runs are touched
+        a.acc_b = 1;
     } else {
         a.acc_A = ctx->zero_pending_A ? 0 : 1;
         a.acc_b = ctx->zero_pending_b ? 0 : 1;
@@ -847,15 +860,23 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
     }
     a.slice_begin = a.slice_end = 0;
     a.c = cst;
+    a.twins = 1;
+    int64_t slice_cap = INT64_MAX;
+    if (vec && H.twins == s.ncomp && H.twins > 1) {  // compute component 0, write every component
+        a.twins = H.twins;
+        a.ndofs = s.ndofs / H.twins;
+        slice_cap = (a.ndofs + 31) / 32;
+    }
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_p2_gather2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_p2_gather2d, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (auto& r : H.cranges) {
         if (r.s1 <= r.s0) continue;
         a.slice_begin = r.s0;
-        a.slice_end = r.s1;
+        a.slice_end = std::min(r.s1, slice_cap);
+        if (a.slice_end <= a.slice_begin) continue;
         a.maxlen = std::max(1, r.maxlen);
         a.maxrows = r.maxrows;
-        k_p2_gather2d<<<(unsigned)((r.s1 - r.s0 + 3) / 4), 128, smem_of(r), ctx->stream>>>(a);
+        k_p2_gather2d<<<(unsigned)((a.slice_end - a.slice_begin + 3) / 4), 128, smem_of(r), ctx->stream>>>(a);
         KERNEL_CHECK(ctx);
     }
     return FEMB_OK;
@@ -876,12 +897,14 @@ int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu) {
     if (st != FEMB_OK) return st;
     FembHMap& H = ctx->hm_vec;
     if (H.space != EG.space || !H.complete) return P2_UNSUPPORTED;
+    // right after femb_matrix_zero the runs can be overwritten instead of read, added to and written back
+    const bool fresh = ctx->zero_pending_A;
     FEMB_TRY(femb_flush_zero(ctx, true, false));
     RhsDev norhs;
     norhs.kind = FEMB_RHS_NONE;
     norhs.ncomp = 1;
     norhs.fvals = nullptr;
-    return launch_p2_gather2d(ctx, H, EG, nullptr, mu, norhs, true);
+    return launch_p2_gather2d(ctx, H, EG, nullptr, mu, norhs, true, fresh);
 }
 
 // returns FEMB_ERR_UNSUPPORTED (no error message) when the closed form does not cover the space / rule / policy
@@ -932,13 +955,14 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     k_cell_p2rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec);
     KERNEL_CHECK(ctx);
     P2Args a;
-    a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr; a.ndofs = s.ndofs;
+    a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr; a.sub0 = a.sublen = nullptr; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.bvec = ctx->bvec;
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
     a.has_rhs = rhs.kind != FEMB_RHS_NONE;
     a.slice_begin = a.slice_end = 0;
     a.c = cst;
+    a.twins = 1;
     ctx->zero_pending_A = false;
     if (a.has_rhs) ctx->zero_pending_b = false;
     if (H.cranges.empty()) {

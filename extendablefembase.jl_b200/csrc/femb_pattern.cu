@@ -775,7 +775,7 @@ __global__ void k_slice_collen(const int64_t* __restrict__ colptr, int64_t ndofs
 __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restrict__ adj_ptr, int64_t ndofs, int64_t nslices, int nd, int nds, int nwords,
                        const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int64_t row_off, int64_t col_off,
                        const int32_t* __restrict__ slice_ptr, uint32_t* __restrict__ hmap, size_t stride, int32_t* __restrict__ nmissing,
-                       uint8_t* __restrict__ needs_zero) {
+                       uint8_t* __restrict__ needs_zero, int32_t* __restrict__ sub0, int32_t* __restrict__ sublen, int32_t* __restrict__ slice_sublen) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nslices * 32) return;
     const int64_t slice = c >> 5;
@@ -788,6 +788,7 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
     const int len = c < ndofs ? (int)(colptr[gc + 1] - 1 - base) : 0;
     uint32_t seen[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // positions written by earlier visits (max_collen <= 254)
     int nseen = 0;
+    uint32_t pmin = 0xFFu, pmax = 0u;  // sub-range of the column the visits write to (sub0 != NULL: positions become relative to it)
     for (int r = 0; r < nrows; r++) {
         const size_t idx = ((size_t)(row0 + r) << 5) + lane;
         uint32_t cell = 0, k = 0xFu, first = 0u;
@@ -802,10 +803,14 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
                 int64_t p = find_slot(colptr, rowval, gc, row_off + (int64_t)celldofs[(int64_t)cell * nd + comp * nds + j]);
                 uint32_t pos = (p < 0) ? 0xFFu : (uint32_t)(p - base);
                 if (p < 0) atomicAdd(nmissing, 1);  // rows without a slot (compressed / adopted patterns): the gather must check
-                else if (!((seen[pos >> 5] >> (pos & 31)) & 1u)) {
-                    seen[pos >> 5] |= 1u << (pos & 31);
-                    first |= 1u << j;
-                    nseen++;
+                else {
+                    pmin = min(pmin, pos);
+                    pmax = max(pmax, pos);
+                    if (!((seen[pos >> 5] >> (pos & 31)) & 1u)) {
+                        seen[pos >> 5] |= 1u << (pos & 31);
+                        first |= 1u << j;
+                        nseen++;
+                    }
                 }
                 words[j >> 2] = (words[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | (pos << (8 * (j & 3)));
             }
@@ -814,6 +819,34 @@ __global__ void k_hmap(const uint32_t* __restrict__ adj, const int32_t* __restri
         hmap[idx] = cell;
         for (int wd = 0; wd < nwords; wd++) hmap[(1 + wd) * stride + idx] = words[wd];
     }
+    if (sub0) {
+        // the block's rows of a column are one contiguous run of it (component-blocked dofs, rows ascending): the gather keeps
+        // accumulators for, and writes, that run only
+        const int sl = pmin <= pmax ? (int)(pmax - pmin + 1) : 0;
+        if (c < ndofs) {
+            sub0[c] = sl ? (int32_t)pmin : 0;
+            sublen[c] = sl;
+        }
+        if (sl) {
+            atomicMax(slice_sublen + slice, sl);
+            if (pmin) {
+                for (int r = 0; r < min(nrows, deg); r++) {
+                    const size_t idx = ((size_t)(row0 + r) << 5) + lane;
+                    for (int wd = 0; wd < nwords; wd++) {
+                        uint32_t w = hmap[(1 + wd) * stride + idx];
+                        const int nb = wd == nwords - 1 ? nds - 4 * wd : 4;
+                        for (int b = 0; b < nb; b++) {
+                            const uint32_t pos = (w >> (8 * b)) & 0xFFu;
+                            if (pos != 0xFFu) w = (w & ~(0xFFu << (8 * b))) | ((pos - pmin) << (8 * b));
+                        }
+                        hmap[(1 + wd) * stride + idx] = w;
+                    }
+                }
+            }
+        }
+        if (nseen < sl) needs_zero[slice] = 1;
+        return;
+    }
     if (nseen < len) needs_zero[slice] = 1;
 }
 
@@ -821,6 +854,8 @@ void femb_free_hmap(FembHMap& H) {
     femb_free(&H.map);
     femb_free(&H.slice_ptr);
     femb_free(&H.slice_zero);
+    femb_free(&H.sub0);
+    femb_free(&H.sublen);
     H.stride = 0;
     H.space = -1;
     H.canon = false;
@@ -870,7 +905,7 @@ int femb_hmap_set_canon(femb_ctx* ctx, FembHMap& H, bool canon) {
 }
 
 // builds the map of the (component-diagonal part of the) square block of space `sid` whose rows / columns start at row_off / col_off
-static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off, int64_t col_off) {
+static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off, int64_t col_off, bool subrange) {
     const FembSpace& s = ctx->spaces[sid];
     const int nds = s.nd / s.ncomp;
     const int64_t nslices = (s.ndofs + 31) / 32;
@@ -906,6 +941,37 @@ static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off,
     cudaFree(clen);
     ctx->launches += 2;
     CUDA_TRY(ctx, e);
+    H.stride = (size_t)rows * 32;
+    H.words = nwords;
+    H.col_off = col_off;
+    FEMB_TRY(femb_alloc(ctx, &H.map, H.stride * (1 + nwords)));
+    FEMB_TRY(femb_alloc(ctx, &H.slice_zero, (size_t)nslices));
+    CUDA_TRY(ctx, cudaMemsetAsync(H.slice_zero, 0, (size_t)nslices, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
+    int32_t* slice_sublen = nullptr;
+    if (subrange) {
+        FEMB_TRY(femb_alloc(ctx, &H.sub0, (size_t)s.ndofs));
+        FEMB_TRY(femb_alloc(ctx, &H.sublen, (size_t)s.ndofs));
+        FEMB_TRY(femb_alloc(ctx, &slice_sublen, (size_t)nslices));
+        CUDA_TRY(ctx, cudaMemsetAsync(slice_sublen, 0, sizeof(int32_t) * nslices, ctx->stream));
+    }
+    k_hmap<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.nd, nds, nwords, s.celldofs, ctx->colptr, ctx->rowval,
+                                                                            row_off, col_off, H.slice_ptr, H.map, H.stride, ctx->errflag, H.slice_zero, H.sub0, H.sublen,
+                                                                            slice_sublen);
+    KERNEL_CHECK(ctx);
+    if (subrange) {  // shared-memory sizing follows the run the gather keeps, not the whole column
+        cudaError_t e2 = cudaMemcpyAsync(h_clen.data(), slice_sublen, sizeof(int32_t) * nslices, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+        femb_free(&slice_sublen);
+        CUDA_TRY(ctx, e2);
+    }
+    {
+        int32_t nmiss = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&nmiss, ctx->errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
+        H.complete = nmiss == 0;
+    }
     // contiguous slice ranges of similar column length (shared memory per thread = maxlen doubles): runs of equal
     // class ceil(len / 32), short runs (< 1/64 of the slices) merged into their predecessor, at most 16 ranges
     std::vector<FembHMap::Range> rg;
@@ -948,23 +1014,6 @@ static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off,
         }
     }
     H.ranges = rg;
-    H.stride = (size_t)rows * 32;
-    H.words = nwords;
-    H.col_off = col_off;
-    FEMB_TRY(femb_alloc(ctx, &H.map, H.stride * (1 + nwords)));
-    FEMB_TRY(femb_alloc(ctx, &H.slice_zero, (size_t)nslices));
-    CUDA_TRY(ctx, cudaMemsetAsync(H.slice_zero, 0, (size_t)nslices, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
-    k_hmap<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(s.adj, s.adj_ptr, s.ndofs, nslices, s.nd, nds, nwords, s.celldofs, ctx->colptr, ctx->rowval,
-                                                                            row_off, col_off, H.slice_ptr, H.map, H.stride, ctx->errflag, H.slice_zero);
-    KERNEL_CHECK(ctx);
-    {
-        int32_t nmiss = 0;
-        CUDA_TRY(ctx, cudaMemcpyAsync(&nmiss, ctx->errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
-        H.complete = nmiss == 0;
-    }
     H.space = sid;
     return FEMB_OK;
 }
@@ -983,7 +1032,20 @@ int femb_build_hmap(femb_ctx* ctx) {
     const int sid = ctx->row_spaces[0];
     const FembSpace& s = ctx->spaces[sid];
     if (s.ncomp != 1 || !hmap_space_ok(ctx, s)) return FEMB_OK;
-    return build_hmap_into(ctx, ctx->hm, sid, 0, 0);
+    return build_hmap_into(ctx, ctx->hm, sid, 0, 0, false);
+}
+
+__global__ void k_check_twins(const int32_t* __restrict__ celldofs, int64_t ncells, int nd, int ncomp, int64_t n, const int32_t* __restrict__ sublen,
+                              int32_t* __restrict__ bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int nds = nd / ncomp;
+    bool ok = true;
+    if (i < ncells)
+        for (int comp = 1; comp < ncomp; comp++)
+            for (int j = 0; j < nds; j++) ok = ok && celldofs[i * nd + comp * nds + j] == celldofs[i * nd + j] + comp * n;
+    if (i < n)
+        for (int comp = 1; comp < ncomp; comp++) ok = ok && sublen[i + comp * n] == sublen[i];
+    if (!ok) atomicAdd(bad, 1);
 }
 
 // lazy: the (u,u) block of FEMatrix([FES_u, ...]) with a component-blocked vector-valued H1 space FES_u (Example210's Laplacian)
@@ -996,7 +1058,23 @@ int femb_build_hmap_vec(femb_ctx* ctx) {
     const FembSpace& s = ctx->spaces[sid];
     if (!have || !hmap_space_ok(ctx, s)) return FEMB_ERR_UNSUPPORTED;
     FEMB_TRY(femb_build_adjacency(ctx, sid));
-    return build_hmap_into(ctx, ctx->hm_vec, sid, ctx->row_off[0], ctx->col_off[0]);
+    FEMB_TRY(build_hmap_into(ctx, ctx->hm_vec, sid, ctx->row_off[0], ctx->col_off[0], true));
+    // component twins: dof (comp, i) = comp * n + i in every cell and equally long runs -> the component blocks of a
+    // component-wise form are copies of each other, a gather may compute one and write all (femb_p2.cu)
+    FembHMap& H = ctx->hm_vec;
+    H.twins = 1;
+    if (s.ncomp > 1 && s.ndofs % s.ncomp == 0 && ctx->ncells > 0) {
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
+        const int64_t n = s.ndofs / s.ncomp;
+        k_check_twins<<<(unsigned)((std::max<int64_t>(ctx->ncells, n) + 255) / 256), 256, 0, ctx->stream>>>(s.celldofs, ctx->ncells, s.nd, s.ncomp, n, H.sublen, ctx->errflag);
+        KERNEL_CHECK(ctx);
+        int32_t bad = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&bad, ctx->errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
+        if (!bad) H.twins = s.ncomp;
+    }
+    return FEMB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
