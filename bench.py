@@ -421,6 +421,10 @@ def leg_c3(D, args, m):
            "roofline_fp64": {"bound": "fp64", "achieved": round(tfl, 2), "peak": f64, "unit": "TFLOP/s", "frac": round(tfl / f64, 4),
                              "flops_per_cell": FLOPS_C3, "peak_source": "tools/fp64_peak.cu (DFMA), profiles/r01_fp64_peak.json"}}
     res["checks"] = {"sum_b": bsum, "int_f": 0.5}
+    tj = os.path.join(ROOT, "profiles", "p1_gather2d_traffic.json")
+    if os.path.exists(tj) and "c3" in json.load(open(tj)):
+        t = json.load(open(tj))["c3"]
+        res["roofline"]["traffic"] = {"bytes_per_launch": round(t["dram_bytes_per_cell"] * grid.ncells), "bytes_per_cell": t["dram_bytes_per_cell"], "source": t["source"]}
     if D.rank == 0 and D.world == 1 and not args.no_cpu:
         res["cpu_baseline"] = cpu_baseline_c3(args.cpu_seconds / 2)
     ctx.close()
