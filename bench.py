@@ -595,7 +595,7 @@ def run_ours(args):
         "config": {"workload": f"H1P1 2-D Poisson stiffness+rhs, simplexgrid n={args.n} ({ncells} triangles, {nnodes} nodes) per GPU" + (", jittered" if args.jitter else ""),
                    "nnz": nnz, "l2": "inputs (%.1f GB/step) far larger than the 126 MB L2; no flush needed" % (bpc * ncells / 1e9),
                    "partition": ("one %d-row slab per rank, interface columns owned by the lower rank, NCCL send+recv of %d bytes on rank 0 per step" % (args.n, getattr(S, "exchange_bytes", 0))) if world > 1 else "single GPU", "scatter": "owner-computes gather (write-once, bit-reproducible)",
-                   "cellvolumes": "xgrid[CellVolumes] passed in" if use_vol else "NULL: |det A|/2 on the device", "host_numa": numa},
+                   "cellvolumes": "xgrid[CellVolumes] passed in (registered with the mesh; the gather reads them in visit order, a plane built once per mesh)" if use_vol else "NULL: |det A|/2 on the device", "host_numa": numa},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                 "note": "femb_assemble_poisson_host: every step uploads Coordinates (connectivity declared unchanged, |T| on the device) and downloads nzval + b",

@@ -202,6 +202,7 @@ int32_t femb_mesh_set(femb_ctx* ctx, int32_t dim, int64_t nnodes, const double* 
     ctx->ncells = ncells;
     FEMB_TRY(femb_h2d(ctx, ctx->coords, coords, (size_t)nnodes * dim));
     if (!same_shape) FEMB_TRY(femb_h2d(ctx, ctx->cellnodes, cellnodes, (size_t)ncells * nnpc));
+    ctx->gvol_valid = false;
     if (cellvolumes) {
         if (!ctx->cellvol) FEMB_TRY(femb_alloc(ctx, &ctx->cellvol, (size_t)ncells));
         FEMB_TRY(femb_h2d(ctx, ctx->cellvol, cellvolumes, (size_t)ncells));

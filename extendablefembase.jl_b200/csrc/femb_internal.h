@@ -139,6 +139,8 @@ struct femb_ctx {
     bool gmap_uniform = false;       // every slice padded to gmap_maxrows rows (row0 = slice * maxrows, no indirection)
     int gmap_maxrows = 0;            // longest slice (rows) = largest number of cells around a dof
     int gmap_space = -1;
+    double* gvol = nullptr;          // scalar P1, 2-D: xgrid[CellVolumes] in visit order [row][lane] (one more plane of the gather map, femb_p1.cu)
+    bool gvol_valid = false;         // false after the volumes or the map changed
     // general H1 gather maps (P2, ...; femb_pattern.cu): hm = the single scalar block of a one-space layout (Example200), hm_vec = the
     // component-diagonal part of block (0,0) of a vector-valued space in a multi-space layout (Example210's Laplacian)
     FembHMap hm, hm_vec;

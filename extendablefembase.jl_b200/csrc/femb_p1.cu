@@ -16,6 +16,7 @@ struct P1Tab {
 struct P1Args {
     const double* coords;
     const double* cellvol;
+    const double* gvol;  // CellVolumes in visit order [row][lane] (femb_ctx::gvol), or NULL
     const int32_t* gslice_ptr;
     const uint32_t* gmap;  // SoA planes na, nb, w, cell (, nc): femb_internal.h
     size_t gstride;
@@ -141,9 +142,12 @@ __device__ __forceinline__ void p1_visit(const unsigned w, const unsigned cell, 
 #ifndef FEMB_P1_MINB
 #define FEMB_P1_MINB 8  // resident CTAs per SM the 2-D gather kernel is compiled for (register cap 65536 / (128 * MINB))
 #endif
-template <bool TRACK, int RHS, bool HAS_VOL, int NQP, bool STAGE, int MINB = FEMB_P1_MINB>  // NQP: compile-time number of quadrature points, 0 = tab.nqp
+template <bool TRACK, int RHS, bool HAS_VOL, int NQP, int STAGE, int MINB = FEMB_P1_MINB>  // NQP: compile-time number of quadrature points, 0 = tab.nqp; STAGE: 0 = map entries by loads, 1 = staged by bulk copies, 2 = + CellVolumes in visit order
 __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args a, const RhsDev rhs, const P1Tab2 tab) {
-    constexpr bool NEED_CELL = HAS_VOL || RHS == FEMB_RHS_QPVALUES;
+    // VOLP: xgrid[CellVolumes] comes as one more staged plane, in visit order (built once per mesh from the registered volumes):
+    // no cell-index plane and no scattered 8-byte load per visit — the given-volume kernel then runs like the |det| / 2 one
+    constexpr bool VOLP = HAS_VOL && STAGE == 2;
+    constexpr bool NEED_CELL = (HAS_VOL && !VOLP) || RHS == FEMB_RHS_QPVALUES;
     constexpr int NPL = NEED_CELL ? 4 : 3;  // gather-map planes this variant reads
     // dynamic shared memory: [4 mbarriers | pad to 128 B][4 warps x flat accumulators (maxlen * 32 + 2 doubles)][(STAGE) u32 [4 warps][4 planes][maxrows][32]]
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -172,12 +176,17 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
     const unsigned mbar = smem0 + warp * 8u;
     const unsigned sstw = smem0 + 128u + 4u * accw + warp * (4u * (unsigned)a.maxrows * 128u);  // this warp's staging block
     const unsigned pst = (unsigned)a.maxrows * 128u;                                              // plane stride in bytes
+    const unsigned svolw = smem0 + 128u + 4u * accw + 16u * pst + warp * 2u * pst;                // (VOLP) this warp's volume plane: maxrows x 32 doubles
     if (STAGE && nrows > 0) {
         if (lane == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             const unsigned bytes = (unsigned)nrows * 128u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * NPL) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * (NPL + (VOLP ? 2 : 0))) : "memory");
+            if (VOLP)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(svolw), "l"(a.gvol + ((size_t)row0 << 5)),
+                             "r"(2u * bytes), "r"(mbar)
+                             : "memory");
 #pragma unroll
             for (int p = 0; p < NPL; p++)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst),
@@ -233,8 +242,9 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
         if (nrows > 0) {
             pa1 = __ldg(xy + lds32(sst));
             pb1 = __ldg(xy + lds32(sst + pst));
-            if (HAS_VOL) vol1 = __ldg(a.cellvol + lds32(sst + 3u * pst));
+            if (HAS_VOL && !VOLP) vol1 = __ldg(a.cellvol + lds32(sst + 3u * pst));
         }
+        const unsigned svol = svolw + lane * 8u;
         constexpr int UNR = FEMB_P1_UNROLL;
 #pragma unroll UNR
         for (int r = 0; r < nrows; r++) {
@@ -242,11 +252,11 @@ __global__ void __launch_bounds__(128, MINB) k_p1_poisson_gather2d(const P1Args 
             const unsigned w = lds32(d + 2u * pst);
             const unsigned cell = NEED_CELL ? lds32(d + 3u * pst) : 0u;
             const double2 pa = pa1, pb = pb1;
-            const double volr = vol1;
+            const double volr = VOLP ? lds64(svol + (unsigned)r * 256u) : vol1;
             if (r + 1 < nrows) {  // coordinates / volume of the next visit
                 pa1 = __ldg(xy + lds32(d + 128u));
                 pb1 = __ldg(xy + lds32(d + 128u + pst));
-                if (HAS_VOL) vol1 = __ldg(a.cellvol + lds32(d + 128u + 3u * pst));
+                if (HAS_VOL && !VOLP) vol1 = __ldg(a.cellvol + lds32(d + 128u + 3u * pst));
             }
             if (w == 0xFFFFFFFFu) continue;
             p1_visit<TRACK, RHS, HAS_VOL, NQP>(w, cell, self, pa, pb, volr, tab, rhs, drop_tol, mu_wsum, sacc, diag, dpos, err, mask, bsum);
@@ -506,7 +516,15 @@ struct P1Launch {
     int64_t nslices;
 };
 
-static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol, P1Launch& L) {
+// CellVolumes in visit order: out[row][lane] = cellvol[cell of that gather-map entry] (padding entries: cell 0)
+__global__ void k_gvol(const uint32_t* __restrict__ cells, const double* __restrict__ cellvol, size_t n, int64_t ncells, double* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cells[i];
+    out[i] = c < (uint64_t)ncells ? cellvol[c] : 0.0;
+}
+
+static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol, P1Launch& L, bool use_volplane) {
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
     P1Tab& tab = L.tab;
@@ -526,7 +544,7 @@ static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const Rhs
     for (int i = 0; i < EG.nqp * ctx->dim; i++) tab.xref[i] = EG.xref[i];
     for (int i = 0; i < EG.nqp * ND; i++) tab.phi[i] = phi[i];
     P1Args& a = L.a;
-    a.coords = ctx->coords; a.cellvol = ctx->cellvol; a.gslice_ptr = ctx->gslice_ptr; a.gmap = ctx->gmap; a.gstride = ctx->gmap_stride;
+    a.coords = ctx->coords; a.cellvol = ctx->cellvol; a.gvol = nullptr; a.gslice_ptr = ctx->gslice_ptr; a.gmap = ctx->gmap; a.gstride = ctx->gmap_stride;
     a.colptr = ctx->colptr; a.ndofs = s.ndofs; a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag;
     a.mu = mu; a.drop_tol = drop_tol;
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
@@ -565,6 +583,20 @@ static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const Rhs
         static const int stage_env = getenv("FEMB_P1_STAGE") ? atoi(getenv("FEMB_P1_STAGE")) : 1;
         a.maxrows = (stage_env && ctx->gmap_maxrows > 0 && ctx->gmap_maxrows <= 12) ? ctx->gmap_maxrows : 0;
         L.smem += (size_t)a.maxrows * 4 * 4 * 32 * sizeof(uint32_t);
+        // CellVolumes in visit order (one more staged plane): built once per registered mesh, for the device-resident assembly
+        static const int volp_env = getenv("FEMB_P1_VOLPLANE") ? atoi(getenv("FEMB_P1_VOLPLANE")) : 1;
+        if (volp_env && use_volplane && a.maxrows > 0 && ctx->cellvol && !ctx->touched && rhs.kind != FEMB_RHS_QPVALUES) {
+            if (!ctx->gvol_valid) {
+                if (!ctx->gvol) FEMB_TRY(femb_alloc(ctx, &ctx->gvol, ctx->gmap_stride));
+                if (ctx->gmap_stride) {
+                    k_gvol<<<(unsigned)((ctx->gmap_stride + 255) / 256), 256, 0, ctx->stream>>>(ctx->gmap + 3 * ctx->gmap_stride, ctx->cellvol, ctx->gmap_stride, ctx->ncells, ctx->gvol);
+                    KERNEL_CHECK(ctx);
+                }
+                ctx->gvol_valid = true;
+            }
+            a.gvol = ctx->gvol;
+            L.smem += (size_t)a.maxrows * 4 * 32 * sizeof(double);
+        }
     }
     return FEMB_OK;
 }
@@ -586,10 +618,11 @@ static int launch_p1_slices(femb_ctx* ctx, P1Launch& L, int64_t s0, int64_t s1, 
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_p1_poisson_gather2d<T, R, V, Q, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_p1_poisson_gather2d<T, R, V, Q, S><<<grid, 128, smem, stream>>>(a, rhs, t2);                                                    \
     } while (0)
-#define FEMB_P1_LAUNCH2Q(T, R, V, Q)                     \
-    do {                                                 \
-        if (a.maxrows > 0) FEMB_P1_LAUNCH2S(T, R, V, Q, true); \
-        else FEMB_P1_LAUNCH2S(T, R, V, Q, false);        \
+#define FEMB_P1_LAUNCH2Q(T, R, V, Q)                                           \
+    do {                                                                       \
+        if (a.maxrows > 0 && V && !T && a.gvol) FEMB_P1_LAUNCH2S(T, R, V, Q, (V && !T) ? 2 : 1); \
+        else if (a.maxrows > 0) FEMB_P1_LAUNCH2S(T, R, V, Q, 1);               \
+        else FEMB_P1_LAUNCH2S(T, R, V, Q, 0);                                  \
     } while (0)
 #define FEMB_P1_LAUNCH2(T, R, V)                 \
     do {                                         \
@@ -618,7 +651,7 @@ static int launch_p1_slices(femb_ctx* ctx, P1Launch& L, int64_t s0, int64_t s1, 
 
 int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
     P1Launch L;
-    FEMB_TRY(prepare_p1_gather(ctx, eg, ei, mu, rhs, drop_tol, L));
+    FEMB_TRY(prepare_p1_gather(ctx, eg, ei, mu, rhs, drop_tol, L, true));
     if (ctx->fused_exchange && ctx->comm && !ctx->peers.empty() && ctx->stream_x) {
         // overlapped interface exchange: assemble the slices holding ghost (send) and owned-interface (recv) columns
         // first, run pack / NCCL / add on a second stream while the bulk of the columns is assembled
@@ -757,7 +790,8 @@ extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t
     ctx->zero_pending_A = true;  // "zero + assemble": the write-once kernel overwrites
     ctx->zero_pending_b = true;
     P1Launch L;
-    FEMB_TRY(prepare_p1_gather(ctx, eg, ei, mu, rhs, drop_tol, L));
+    ctx->gvol_valid = false;  // this call uploads new volumes chunk by chunk: the visit-order copy is not used and goes stale
+    FEMB_TRY(prepare_p1_gather(ctx, eg, ei, mu, rhs, drop_tol, L, false));
     FEMB_TRY(femb_timer_begin(ctx));
     const int dim = ctx->dim;
     int64_t hi_n = 0, hi_c = 0;

@@ -25,6 +25,8 @@ void femb_free_pattern(femb_ctx* ctx) {
     ctx->gmap_rows = 0;
     ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
+    femb_free(&ctx->gvol);
+    ctx->gvol_valid = false;
     ctx->chunk_n = 0;
     femb_free_hmap(ctx->hm);
     femb_free_hmap(ctx->hm_vec);
@@ -673,6 +675,8 @@ int femb_build_gmap(femb_ctx* ctx) {
     ctx->gmap_rows = 0;
     ctx->gmap_stride = 0;
     ctx->gmap_space = -1;
+    femb_free(&ctx->gvol);
+    ctx->gvol_valid = false;
     ctx->chunk_n = 0;  // chunk plan of the streamed assembly depends on the gather map
     if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
     int sid = ctx->row_spaces[0];
