@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfemb.so")
-SOURCES = ["femb_api.cu", "femb_pattern.cu", "femb_assemble.cu", "femb_generic.cu", "femb_p1.cu", "femb_h1.cu", "femb_p2.cu", "femb_ns.cu", "femb_grid.cu", "femb_system.cu", "femb_comm.cu"]
+SOURCES = ["femb_api.cu", "femb_pattern.cu", "femb_assemble.cu", "femb_generic.cu", "femb_p1.cu", "femb_h1.cu", "femb_p2.cu", "femb_hdiv.cu", "femb_ns.cu", "femb_grid.cu", "femb_system.cu", "femb_comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -654,7 +654,15 @@ extern "C" int32_t femb_assemble_bilinear(femb_ctx* ctx, int32_t er, int32_t ec,
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->dirty_A = true;
     FEMB_TRY(femb_timer_begin(ctx));
-    FEMB_TRY(launch_bilinear(ctx, er, ec, ctx->evals[er].op, ctx->evals[ec].op, brow, bcol, factor, flags, drop_tol));
+    int st = FEMB_ERR_UNSUPPORTED;
+    if (ctx->scatter == FEMB_SCATTER_GATHER && !ctx->touched && !(drop_tol > 0.0)) {
+        // HDIVRT0 on tetrahedra: closed-form local matrices, owner-computes mass gather, conflict-free divergence blocks
+        if (er == ec && flags == 0 && ctx->evals[er].op == FEMB_OP_IDENTITY) st = launch_rt0_mass_gather(ctx, er, brow, bcol, factor);
+        else if (ctx->evals[er].op == FEMB_OP_DIVERGENCE && ctx->evals[ec].op == FEMB_OP_IDENTITY && (flags & ~FEMB_BIL_TRANSPOSE_COPY) == 0)
+            st = launch_rt0_div(ctx, er, ec, brow, bcol, factor, flags);
+    }
+    if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, er, ec, ctx->evals[er].op, ctx->evals[ec].op, brow, bcol, factor, flags, drop_tol);
+    if (st != FEMB_OK) return st;
     return femb_timer_end(ctx);
 }
 

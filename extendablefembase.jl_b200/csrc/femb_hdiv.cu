@@ -1,0 +1,334 @@
+// HDIVRT0 on tetrahedra (C4 of BASELINE.json: mass (v_j, v_k) + (div v_j, q) against L2P0) without the generic quadrature
+// machinery.  The contravariant Piola image of the reference basis (src/fedefs/hdiv_rt0.jl:86-100, feevaluator_hdiv.jl:2-19)
+// is  phi_j(x) = s_j (2 / det) (x - p_j),  p_j = the vertex opposite face j, s_j = xgrid[CellFaceSigns][j, cell], so
+//   M_jk = s_j s_k (4 |T| / det^2) ( (c - p_j).(c - p_k) + (1/20) sum_i |x_i - c|^2 ),  c = centroid        (exact; the order-2
+//   rule the caller uses integrates the same quadratic exactly), and  int div phi_j = s_j |T| trace / det  (= +-1).
+// The launcher accepts the closed form only if it reproduces the evaluator's own tables on a test cell.
+//  * mass: cell pre-pass writes the 4 x 4 local matrix as four 32-byte columns; one thread per face-dof column gathers its
+//    (at most two) cells: write-once, bit-reproducible, one sector per visit (map staged by bulk copies as in femb_p2.cu);
+//  * divergence blocks: every entry of (v, q) and (q, v) has exactly ONE contributing cell -> plain stores through the
+//    slot maps, no reductions.
+#include <cstdlib>
+
+#include "femb_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// vertex opposite face j (0-based, hdiv_rt0.jl:86-100: the reference functions are 2 (xref - p_j) with p = e3, e2, 0, e1)
+__host__ __device__ constexpr int rt0_opp(int j) { return j == 0 ? 3 : (j == 1 ? 2 : (j == 2 ? 0 : 1)); }
+
+__global__ void __launch_bounds__(128) k_cell_rt0rec(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
+                                                     const int32_t* __restrict__ signs, int64_t ncells, double* __restrict__ out) {
+    __shared__ double tile[128][17];
+    const int64_t cell0 = blockIdx.x * (int64_t)blockDim.x;
+    const int64_t cell = cell0 + threadIdx.x;
+    if (cell < ncells) {
+        double x[4][3];
+        load_nodes<3>(coords, cellnodes, cell, x);
+        double A[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) A[d][i] = x[i + 1][d] - x[0][d];
+        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * (1.0 / 6.0);
+        double c[3], S = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) c[d] = 0.25 * (((x[0][d] + x[1][d]) + x[2][d]) + x[3][d]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int d = 0; d < 3; d++) S += (x[i][d] - c[d]) * (x[i][d] - c[d]);
+        S *= 0.05;
+        const double sc = 4.0 * vol / (det * det);
+        double dv[4][3], sg[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sg[j] = (double)__ldg(signs + cell * 4 + j);
+#pragma unroll
+            for (int d = 0; d < 3; d++) dv[j][d] = c[d] - x[rt0_opp(j)][d];
+        }
+        double* o = tile[threadIdx.x];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[k * 4 + j] = (sg[j] * sg[k]) * sc * (((dv[j][0] * dv[k][0] + dv[j][1] * dv[k][1]) + dv[j][2] * dv[k][2]) + S);
+    }
+    __syncthreads();
+    const int64_t nloc = min((int64_t)128, ncells - cell0);
+    double* dst = out + cell0 * 16;
+    for (int i = threadIdx.x; i < nloc * 16; i += 128) dst[i] = tile[i / 16][i % 16];
+}
+
+struct RGArgs {
+    const double* rec;
+    const int32_t* slice_ptr;
+    const uint8_t* slice_zero;
+    const uint32_t* map;
+    size_t stride;
+    const int64_t* colptr;
+    const int32_t *sub0, *sublen;
+    int64_t ndofs;
+    double* nzval;
+    double factor;
+    int acc_A;
+    int64_t slice_begin, slice_end;
+    int maxlen, maxrows;
+};
+
+// one thread per face-dof column, 4 slices (warps) per CTA; map planes (cell, 4 position bytes, k + first-touch flags) staged
+// by bulk copies.  dynamic shared memory: [4 mbarriers | pad to 128 B][acc: maxlen x 128 doubles][4 warps x 3 planes x maxrows x 128 B]
+__global__ void __launch_bounds__(128, 8) k_rt0_mass_gather(const RGArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= a.slice_end) return;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned pst = (unsigned)a.maxrows * 128u;
+    const unsigned mbar = smem0 + warp * 8u;
+    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * 1024u + warp * 3u * pst;
+    const int64_t c = slice * 32 + lane;
+    const bool valid = c < a.ndofs;
+    const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
+    if (nrows > 0 && lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)nrows * 128u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * 3u) : "memory");
+        const uint32_t* g = a.map + ((size_t)row0 << 5);
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst), "l"(g + (size_t)p * a.stride),
+                         "r"(bytes), "r"(mbar)
+                         : "memory");
+    }
+    const bool zero_first = __ldg(a.slice_zero + slice) != 0;
+    int64_t base = 0;
+    int len = 0;
+    if (valid) {
+        base = a.colptr[c] - 1;
+        len = (int)(a.colptr[c + 1] - 1 - base);
+        if (a.sub0) {  // the block's run of the column
+            base += a.sub0[c];
+            len = a.sublen[c];
+        }
+    }
+    const unsigned sacc = smem0 + 128u + tid * 8u;
+    if (zero_first) {
+        for (int i = 0; i < len; i++) sts64(sacc + i * 1024u, 0.0);
+    }
+    __syncwarp();
+    const unsigned fmask = zero_first ? 0u : 0xFFFFFFFFu;
+    const unsigned sst = sstw + lane * 4u;
+    if (nrows > 0) {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+    }
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    if (nrows > 0) ldg256(a.rec + (size_t)lds32(sst) * 16 + 4u * ((lds32(sst + 2u * pst) >> 16) & 3u), r0, r1, r2, r3);
+    for (int r = 0; r < nrows; r++) {
+        const unsigned ra = sst + (unsigned)r * 128u;
+        const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst);
+        const unsigned k = (wb >> 16) & 0xFu;
+        const unsigned first = (wb >> 20) & fmask;
+        const double v[4] = {r0 * a.factor, r1 * a.factor, r2 * a.factor, r3 * a.factor};
+        if (r + 1 < nrows) ldg256(a.rec + (size_t)lds32(ra + 128u) * 16 + 4u * ((lds32(ra + 128u + 2u * pst) >> 16) & 3u), r0, r1, r2, r3);
+        if (k == 0xFu) continue;
+        unsigned ad[4];
+        double o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) ad[j] = sacc + ((wa >> (8 * j)) & 0xFFu) * 1024u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) sts64(ad[j], o[j] + v[j]);
+    }
+    if (!valid) return;
+    double* out = a.nzval + base;
+    for (int i = 0; i < len; i++) {
+        const double t = lds64(sacc + i * 1024u);
+        out[i] = a.acc_A ? out[i] + t : t;
+    }
+}
+
+// (div v_j, q_T) and its transposed copy: one contributing cell per entry -> plain adds through the slot maps
+__global__ void k_rt0_div(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol, const int32_t* __restrict__ signs,
+                          int64_t ncells, double f0, double f1, double f2, double f3, const int32_t* __restrict__ slots, const int32_t* __restrict__ slots_t,
+                          double* __restrict__ nzval, int32_t* __restrict__ errflag) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cell >= ncells) return;
+    double x[4][3];
+    load_nodes<3>(coords, cellnodes, cell, x);
+    double A[3][3];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) A[d][i] = x[i + 1][d] - x[0][d];
+    const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                       A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+    const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * (1.0 / 6.0);
+    const double f[4] = {f0, f1, f2, f3};
+    unsigned err = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const double v = (f[j] * ((double)__ldg(signs + cell * 4 + j) / det)) * vol;
+        const int32_t s = __ldg(slots + cell * 4 + j);
+        if (s < 0) err = 1u;
+        else nzval[s] += v;
+        if (slots_t) {
+            const int32_t st = __ldg(slots_t + cell * 4 + j);
+            if (st < 0) err = 1u;
+            else nzval[st] += v;
+        }
+    }
+    if (err) atomicAdd(errflag, 1);
+}
+
+bool rt0_enabled() {
+    static const bool on = [] { const char* e = getenv("FEMB_RT0_CLOSED"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+bool is_rt0_3d(const femb_ctx* ctx, const FembSpace& s) {
+    return ctx->dim == 3 && s.family == FEMB_FAMILY_HDIV && s.handler == FEMB_HANDLER_RT0_SIGNS && s.nd == 4 && s.nd_all == 4 && s.signs && s.nsign == 4;
+}
+
+}  // namespace
+
+int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor) {
+    if (!rt0_enabled()) return FEMB_ERR_UNSUPPORTED;
+    const FembEval& E = ctx->evals[er];
+    const FembSpace& s = ctx->spaces[E.space];
+    if (!is_rt0_3d(ctx, s) || brow != 0 || bcol != 0 || ctx->nrs < 1 || ctx->row_spaces[0] != E.space || ctx->col_spaces[0] != E.space) return FEMB_ERR_UNSUPPORTED;
+    if (E.h_refvals.size() != (size_t)E.nqp * 4 * 3) return FEMB_ERR_UNSUPPORTED;
+    {
+        // the closed form must reproduce  |T| sum_q w_q (A phi_j(q) / det).(A phi_k(q) / det)  of the evaluator's table on a test cell
+        const double X[4][3] = {{0.1, 0.0, 0.05}, {1.1, 0.2, 0.0}, {0.3, 0.9, 0.1}, {0.2, 0.1, 1.2}};
+        double A[3][3], c[3], S = 0.0;
+        for (int d = 0; d < 3; d++) {
+            for (int i = 0; i < 3; i++) A[d][i] = X[i + 1][d] - X[0][d];
+            c[d] = 0.25 * (X[0][d] + X[1][d] + X[2][d] + X[3][d]);
+        }
+        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        const double vol = fabs(det) / 6.0;
+        for (int i = 0; i < 4; i++)
+            for (int d = 0; d < 3; d++) S += (X[i][d] - c[d]) * (X[i][d] - c[d]);
+        S *= 0.05;
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++) {
+                double ref = 0.0, dot = 0.0;
+                for (int q = 0; q < E.nqp; q++) {
+                    double pj[3] = {0, 0, 0}, pk[3] = {0, 0, 0};
+                    for (int d = 0; d < 3; d++)
+                        for (int l = 0; l < 3; l++) {
+                            pj[d] += A[d][l] * E.h_refvals[((size_t)q * 4 + j) * 3 + l];
+                            pk[d] += A[d][l] * E.h_refvals[((size_t)q * 4 + k) * 3 + l];
+                        }
+                    ref += E.w[q] * (pj[0] * pk[0] + pj[1] * pk[1] + pj[2] * pk[2]);
+                }
+                ref *= vol / (det * det);
+                for (int d = 0; d < 3; d++) dot += (c[d] - X[rt0_opp(j)][d]) * (c[d] - X[rt0_opp(k)][d]);
+                const double closed = 4.0 * vol / (det * det) * (dot + S);
+                if (fabs(ref - closed) > 1e-12 * fabs(closed) + 1e-14) return FEMB_ERR_UNSUPPORTED;
+            }
+    }
+    int st = femb_build_hmap_vec(ctx);
+    if (st != FEMB_OK) return st;
+    FembHMap& H = ctx->hm_vec;
+    if (H.space != E.space || !H.complete || H.words != 2) return FEMB_ERR_UNSUPPORTED;
+    for (auto& r : H.ranges)
+        if (r.split != 1) return FEMB_ERR_UNSUPPORTED;
+    if (!ctx->rt0rec) FEMB_TRY(femb_alloc(ctx, &ctx->rt0rec, (size_t)ctx->ncells * 16));
+    if (ctx->ncells == 0) return FEMB_OK;
+    const bool fresh = ctx->zero_pending_A;  // right after femb_matrix_zero the runs are overwritten, not read-modify-written
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    if (H.cranges.empty()) {
+        const int64_t nslices = (s.ndofs + 31) / 32;
+        std::vector<int32_t> hptr((size_t)nslices + 1);
+        CUDA_TRY(ctx, cudaMemcpyAsync(hptr.data(), H.slice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<FembHMap::Range> out = H.ranges;
+        for (auto& c : out) {
+            c.maxrows = 1;
+            for (int64_t sl = c.s0; sl < c.s1; sl++) c.maxrows = std::max(c.maxrows, hptr[sl + 1] - hptr[sl]);
+        }
+        H.cranges = out;
+    }
+    auto smem_of = [](const FembHMap::Range& r) { return 128 + (size_t)std::max(1, r.maxlen) * 1024 + 4 * 3 * (size_t)r.maxrows * 128; };
+    size_t need = 0;
+    for (auto& r : H.cranges) need = std::max(need, smem_of(r));
+    if (need > 200 * 1024) return FEMB_ERR_UNSUPPORTED;
+    k_cell_rt0rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.signs, ctx->ncells, ctx->rt0rec);
+    KERNEL_CHECK(ctx);
+    RGArgs a;
+    a.rec = ctx->rt0rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride;
+    a.colptr = ctx->colptr + H.col_off; a.sub0 = H.sub0; a.sublen = H.sublen; a.ndofs = s.ndofs; a.nzval = ctx->nzval;
+    a.factor = factor;
+    a.acc_A = fresh ? 0 : 1;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_rt0_mass_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_rt0_mass_gather, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (auto& r : H.cranges) {
+        if (r.s1 <= r.s0) continue;
+        a.slice_begin = r.s0;
+        a.slice_end = r.s1;
+        a.maxlen = std::max(1, r.maxlen);
+        a.maxrows = r.maxrows;
+        k_rt0_mass_gather<<<(unsigned)((r.s1 - r.s0 + 3) / 4), 128, smem_of(r), ctx->stream>>>(a);
+        KERNEL_CHECK(ctx);
+    }
+    return FEMB_OK;
+}
+
+int launch_rt0_div(femb_ctx* ctx, int er, int ec, int brow, int bcol, double factor, int flags) {
+    if (!rt0_enabled()) return FEMB_ERR_UNSUPPORTED;
+    const FembEval& ER = ctx->evals[er];
+    const FembEval& EC = ctx->evals[ec];
+    const FembSpace& rs = ctx->spaces[ER.space];
+    const FembSpace& cs = ctx->spaces[EC.space];
+    if (!is_rt0_3d(ctx, rs) || cs.family != FEMB_FAMILY_L2 || cs.nd != 1 || cs.ncomp != 1 || ER.nqp != EC.nqp) return FEMB_ERR_UNSUPPORTED;
+    if (brow < 0 || brow >= ctx->nrs || bcol < 0 || bcol >= ctx->ncs || ctx->row_spaces[brow] != ER.space || ctx->col_spaces[bcol] != EC.space) return FEMB_ERR_UNSUPPORTED;
+    if (ER.h_refderivs.size() != (size_t)ER.nqp * 4 * 9 || EC.h_refvals.size() != (size_t)EC.nqp) return FEMB_ERR_UNSUPPORTED;
+    const FembBlock* blk = find_block(ctx, brow, bcol);
+    const FembBlock* blk_t = nullptr;
+    int tr = -1, tc = -1;
+    if (flags & FEMB_BIL_TRANSPOSE_COPY) {
+        for (int i = 0; i < ctx->nrs; i++) if (ctx->row_spaces[i] == EC.space) tr = i;
+        for (int i = 0; i < ctx->ncs; i++) if (ctx->col_spaces[i] == ER.space) tc = i;
+        blk_t = (tr >= 0 && tc >= 0) ? find_block(ctx, tr, tc) : nullptr;
+        if (!blk_t) return FEMB_ERR_UNSUPPORTED;
+    }
+    if (!blk) return FEMB_ERR_UNSUPPORTED;
+    FEMB_TRY(femb_build_slotmaps(ctx, brow, bcol));
+    if (blk_t) FEMB_TRY(femb_build_slotmaps(ctx, tr, tc));
+    blk = find_block(ctx, brow, bcol);
+    blk_t = blk_t ? find_block(ctx, tr, tc) : nullptr;
+    // sum_q w_q trace(D phi_j)(q) q_T(q): constant per reference function (feevaluator_hdiv.jl:66-83, the L2P0 value is 1)
+    double f[4];
+    for (int j = 0; j < 4; j++) {
+        f[j] = 0.0;
+        for (int q = 0; q < ER.nqp; q++) {
+            double tr3 = 0.0;
+            for (int d = 0; d < 3; d++) tr3 += ER.h_refderivs[((size_t)q * 4 + j) * 9 + d * 3 + d];
+            f[j] += ER.w[q] * tr3 * EC.h_refvals[q];
+        }
+        f[j] *= factor;
+    }
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    if (ctx->ncells == 0) return FEMB_OK;
+    k_rt0_div<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, rs.signs, ctx->ncells, f[0], f[1], f[2], f[3], blk->slots,
+                                                                             blk_t ? blk_t->slots : nullptr, ctx->nzval, ctx->errflag);
+    KERNEL_CHECK(ctx);
+    return FEMB_OK;
+}

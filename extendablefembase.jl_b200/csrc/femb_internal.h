@@ -146,6 +146,7 @@ struct femb_ctx {
     FembHMap hm, hm_vec;
     double* cellrhs = nullptr;     // [cell][qp][comp]: factor w_q |T| f(x_q), pre-pass of the Identity rhs gather
     size_t cellrhs_n = 0;
+    double* rt0rec = nullptr;      // [cell][16]: local RT0 mass matrix, one 32-byte column per face dof (femb_hdiv.cu)
     double* p2rec = nullptr;       // [cell][28]: per-cell record of the closed-form P2 gather (femb_p2.cu)
     double* cellcoef = nullptr;    // [cell][FEMB_COEF_STRIDE]: Kc (3 / 6) then |T| f(x_q) per quadrature point (pre-pass of the gather)
 
@@ -272,7 +273,7 @@ int femb_cellnodes_compare_async(femb_ctx* ctx, const int32_t* cellnodes, cudaSt
 int femb_cellnodes_differ(femb_ctx* ctx, bool* differ);
 // pattern.cu
 int femb_build_adjacency(femb_ctx* ctx, int space_id);
-int femb_build_slotmaps(femb_ctx* ctx);
+int femb_build_slotmaps(femb_ctx* ctx, int only_brow = -1, int only_bcol = -1);  // every block, or one
 int femb_build_gmap(femb_ctx* ctx);
 int femb_build_hmap(femb_ctx* ctx);
 int femb_build_hmap_vec(femb_ctx* ctx);  // lazy: component-diagonal map of block (0,0) of a vector-valued H1 space

@@ -60,3 +60,6 @@ int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu);
 // femb_p2.cu (FEMB_ERR_UNSUPPORTED, without an error message, when the closed form does not apply)
 int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol);
 int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu);
+// femb_hdiv.cu: HDIVRT0 on tetrahedra in closed form (FEMB_ERR_UNSUPPORTED, without an error message, when not covered)
+int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor);
+int launch_rt0_div(femb_ctx* ctx, int er, int ec, int brow, int bcol, double factor, int flags);

@@ -32,6 +32,7 @@ void femb_free_pattern(femb_ctx* ctx) {
     femb_free_hmap(ctx->hm_vec);
     femb_free(&ctx->cellcoef);
     femb_free(&ctx->p2rec);
+    femb_free(&ctx->rt0rec);
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
     ctx->nnz = 0;
@@ -576,11 +577,12 @@ __global__ void k_slotmap(const int32_t* __restrict__ rdofs, int ndr, int64_t ro
     slots[t] = (int32_t)find_slot(colptr, rowval, col, row1);
 }
 
-int femb_build_slotmaps(femb_ctx* ctx) {
+int femb_build_slotmaps(femb_ctx* ctx, int only_brow, int only_bcol) {
     if (ctx->nnz >= ((int64_t)1 << 31))
         return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "nnz >= 2^31: the cell-parallel kernels use 32-bit slot maps (the owner-computes gather paths do not)");
     for (auto& b : ctx->blocks) {
         if (b.slots) continue;  // built on first use
+        if (only_brow >= 0 && (b.brow != only_brow || b.bcol != only_bcol)) continue;
         const FembSpace& rs = ctx->spaces[ctx->row_spaces[b.brow]];
         const FembSpace& cs = ctx->spaces[ctx->col_spaces[b.bcol]];
         int64_t n = ctx->ncells * rs.nd * cs.nd;
@@ -911,9 +913,9 @@ int femb_hmap_set_canon(femb_ctx* ctx, FembHMap& H, bool canon) {
 // builds the map of the (component-diagonal part of the) square block of space `sid` whose rows / columns start at row_off / col_off
 static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off, int64_t col_off, bool subrange) {
     const FembSpace& s = ctx->spaces[sid];
-    const int nds = s.nd / s.ncomp;
+    const int nds = s.family == FEMB_FAMILY_HDIV ? s.nd : s.nd / s.ncomp;  // (Hdiv: vector-valued functions, one block of nd dofs)
     const int64_t nslices = (s.ndofs + 31) / 32;
-    const int nwords = (nds + 3) / 4;
+    const int nwords = (nds + 5) / 4;  // the position bytes + two spare bytes (k, first-touch flags) in the last word
     int32_t *deg = nullptr, *clen = nullptr;
     void* tmp = nullptr;
     {
@@ -1023,6 +1025,7 @@ static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off,
 }
 
 static bool hmap_space_ok(const femb_ctx* ctx, const FembSpace& s) {
+    if (s.family == FEMB_FAMILY_HDIV) return s.handler == FEMB_HANDLER_RT0_SIGNS && s.nd == s.nd_all && s.nd <= 4 && ctx->max_collen <= 254;  // RT0 (femb_hdiv.cu)
     if (s.family != FEMB_FAMILY_H1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd % s.ncomp || ctx->max_collen > 254) return false;
     const int nds = s.nd / s.ncomp;
     return nds <= 12 && ((nds & 3) == 1 || (nds & 3) == 2);  // the last position word must have two spare bytes (k + first-touch flags)
@@ -1067,7 +1070,7 @@ int femb_build_hmap_vec(femb_ctx* ctx) {
     // component-wise form are copies of each other, a gather may compute one and write all (femb_p2.cu)
     FembHMap& H = ctx->hm_vec;
     H.twins = 1;
-    if (s.ncomp > 1 && s.ndofs % s.ncomp == 0 && ctx->ncells > 0) {
+    if (s.family == FEMB_FAMILY_H1 && s.ncomp > 1 && s.ndofs % s.ncomp == 0 && ctx->ncells > 0) {
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->errflag, 0, sizeof(int32_t), ctx->stream));
         const int64_t n = s.ndofs / s.ncomp;
         k_check_twins<<<(unsigned)((std::max<int64_t>(ctx->ncells, n) + 255) / 256), 256, 0, ctx->stream>>>(s.celldofs, ctx->ncells, s.nd, s.ncomp, n, H.sublen, ctx->errflag);
