@@ -40,7 +40,7 @@ def _stamp() -> str:
         if os.path.isfile(p):
             h.update(name.encode())
             h.update(open(p, "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(f.replace(ROOT, "<root>") for f in NVCC_FLAGS).encode())  # (the checkout may live under another path on the GPU box)
     return h.hexdigest()
 
 
@@ -50,11 +50,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return os.environ["FEMB_LIB"]  # an alternative, already built library was requested
     stamp_file = os.path.join(HERE, "build", "stamp")
     stamp = _stamp()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+
+    def fresh() -> bool:
+        return os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp
+
+    if not force and fresh():
         return LIB
-    nvcc = _nvcc()
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
+    # several ranks of one node may get here at once: one builds, the others wait on the lock and find the fresh stamp
+    import fcntl
+
+    with open(os.path.join(bdir, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return LIB
+        return _build_locked(bdir, stamp, stamp_file, verbose)
+
+
+def _build_locked(bdir: str, stamp: str, stamp_file: str, verbose: bool) -> str:
+    nvcc = _nvcc()
     objs, procs = [], []
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
@@ -70,10 +85,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(out, file=sys.stderr)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB)  # never a half-written library under the final name
     with open(stamp_file, "w") as f:
         f.write(stamp)
     return LIB
