@@ -109,6 +109,8 @@ void femb_free_exchange(femb_ctx* ctx) {
     ctx->nsend = ctx->nrecv = ctx->nsendb = ctx->nrecvb = 0;
     ctx->xdof_send_lo = ctx->xdof_recv_lo = 0;
     ctx->xdof_send_hi = ctx->xdof_recv_hi = -1;
+    ctx->xslices.clear();
+    ctx->exchange_version++;
 }
 
 int femb_exchange_on(femb_ctx* ctx, cudaStream_t stream) {
@@ -245,6 +247,12 @@ int32_t femb_comm_set_exchange(femb_ctx* ctx, int32_t npeers, const int32_t* pee
         ctx->xdof_recv_lo = *std::min_element(recv_b, recv_b + nrecvb);
         ctx->xdof_recv_hi = *std::max_element(recv_b, recv_b + nrecvb);
     }
+    ctx->xslices.clear();
+    for (int64_t i = 0; i < nsendb; i++) ctx->xslices.push_back(send_b[i] >> 5);
+    for (int64_t i = 0; i < nrecvb; i++) ctx->xslices.push_back(recv_b[i] >> 5);
+    std::sort(ctx->xslices.begin(), ctx->xslices.end());
+    ctx->xslices.erase(std::unique(ctx->xslices.begin(), ctx->xslices.end()), ctx->xslices.end());
+    ctx->exchange_version++;
     ctx->exchange_nnz = ctx->nnz;
     return FEMB_OK;
 }

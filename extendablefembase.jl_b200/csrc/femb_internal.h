@@ -75,6 +75,9 @@ struct FembHMap {
     bool canon = false;             // positions / first-touch flags of every entry are in P2 role order (femb_p2.cu) instead of local dof order
     struct Range { int64_t s0, s1; int maxlen; int split; int mode = 2; int maxrows = 0; };  // split: threads per column (1, or 4 for high-degree columns)
     std::vector<Range> ranges;      // contiguous slice ranges with their longest CSC column (shared-memory sizing)
+    struct XList { int32_t* ifc = nullptr; int64_t n_ifc = 0; int32_t* rest = nullptr; int64_t n_rest = 0; };  // per crange: interface slices / all others
+    std::vector<XList> xlists;
+    int xlists_version = -1;
     std::vector<Range> cranges;     // femb_p2.cu: `ranges` cut where the kind of dof changes (mode 0 = vertex dofs, 1 = edge dofs, 2 = both)
 };
 
@@ -202,6 +205,8 @@ struct femb_ctx {
     int64_t exchange_nnz = -1;      // nnz of the pattern the plan was validated against
     // fused (overlapped) exchange: dof ranges that must be assembled before the exchange may start
     bool fused_exchange = false;
+    std::vector<int64_t> xslices;   // sorted: the 32-column slices that hold a ghost (sent) or an owned interface (received) dof
+    int exchange_version = 0;       // bumped by every change of the plan (cached per-pattern launch lists check it)
     bool exchange_done = false;     // set by the assembly path that performed the (overlapped) exchange itself
     int64_t xdof_send_lo = 0, xdof_send_hi = -1, xdof_recv_lo = 0, xdof_recv_hi = -1;  // [lo, hi] of send_b / recv_b
     cudaStream_t stream_x = nullptr;

@@ -64,6 +64,7 @@ struct P2Args {
     double* bvec;
     int acc_A, acc_b, has_rhs;
     int64_t slice_begin, slice_end;
+    const int32_t* slice_list;  // NULL, or the slices of this launch (overlapped interface exchange): slice_begin .. slice_end then index the list
     int twins;            // 2-D vector maps: the columns c, c + ndofs, ... (one per component) receive the same values
     int maxlen, maxrows;  // of the launch range: longest CSC column, most visits of a slice (shared-memory layout)
     P2Const c;
@@ -361,8 +362,9 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double bpart[SPLIT == 1 ? 1 : 4][32];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const int64_t slice = a.slice_begin + (SPLIT == 1 ? (int64_t)blockIdx.x * 4 + warp : (int64_t)blockIdx.x);
+    int64_t slice = a.slice_begin + (SPLIT == 1 ? (int64_t)blockIdx.x * 4 + warp : (int64_t)blockIdx.x);
     if (SPLIT == 1 && slice >= a.slice_end) return;
+    if (a.slice_list) slice = __ldg(a.slice_list + slice);
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned pst = (unsigned)a.maxrows * 128u;
     const unsigned mbar = smem0 + (SPLIT == 1 ? warp : 0u) * 8u;
@@ -859,6 +861,7 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
         if (a.has_rhs) ctx->zero_pending_b = false;
     }
     a.slice_begin = a.slice_end = 0;
+    a.slice_list = nullptr;
     a.c = cst;
     a.twins = 1;
     int64_t slice_cap = INT64_MAX;
@@ -961,6 +964,7 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
     a.has_rhs = rhs.kind != FEMB_RHS_NONE;
     a.slice_begin = a.slice_end = 0;
+    a.slice_list = nullptr;
     a.c = cst;
     a.twins = 1;
     ctx->zero_pending_A = false;
@@ -1019,16 +1023,67 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
                 CUDA_TRY(ctx, cudaFuncSetAttribute(kern[sp][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[sp][m]));
                 CUDA_TRY(ctx, cudaFuncSetAttribute(kern[sp][m], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             }
-        for (auto& r : H.cranges) {
-            if (r.s1 <= r.s0) continue;
-            a.slice_begin = r.s0;
-            a.slice_end = r.s1;
+        auto launch = [&](const FembHMap::Range& r, const int32_t* list, int64_t b0, int64_t b1, cudaStream_t stream) -> int {
+            if (b1 <= b0) return FEMB_OK;
+            a.slice_list = list;
+            a.slice_begin = b0;
+            a.slice_end = b1;
             a.maxlen = std::max(1, r.maxlen);
             a.maxrows = r.maxrows;
             void* params[1] = {(void*)&a};
-            const unsigned grid = r.split == 4 ? (unsigned)(r.s1 - r.s0) : (unsigned)((r.s1 - r.s0 + 3) / 4);
-            CUDA_TRY(ctx, cudaLaunchKernel(kern[r.split == 4][r.mode], dim3(grid), dim3(128), params, smem_of(r), ctx->stream));
+            const unsigned grid = r.split == 4 ? (unsigned)(b1 - b0) : (unsigned)((b1 - b0 + 3) / 4);
+            CUDA_TRY(ctx, cudaLaunchKernel(kern[r.split == 4][r.mode], dim3(grid), dim3(128), params, smem_of(r), stream));
             KERNEL_CHECK(ctx);
+            return FEMB_OK;
+        };
+        const bool fused = ctx->fused_exchange && ctx->comm && !ctx->peers.empty() && ctx->stream_x && !ctx->xslices.empty();
+        if (fused) {
+            // overlapped interface exchange (as the P1 path): the slices that hold ghost or owned-interface columns are
+            // assembled first on the high-priority stream, followed there by pack / NCCL / add, while the main stream
+            // assembles all other slices.  Vertex and edge dofs are numbered apart, so the interface is a LIST of slices.
+            if (H.xlists_version != ctx->exchange_version) {
+                for (auto& x : H.xlists) {
+                    femb_free(&x.ifc);
+                    femb_free(&x.rest);
+                }
+                H.xlists.assign(H.cranges.size(), FembHMap::XList());
+                for (size_t i = 0; i < H.cranges.size(); i++) {
+                    const auto& r = H.cranges[i];
+                    std::vector<int32_t> li, lr;
+                    auto it = std::lower_bound(ctx->xslices.begin(), ctx->xslices.end(), r.s0);
+                    for (int64_t sl = r.s0; sl < r.s1; sl++) {
+                        if (it != ctx->xslices.end() && *it == sl) {
+                            li.push_back((int32_t)sl);
+                            ++it;
+                        } else {
+                            lr.push_back((int32_t)sl);
+                        }
+                    }
+                    auto& x = H.xlists[i];
+                    x.n_ifc = (int64_t)li.size();
+                    x.n_rest = (int64_t)lr.size();
+                    if (x.n_ifc) {
+                        FEMB_TRY(femb_alloc(ctx, &x.ifc, li.size()));
+                        FEMB_TRY(femb_h2d(ctx, x.ifc, li.data(), li.size()));
+                    }
+                    if (x.n_rest) {
+                        FEMB_TRY(femb_alloc(ctx, &x.rest, lr.size()));
+                        FEMB_TRY(femb_h2d(ctx, x.rest, lr.data(), lr.size()));
+                    }
+                }
+                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                H.xlists_version = ctx->exchange_version;
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_x0, ctx->stream));  // the records (and everything queued before) come first
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_x, ctx->ev_x0, 0));
+            for (size_t i = 0; i < H.cranges.size(); i++) FEMB_TRY(launch(H.cranges[i], H.xlists[i].ifc, 0, H.xlists[i].n_ifc, ctx->stream_x));
+            FEMB_TRY(femb_exchange_on(ctx, ctx->stream_x));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_x1, ctx->stream_x));
+            for (size_t i = 0; i < H.cranges.size(); i++) FEMB_TRY(launch(H.cranges[i], H.xlists[i].rest, 0, H.xlists[i].n_rest, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x1, 0));
+            ctx->exchange_done = true;
+        } else {
+            for (auto& r : H.cranges) FEMB_TRY(launch(r, nullptr, r.s0, r.s1, ctx->stream));
         }
     }
     return FEMB_OK;

@@ -867,6 +867,12 @@ void femb_free_hmap(FembHMap& H) {
     H.canon = false;
     H.ranges.clear();
     H.cranges.clear();
+    for (auto& x : H.xlists) {
+        femb_free(&x.ifc);
+        femb_free(&x.rest);
+    }
+    H.xlists.clear();
+    H.xlists_version = -1;
 }
 
 // in-place permutation of the position bytes and first-touch flags of every map entry: role order <-> local dof order
