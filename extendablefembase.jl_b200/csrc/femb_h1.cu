@@ -810,13 +810,14 @@ int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
 // Example210:284-290,368): every component is the scalar P2 stiffness, the cross-component entries are exact zeros.  Owner-
 // computes by column like the scalar case (write-once per launch, bit-reproducible); the columns also hold rows of other
 // blocks, so the result is ADDED to nzval (the lazy zero is flushed first).  FEMB_ERR_UNSUPPORTED when not covered.
-int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu) {
+int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu, int ei, const RhsDev* rhs, bool* rhs_done) {
+    if (rhs_done) *rhs_done = false;
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
     if (s.ncomp < 2 || ctx->touched || EG.nqp > 10) return FEMB_ERR_UNSUPPORTED;
     {
         // P2 on triangles: closed-form kernel (femb_p2.cu)
-        const int st2 = launch_p2_gather_vec(ctx, eg, mu);
+        const int st2 = launch_p2_gather_vec(ctx, eg, mu, ei, rhs, rhs_done);
         if (st2 != FEMB_ERR_UNSUPPORTED) return st2;
     }
     if (EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * s.ncomp * ctx->dim) return FEMB_ERR_UNSUPPORTED;

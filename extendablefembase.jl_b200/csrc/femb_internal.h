@@ -149,6 +149,7 @@ struct femb_ctx {
     FembHMap hm, hm_vec;
     double* cellrhs = nullptr;     // [cell][qp][comp]: factor w_q |T| f(x_q), pre-pass of the Identity rhs gather
     size_t cellrhs_n = 0;
+    double* p2vrhs = nullptr;      // [cell][6][2]: local entries of a two-component load on P2 triangles (fused rhs of Example210, femb_p2.cu)
     double* rt0rec = nullptr;      // [cell][16]: local RT0 mass matrix, one 32-byte column per face dof (femb_hdiv.cu)
     double* p2rec = nullptr;       // [cell][28]: per-cell record of the closed-form P2 gather (femb_p2.cu)
     double* cellcoef = nullptr;    // [cell][FEMB_COEF_STRIDE]: Kc (3 / 6) then |T| f(x_q) per quadrature point (pre-pass of the gather)

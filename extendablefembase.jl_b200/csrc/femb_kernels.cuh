@@ -56,10 +56,10 @@ int launch_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
 // femb_h1.cu (both return FEMB_ERR_UNSUPPORTED, without an error message, when the path does not cover the space)
 int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_tol);
 int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol);
-int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu);
+int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu, int ei = -1, const RhsDev* rhs = nullptr, bool* rhs_done = nullptr);
 // femb_p2.cu (FEMB_ERR_UNSUPPORTED, without an error message, when the closed form does not apply)
 int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol);
-int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu);
+int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu, int ei = -1, const RhsDev* rhs = nullptr, bool* rhs_done = nullptr);
 // femb_hdiv.cu: HDIVRT0 on tetrahedra in closed form (FEMB_ERR_UNSUPPORTED, without an error message, when not covered)
 int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor);
 int launch_rt0_div(femb_ctx* ctx, int er, int ec, int brow, int bcol, double factor, int flags);

@@ -247,12 +247,13 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
         // component-blocked basis: the 12x12 local matrix is two copies of the scalar 6x6 P2 stiffness; its
         // off-diagonal blocks are exact zeros (their slots stay in the pattern, adding 0.0 changes nothing)
         // default policy: owner-computes gather per component (write-once per launch, bit-reproducible); else the DMMA scatter
-        st = ctx->scatter == FEMB_SCATTER_GATHER ? launch_h1_gather_vec(ctx, egu, mu) : FEMB_ERR_UNSUPPORTED;
+        bool rhs_done = false;  // the load of the velocity space is fused into the Laplacian gather where that kernel covers it
+        st = ctx->scatter == FEMB_SCATTER_GATHER ? launch_h1_gather_vec(ctx, egu, mu, eiu, &rhs, &rhs_done) : FEMB_ERR_UNSUPPORTED;
         if (st == FEMB_ERR_UNSUPPORTED) st = ctx->scatter == FEMB_SCATTER_COLORED ? FEMB_ERR_UNSUPPORTED : launch_stiffness_dmma(ctx, egu, mu, -1.0);
         if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, egu, egu, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, 0, 0.0);
         // Bloc[j,k] = -sum_qp w (g[1,j]+g[4,j]) psi_k * |T| into (u,p) and (p,u) (Example210:293-301,376-380)
         if (st == FEMB_OK) st = launch_bilinear(ctx, egu, eip, FEMB_OP_GRADTRACE, FEMB_OP_IDENTITY, 0, 1, -1.0, FEMB_BIL_TRANSPOSE_COPY, 0.0);
-        if (st == FEMB_OK && rhs.kind != FEMB_RHS_NONE) st = launch_linear(ctx, eiu, 0, 1.0, rhs);
+        if (st == FEMB_OK && rhs.kind != FEMB_RHS_NONE && !rhs_done) st = launch_linear(ctx, eiu, 0, 1.0, rhs);
     }
     if (st == FEMB_OK && nonlinear) {
         st = femb_build_slotmaps(ctx);

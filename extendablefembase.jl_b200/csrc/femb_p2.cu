@@ -64,6 +64,7 @@ struct P2Args {
     double* bvec;
     int acc_A, acc_b, has_rhs;
     int64_t slice_begin, slice_end;
+    const double* vrhs;         // 2-D vector maps: local rhs entries [cell][6][2] of a two-component load (fused rhs of Example210), or NULL
     const int32_t* slice_list;  // NULL, or the slices of this launch (overlapped interface exchange): slice_begin .. slice_end then index the list
     int twins;            // 2-D vector maps: the columns c, c + ndofs, ... (one per component) receive the same values
     int maxlen, maxrows;  // of the launch range: longest CSC column, most visits of a slice (shared-memory layout)
@@ -575,7 +576,7 @@ struct P2Wphi2 {
 };
 
 __global__ void __launch_bounds__(128) k_cell_p2rec2d(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
-                                                      int64_t ncells, double mu, RhsDev rhs, QuadDev q, P2Wphi2 wp, double* __restrict__ out) {
+                                                      int64_t ncells, double mu, RhsDev rhs, QuadDev q, P2Wphi2 wp, double* __restrict__ out, double* __restrict__ vrhs) {
     __shared__ double tile[128][P2_REC2 + 1];
     const int64_t cell0 = blockIdx.x * (int64_t)blockDim.x;
     const int64_t cell = cell0 + threadIdx.x;
@@ -592,7 +593,25 @@ __global__ void __launch_bounds__(128) k_cell_p2rec2d(const double* __restrict__
         double bl[6];
 #pragma unroll
         for (int j = 0; j < 6; j++) bl[j] = 0.0;
-        if (rhs.kind != FEMB_RHS_NONE) {
+        if (vrhs) {
+            // two-component load (Example210:304-318 with the component-blocked basis): b_(c,j) = |T| sum_q w_q phi_j(x_q) f_c(x_q)
+            double b0[6], b1[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) b0[j] = b1[j] = 0.0;
+            for (int qp = 0; qp < q.nqp; qp++) {
+                const double xq[2] = {x[0][0] + a00 * q.xref[qp * 2] + a01 * q.xref[qp * 2 + 1], x[0][1] + a10 * q.xref[qp * 2] + a11 * q.xref[qp * 2 + 1]};
+                double f[3];
+                eval_rhs<2>(rhs, xq, cell, qp, q.nqp, f);
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    b0[j] += wp.v[qp][j] * f[0];
+                    b1[j] += wp.v[qp][j] * f[1];
+                }
+            }
+            double2* o2 = reinterpret_cast<double2*>(vrhs) + cell * 6;
+#pragma unroll
+            for (int j = 0; j < 6; j++) o2[j] = make_double2(b0[j] * vol, b1[j] * vol);
+        } else if (rhs.kind != FEMB_RHS_NONE) {
             for (int qp = 0; qp < q.nqp; qp++) {
                 double f;
                 if (rhs.kind == FEMB_RHS_AFFINE) {
@@ -672,7 +691,13 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
     }
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-    if (nrows > 0) ldg256(a.rec + (size_t)lds32(sst) * P2_REC2 + 4u * min((lds32(sst + 2u * pst) >> 16) & 0xFu, 5u), r0, r1, r2, r3);
+    double2 q1 = make_double2(0.0, 0.0);
+    double vb0 = 0.0, vb1 = 0.0;
+    if (nrows > 0) {
+        const unsigned k0 = min((lds32(sst + 2u * pst) >> 16) & 0xFu, 5u);
+        ldg256(a.rec + (size_t)lds32(sst) * P2_REC2 + 4u * k0, r0, r1, r2, r3);
+        if (a.vrhs) q1 = __ldg(reinterpret_cast<const double2*>(a.vrhs) + (size_t)lds32(sst) * 6 + k0);
+    }
     double racc[3] = {0.0, 0.0, 0.0};
     unsigned rad[3] = {0u, 0u, 0u};
     for (int r = 0; r < nrows; r++) {
@@ -681,8 +706,15 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
         const unsigned k = (wb >> 16) & 0xFu;
         const unsigned first = (wb >> 20) & fmask;
         const double c0 = r0, c1 = r1, c2 = r2, c3 = r3;
-        if (r + 1 < nrows) ldg256(a.rec + (size_t)lds32(ra + 128u) * P2_REC2 + 4u * min((lds32(ra + 128u + 2u * pst) >> 16) & 0xFu, 5u), r0, r1, r2, r3);
+        const double2 qc = q1;
+        if (r + 1 < nrows) {
+            const unsigned k1 = min((lds32(ra + 128u + 2u * pst) >> 16) & 0xFu, 5u);
+            ldg256(a.rec + (size_t)lds32(ra + 128u) * P2_REC2 + 4u * k1, r0, r1, r2, r3);
+            if (a.vrhs) q1 = __ldg(reinterpret_cast<const double2*>(a.vrhs) + (size_t)lds32(ra + 128u) * 6 + k1);
+        }
         if (k == 0xFu) continue;
+        vb0 += qc.x;
+        vb1 += qc.y;
         unsigned ad[6];
 #pragma unroll
         for (int j = 0; j < 6; j++) ad[j] = sacc + (((j < 4 ? wa : wb) >> (8 * (j & 3))) & 0xFFu) * 1024u;
@@ -768,6 +800,10 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
         if (a.acc_b) a.bvec[c] += bsum;
         else a.bvec[c] = bsum;
     }
+    if (a.vrhs) {  // (twins = 2: the scalar dof c carries both components)
+        a.bvec[c] += vb0;
+        a.bvec[c + a.ndofs] += vb1;
+    }
 }
 
 }  // namespace
@@ -791,7 +827,8 @@ void femb_p2_role_perm(uint8_t perm[12][12], int dim) {
 
 // P2 on triangles: H = the scalar map (Example200) or the component-diagonal map of a vector space (Example210's Laplacian:
 // EI = nullptr, the result is added to nzval).  FEMB_ERR_UNSUPPORTED (no message) when the closed form does not apply.
-static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, const FembEval* EI, double mu, const RhsDev& rhs, bool vec, bool vec_fresh = false) {
+static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, const FembEval* EI, double mu, const RhsDev& rhs, bool vec, bool vec_fresh = false,
+                              bool vec_rhs = false) {
     const FembSpace& s = ctx->spaces[EG.space];
     const int nc = s.ncomp;
     if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * nc * 2) return P2_UNSUPPORTED;
@@ -845,7 +882,9 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
     for (int q = 0; q < FEMB_COEF_STRIDE - 6; q++)
         for (int j = 0; j < 6; j++) wp.v[q][j] = (EI && q < EG.nqp) ? EG.w[q] * EI->h_refvals[((size_t)q * s.nd_all + j) * nc] : 0.0;
     QuadDev q = quad_dev(EG, 2);
-    k_cell_p2rec2d<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec);
+    if (vec_rhs && !ctx->p2vrhs) FEMB_TRY(femb_alloc(ctx, &ctx->p2vrhs, (size_t)ctx->ncells * 12));
+    k_cell_p2rec2d<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec,
+                                                                                 vec_rhs ? ctx->p2vrhs : nullptr);
     KERNEL_CHECK(ctx);
     P2Args a;
     a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr + H.col_off; a.sub0 = H.sub0; a.sublen = H.sublen; a.ndofs = s.ndofs;
@@ -862,6 +901,7 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
     }
     a.slice_begin = a.slice_end = 0;
     a.slice_list = nullptr;
+    a.vrhs = vec_rhs ? ctx->p2vrhs : nullptr;
     a.c = cst;
     a.twins = 1;
     int64_t slice_cap = INT64_MAX;
@@ -891,7 +931,8 @@ static bool p2_closed_enabled() {
 }
 
 // mu (grad u, grad v) of a component-blocked vector-valued P2 space on triangles in block (0,0) (Example210's Laplacian), added to nzval
-int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu) {
+int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu, int ei, const RhsDev* rhs, bool* rhs_done) {
+    if (rhs_done) *rhs_done = false;
     if (!p2_closed_enabled()) return P2_UNSUPPORTED;
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
@@ -903,6 +944,15 @@ int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu) {
     // right after femb_matrix_zero the runs can be overwritten instead of read, added to and written back
     const bool fresh = ctx->zero_pending_A;
     FEMB_TRY(femb_flush_zero(ctx, true, false));
+    // the load of the same space rides along (Example210:304-318): its local entries come from the pre-pass, the gather sums them
+    const bool with_rhs = rhs && rhs_done && rhs->kind != FEMB_RHS_NONE && rhs->ncomp == 2 && s.ncomp == 2 && H.twins == 2 && ei >= 0 && ctx->evals[ei].space == EG.space &&
+                          ctx->evals[ei].op == FEMB_OP_IDENTITY && ctx->evals[ei].nqp == EG.nqp && ctx->bvec;
+    if (with_rhs) {
+        FEMB_TRY(femb_flush_zero(ctx, false, true));
+        const int st2 = launch_p2_gather2d(ctx, H, EG, &ctx->evals[ei], mu, *rhs, true, fresh, true);
+        if (st2 == FEMB_OK) *rhs_done = true;
+        return st2;
+    }
     RhsDev norhs;
     norhs.kind = FEMB_RHS_NONE;
     norhs.ncomp = 1;
@@ -965,6 +1015,7 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     a.has_rhs = rhs.kind != FEMB_RHS_NONE;
     a.slice_begin = a.slice_end = 0;
     a.slice_list = nullptr;
+    a.vrhs = nullptr;
     a.c = cst;
     a.twins = 1;
     ctx->zero_pending_A = false;

@@ -33,6 +33,7 @@ void femb_free_pattern(femb_ctx* ctx) {
     femb_free(&ctx->cellcoef);
     femb_free(&ctx->p2rec);
     femb_free(&ctx->rt0rec);
+    femb_free(&ctx->p2vrhs);
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
     ctx->nnz = 0;
