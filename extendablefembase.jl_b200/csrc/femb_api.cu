@@ -99,6 +99,9 @@ int32_t femb_destroy(femb_ctx* ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     for (auto e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->stream_aux) cudaStreamDestroy(ctx->stream_aux);
+    if (ctx->ev_a0) cudaEventDestroy(ctx->ev_a0);
+    if (ctx->ev_a1) cudaEventDestroy(ctx->ev_a1);
     if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
     if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

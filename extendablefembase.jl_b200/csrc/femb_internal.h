@@ -92,6 +92,8 @@ struct femb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // streamed host-to-host assembly (femb_assemble_poisson_host)
     cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
+    cudaStream_t stream_aux = nullptr;          // second compute stream (femb_p2.cu: vertex-column and edge-column kernels side by side)
+    cudaEvent_t ev_a0 = nullptr, ev_a1 = nullptr;
     std::vector<cudaEvent_t> chunk_ev;          // 2 per chunk: upload done, kernel done
     std::vector<int64_t> chunk_slice, chunk_nmax, chunk_cmax, chunk_cp;  // per chunk: first slice, max node / cell id referenced, colptr at the chunk start (0-based)
     int chunk_n = 0;

@@ -1134,7 +1134,28 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
             CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_x1, 0));
             ctx->exchange_done = true;
         } else {
-            for (auto& r : H.cranges) FEMB_TRY(launch(r, nullptr, r.s0, r.s1, ctx->stream));
+            // the vertex-column kernel (barriers of its 4-warp split, L1 67 %) and the edge-column kernel (L1 79 %) leave different
+            // resources idle: run them side by side on two streams
+            static const bool conc = [] { const char* e = getenv("FEMB_P2_CONCURRENT"); return !(e && e[0] == '0'); }();
+            bool any0 = false, any1 = false;
+            for (auto& r : H.cranges) (r.mode == 0 ? any0 : any1) = true;
+            if (conc && any0 && any1) {
+                if (!ctx->stream_aux) {
+                    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking));
+                    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_a0, cudaEventDisableTiming));
+                    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_a1, cudaEventDisableTiming));
+                }
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a0, ctx->stream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_a0, 0));
+                for (auto& r : H.cranges)
+                    if (r.mode == 0) FEMB_TRY(launch(r, nullptr, r.s0, r.s1, ctx->stream_aux));
+                CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a1, ctx->stream_aux));
+                for (auto& r : H.cranges)
+                    if (r.mode != 0) FEMB_TRY(launch(r, nullptr, r.s0, r.s1, ctx->stream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_a1, 0));
+            } else {
+                for (auto& r : H.cranges) FEMB_TRY(launch(r, nullptr, r.s0, r.s1, ctx->stream));
+            }
         }
     }
     return FEMB_OK;
