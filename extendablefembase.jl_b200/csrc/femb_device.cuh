@@ -254,24 +254,33 @@ struct RhsDev {
     const double* fvals;  // [cell][qp][comp]
 };
 
-template <int DIM>
+// NC > 0: the caller knows the number of components at compile time (every index into f is then static: registers, not local memory)
+template <int DIM, int NC = 0>
 __device__ __forceinline__ void eval_rhs(const RhsDev& r, const double* x, int64_t cell, int qp, int nqp, double* f) {
+    const int nc = NC > 0 ? NC : r.ncomp;
     if (r.kind == FEMB_RHS_AFFINE) {
-        for (int c = 0; c < r.ncomp; c++) {
+#pragma unroll
+        for (int c = 0; c < nc; c++) {
             double s = r.p[c * (DIM + 1)];
 #pragma unroll
             for (int d = 0; d < DIM; d++) s += r.p[c * (DIM + 1) + 1 + d] * x[d];
             f[c] = s;
         }
     } else if (r.kind == FEMB_RHS_QPVALUES) {
-        for (int c = 0; c < r.ncomp; c++) f[c] = __ldg(r.fvals + ((size_t)cell * nqp + qp) * r.ncomp + c);
+#pragma unroll
+        for (int c = 0; c < nc; c++) f[c] = __ldg(r.fvals + ((size_t)cell * nqp + qp) * nc + c);
     } else if (r.kind == FEMB_RHS_EX210) {  // Example210:44-48
         const double pi = 3.14159265358979323846;
         double mu = r.p[0], t = r.p[1];
         double e = 8.0 * pi * pi * mu * exp(-8.0 * pi * pi * mu * t);
-        f[0] = e * sin(2.0 * pi * x[0]) * sin(2.0 * pi * x[1]);
-        f[1] = e * cos(2.0 * pi * x[0]) * cos(2.0 * pi * x[1]);
+        if (NC == 0 || NC >= 2) {
+            f[0] = e * sin(2.0 * pi * x[0]) * sin(2.0 * pi * x[1]);
+            f[NC == 1 ? 0 : 1] = e * cos(2.0 * pi * x[0]) * cos(2.0 * pi * x[1]);
+        } else {
+            f[0] = 0.0;  // (a two-component load)
+        }
     } else {
-        for (int c = 0; c < r.ncomp; c++) f[c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < nc; c++) f[c] = 0.0;
     }
 }

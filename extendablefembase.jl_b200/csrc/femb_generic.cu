@@ -8,6 +8,18 @@
 //   stage 5  right-hand side                    (Example200:165-178, Example210:304-318,358-363)
 #include "femb_kernels.cuh"
 
+// result lengths the operators of this path produce (Length4Operator): compile-time R keeps per-thread result arrays in registers
+#define FEMB_DISPATCH_R(R, CALL)                         \
+    switch (R) {                                         \
+        case 1: CALL(1); break;                          \
+        case 2: CALL(2); break;                          \
+        case 3: CALL(3); break;                          \
+        case 4: CALL(4); break;                          \
+        case 6: CALL(6); break;                          \
+        case 9: CALL(9); break;                          \
+        default: return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "operator result length %d is not instantiated", (int)(R)); \
+    }
+
 // ---------------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------------
@@ -160,34 +172,34 @@ extern "C" int32_t femb_qp_coords(femb_ctx* ctx, double* out) {
 // compute_error (Example210_LowLevelNavierStokes.jl:110-154): error[d, cell] = sum_qp (uh_d(x_qp) - u_d(x_qp))^p |T| w_qp with
 // uh = eval_febe! of the coefficient vector through any registered evaluator (Identity: L^p error, Gradient: its seminorm)
 // ---------------------------------------------------------------------------------------------------
-template <int DIM>
+template <int DIM, int R>  // R: result length of the operator at compile time (static indices: no local memory)
 __global__ void k_eval_error(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol, int64_t ncells,
-                             SpaceDev s, int op, int R, QuadDev q, const double* __restrict__ rv, const double* __restrict__ rd,
+                             SpaceDev s, int op, QuadDev q, const double* __restrict__ rv, const double* __restrict__ rd,
                              const double* __restrict__ coef, const double* __restrict__ exact, int p, double* __restrict__ out) {
     const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (cell >= ncells) return;
     Geo<DIM> g;
     load_geo<DIM>(coords, cellnodes, cellvol, cell, g);
-    double err[9];
-    for (int r = 0; r < R; r++) err[r] = 0.0;
+    double err[R];
+    _Pragma("unroll") for (int r = 0; r < R; r++) err[r] = 0.0;
     for (int qp = 0; qp < q.nqp; qp++) {
-        double uh[9];
-        for (int r = 0; r < R; r++) uh[r] = 0.0;
+        double uh[R];
+        _Pragma("unroll") for (int r = 0; r < R; r++) uh[r] = 0.0;
         for (int dof = 0; dof < s.nd; dof++) {
-            double v[9];
-            for (int r = 0; r < R; r++) v[r] = 0.0;
-            eval_op<DIM>(s, op, g, cell, dof, qp, rv, rd, v);
+            double v[R];
+            _Pragma("unroll") for (int r = 0; r < R; r++) v[r] = 0.0;
+            eval_op<DIM, R>(s, op, g, cell, dof, qp, rv, rd, v);
             const double c = coef[s.celldofs[cell * s.nd + dof] - 1];
-            for (int r = 0; r < R; r++) uh[r] += c * v[r];
+            _Pragma("unroll") for (int r = 0; r < R; r++) uh[r] += c * v[r];
         }
-        for (int r = 0; r < R; r++) {
+        _Pragma("unroll") for (int r = 0; r < R; r++) {
             const double diff = uh[r] - (exact ? exact[((size_t)cell * q.nqp + qp) * R + r] : 0.0);
             double pw = 1.0;
             for (int i = 0; i < p; i++) pw *= diff;
             err[r] += pw * g.vol * q.w[qp];
         }
     }
-    for (int r = 0; r < R; r++) out[cell * R + r] = err[r];
+    _Pragma("unroll") for (int r = 0; r < R; r++) out[cell * R + r] = err[r];
 }
 
 extern "C" int32_t femb_eval_error(femb_ctx* ctx, int32_t id, const double* coefficients, const double* exact_qp, int32_t p, double* error_out) {
@@ -208,12 +220,25 @@ extern "C" int32_t femb_eval_error(femb_ctx* ctx, int32_t id, const double* coef
     if (st == FEMB_OK) {
         const unsigned grid = (unsigned)((ctx->ncells + 127) / 128);
         const QuadDev q = quad_dev(e, ctx->dim);
-        if (ctx->dim == 2)
-            k_eval_error<2><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, space_dev(s), e.op, e.resultdim, q, e.refvals,
-                                                          e.refderivs, dcoef, dexact, p, dout);
-        else
-            k_eval_error<3><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, space_dev(s), e.op, e.resultdim, q, e.refvals,
-                                                          e.refderivs, dcoef, dexact, p, dout);
+#define FEMB_EE(RR)                                                                                                                                         \
+    do {                                                                                                                                                \
+        if (ctx->dim == 2)                                                                                                                              \
+            k_eval_error<2, RR><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, space_dev(s), e.op, q, e.refvals, \
+                                                               e.refderivs, dcoef, dexact, p, dout);                                                    \
+        else                                                                                                                                            \
+            k_eval_error<3, RR><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, space_dev(s), e.op, q, e.refvals, \
+                                                               e.refderivs, dcoef, dexact, p, dout);                                                    \
+    } while (0)
+        switch (e.resultdim) {
+            case 1: FEMB_EE(1); break;
+            case 2: FEMB_EE(2); break;
+            case 3: FEMB_EE(3); break;
+            case 4: FEMB_EE(4); break;
+            case 6: FEMB_EE(6); break;
+            case 9: FEMB_EE(9); break;
+            default: st = femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "operator result length %d is not instantiated", e.resultdim);
+        }
+#undef FEMB_EE
         ctx->launches++;
         st = femb_d2h(ctx, error_out, dout, (size_t)ctx->ncells * e.resultdim);
         if (st == FEMB_OK) st = femb_sync(ctx);
@@ -249,13 +274,13 @@ struct BilArgs {
 };
 
 
-template <int DIM>
+template <int DIM, int R>
 __global__ void __launch_bounds__(128) k_bilinear(BilArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Geo<DIM>* geo = reinterpret_cast<Geo<DIM>*>(smem_raw);
     double* rowv = reinterpret_cast<double*>(geo + a.cpb);
     const int ndr = a.rs.nd, ndc = a.cs.nd;
-    const int per_r = a.nqp * a.R * ndr, per_c = a.nqp * a.R * ndc;
+    const int per_r = a.nqp * R * ndr, per_c = a.nqp * R * ndc;
     double* colv = a.same ? rowv : rowv + (size_t)a.cpb * per_r;
     const int64_t base = a.p0 + (int64_t)blockIdx.x * a.cpb;
     const int ncl = (int)min((int64_t)a.cpb, a.p1 - base);
@@ -270,18 +295,20 @@ __global__ void __launch_bounds__(128) k_bilinear(BilArgs a) {
         int cl = i / (a.nqp * ndr), rem = i - cl * (a.nqp * ndr);
         int qp = rem / ndr, dof = rem - qp * ndr;
         int64_t cell = a.perm ? a.perm[base + cl] : base + cl;
-        double v[9];
-        eval_op<DIM>(a.rs, a.op_r, geo[cl], cell, dof, qp, a.rv_r, a.rd_r, v);
-        for (int r = 0; r < a.R; r++) rowv[(size_t)cl * per_r + (qp * a.R + r) * ndr + dof] = v[r];
+        double v[R];
+        eval_op<DIM, R>(a.rs, a.op_r, geo[cl], cell, dof, qp, a.rv_r, a.rd_r, v);
+#pragma unroll
+        for (int r = 0; r < R; r++) rowv[(size_t)cl * per_r + (qp * R + r) * ndr + dof] = v[r];
     }
     if (!a.same) {
         for (int i = tid; i < ncl * a.nqp * ndc; i += nt) {
             int cl = i / (a.nqp * ndc), rem = i - cl * (a.nqp * ndc);
             int qp = rem / ndc, dof = rem - qp * ndc;
             int64_t cell = a.perm ? a.perm[base + cl] : base + cl;
-            double v[9];
-            eval_op<DIM>(a.cs, a.op_c, geo[cl], cell, dof, qp, a.rv_c, a.rd_c, v);
-            for (int r = 0; r < a.R; r++) colv[(size_t)cl * per_c + (qp * a.R + r) * ndc + dof] = v[r];
+            double v[R];
+            eval_op<DIM, R>(a.cs, a.op_c, geo[cl], cell, dof, qp, a.rv_c, a.rd_c, v);
+#pragma unroll
+            for (int r = 0; r < R; r++) colv[(size_t)cl * per_c + (qp * R + r) * ndc + dof] = v[r];
         }
     }
     __syncthreads();
@@ -297,7 +324,7 @@ __global__ void __launch_bounds__(128) k_bilinear(BilArgs a) {
         double temp = 0.0;
         for (int qp = 0; qp < a.nqp; qp++) {
             double d = 0.0;
-            for (int r = 0; r < a.R; r++) d += rp[(qp * a.R + r) * ndr] * cp[(qp * a.R + r) * ndc];
+            for (int r = 0; r < R; r++) d += rp[(qp * R + r) * ndr] * cp[(qp * R + r) * ndc];
             temp += a.w[qp] * d;
         }
         const double vol = (a.flags & FEMB_BIL_NO_VOLUME) ? 1.0 : geo[cl].vol;
@@ -433,7 +460,10 @@ int launch_bilinear(femb_ctx* ctx, int er, int ec, int op_r, int op_c, int brow,
     a.cpb = cpb;
     size_t smem = cpb * (per_cell + geo_bytes);
     FEMB_TRY(femb_flush_zero(ctx, true, false));
-    void (*kern)(BilArgs) = ctx->dim == 2 ? k_bilinear<2> : k_bilinear<3>;
+    void (*kern)(BilArgs) = nullptr;
+#define FEMB_BK(RR) kern = ctx->dim == 2 ? k_bilinear<2, RR> : k_bilinear<3, RR>
+    FEMB_DISPATCH_R(a.R, FEMB_BK)
+#undef FEMB_BK
     // row-blocked kernel for the common (dim, nqp, R) combinations: one thread per (cell, row dof)
     void (*rows)(BilArgs) = nullptr;
     const int key = ctx->dim * 10000 + a.nqp * 100 + a.R;
@@ -484,9 +514,9 @@ int launch_bilinear(femb_ctx* ctx, int er, int ec, int op_r, int op_c, int brow,
 // linear form: owner-computes gather over the dof -> cell adjacency (write-once, fixed order)
 // ---------------------------------------------------------------------------------------------------
 // LIGHT: H1 / L2 Identity needs no inverse map — only A (for x_qp) and |T|: skips the divisions of mapderiv!
-template <int DIM, bool LIGHT>
+template <int DIM, bool LIGHT, int R>
 __global__ void __launch_bounds__(128) k_linear_gather(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes,
-                                                       const double* __restrict__ cellvol, SpaceDev s, int op, int R, QuadDev q,
+                                                       const double* __restrict__ cellvol, SpaceDev s, int op, QuadDev q,
                                                        const double* __restrict__ rv, const double* __restrict__ rd,
                                                        const int32_t* __restrict__ adj_ptr, const uint32_t* __restrict__ adj, int64_t ndofs,
                                                        RhsDev rhs, double factor, double* __restrict__ b) {
@@ -520,11 +550,12 @@ __global__ void __launch_bounds__(128) k_linear_gather(const double* __restrict_
         }
         double temp = 0.0;
         for (int qp = 0; qp < q.nqp; qp++) {
-            double x[DIM], f[3], v[9];
+            double x[DIM], f[R], v[R];
             eval_trafo<DIM>(g, q.xref + qp * DIM, x);
-            eval_rhs<DIM>(rhs, x, cell, qp, q.nqp, f);
-            eval_op<DIM>(s, op, g, cell, k, qp, rv, rd, v);
+            eval_rhs<DIM, R>(rhs, x, cell, qp, q.nqp, f);
+            eval_op<DIM, R>(s, op, g, cell, k, qp, rv, rd, v);
             double dt = 0.0;
+#pragma unroll
             for (int r = 0; r < R; r++) dt += v[r] * f[r];
             temp += q.w[qp] * dt;
         }
@@ -535,7 +566,7 @@ __global__ void __launch_bounds__(128) k_linear_gather(const double* __restrict_
 
 // Identity rhs of H1 / L2 spaces in two passes: the (possibly expensive) data f(x_q) is evaluated ONCE per cell and
 // quadrature point instead of once per (dof, cell) pair, then gathered per dof in a fixed order (write-once).
-template <int DIM>
+template <int DIM, int NC>
 __global__ void __launch_bounds__(128) k_cell_rhs(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
                                                   int64_t ncells, QuadDev q, RhsDev rhs, double factor, double* __restrict__ out) {
     const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -556,7 +587,7 @@ __global__ void __launch_bounds__(128) k_cell_rhs(const double* __restrict__ coo
                    A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0])) * (1.0 / 6.0);
     }
     for (int qp = 0; qp < q.nqp; qp++) {
-        double x[DIM], f[3];
+        double x[DIM], f[NC];
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             double sx = xn[0][d];
@@ -564,8 +595,9 @@ __global__ void __launch_bounds__(128) k_cell_rhs(const double* __restrict__ coo
             for (int i = 0; i < DIM; i++) sx += A[d][i] * q.xref[qp * DIM + i];
             x[d] = sx;
         }
-        eval_rhs<DIM>(rhs, x, cell, qp, q.nqp, f);
-        for (int c = 0; c < rhs.ncomp; c++) out[((size_t)cell * q.nqp + qp) * rhs.ncomp + c] = f[c] * (q.w[qp] * vol * factor);
+        eval_rhs<DIM, NC>(rhs, x, cell, qp, q.nqp, f);
+#pragma unroll
+        for (int c = 0; c < NC; c++) out[((size_t)cell * q.nqp + qp) * NC + c] = f[c] * (q.w[qp] * vol * factor);
     }
 }
 
@@ -608,24 +640,40 @@ int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const RhsDev& 
             ctx->cellrhs_n = need;
         }
         const unsigned gc = (unsigned)((ctx->ncells + 127) / 128);
-        if (ctx->dim == 2) k_cell_rhs<2><<<gc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, q, rhs, factor, ctx->cellrhs);
-        else k_cell_rhs<3><<<gc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, q, rhs, factor, ctx->cellrhs);
+#define FEMB_CR(NC)                                                                                                                                   \
+    do {                                                                                                                                          \
+        if (ctx->dim == 2) k_cell_rhs<2, NC><<<gc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, q, rhs, factor, ctx->cellrhs); \
+        else k_cell_rhs<3, NC><<<gc, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, q, rhs, factor, ctx->cellrhs);               \
+    } while (0)
+        if (rhs.ncomp == 1) FEMB_CR(1);
+        else if (rhs.ncomp == 2) FEMB_CR(2);
+        else if (rhs.ncomp == 3) FEMB_CR(3);
+        else return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "rhs with %d components", rhs.ncomp);
+#undef FEMB_CR
         KERNEL_CHECK(ctx);
         k_linear_gather_id<<<grid, 128, 0, ctx->stream>>>(space_dev(s), E.nqp, rhs.ncomp, E.refvals, ctx->cellrhs, s.adj_ptr, s.adj, s.ndofs,
                                                           ctx->bvec + ctx->row_off[brow]);
         KERNEL_CHECK(ctx);
         return FEMB_OK;
     }
-#define FEMB_LIN(D, L)                                                                                                                          \
-    k_linear_gather<D, L><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, E.resultdim, q, E.refvals, \
-                                                         E.refderivs, s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow])
-    if (ctx->dim == 2) {
-        if (light) FEMB_LIN(2, true);
-        else FEMB_LIN(2, false);
-    } else {
-        if (light) FEMB_LIN(3, true);
-        else FEMB_LIN(3, false);
-    }
+#define FEMB_LIN(D, L, RR)                                                                                                                        \
+    k_linear_gather<D, L, RR><<<grid, 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), E.op, q, E.refvals, E.refderivs, \
+                                                             s.adj_ptr, s.adj, s.ndofs, rhs, factor, ctx->bvec + ctx->row_off[brow])
+#define FEMB_LIN_R(RR)                       \
+    do {                                     \
+        if (ctx->dim == 2) {                 \
+            if (light) FEMB_LIN(2, true, RR); \
+            else FEMB_LIN(2, false, RR);     \
+        } else {                             \
+            if (light) FEMB_LIN(3, true, RR); \
+            else FEMB_LIN(3, false, RR);     \
+        }                                    \
+    } while (0)
+    if (E.resultdim == 1) FEMB_LIN_R(1);
+    else if (E.resultdim == 2) FEMB_LIN_R(2);
+    else if (E.resultdim == 3) FEMB_LIN_R(3);
+    else return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "rhs with %d components", E.resultdim);
+#undef FEMB_LIN_R
 #undef FEMB_LIN
     KERNEL_CHECK(ctx);
     return FEMB_OK;
