@@ -63,6 +63,9 @@ struct P2Args {
     double* nzval;
     double* bvec;
     int acc_A, acc_b, has_rhs;
+    int filt;         // value filter |v| <= drop_tol (Example200:150) and / or positions missing from a compressed pattern (0xFF -> dump row `maxlen`)
+    double drop_tol;
+    int32_t* errflag;
     int64_t slice_begin, slice_end;
     const double* vrhs;         // 2-D vector maps: local rhs entries [cell][6][2] of a two-component load (fused rhs of Example210), or NULL
     const int32_t* slice_list;  // NULL, or the slices of this launch (overlapped interface exchange): slice_begin .. slice_end then index the list
@@ -276,7 +279,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // map entries of all visits sit in shared memory (sst: this lane's column of the staged planes, pst: plane stride).
 template <int SPLIT, int MODE, int DEPTH>
 __device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int r, int nrows, unsigned sst, unsigned pst, unsigned sacc, unsigned fmask, unsigned warp,
-                                         double& bsum, double (&racc)[3], unsigned (&rad)[3]) {
+                                         double& bsum, double (&racc)[3], unsigned (&rad)[3], unsigned& err) {
     constexpr unsigned ncol = 128 / SPLIT;
     const unsigned ra = sst + (unsigned)r * 128u;
     const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst), wc = lds32(ra + 3u * pst);
@@ -293,6 +296,16 @@ __device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int 
     if (on) {
         const double bl = p2_column<MODE>(a.c, k, cur, v);
         if (a.has_rhs) bsum += bl;
+        if (a.filt) {  // (uniform) the reference's value filter; rows without a slot go to the dump row and must be filtered values
+#pragma unroll
+            for (int j = 0; j < 10; j++) {
+                const unsigned w = j < 4 ? wa : (j < 8 ? wb : wc);
+                const bool missing = ((w >> (8 * (j & 3))) & 0xFFu) == 0xFFu, big = fabs(v[j]) > a.drop_tol;
+                if (missing) ad[j] = sacc + (unsigned)a.maxlen * (ncol * 8u);
+                if (missing && big) err = 1u;
+                v[j] = big ? v[j] : 0.0;
+            }
+        }
     }
     if (r + DEPTH * SPLIT < nrows) {  // (uniform in the warp)
         const unsigned rn = ra + (unsigned)(DEPTH * SPLIT) * 128u;
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned pst = (unsigned)a.maxrows * 128u;
     const unsigned mbar = smem0 + (SPLIT == 1 ? warp : 0u) * 8u;
-    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * (ncol * 8u) + (SPLIT == 1 ? warp * 4u * pst : 0u);
+    const unsigned sstw = smem0 + 128u + (unsigned)(a.maxlen + 1) * (ncol * 8u) + (SPLIT == 1 ? warp * 4u * pst : 0u);
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
@@ -434,14 +447,14 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
         if (r < nrows) p2_load_rec<MODE>(a.rec, lds32(sst + (unsigned)r * 128u), (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu, a.has_rhs, rec[u]);
     }
     double racc[3] = {0.0, 0.0, 0.0};
-    unsigned rad[3] = {0u, 0u, 0u};
+    unsigned rad[3] = {0u, 0u, 0u}, err = 0u;
     for (int it = 0; it < niter; it += DEPTH) {
 #pragma unroll
         for (int u = 0; u < DEPTH; u++) {
             if (u == 0 || it + u < niter) {  // (uniform in the CTA)
                 const int r = (it + u) * SPLIT + rfirst;
                 // (SPLIT = 4: a warp whose row index is past nrows only takes part in the barriers)
-                if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, sacc, fmask, warp, bsum, racc, rad);
+                if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, sacc, fmask, warp, bsum, racc, rad, err);
                 else {
 #pragma unroll 1
                     for (int ph = 0; ph < SPLIT; ph++) __syncthreads();
@@ -449,6 +462,7 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
             }
         }
     }
+    if (err) atomicAdd(a.errflag, 1);
     if (SPLIT == 1 && MODE == 1 && rad[2] != 0u) {  // (a column with at least one visit)
 #pragma unroll
         for (int t = 0; t < 3; t++) sts64(rad[t], racc[t]);
@@ -650,7 +664,7 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned pst = (unsigned)a.maxrows * 128u;
     const unsigned mbar = smem0 + warp * 8u;
-    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * 1024u + warp * 3u * pst;
+    const unsigned sstw = smem0 + 128u + (unsigned)(a.maxlen + 1) * 1024u + warp * 3u * pst;
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
@@ -699,7 +713,7 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
         if (a.vrhs) q1 = __ldg(reinterpret_cast<const double2*>(a.vrhs) + (size_t)lds32(sst) * 6 + k0);
     }
     double racc[3] = {0.0, 0.0, 0.0};
-    unsigned rad[3] = {0u, 0u, 0u};
+    unsigned rad[3] = {0u, 0u, 0u}, err = 0u;
     for (int r = 0; r < nrows; r++) {
         const unsigned ra = sst + (unsigned)r * 128u;
         const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst);
@@ -726,6 +740,15 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
             v[3] = a.c.gd * c0 + a.c.go * gkk; v[4] = a.c.gd * c1 + a.c.go * gkk;
             v[5] = a.c.go * (c0 + c1);
             if (a.has_rhs) bsum += c2;
+            if (a.filt) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const bool missing = (((j < 4 ? wa : wb) >> (8 * (j & 3))) & 0xFFu) == 0xFFu, big = fabs(v[j]) > a.drop_tol;
+                    if (missing) ad[j] = sacc + (unsigned)a.maxlen * 1024u;
+                    if (missing && big) err = 1u;
+                    v[j] = big ? v[j] : 0.0;
+                }
+            }
             double o[6];
 #pragma unroll
             for (int j = 0; j < 6; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
@@ -738,6 +761,15 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
             v[3] = a.c.mus * (gii + gjj) + 2.0 * a.c.mud * c0;
             v[4] = a.c.mus * c2; v[5] = a.c.mus * c1;
             if (a.has_rhs) bsum += c3;
+            if (a.filt) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const bool missing = (((j < 4 ? wa : wb) >> (8 * (j & 3))) & 0xFFu) == 0xFFu, big = fabs(v[j]) > a.drop_tol;
+                    if (missing) ad[j] = sacc + (unsigned)a.maxlen * 1024u;
+                    if (missing && big) err = 1u;
+                    v[j] = big ? v[j] : 0.0;
+                }
+            }
             const bool sw = ad[0] > ad[1];  // CSC positions ascend with the row: orders the two endpoints globally
             racc[0] += sw ? v[1] : v[0];
             racc[1] += sw ? v[0] : v[1];
@@ -753,6 +785,7 @@ __global__ void __launch_bounds__(128, 6) k_p2_gather2d(const P2Args a) {
             for (int t = 0; t < 3; t++) sts64(ad[J[t]], o[t] + v[J[t]]);
         }
     }
+    if (err) atomicAdd(a.errflag, 1);
     if (rad[2] != 0u) {
 #pragma unroll
         for (int t = 0; t < 3; t++) sts64(rad[t], racc[t]);
@@ -828,7 +861,7 @@ void femb_p2_role_perm(uint8_t perm[12][12], int dim) {
 // P2 on triangles: H = the scalar map (Example200) or the component-diagonal map of a vector space (Example210's Laplacian:
 // EI = nullptr, the result is added to nzval).  FEMB_ERR_UNSUPPORTED (no message) when the closed form does not apply.
 static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, const FembEval* EI, double mu, const RhsDev& rhs, bool vec, bool vec_fresh = false,
-                              bool vec_rhs = false) {
+                              bool vec_rhs = false, double drop_tol = 0.0) {
     const FembSpace& s = ctx->spaces[EG.space];
     const int nc = s.ncomp;
     if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * nc * 2) return P2_UNSUPPORTED;
@@ -874,7 +907,7 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
         }
         H.cranges = out;
     }
-    auto smem_of = [](const FembHMap::Range& r) { return 128 + (size_t)std::max(1, r.maxlen) * 1024 + 4 * 3 * (size_t)r.maxrows * 128; };
+    auto smem_of = [](const FembHMap::Range& r) { return 128 + (size_t)(std::max(1, r.maxlen) + 1) * 1024 + 4 * 3 * (size_t)r.maxrows * 128; };
     size_t need = 0;
     for (auto& r : H.cranges) need = std::max(need, smem_of(r));
     if (need > 200 * 1024) return P2_UNSUPPORTED;
@@ -899,6 +932,9 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
         ctx->zero_pending_A = false;
         if (a.has_rhs) ctx->zero_pending_b = false;
     }
+    a.filt = (!H.complete || drop_tol > 0.0) ? 1 : 0;
+    a.drop_tol = drop_tol > 0.0 ? drop_tol : 0.0;
+    a.errflag = ctx->errflag;
     a.slice_begin = a.slice_end = 0;
     a.slice_list = nullptr;
     a.vrhs = vec_rhs ? ctx->p2vrhs : nullptr;
@@ -967,11 +1003,11 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     const FembSpace& s = ctx->spaces[EG.space];
     FembHMap& H = ctx->hm;
     if (ctx->dim == 2) {
-        if (s.nd != 6 || s.ncomp != 1 || !H.map || H.space != EG.space || !H.complete || ctx->touched || drop_tol > 0.0) return P2_UNSUPPORTED;
+        if (s.nd != 6 || s.ncomp != 1 || !H.map || H.space != EG.space || ctx->touched) return P2_UNSUPPORTED;
         if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return P2_UNSUPPORTED;
-        return launch_p2_gather2d(ctx, H, EG, rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr, mu, rhs, false);
+        return launch_p2_gather2d(ctx, H, EG, rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr, mu, rhs, false, false, false, drop_tol);
     }
-    if (ctx->dim != 3 || s.nd != 10 || s.ncomp != 1 || !H.map || H.space != EG.space || !H.complete || ctx->touched || drop_tol > 0.0) return P2_UNSUPPORTED;
+    if (ctx->dim != 3 || s.nd != 10 || s.ncomp != 1 || !H.map || H.space != EG.space || ctx->touched) return P2_UNSUPPORTED;
     if (EG.nqp > FEMB_COEF_STRIDE - 6 || EG.h_refderivs.size() != (size_t)EG.nqp * s.nd_all * 3) return P2_UNSUPPORTED;
     if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return P2_UNSUPPORTED;
     const FembEval* EI = rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr;
@@ -1013,6 +1049,9 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
     a.has_rhs = rhs.kind != FEMB_RHS_NONE;
+    a.filt = (!H.complete || drop_tol > 0.0) ? 1 : 0;
+    a.drop_tol = drop_tol > 0.0 ? drop_tol : 0.0;
+    a.errflag = ctx->errflag;
     a.slice_begin = a.slice_end = 0;
     a.slice_list = nullptr;
     a.vrhs = nullptr;
@@ -1063,7 +1102,7 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
                                   {(const void*)k_p2_gather<4, 0>, (const void*)k_p2_gather<4, 1>, (const void*)k_p2_gather<4, 2>}};
         auto smem_of = [](const FembHMap::Range& r) {
             const size_t ncol = r.split == 4 ? 32 : 128, nstage = r.split == 4 ? 1 : 4;
-            return 128 + (size_t)std::max(1, r.maxlen) * ncol * sizeof(double) + nstage * 4 * (size_t)r.maxrows * 128;
+            return 128 + (size_t)(std::max(1, r.maxlen) + 1) * ncol * sizeof(double) + nstage * 4 * (size_t)r.maxrows * 128;
         };
         size_t need[2][3] = {{0, 0, 0}, {0, 0, 0}};
         for (auto& r : H.cranges) need[r.split == 4][r.mode] = std::max(need[r.split == 4][r.mode], smem_of(r));
