@@ -58,7 +58,13 @@ int launch_stiffness_dmma(femb_ctx* ctx, int eg, double mu, double drop_tol);
 int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol);
 int launch_h1_gather_vec(femb_ctx* ctx, int eg, double mu, int ei = -1, const RhsDev* rhs = nullptr, bool* rhs_done = nullptr);
 // femb_p2.cu (FEMB_ERR_UNSUPPORTED, without an error message, when the closed form does not apply)
-int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol);
+// host-to-host variant (femb_assemble_poisson_host): finished nzval / b ranges are downloaded chunk by chunk on stream_d2h
+struct P2HostOut {
+    double* nzval_out;
+    double* b_out;
+    int nchunks;
+};
+int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol, const P2HostOut* host = nullptr);
 int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu, int ei = -1, const RhsDev* rhs = nullptr, bool* rhs_done = nullptr);
 // femb_hdiv.cu: HDIVRT0 on tetrahedra in closed form (FEMB_ERR_UNSUPPORTED, without an error message, when not covered)
 int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor);

@@ -775,6 +775,48 @@ extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t
     if ((cellvol != nullptr) != (ctx->cellvol != nullptr)) return femb_fail(ctx, FEMB_ERR_ARG, "cellvolumes must be given iff the registered mesh has them");
     const FembEval& EG = ctx->evals[eg];
     if (EG.op != FEMB_OP_GRADIENT) return femb_fail(ctx, FEMB_ERR_ARG, "eval_grad must be a Gradient evaluator");
+    if (!(ctx->gmap && ctx->gmap_space == EG.space) && ctx->hm.map && ctx->hm.space == EG.space && !ctx->touched && ctx->dim == 3 &&
+        (rhs_kind == FEMB_RHS_NONE || rhs_kind == FEMB_RHS_AFFINE)) {
+        // scalar P2 on tetrahedra (closed-form gather, femb_p2.cu): upload the geometry, assemble range by range, download the
+        // finished nzval / b ranges behind the kernels
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        RhsDev rhs2;
+        double* dev_f2 = nullptr;
+        FEMB_TRY(make_rhs(ctx, rhs_kind, params, 1, EG.nqp, rhs2, &dev_f2));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!ctx->stream_h2d) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking));
+        if (!ctx->stream_d2h) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking));
+        ctx->gvol_valid = false;
+        ctx->zero_pending_A = true;
+        ctx->zero_pending_b = true;
+        FEMB_TRY(femb_timer_begin(ctx));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coords, coords, sizeof(double) * ctx->nnodes * 3, cudaMemcpyHostToDevice, ctx->stream_h2d));
+        if (cellvol) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->cellvol, cellvol, sizeof(double) * ctx->ncells, cudaMemcpyHostToDevice, ctx->stream_h2d));
+        if (ctx->chunk_ev.empty()) {
+            cudaEvent_t ev;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->chunk_ev.push_back(ev);
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[0], ctx->stream_h2d));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[0], 0));
+        P2HostOut ho = {nzval_out, b_out, std::max(1, (int)nchunks)};
+        int st2 = launch_p2_gather(ctx, eg, ei, mu, rhs2, drop_tol, &ho);
+        if (st2 == FEMB_OK && cellnodes) st2 = femb_cellnodes_compare_async(ctx, cellnodes, ctx->stream_h2d);
+        if (st2 == FEMB_OK) st2 = femb_timer_end(ctx);
+        cudaError_t e1 = cudaStreamSynchronize(ctx->stream_h2d), e2 = cudaStreamSynchronize(ctx->stream_d2h);
+        cudaFree(dev_f2);
+        if (st2 == FEMB_ERR_UNSUPPORTED) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "the streamed path covers scalar P1 and (closed-form) P2 on tetrahedra; use femb_mesh_set + femb_assemble_poisson + femb_matrix_get");
+        if (st2 != FEMB_OK) return st2;
+        CUDA_TRY(ctx, e1);
+        CUDA_TRY(ctx, e2);
+        if (cellnodes) {
+            bool differ = false;
+            FEMB_TRY(femb_cellnodes_differ(ctx, &differ));
+            if (differ)
+                return femb_fail(ctx, FEMB_ERR_ARG, "femb_assemble_poisson_host: cellnodes differs from the connectivity the pattern was built from; call femb_mesh_set and rebuild the pattern");
+        }
+        return femb_sync(ctx);
+    }
     if (!(ctx->gmap && ctx->gmap_space == EG.space) || ctx->touched || (rhs_kind != FEMB_RHS_NONE && rhs_kind != FEMB_RHS_AFFINE) ||
         (ctx->dim == 2 && EG.nqp > FEMB_P1_MAXQP))
         return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "the streamed path covers scalar P1 with rhs NONE/AFFINE and no pattern tracking; use femb_mesh_set + femb_assemble_poisson + femb_matrix_get");

@@ -997,7 +997,7 @@ int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu, int ei, const RhsDev*
 }
 
 // returns FEMB_ERR_UNSUPPORTED (no error message) when the closed form does not cover the space / rule / policy
-int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol) {
+int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs, double drop_tol, const P2HostOut* host) {
     if (!p2_closed_enabled()) return P2_UNSUPPORTED;
     const FembEval& EG = ctx->evals[eg];
     const FembSpace& s = ctx->spaces[EG.space];
@@ -1005,6 +1005,7 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     if (ctx->dim == 2) {
         if (s.nd != 6 || s.ncomp != 1 || !H.map || H.space != EG.space || ctx->touched) return P2_UNSUPPORTED;
         if (rhs.kind != FEMB_RHS_NONE && rhs.kind != FEMB_RHS_AFFINE && rhs.kind != FEMB_RHS_QPVALUES) return P2_UNSUPPORTED;
+        if (host) return P2_UNSUPPORTED;  // (the streamed variant exists for tetrahedra)
         return launch_p2_gather2d(ctx, H, EG, rhs.kind != FEMB_RHS_NONE ? &ctx->evals[ei] : nullptr, mu, rhs, false, false, false, drop_tol);
     }
     if (ctx->dim != 3 || s.nd != 10 || s.ncomp != 1 || !H.map || H.space != EG.space || ctx->touched) return P2_UNSUPPORTED;
@@ -1126,8 +1127,48 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
             KERNEL_CHECK(ctx);
             return FEMB_OK;
         };
-        const bool fused = ctx->fused_exchange && ctx->comm && !ctx->peers.empty() && ctx->stream_x && !ctx->xslices.empty();
-        if (fused) {
+        const bool fused = !host && ctx->fused_exchange && ctx->comm && !ctx->peers.empty() && ctx->stream_x && !ctx->xslices.empty();
+        if (host) {
+            // streamed: every launch range is cut into chunks of slices; a finished chunk's nzval / b range goes to the host on
+            // stream_d2h while the next chunk is assembled (the columns of a slice range are one contiguous range of nzval)
+            const int64_t nsl_all = (s.ndofs + 31) / 32;
+            int64_t total = 0;
+            for (auto& r : H.cranges) total += r.s1 - r.s0;
+            std::vector<std::pair<size_t, std::pair<int64_t, int64_t>>> chunks;  // (crange, [b0, b1))
+            for (size_t i = 0; i < H.cranges.size(); i++) {
+                const auto& r = H.cranges[i];
+                const int64_t n = r.s1 - r.s0;
+                if (n <= 0) continue;
+                const int64_t nc = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((double)std::max(1, host->nchunks) * (double)n / (double)std::max<int64_t>(1, total) + 0.5)));
+                for (int64_t c = 0; c < nc; c++) chunks.push_back({i, {r.s0 + n * c / nc, r.s0 + n * (c + 1) / nc}});
+            }
+            // column pointers at the chunk boundaries
+            std::vector<int64_t> cp(chunks.size() * 2);
+            for (size_t c = 0; c < chunks.size(); c++) {
+                const int64_t d0 = std::min<int64_t>(chunks[c].second.first * 32, s.ndofs), d1 = std::min<int64_t>(chunks[c].second.second * 32, s.ndofs);
+                CUDA_TRY(ctx, cudaMemcpyAsync(&cp[2 * c], ctx->colptr + d0, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_TRY(ctx, cudaMemcpyAsync(&cp[2 * c + 1], ctx->colptr + d1, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            (void)nsl_all;
+            while (ctx->chunk_ev.size() < chunks.size()) {
+                cudaEvent_t ev;
+                CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                ctx->chunk_ev.push_back(ev);
+            }
+            for (size_t c = 0; c < chunks.size(); c++) {
+                const auto& r = H.cranges[chunks[c].first];
+                const int64_t b0 = chunks[c].second.first, b1 = chunks[c].second.second;
+                FEMB_TRY(launch(r, nullptr, b0, b1, ctx->stream));
+                CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ctx->chunk_ev[c], 0));
+                const int64_t p0 = cp[2 * c] - 1, p1 = cp[2 * c + 1] - 1;
+                if (p1 > p0) CUDA_TRY(ctx, cudaMemcpyAsync(host->nzval_out + p0, ctx->nzval + p0, sizeof(double) * (p1 - p0), cudaMemcpyDeviceToHost, ctx->stream_d2h));
+                const int64_t d0 = std::min<int64_t>(b0 * 32, s.ndofs), d1 = std::min<int64_t>(b1 * 32, s.ndofs);
+                if (a.has_rhs && host->b_out && d1 > d0)
+                    CUDA_TRY(ctx, cudaMemcpyAsync(host->b_out + d0, ctx->bvec + d0, sizeof(double) * (d1 - d0), cudaMemcpyDeviceToHost, ctx->stream_d2h));
+            }
+        } else if (fused) {
             // overlapped interface exchange (as the P1 path): the slices that hold ghost or owned-interface columns are
             // assembled first on the high-priority stream, followed there by pack / NCCL / add, while the main stream
             // assembles all other slices.  Vertex and edge dofs are numbered apart, so the interface is a LIST of slices.

@@ -264,8 +264,9 @@ int32_t femb_assemble_poisson(femb_ctx* ctx, int32_t eval_grad, int32_t eval_id,
  * upload of Coordinates / CellVolumes (prefix needed by the next chunk) and CellNodes, the fused kernel per chunk,
  * and download of the finished nzval / b ranges overlap.  Equivalent to femb_mesh_set (same shapes: the symbolic
  * phase is reused) + femb_matrix_zero + femb_vector_zero + femb_assemble_poisson + femb_matrix_get +
- * femb_vector_get, bit for bit.  Scalar P1 with rhs_kind NONE / AFFINE; pin the host arrays with
- * femb_host_register for the copies to overlap.  cellvol must be given iff the registered mesh has volumes.
+ * femb_vector_get, bit for bit.  Scalar P1 with rhs_kind NONE / AFFINE, and scalar P2 on tetrahedra (closed-form gather:
+ * the geometry is uploaded once, the finished nzval / b ranges of every launch chunk follow the kernels); pin the host
+ * arrays with femb_host_register for the copies to overlap.  cellvol must be given iff the registered mesh has volumes.
  * cellnodes = NULL declares the connectivity unchanged (the numeric phase reads the geometry only: the fast, default way
  * to call this).  cellnodes != NULL is uploaded behind the geometry and compared with the registered connectivity on
  * the device; if it differs the call returns FEMB_ERR_ARG (the buffers then hold the matrix of the OLD topology and must

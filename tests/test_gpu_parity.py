@@ -1078,3 +1078,35 @@ def test_p2_closed_form_and_quadrature_kernels_agree(dim):
                 assert abs(v - ref.get((int(r), c), 0.0)) <= RTOL * scale
     assert np.array_equal(results[0], results[2])  # bit-reproducible across the re-ordering of the map
     assert np.abs(results[0] - results[1]).max() <= RTOL * scale
+
+
+@pytest.mark.parametrize("m,nchunks,use_vol", [(9, 5, True), (14, 12, False)])
+def test_streamed_host_assembly_p2_tets_is_bit_identical(m, nchunks, use_vol):
+    """femb_assemble_poisson_host for scalar P2 on tetrahedra (closed-form gather; geometry uploaded, finished nzval / b ranges
+    downloaded behind the kernels) == mesh_set + assemble + get, bit for bit, and it follows the uploaded geometry."""
+    from femb_b200.assembly import _Session
+
+    grid = _grid3d(m, True)
+    fes = fb.FESpace(fb.H1P2(1, 3), grid)
+    qf = fb.QuadratureRule(grid.geometry, 2)
+    S = _Session([fes], qf, cellvolumes=use_vol)
+    ctx = S.ctx
+    eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+    nnz = ctx.pattern_build([(0, 0)])
+    p = np.array([0.3, 1.0, -1.0, 0.5])
+    coords2 = np.ascontiguousarray(grid["Coordinates"] * 1.25 + 0.1)
+    vol2 = np.ascontiguousarray(grid["CellVolumes"] * 1.25 ** 3) if use_vol else None
+    nz2, b2 = np.full(nnz, np.nan), np.full(fes.ndofs, np.nan)
+    ctx.assemble_poisson_host(eg._eid, ei._eid, 1.7, _lib.RHS_AFFINE, p, 0.0, coords2, grid["CellNodes"], vol2, nz2, b2, nchunks)
+    assert np.isfinite(nz2).all() and np.isfinite(b2).all()  # every range came back
+    ctx.mesh_set(coords2, grid["CellNodes"], vol2)
+    ctx.matrix_zero()
+    ctx.vector_zero()
+    ctx.assemble_poisson(eg._eid, ei._eid, 1.7, _lib.RHS_AFFINE, p, 0.0)
+    nz3, b3 = ctx.matrix_get(), ctx.vector_get(fes.ndofs)
+    assert np.array_equal(nz2, nz3) and np.array_equal(b2, b3)
+    # and against the oracle on the new geometry
+    rhs = fb.AffineFunction([0.3], [[1.0, -1.0, 0.5]])
+    colptr, rowval, nzref, bref = orc.example200_assemble(_oracle_el(fb.H1P2(1, 3)), grid.geometry, coords2, grid["CellNodes"],
+                                                           vol2 if use_vol else np.ascontiguousarray(grid["CellVolumes"] * 1.25 ** 3), fes["CellDofs"], fes.ndofs, 1.7, rhs)
+    assert np.abs(b2 - bref).max() <= RTOL * np.abs(bref).max()

@@ -31,7 +31,7 @@ def timeit(fn, ctx, steps, warmup):
     return ms
 
 
-def c3_p2_3d(m, steps, warmup, order=2, check=False):
+def c3_p2_3d(m, steps, warmup, order=2, check=False, e2e=False):
     X = np.linspace(0, 1, m + 1)
     t0 = time.time()
     grid = fb.simplexgrid(X, X, X)
@@ -57,6 +57,26 @@ def c3_p2_3d(m, steps, warmup, order=2, check=False):
     ms = timeit(step, ctx, steps, warmup)
     res = {"config": f"C3 H1P{order}{{1,3}} Poisson stiffness+rhs, Kuhn m={m}", "ncells": grid.ncells, "ndofs": fes.ndofs, "nnz": nnz, "ms_per_step": ms,
            "cells_per_s": grid.ncells / (ms * 1e-3), "host_setup_s": t1 - t0, "pattern_s": t2 - t1}
+    if e2e and order == 2:
+        # host buffers end to end (femb_assemble_poisson_host): geometry up, finished nzval / b ranges down behind the kernels
+        nz_host, b_host = np.empty(nnz), np.empty(fes.ndofs)
+        coords, vols = np.ascontiguousarray(grid["Coordinates"]), np.ascontiguousarray(grid["CellVolumes"])
+        for arr in (coords, vols, nz_host, b_host):
+            ctx.host_register(arr)
+
+        def step_e2e():
+            ctx.assemble_poisson_host(eg._eid, ei._eid, 1.0, _lib.RHS_AFFINE, p, 0.0, coords, None, vols, nz_host, b_host, 32)
+
+        for _ in range(2):
+            step_e2e()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_e2e()
+        ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+        res.update({"e2e_ms_per_step": ms_e2e, "e2e_cells_per_s": grid.ncells / (ms_e2e * 1e-3), "e2e_h2d_bytes": coords.nbytes + vols.nbytes, "e2e_d2h_bytes": nz_host.nbytes + b_host.nbytes,
+                    "e2e_d2h_GBps": (nz_host.nbytes + b_host.nbytes) / (ms_e2e * 1e-3) / 1e9})
+        for arr in (coords, vols, nz_host, b_host):
+            ctx.host_unregister(arr)
     if check:
         # size-independent properties of the full result: 1^T A = 0 (every column sums to zero), diag > 0, sum(b) = int f
         nz = ctx.matrix_get()
@@ -260,6 +280,7 @@ if __name__ == "__main__":
     ap.add_argument("--n5", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--e2e", action="store_true", help="C3: also time femb_assemble_poisson_host (host buffers, copies inside the timed region)")
     ap.add_argument("--scatter", type=int, default=None, help="C4: 0 atomic, 1 coloured, 2 gather (default policy of the library)")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
@@ -267,7 +288,7 @@ if __name__ == "__main__":
     res = []
     for w in a.which.split(","):
         if w == "c3":
-            res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 2, a.check))
+            res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 2, a.check, a.e2e))
         elif w == "c3p1":
             res.append(c3_p2_3d(a.m3, a.steps, a.warmup, 1))
         elif w == "c4":
