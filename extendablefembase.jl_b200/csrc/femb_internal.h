@@ -78,6 +78,9 @@ struct FembHMap {
     struct XList { int32_t* ifc = nullptr; int64_t n_ifc = 0; int32_t* rest = nullptr; int64_t n_rest = 0; };  // per crange: interface slices / all others
     std::vector<XList> xlists;
     int xlists_version = -1;
+    int32_t* vrow = nullptr;        // femb_p2.cu (3-D): per slice the first row of its vertex-dof sectors in vrec, -1 = none
+    uint32_t* vinv = nullptr;       // [cell][4]: slot in vrec of the cell's vertex-dof visits
+    double* vrec = nullptr;         // vertex-dof sectors in visit order (4 doubles per slot)
     std::vector<Range> cranges;     // femb_p2.cu: `ranges` cut where the kind of dof changes (mode 0 = vertex dofs, 1 = edge dofs, 2 = both)
 };
 

@@ -26,6 +26,9 @@ static int p2_unsupported(int line) {
 
 namespace {
 
+#ifndef P2_FILT_ON
+#define P2_FILT_ON 1
+#endif
 #ifndef P2_MINB
 #define P2_MINB 4
 #endif
@@ -41,7 +44,7 @@ namespace {
 
 // doubles per cell (the vertex part and the edge part are one aligned 128-byte line each): 4 vertex sectors [G_k,o1 G_k,o2 G_k,o3 bl_k],
 // then [G01 G02 G03 G12] and three sectors [G13 G23 bl_a bl_b], (a b) = (4 5) (6 7) (8 9): edge dof 4 + e reads sectors 4 and 5 + e / 2
-constexpr int P2_REC = 32;
+constexpr int P2_REC = 16;  // (round 2, later: the vertex sectors moved to the visit-order array `vrec`; the per-cell record is the edge line)
 
 struct P2Const {
     double alpha, beta, gd, go, mus, mud;
@@ -67,6 +70,8 @@ struct P2Args {
     double drop_tol;
     int32_t* errflag;
     int64_t slice_begin, slice_end;
+    const double* vrec;         // 3-D: vertex-dof sectors [G_k,o1 G_k,o2 G_k,o3 bl_k] in VISIT order: entry (vrow[slice] + r) * 32 + lane
+    const int32_t* vrow;        // per slice: first row of the slice in vrec, or -1 (no vertex dofs in the slice)
     const double* vrhs;         // 2-D vector maps: local rhs entries [cell][6][2] of a two-component load (fused rhs of Example210), or NULL
     const int32_t* slice_list;  // NULL, or the slices of this launch (overlapped interface exchange): slice_begin .. slice_end then index the list
     int twins;            // 2-D vector maps: the columns c, c + ndofs, ... (one per component) receive the same values
@@ -141,7 +146,8 @@ __device__ __forceinline__ void stg256(double* p, double a, double b, double c, 
 // a vertex-column visit needs one 32-byte sector and an edge-column visit two or three
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_cell_p2rec(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
-                                                    int64_t ncells, double mu, RhsDev rhs, QuadDev q, P2Wphi wp, double* __restrict__ out) {
+                                                    int64_t ncells, double mu, RhsDev rhs, QuadDev q, P2Wphi wp, double* __restrict__ out, const uint32_t* __restrict__ vinv,
+                                                    double* __restrict__ vrec) {
     __shared__ double tile[128][P2_REC + 1];  // staged so that the records leave the SM coalesced
     const int64_t cell0 = blockIdx.x * (int64_t)blockDim.x;
     const int64_t cell = cell0 + threadIdx.x;
@@ -199,15 +205,17 @@ __global__ void __launch_bounds__(128) k_cell_p2rec(const double* __restrict__ c
                 for (int j = 0; j < 10; j++) bl[j] += wp.v[qp][j] * f;
             }
         }
+        // vertex sectors: straight to the slot of the (vertex dof, cell) visit in the gather map's order (the vertex-column
+        // kernel then streams them with its bulk copies instead of gathering 32 bytes per lane and visit)
+        stg256(vrec + (size_t)__ldg(vinv + cell * 4 + 0) * 4, G01, G02, G03, bl[0]);
+        stg256(vrec + (size_t)__ldg(vinv + cell * 4 + 1) * 4, G01, G12, G13, bl[1]);
+        stg256(vrec + (size_t)__ldg(vinv + cell * 4 + 2) * 4, G02, G12, G23, bl[2]);
+        stg256(vrec + (size_t)__ldg(vinv + cell * 4 + 3) * 4, G03, G13, G23, bl[3]);
         double* o = tile[threadIdx.x];
-        o[0] = G01; o[1] = G02; o[2] = G03; o[3] = bl[0];
-        o[4] = G01; o[5] = G12; o[6] = G13; o[7] = bl[1];
-        o[8] = G02; o[9] = G12; o[10] = G23; o[11] = bl[2];
-        o[12] = G03; o[13] = G13; o[14] = G23; o[15] = bl[3];
-        o[16] = G01; o[17] = G02; o[18] = G03; o[19] = G12;
-        o[20] = G13; o[21] = G23; o[22] = bl[4]; o[23] = bl[5];
-        o[24] = G13; o[25] = G23; o[26] = bl[6]; o[27] = bl[7];
-        o[28] = G13; o[29] = G23; o[30] = bl[8]; o[31] = bl[9];
+        o[0] = G01; o[1] = G02; o[2] = G03; o[3] = G12;
+        o[4] = G13; o[5] = G23; o[6] = bl[4]; o[7] = bl[5];
+        o[8] = G13; o[9] = G23; o[10] = bl[6]; o[11] = bl[7];
+        o[12] = G13; o[13] = G23; o[14] = bl[8]; o[15] = bl[9];
     }
     __syncthreads();
     const int64_t nloc = min((int64_t)128, ncells - cell0);
@@ -215,21 +223,18 @@ __global__ void __launch_bounds__(128) k_cell_p2rec(const double* __restrict__ c
     for (int i = threadIdx.x; i < nloc * P2_REC; i += 128) dst[i] = tile[i / P2_REC][i % P2_REC];
 }
 
-// record pieces of a visit, loaded one visit ahead.  MODE 0: slices of vertex dofs only (r[0..3] = the dof's sector), MODE 1:
-// edge dofs only (r[0..5] = the six G, r[6 + (k & 1)] = bl_k), MODE 2: any.  The wide loads are unconditional
-// (padding entries point at cell 0): a conditionally written destination would need a copy that waits for the load.
+// record pieces of a visit, loaded one visit ahead (MODE 1: edge dofs only, MODE 2: any; MODE 0 reads its vertex sectors from
+// the staged visit-order block instead).  Edge dof 4 + e: r[0..3] = (G01 G02 G03 G12), r[4..7] = (G13 G23 bl_a bl_b) of its pair;
+// vertex dof (MODE 2): r[0..3] = its sector from the visit-order array (vp = this lane's slot of the visit).  The wide loads are
+// unconditional (padding entries point at cell 0): a conditionally written destination would need a copy that waits for the load.
 template <int MODE>
-__device__ __forceinline__ void p2_load_rec(const double* __restrict__ rec, unsigned cell, unsigned k, int has_rhs, double (&r)[8]) {
+__device__ __forceinline__ void p2_load_rec(const double* __restrict__ rec, unsigned cell, unsigned k, const double* __restrict__ vp, double (&r)[8]) {
 #ifdef P2_DBG_REC
     cell &= 1023u;  // timing experiment: every record load hits the cache
 #endif
     const double* p = rec + (size_t)cell * P2_REC;
-    if (MODE == 0) {
-        ldg256(p + 4u * (k & 3u), r[0], r[1], r[2], r[3]);
-    } else {
-        ldg256(p + ((MODE == 2 && k < 4u) ? 4u * k : 16u), r[0], r[1], r[2], r[3]);
-        ldg256(p + 20 + 4u * min(((k - 4u) >> 1) & 3u, 2u), r[4], r[5], r[6], r[7]);
-    }
+    ldg256((MODE == 2 && k < 4u) ? vp : p, r[0], r[1], r[2], r[3]);
+    ldg256(p + 4 + 4u * min(((k - 4u) >> 1) & 3u, 2u), r[4], r[5], r[6], r[7]);
 }
 
 // the ten entries of the visit's local column in role order (p2_column_closed) and the local rhs entry
@@ -278,14 +283,21 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // DEPTH visits ahead into the same registers (the caller unrolls over a ring of DEPTH buffers: no register copies).  The
 // map entries of all visits sit in shared memory (sst: this lane's column of the staged planes, pst: plane stride).
 template <int SPLIT, int MODE, int DEPTH>
-__device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int r, int nrows, unsigned sst, unsigned pst, unsigned sacc, unsigned fmask, unsigned warp,
-                                         double& bsum, double (&racc)[3], unsigned (&rad)[3], unsigned& err) {
+__device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int r, int nrows, unsigned sst, unsigned pst, unsigned srec, const double* __restrict__ vp0,
+                                         unsigned sacc, unsigned fmask, unsigned warp, double& bsum, double (&racc)[3], unsigned (&rad)[3], unsigned& err) {
     constexpr unsigned ncol = 128 / SPLIT;
+    // staged planes: MODE 0 keeps the three position words only (slots 0..2), the others the cell plane first
     const unsigned ra = sst + (unsigned)r * 128u;
-    const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst), wc = lds32(ra + 3u * pst);
+    const unsigned wbase = MODE == 0 ? ra : ra + pst;
+    const unsigned wa = lds32(wbase), wb = lds32(wbase + pst), wc = lds32(wbase + 2u * pst);
     const unsigned k = (wc >> 16) & 0xFu;
     const unsigned first = (wc >> 20) & fmask;
     const bool on = k != 0xFu;
+    if (MODE == 0) {  // this lane's sector of the visit from the staged visit-order block
+        const unsigned sr = srec + (unsigned)r * 1024u;
+        lds128(sr, cur[0], cur[1]);
+        lds128(sr + 16u, cur[2], cur[3]);
+    }
     double v[10];
     unsigned ad[10];
 #pragma unroll
@@ -296,7 +308,7 @@ __device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int 
     if (on) {
         const double bl = p2_column<MODE>(a.c, k, cur, v);
         if (a.has_rhs) bsum += bl;
-        if (a.filt) {  // (uniform) the reference's value filter; rows without a slot go to the dump row and must be filtered values
+        if (P2_FILT_ON && a.filt) {  // (uniform) the reference's value filter; rows without a slot go to the dump row and must be filtered values
 #pragma unroll
             for (int j = 0; j < 10; j++) {
                 const unsigned w = j < 4 ? wa : (j < 8 ? wb : wc);
@@ -307,9 +319,9 @@ __device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int 
             }
         }
     }
-    if (r + DEPTH * SPLIT < nrows) {  // (uniform in the warp)
+    if (MODE != 0 && r + DEPTH * SPLIT < nrows) {  // (uniform in the warp)
         const unsigned rn = ra + (unsigned)(DEPTH * SPLIT) * 128u;
-        p2_load_rec<MODE>(a.rec, lds32(rn), (lds32(rn + 3u * pst) >> 16) & 0xFu, a.has_rhs, cur);
+        p2_load_rec<MODE>(a.rec, lds32(rn), (lds32(rn + 3u * pst) >> 16) & 0xFu, vp0 + (size_t)(r + DEPTH * SPLIT) * 128, cur);
     }
 #ifdef P2_DBG_NOACC
     if (on) {  // timing experiment: no shared-memory accumulation
@@ -382,20 +394,29 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned pst = (unsigned)a.maxrows * 128u;
     const unsigned mbar = smem0 + (SPLIT == 1 ? warp : 0u) * 8u;
-    const unsigned sstw = smem0 + 128u + (unsigned)(a.maxlen + 1) * (ncol * 8u) + (SPLIT == 1 ? warp * 4u * pst : 0u);
+    // per slice (warp with SPLIT = 1, CTA with SPLIT = 4): MODE 0 stages 3 map planes + the visit-order sectors (8 x pst),
+    // the other modes the 4 map planes
+    constexpr unsigned NPL = MODE == 0 ? 3u : 4u;
+    constexpr unsigned STG = MODE == 0 ? 11u : 4u;  // staging block per slice in units of pst
+    const unsigned sstw = smem0 + 128u + (unsigned)(a.maxlen + 1) * (ncol * 8u) + (SPLIT == 1 ? warp * STG * pst : 0u);
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
+    const int vrow = (MODE != 1) ? __ldg(a.vrow + slice) : -1;
     if (nrows > 0 && (SPLIT == 1 ? lane == 0 : tid == 0)) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const unsigned bytes = (unsigned)nrows * 128u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * 4u) : "memory");
-        const uint32_t* g = a.map + ((size_t)row0 << 5);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * (MODE == 0 ? 11u : 4u)) : "memory");
+        const uint32_t* g = a.map + ((size_t)row0 << 5) + (MODE == 0 ? a.stride : 0);
 #pragma unroll
-        for (int p = 0; p < 4; p++)
+        for (int p = 0; p < (int)NPL; p++)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst), "l"(g + (size_t)p * a.stride),
                          "r"(bytes), "r"(mbar)
+                         : "memory");
+        if (MODE == 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + 3u * pst), "l"(a.vrec + (size_t)vrow * 128),
+                         "r"(bytes * 8u), "r"(mbar)
                          : "memory");
     }
     const bool zero_first = __ldg(a.slice_zero + slice) != 0;
@@ -426,25 +447,28 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
     }
 #ifndef P2_NO_PREFETCH
-    for (int r = rfirst + SPLIT; r < nrows; r += SPLIT) {  // every record of this lane's later visits -> L2, now
-        const unsigned k = (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu;
-        const double* p = a.rec + (size_t)lds32(sst + (unsigned)r * 128u) * P2_REC;
-        if (MODE == 0 || (MODE == 2 && k < 4u)) {
-            prefetch_l2(p + 4u * (k & 3u));
-        } else if (k != 0xFu) {
-            prefetch_l2(p + 16);
-            prefetch_l2(p + 20 + 4u * min(((k - 4u) >> 1) & 3u, 2u));
+    if (MODE != 0) {  // every edge record of this lane's later visits -> L2, now (with one record in flight per lane this is worth 8 %)
+        for (int r = rfirst + SPLIT; r < nrows; r += SPLIT) {
+            const unsigned k = (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu;
+            const double* p = a.rec + (size_t)lds32(sst + (unsigned)r * 128u) * P2_REC;
+            if (k - 4u < 6u) {
+                prefetch_l2(p);
+                prefetch_l2(p + 4 + 4u * ((k - 4u) >> 1));
+            }
         }
     }
 #endif
-    constexpr int DEPTH = MODE == 0 ? P2_DEPTH0 : P2_DEPTH;  // records in flight per lane (a vertex-dof record is 4 doubles, an edge-dof record 9)
+    constexpr int DEPTH = MODE == 0 ? 1 : P2_DEPTH;  // records in flight per lane (MODE 0: none, its sectors are staged)
+    const unsigned srec = sstw + 3u * pst + lane * 32u;                                                    // MODE 0: this lane's sector of row 0
+    const double* vp0 = (MODE == 2 && vrow >= 0) ? a.vrec + ((size_t)vrow * 32 + lane) * 4 : a.rec;  // MODE 2: this lane's slot of row 0
     double rec[DEPTH][8];
 #pragma unroll
     for (int u = 0; u < DEPTH; u++) {
 #pragma unroll
         for (int i = 0; i < 8; i++) rec[u][i] = 0.0;
         const int r = rfirst + u * SPLIT;
-        if (r < nrows) p2_load_rec<MODE>(a.rec, lds32(sst + (unsigned)r * 128u), (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu, a.has_rhs, rec[u]);
+        if (MODE != 0 && r < nrows)
+            p2_load_rec<MODE>(a.rec, lds32(sst + (unsigned)r * 128u), (lds32(sst + 3u * pst + (unsigned)r * 128u) >> 16) & 0xFu, vp0 + (size_t)r * 128, rec[u]);
     }
     double racc[3] = {0.0, 0.0, 0.0};
     unsigned rad[3] = {0u, 0u, 0u}, err = 0u;
@@ -454,7 +478,7 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
             if (u == 0 || it + u < niter) {  // (uniform in the CTA)
                 const int r = (it + u) * SPLIT + rfirst;
                 // (SPLIT = 4: a warp whose row index is past nrows only takes part in the barriers)
-                if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, sacc, fmask, warp, bsum, racc, rad, err);
+                if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, srec, vp0, sacc, fmask, warp, bsum, racc, rad, err);
                 else {
 #pragma unroll 1
                     for (int ph = 0; ph < SPLIT; ph++) __syncthreads();
@@ -521,6 +545,22 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
     if (a.has_rhs && (SPLIT == 1 || warp == 0)) {
         if (a.acc_b) a.bvec[c] += bsum;
         else a.bvec[c] = bsum;
+    }
+}
+
+// vinv[cell * 4 + k] = slot of the (vertex dof k of the cell, cell) visit in the visit-order array (one warp per slice)
+__global__ void k_p2_vinv(const uint32_t* __restrict__ map, size_t stride, const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ vrow, int64_t nslices,
+                          uint32_t* __restrict__ vinv) {
+    const int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (slice >= nslices) return;
+    const int v0 = vrow[slice];
+    if (v0 < 0) return;
+    const int row0 = slice_ptr[slice], nrows = slice_ptr[slice + 1] - row0;
+    for (int r = 0; r < nrows; r++) {
+        const size_t idx = ((size_t)(row0 + r) << 5) + lane;
+        const unsigned k = (map[3 * stride + idx] >> 16) & 0xFu;
+        if (k < 4u) vinv[(size_t)map[idx] * 4 + k] = (uint32_t)(((size_t)(v0 + r) << 5) + lane);
     }
 }
 
@@ -892,7 +932,7 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
             }
         }
     }
-    if (!ctx->p2rec) FEMB_TRY(femb_alloc(ctx, &ctx->p2rec, (size_t)ctx->ncells * P2_REC));
+    if (!ctx->p2rec) FEMB_TRY(femb_alloc(ctx, &ctx->p2rec, (size_t)ctx->ncells * P2_REC2));
     if (ctx->ncells == 0) return FEMB_OK;
     FEMB_TRY(femb_hmap_set_canon(ctx, H, true));
     if (H.cranges.empty()) {
@@ -938,6 +978,8 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
     a.slice_begin = a.slice_end = 0;
     a.slice_list = nullptr;
     a.vrhs = vec_rhs ? ctx->p2vrhs : nullptr;
+    a.vrec = nullptr;
+    a.vrow = nullptr;
     a.c = cst;
     a.twins = 1;
     int64_t slice_cap = INT64_MAX;
@@ -1038,12 +1080,6 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     if (!ctx->p2rec) FEMB_TRY(femb_alloc(ctx, &ctx->p2rec, (size_t)ctx->ncells * P2_REC));
     if (ctx->ncells == 0) return FEMB_OK;
     FEMB_TRY(femb_hmap_set_canon(ctx, H, true));
-    P2Wphi wp;
-    for (int q = 0; q < FEMB_COEF_STRIDE - 6; q++)
-        for (int j = 0; j < 10; j++) wp.v[q][j] = (EI && q < EG.nqp) ? EG.w[q] * EI->h_refvals[(size_t)q * s.nd_all + j] : 0.0;
-    QuadDev q = quad_dev(EG, 3);
-    k_cell_p2rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec);
-    KERNEL_CHECK(ctx);
     P2Args a;
     a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr; a.sub0 = a.sublen = nullptr; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.bvec = ctx->bvec;
@@ -1058,8 +1094,6 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     a.vrhs = nullptr;
     a.c = cst;
     a.twins = 1;
-    ctx->zero_pending_A = false;
-    if (a.has_rhs) ctx->zero_pending_b = false;
     if (H.cranges.empty()) {
         // cut the launch ranges where the kind of dof changes (vertex dofs | the slice that holds both | edge dofs): the
         // kernels are specialised per kind (MODE), which keeps the vertex-dof kernel at one 32-byte record load per visit
@@ -1098,12 +1132,46 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
         }
         H.cranges = out;
     }
+    if (!H.vrow) {
+        // visit-order slots of the vertex-dof sectors: per slice the first row in vrec (slices without vertex dofs: -1), and the
+        // inverse map (cell, local vertex) -> slot for the cell pre-pass
+        const int64_t nslices = (s.ndofs + 31) / 32;
+        std::vector<int32_t> hptr((size_t)nslices + 1), hv((size_t)nslices, -1);
+        CUDA_TRY(ctx, cudaMemcpy(hptr.data(), H.slice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost));
+        int64_t rows = 0;
+        for (auto& r : H.cranges) {
+            if (r.mode == 1) continue;
+            for (int64_t sl = r.s0; sl < r.s1; sl++) {
+                hv[sl] = (int32_t)rows;
+                rows += hptr[sl + 1] - hptr[sl];
+            }
+        }
+        if (rows >= ((int64_t)1 << 26)) return P2_UNSUPPORTED;  // (slots are 32-bit: rows * 32 < 2^31)
+        FEMB_TRY(femb_alloc(ctx, &H.vrow, (size_t)nslices));
+        FEMB_TRY(femb_h2d(ctx, H.vrow, hv.data(), (size_t)nslices));
+        FEMB_TRY(femb_alloc(ctx, &H.vinv, (size_t)ctx->ncells * 4));
+        FEMB_TRY(femb_alloc(ctx, &H.vrec, (size_t)std::max<int64_t>(rows, 1) * 128));
+        CUDA_TRY(ctx, cudaMemsetAsync(H.vrec, 0, sizeof(double) * (size_t)std::max<int64_t>(rows, 1) * 128, ctx->stream));
+        k_p2_vinv<<<(unsigned)((nslices * 32 + 127) / 128), 128, 0, ctx->stream>>>(H.map, H.stride, H.slice_ptr, H.vrow, nslices, H.vinv);
+        KERNEL_CHECK(ctx);
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    P2Wphi wp;
+    for (int q = 0; q < FEMB_COEF_STRIDE - 6; q++)
+        for (int j = 0; j < 10; j++) wp.v[q][j] = (EI && q < EG.nqp) ? EG.w[q] * EI->h_refvals[(size_t)q * s.nd_all + j] : 0.0;
+    QuadDev q = quad_dev(EG, 3);
+    k_cell_p2rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, mu, rhs, q, wp, ctx->p2rec, H.vinv, H.vrec);
+    KERNEL_CHECK(ctx);
+    a.vrec = H.vrec;
+    a.vrow = H.vrow;
+    ctx->zero_pending_A = false;  // (from here on the call cannot decline any more)
+    if (a.has_rhs) ctx->zero_pending_b = false;
     {
         const void* kern[2][3] = {{(const void*)k_p2_gather<1, 0>, (const void*)k_p2_gather<1, 1>, (const void*)k_p2_gather<1, 2>},
                                   {(const void*)k_p2_gather<4, 0>, (const void*)k_p2_gather<4, 1>, (const void*)k_p2_gather<4, 2>}};
         auto smem_of = [](const FembHMap::Range& r) {
-            const size_t ncol = r.split == 4 ? 32 : 128, nstage = r.split == 4 ? 1 : 4;
-            return 128 + (size_t)(std::max(1, r.maxlen) + 1) * ncol * sizeof(double) + nstage * 4 * (size_t)r.maxrows * 128;
+            const size_t ncol = r.split == 4 ? 32 : 128, nstage = r.split == 4 ? 1 : 4, planes = r.mode == 0 ? 11 : 4;  // (mode 0: 3 map planes + 8 of sectors)
+            return 128 + (size_t)(std::max(1, r.maxlen) + 1) * ncol * sizeof(double) + nstage * planes * (size_t)r.maxrows * 128;
         };
         size_t need[2][3] = {{0, 0, 0}, {0, 0, 0}};
         for (auto& r : H.cranges) need[r.split == 4][r.mode] = std::max(need[r.split == 4][r.mode], smem_of(r));

@@ -874,6 +874,9 @@ void femb_free_hmap(FembHMap& H) {
     }
     H.xlists.clear();
     H.xlists_version = -1;
+    femb_free(&H.vrow);
+    femb_free(&H.vinv);
+    femb_free(&H.vrec);
 }
 
 // in-place permutation of the position bytes and first-touch flags of every map entry: role order <-> local dof order
