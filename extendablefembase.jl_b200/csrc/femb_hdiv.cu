@@ -27,10 +27,8 @@ __device__ __forceinline__ unsigned lds32(unsigned addr) {
 __host__ __device__ constexpr int rt0_opp(int j) { return j == 0 ? 3 : (j == 1 ? 2 : (j == 2 ? 0 : 1)); }
 
 __global__ void __launch_bounds__(128) k_cell_rt0rec(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
-                                                     const int32_t* __restrict__ signs, int64_t ncells, double* __restrict__ out) {
-    __shared__ double tile[128][17];
-    const int64_t cell0 = blockIdx.x * (int64_t)blockDim.x;
-    const int64_t cell = cell0 + threadIdx.x;
+                                                     const int32_t* __restrict__ signs, int64_t ncells, const uint32_t* __restrict__ finv, double* __restrict__ out) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (cell < ncells) {
         double x[4][3];
         load_nodes<3>(coords, cellnodes, cell, x);
@@ -58,16 +56,25 @@ __global__ void __launch_bounds__(128) k_cell_rt0rec(const double* __restrict__ 
 #pragma unroll
             for (int d = 0; d < 3; d++) dv[j][d] = c[d] - x[rt0_opp(j)][d];
         }
-        double* o = tile[threadIdx.x];
+        // column k of the local mass matrix goes straight to the slot of the (face dof, cell) visit in the gather map's order: the
+        // gather streams its records with the bulk copies of the map instead of fetching one 32-byte sector per lane and visit
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < 4; k++) {
+            double m[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) o[k * 4 + j] = (sg[j] * sg[k]) * sc * (((dv[j][0] * dv[k][0] + dv[j][1] * dv[k][1]) + dv[j][2] * dv[k][2]) + S);
+            for (int j = 0; j < 4; j++) m[j] = (sg[j] * sg[k]) * sc * (((dv[j][0] * dv[k][0] + dv[j][1] * dv[k][1]) + dv[j][2] * dv[k][2]) + S);
+            double* o = out + (size_t)__ldg(finv + cell * 4 + k) * 4;
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(o), "d"(m[0]), "d"(m[1]), "d"(m[2]), "d"(m[3]) : "memory");
+        }
     }
-    __syncthreads();
-    const int64_t nloc = min((int64_t)128, ncells - cell0);
-    double* dst = out + cell0 * 16;
-    for (int i = threadIdx.x; i < nloc * 16; i += 128) dst[i] = tile[i / 16][i % 16];
+}
+
+// finv[cell * 4 + k] = entry (row * 32 + lane) of the (face dof k of the cell, cell) visit in the gather map
+__global__ void k_rt0_finv(const uint32_t* __restrict__ map, size_t stride, uint32_t* __restrict__ finv) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= stride) return;
+    const unsigned k = (map[2 * stride + idx] >> 16) & 0xFu;
+    if (k < 4u) finv[(size_t)map[idx] * 4 + k] = (uint32_t)idx;
 }
 
 struct RGArgs {
@@ -87,7 +94,8 @@ struct RGArgs {
 };
 
 // one thread per face-dof column, 4 slices (warps) per CTA; map planes (cell, 4 position bytes, k + first-touch flags) staged
-// by bulk copies.  dynamic shared memory: [4 mbarriers | pad to 128 B][acc: maxlen x 128 doubles][4 warps x 3 planes x maxrows x 128 B]
+// by bulk copies together with the visit-order records.  dynamic shared memory: [4 mbarriers | pad to 128 B][acc: maxlen x 128 doubles]
+// [4 warps x (2 planes + 8 of records) x maxrows x 128 B]
 __global__ void __launch_bounds__(128, 8) k_rt0_mass_gather(const RGArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(128, 8) k_rt0_mass_gather(const RGArgs a) {
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned pst = (unsigned)a.maxrows * 128u;
     const unsigned mbar = smem0 + warp * 8u;
-    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * 1024u + warp * 3u * pst;
+    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * 1024u + warp * 10u * pst;
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
@@ -104,13 +112,16 @@ __global__ void __launch_bounds__(128, 8) k_rt0_mass_gather(const RGArgs a) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const unsigned bytes = (unsigned)nrows * 128u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * 3u) : "memory");
-        const uint32_t* g = a.map + ((size_t)row0 << 5);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * 10u) : "memory");
+        const uint32_t* g = a.map + ((size_t)row0 << 5) + a.stride;  // (the cell plane is not needed: the records come in visit order)
 #pragma unroll
-        for (int p = 0; p < 3; p++)
+        for (int p = 0; p < 2; p++)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst), "l"(g + (size_t)p * a.stride),
                          "r"(bytes), "r"(mbar)
                          : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + 2u * pst), "l"(a.rec + ((size_t)row0 << 7)), "r"(bytes * 8u),
+                     "r"(mbar)
+                     : "memory");
     }
     const bool zero_first = __ldg(a.slice_zero + slice) != 0;
     int64_t base = 0;
@@ -135,16 +146,17 @@ __global__ void __launch_bounds__(128, 8) k_rt0_mass_gather(const RGArgs a) {
         while (!done)
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
     }
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-    if (nrows > 0) ldg256(a.rec + (size_t)lds32(sst) * 16 + 4u * ((lds32(sst + 2u * pst) >> 16) & 3u), r0, r1, r2, r3);
+    const unsigned srec = sstw + 2u * pst + lane * 32u;
     for (int r = 0; r < nrows; r++) {
         const unsigned ra = sst + (unsigned)r * 128u;
-        const unsigned wa = lds32(ra + pst), wb = lds32(ra + 2u * pst);
+        const unsigned wa = lds32(ra), wb = lds32(ra + pst);
         const unsigned k = (wb >> 16) & 0xFu;
         const unsigned first = (wb >> 20) & fmask;
-        const double v[4] = {r0 * a.factor, r1 * a.factor, r2 * a.factor, r3 * a.factor};
-        if (r + 1 < nrows) ldg256(a.rec + (size_t)lds32(ra + 128u) * 16 + 4u * ((lds32(ra + 128u + 2u * pst) >> 16) & 3u), r0, r1, r2, r3);
         if (k == 0xFu) continue;
+        double r0, r1, r2, r3;
+        lds128(srec + (unsigned)r * 1024u, r0, r1);
+        lds128(srec + (unsigned)r * 1024u + 16u, r2, r3);
+        const double v[4] = {r0 * a.factor, r1 * a.factor, r2 * a.factor, r3 * a.factor};
         unsigned ad[4];
         double o[4];
 #pragma unroll
@@ -250,7 +262,17 @@ int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double fac
     if (H.space != E.space || !H.complete || H.words != 2) return FEMB_ERR_UNSUPPORTED;
     for (auto& r : H.ranges)
         if (r.split != 1) return FEMB_ERR_UNSUPPORTED;
-    if (!ctx->rt0rec) FEMB_TRY(femb_alloc(ctx, &ctx->rt0rec, (size_t)ctx->ncells * 16));
+    if (!ctx->rt0rec) {
+        FEMB_TRY(femb_alloc(ctx, &ctx->rt0rec, (size_t)std::max<size_t>(H.stride, 1) * 4));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->rt0rec, 0, sizeof(double) * std::max<size_t>(H.stride, 1) * 4, ctx->stream));
+    }
+    if (!H.vinv) {
+        FEMB_TRY(femb_alloc(ctx, &H.vinv, (size_t)std::max<int64_t>(ctx->ncells, 1) * 4));
+        if (H.stride) {
+            k_rt0_finv<<<(unsigned)((H.stride + 255) / 256), 256, 0, ctx->stream>>>(H.map, H.stride, H.vinv);
+            KERNEL_CHECK(ctx);
+        }
+    }
     if (ctx->ncells == 0) return FEMB_OK;
     const bool fresh = ctx->zero_pending_A;  // right after femb_matrix_zero the runs are overwritten, not read-modify-written
     FEMB_TRY(femb_flush_zero(ctx, true, false));
@@ -266,11 +288,11 @@ int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double fac
         }
         H.cranges = out;
     }
-    auto smem_of = [](const FembHMap::Range& r) { return 128 + (size_t)std::max(1, r.maxlen) * 1024 + 4 * 3 * (size_t)r.maxrows * 128; };
+    auto smem_of = [](const FembHMap::Range& r) { return 128 + (size_t)std::max(1, r.maxlen) * 1024 + 4 * 10 * (size_t)r.maxrows * 128; };
     size_t need = 0;
     for (auto& r : H.cranges) need = std::max(need, smem_of(r));
     if (need > 200 * 1024) return FEMB_ERR_UNSUPPORTED;
-    k_cell_rt0rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.signs, ctx->ncells, ctx->rt0rec);
+    k_cell_rt0rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.signs, ctx->ncells, H.vinv, ctx->rt0rec);
     KERNEL_CHECK(ctx);
     RGArgs a;
     a.rec = ctx->rt0rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride;

@@ -1164,8 +1164,6 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     KERNEL_CHECK(ctx);
     a.vrec = H.vrec;
     a.vrow = H.vrow;
-    ctx->zero_pending_A = false;  // (from here on the call cannot decline any more)
-    if (a.has_rhs) ctx->zero_pending_b = false;
     {
         const void* kern[2][3] = {{(const void*)k_p2_gather<1, 0>, (const void*)k_p2_gather<1, 1>, (const void*)k_p2_gather<1, 2>},
                                   {(const void*)k_p2_gather<4, 0>, (const void*)k_p2_gather<4, 1>, (const void*)k_p2_gather<4, 2>}};
@@ -1177,11 +1175,13 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
         for (auto& r : H.cranges) need[r.split == 4][r.mode] = std::max(need[r.split == 4][r.mode], smem_of(r));
         for (int sp = 0; sp < 2; sp++)
             for (int m = 0; m < 3; m++) {
-                if (need[sp][m] > 200 * 1024) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "P2 gather: columns too long for the shared-memory accumulators");
+                if (need[sp][m] > 200 * 1024) return P2_UNSUPPORTED;  // columns too long for the shared-memory accumulators: the general kernel decides
                 if (!need[sp][m]) continue;
                 CUDA_TRY(ctx, cudaFuncSetAttribute(kern[sp][m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need[sp][m]));
                 CUDA_TRY(ctx, cudaFuncSetAttribute(kern[sp][m], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             }
+        ctx->zero_pending_A = false;  // (from here on the call cannot decline any more)
+        if (a.has_rhs) ctx->zero_pending_b = false;
         auto launch = [&](const FembHMap::Range& r, const int32_t* list, int64_t b0, int64_t b1, cudaStream_t stream) -> int {
             if (b1 <= b0) return FEMB_OK;
             a.slice_list = list;
