@@ -255,8 +255,11 @@ def test_example210(n, jit):
 @pytest.mark.parametrize("name,dim,n", [("HDIVRT0", 2, 9), ("HDIVBDM1", 2, 7), ("HDIVRT0", 3, 4), ("HDIVBDM1", 3, 3)])
 def test_hdiv_mixed(name, dim, n):
     grid = _grid2d(n, True) if dim == 2 else _grid3d(n, True)
+    _check_hdiv_mixed(grid, {"HDIVRT0": fb.HDIVRT0, "HDIVBDM1": fb.HDIVBDM1}[name](dim))
+
+
+def _check_hdiv_mixed(grid, ft):
     g = grid.geometry
-    ft = {"HDIVRT0": fb.HDIVRT0, "HDIVBDM1": fb.HDIVBDM1}[name](dim)
     FESv, FESq = fb.FESpace(ft, grid), fb.FESpace(fb.L2P0(1), grid)
     A = fb.FEMatrix([FESv, FESq])
     fb.assemble_hdiv_mixed(A, FESv, FESq)
@@ -1110,3 +1113,43 @@ def test_streamed_host_assembly_p2_tets_is_bit_identical(m, nchunks, use_vol):
     colptr, rowval, nzref, bref = orc.example200_assemble(_oracle_el(fb.H1P2(1, 3)), grid.geometry, coords2, grid["CellNodes"],
                                                            vol2 if use_vol else np.ascontiguousarray(grid["CellVolumes"] * 1.25 ** 3), fes["CellDofs"], fes.ndofs, 1.7, rhs)
     assert np.abs(b2 - bref).max() <= RTOL * np.abs(bref).max()
+
+
+def _mirrored3d(n, every=3):
+    """jittered Kuhn mesh with every `every`-th cell negatively oriented (two nodes swapped: det A < 0)"""
+    grid = _grid3d(n, True)
+    cn = grid["CellNodes"].copy()
+    cn[1::every] = cn[1::every][:, [0, 1, 3, 2]]
+    return fb.ExtendableGrid(grid["Coordinates"], cn, "Tetrahedron3D")
+
+
+def test_closed_form_kernels_on_mirrored_cells():
+    """negatively oriented cells and ragged sizes (cell / dof counts that are no multiples of 128 / 32) through the closed-form
+    paths: P2 on tetrahedra (G_ab is orientation-independent, |T| comes from CellVolumes); tiny RT0 meshes"""
+    from femb_b200.assembly import _Session
+
+    for n in (1, 2, 5):
+        grid = _mirrored3d(n)
+        fes = fb.FESpace(fb.H1P2(1, 3), grid)
+        qf = fb.QuadratureRule(grid.geometry, 2)
+        S = _Session([fes], qf)
+        ctx = S.ctx
+        eg, ei = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity")
+        ctx.pattern_build([(0, 0)])
+        rhs = fb.AffineFunction([0.25], [[1.0, -1.0, 0.5]])
+        colptr, rowval, nzref, bref = orc.example200_assemble(_oracle_el(fb.H1P2(1, 3)), grid.geometry, grid["Coordinates"], grid["CellNodes"], grid["CellVolumes"],
+                                                               fes["CellDofs"], fes.ndofs, 0.7, rhs)
+        ctx.matrix_zero()
+        ctx.vector_zero()
+        ctx.assemble_poisson(eg._eid, ei._eid, 0.7, _lib.RHS_AFFINE, np.array([0.25, 1.0, -1.0, 0.5]), 0.0)
+        nz, b = ctx.matrix_get(), ctx.vector_get(fes.ndofs)
+        cp, rv = ctx.pattern_get(fes.ndofs)
+        import scipy.sparse as sp
+
+        got = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(fes.ndofs, fes.ndofs))
+        want = sp.csc_matrix((nzref, rowval - 1, colptr - 1), shape=(fes.ndofs, fes.ndofs))
+        assert abs(got - want).max() <= RTOL * np.abs(nzref).max()
+        assert np.abs(b - bref).max() <= RTOL * np.abs(bref).max()
+    # (Hdiv spaces on mirrored cells are not a case: the face orientations of ExtendableGrids assume consistently oriented cells)
+    for n in (1, 2):  # ragged sizes through the RT0 closed form: 6 / 48 cells
+        _check_hdiv_mixed(_grid3d(n, True), fb.HDIVRT0(3))
