@@ -277,6 +277,9 @@ __device__ __forceinline__ unsigned lds32(unsigned addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+// ordered hand-over between the four warps of a SPLIT = 4 CTA: warp w waits on barrier 1 + w, its predecessor arrives there
+__device__ __forceinline__ void p2_token_wait(unsigned warp) { asm volatile("bar.sync %0, 64;" ::"r"(1u + warp) : "memory"); }
+__device__ __forceinline__ void p2_token_pass(unsigned warp) { asm volatile("bar.arrive %0, 64;" ::"r"(1u + ((warp + 1u) & 3u)) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // one visit: compute with the record in `cur` (loaded DEPTH visits ago), then start the load of the record of the visit
@@ -361,17 +364,18 @@ __device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int 
             for (int j = 0; j < 10; j++) sts64(ad[j], o[j] + v[j]);
         }
     } else {
-#pragma unroll 1
-        for (int ph = 0; ph < SPLIT; ph++) {
-            if (on && (int)warp == ph) {
-                double o[10];
+        // visit order r = 0, 1, 2, ... = warp 0, 1, 2, 3, 0, ...: a token travels round the four warps through named barriers
+        // (producer: bar.arrive after its stores, consumer: bar.sync before its loads — two warps per barrier), so a warp only
+        // waits for its predecessor's accumulation and computes its next column meanwhile (no CTA-wide barrier per visit)
+        p2_token_wait(warp);
+        if (on) {
+            double o[10];
 #pragma unroll
-                for (int j = 0; j < 10; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
+            for (int j = 0; j < 10; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
 #pragma unroll
-                for (int j = 0; j < 10; j++) sts64(ad[j], o[j] + v[j]);
-            }
-            __syncthreads();
+            for (int j = 0; j < 10; j++) sts64(ad[j], o[j] + v[j]);
         }
+        p2_token_pass(warp);
     }
 }
 
@@ -472,6 +476,7 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
     }
     double racc[3] = {0.0, 0.0, 0.0};
     unsigned rad[3] = {0u, 0u, 0u}, err = 0u;
+    if (SPLIT > 1 && warp == 3u) p2_token_pass(warp);  // the token starts at warp 0
     for (int it = 0; it < niter; it += DEPTH) {
 #pragma unroll
         for (int u = 0; u < DEPTH; u++) {
@@ -479,13 +484,14 @@ __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gath
                 const int r = (it + u) * SPLIT + rfirst;
                 // (SPLIT = 4: a warp whose row index is past nrows only takes part in the barriers)
                 if (SPLIT == 1 || r < nrows) p2_visit<SPLIT, MODE, DEPTH>(a, rec[u], r, nrows, sst, pst, srec, vp0, sacc, fmask, warp, bsum, racc, rad, err);
-                else {
-#pragma unroll 1
-                    for (int ph = 0; ph < SPLIT; ph++) __syncthreads();
+                else {  // (SPLIT = 4: a warp whose row index is past nrows only hands the token on)
+                    p2_token_wait(warp);
+                    p2_token_pass(warp);
                 }
             }
         }
     }
+    if (SPLIT > 1 && warp == 0u) p2_token_wait(warp);  // take the token back: every visit has been accumulated
     if (err) atomicAdd(a.errflag, 1);
     if (SPLIT == 1 && MODE == 1 && rad[2] != 0u) {  // (a column with at least one visit)
 #pragma unroll
