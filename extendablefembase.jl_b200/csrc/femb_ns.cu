@@ -1,4 +1,6 @@
 // Example210 (Taylor-Hood Navier-Stokes): Newton-linearised convection kernels and the update_system! entry point.
+#include <cstdlib>
+
 #include "femb_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -220,6 +222,104 @@ __global__ void __launch_bounds__(128, 3) k_convection2d_blocks(const Conv2Args 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Example210 div-pressure blocks in closed form (Example210:293-301,376-380): Bloc[(c,j),k] = -|T| int d_c phi_j lambda_k for the
+// component-blocked P2 velocity / P1 pressure pair on triangles.  With D_ca = |T| d_c lambda_a:
+//   vertex function i:  -(4 m_ik - 1/3) D_ci          (= -D_ck / 3 for i = k, 0 otherwise)
+//   edge function (ab): -4 (m_ak D_cb + m_bk D_ca),   m = 1/6 (equal indices) or 1/12
+// One thread per cell, 36 values, scattered into (u,p) and (p,u) through the slot maps.  The launcher accepts the closed form
+// only if it reproduces the evaluators' quadrature tables on a test cell; else the generic kernel runs.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_th_divpressure2d(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
+                                                          int64_t ncells, double factor, const int32_t* __restrict__ slots, const int32_t* __restrict__ slots_t,
+                                                          double* __restrict__ nzval, int32_t* __restrict__ errflag) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cell >= ncells) return;
+    double x[3][2];
+    load_nodes<2>(coords, cellnodes, cell, x);
+    const double a00 = x[1][0] - x[0][0], a01 = x[2][0] - x[0][0], a10 = x[1][1] - x[0][1], a11 = x[2][1] - x[0][1];
+    const double det = a00 * a11 - a01 * a10;
+    const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * 0.5;
+    const double sc = vol / det;
+    // det * grad lambda_1 = (a11, -a01), det * grad lambda_2 = (-a10, a00), grad lambda_0 = -(sum)
+    double D[2][3];
+    D[0][1] = a11 * sc; D[1][1] = -a01 * sc;
+    D[0][2] = -a10 * sc; D[1][2] = a00 * sc;
+    D[0][0] = -(D[0][1] + D[0][2]); D[1][0] = -(D[1][1] + D[1][2]);
+    unsigned err = 0u;
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                double v;
+                if (j < 3) {
+                    if (j != k) continue;  // (exact zero: the reference adds 0.0 there)
+                    v = D[c][k] * (1.0 / 3.0);
+                } else {
+                    const int ea = (j == 3) ? 0 : ((j == 4) ? 1 : 0), eb = (j == 3) ? 1 : 2;  // local edges (0 1), (1 2), (0 2)
+                    const double ma = (ea == k) ? (1.0 / 6.0) : (1.0 / 12.0), mb = (eb == k) ? (1.0 / 6.0) : (1.0 / 12.0);
+                    v = 4.0 * (ma * D[c][eb] + mb * D[c][ea]);
+                }
+                v *= factor;
+                const int32_t s = __ldg(slots + (cell * 12 + c * 6 + j) * 3 + k);
+                const int32_t t = __ldg(slots_t + (cell * 3 + k) * 12 + c * 6 + j);
+                if (s < 0 || t < 0) err = 1u;
+                else {
+                    atomicAdd(nzval + s, v);
+                    atomicAdd(nzval + t, v);
+                }
+            }
+    if (err) atomicAdd(errflag, 1);
+}
+
+// FEMB_ERR_UNSUPPORTED (no message) when the closed form does not apply
+static int launch_th_divpressure(femb_ctx* ctx, int egu, int eip, double factor) {
+    static const bool on = [] { const char* e = getenv("FEMB_TH_CLOSED"); return !(e && e[0] == '0'); }();
+    const FembEval& EG = ctx->evals[egu];
+    const FembEval& EP = ctx->evals[eip];
+    const FembSpace& us = ctx->spaces[EG.space];
+    const FembSpace& ps = ctx->spaces[EP.space];
+    if (!on || ctx->dim != 2 || ctx->scatter == FEMB_SCATTER_COLORED || ctx->touched || us.family != FEMB_FAMILY_H1 || us.ncomp != 2 || us.nd != 12 || us.nd_all != 12 ||
+        us.handler != FEMB_HANDLER_NONE || ps.family != FEMB_FAMILY_H1 || ps.ncomp != 1 || ps.nd != 3 || ps.nd_all != 3 || EG.nqp != EP.nqp)
+        return FEMB_ERR_UNSUPPORTED;
+    if (EG.h_refderivs.size() != (size_t)EG.nqp * 12 * 4 || EP.h_refvals.size() != (size_t)EP.nqp * 3) return FEMB_ERR_UNSUPPORTED;
+    {
+        // reference cell check: sum_q w_q (d_c phi_j)(q) lambda_k(q) for the first-component functions against the constants above
+        for (int j = 0; j < 6; j++)
+            for (int k = 0; k < 3; k++)
+                for (int c = 0; c < 2; c++) {
+                    double ref = 0.0;
+                    for (int q = 0; q < EG.nqp; q++) ref += EG.w[q] * EG.h_refderivs[(((size_t)q * 12 + j) * 2 + 0) * 2 + c] * EP.h_refvals[(size_t)q * 3 + k];
+                    // on the reference triangle: d_c lambda_1 = (1,0), d_c lambda_2 = (0,1), d_c lambda_0 = (-1,-1)
+                    const double dl[3] = {-1.0, c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0};
+                    double closed;
+                    if (j < 3) closed = (j == k) ? dl[k] / 3.0 : 0.0;
+                    else {
+                        const int ea = (j == 3) ? 0 : ((j == 4) ? 1 : 0), eb = (j == 3) ? 1 : 2;
+                        closed = 4.0 * (((ea == k) ? 1.0 / 6.0 : 1.0 / 12.0) * dl[eb] + ((eb == k) ? 1.0 / 6.0 : 1.0 / 12.0) * dl[ea]);
+                    }
+                    if (fabs(ref - closed) > 5e-12) return FEMB_ERR_UNSUPPORTED;
+                    // the second-component functions must be the same scalar functions in component 1
+                    double ref2 = 0.0;
+                    for (int q = 0; q < EG.nqp; q++) ref2 += EG.w[q] * EG.h_refderivs[(((size_t)q * 12 + 6 + j) * 2 + 1) * 2 + c] * EP.h_refvals[(size_t)q * 3 + k];
+                    if (fabs(ref2 - closed) > 5e-12) return FEMB_ERR_UNSUPPORTED;
+                }
+    }
+    FEMB_TRY(femb_build_slotmaps(ctx, 0, 1));
+    FEMB_TRY(femb_build_slotmaps(ctx, 1, 0));
+    const FembBlock* b01 = find_block(ctx, 0, 1);
+    const FembBlock* b10 = find_block(ctx, 1, 0);
+    if (!b01 || !b10 || !b01->slots || !b10->slots) return FEMB_ERR_UNSUPPORTED;
+    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    if (ctx->ncells == 0) return FEMB_OK;
+    k_th_divpressure2d<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, factor, b01->slots, b10->slots,
+                                                                                      ctx->nzval, ctx->errflag);
+    KERNEL_CHECK(ctx);
+    return FEMB_OK;
+}
+
 extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_t eiu, int32_t eip, double mu, int32_t linear, int32_t nonlinear,
                                               int32_t rhs_kind, const double* data) {
     FEMB_CHECK_CTX(ctx);
@@ -252,7 +352,10 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
         if (st == FEMB_ERR_UNSUPPORTED) st = ctx->scatter == FEMB_SCATTER_COLORED ? FEMB_ERR_UNSUPPORTED : launch_stiffness_dmma(ctx, egu, mu, -1.0);
         if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, egu, egu, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, 0, 0.0);
         // Bloc[j,k] = -sum_qp w (g[1,j]+g[4,j]) psi_k * |T| into (u,p) and (p,u) (Example210:293-301,376-380)
-        if (st == FEMB_OK) st = launch_bilinear(ctx, egu, eip, FEMB_OP_GRADTRACE, FEMB_OP_IDENTITY, 0, 1, -1.0, FEMB_BIL_TRANSPOSE_COPY, 0.0);
+        if (st == FEMB_OK) {
+            st = launch_th_divpressure(ctx, egu, eip, -1.0);  // closed form for the P2 / P1 pair on triangles
+            if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, egu, eip, FEMB_OP_GRADTRACE, FEMB_OP_IDENTITY, 0, 1, -1.0, FEMB_BIL_TRANSPOSE_COPY, 0.0);
+        }
         if (st == FEMB_OK && rhs.kind != FEMB_RHS_NONE && !rhs_done) st = launch_linear(ctx, eiu, 0, 1.0, rhs);
     }
     if (st == FEMB_OK && nonlinear) {
