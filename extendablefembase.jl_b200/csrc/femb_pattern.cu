@@ -1044,6 +1044,7 @@ static bool hmap_space_ok(const femb_ctx* ctx, const FembSpace& s) {
 int femb_build_hmap(femb_ctx* ctx) {
     femb_free_hmap(ctx->hm);
     femb_free_hmap(ctx->hm_vec);
+    femb_free(&ctx->rt0rec);  // (laid out by the entries of hm_vec)
     if (ctx->gmap_space >= 0) return FEMB_OK;  // scalar P1 has its own map
     if (ctx->nrs != 1 || ctx->ncs != 1 || ctx->row_spaces[0] != ctx->col_spaces[0] || ctx->blocks.size() != 1) return FEMB_OK;
     const int sid = ctx->row_spaces[0];
