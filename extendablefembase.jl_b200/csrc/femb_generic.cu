@@ -705,7 +705,10 @@ extern "C" int32_t femb_assemble_bilinear(femb_ctx* ctx, int32_t er, int32_t ec,
     int st = FEMB_ERR_UNSUPPORTED;
     if (ctx->scatter == FEMB_SCATTER_GATHER && !ctx->touched && !(drop_tol > 0.0)) {
         // HDIVRT0 on tetrahedra: closed-form local matrices, owner-computes mass gather, conflict-free divergence blocks
-        if (er == ec && flags == 0 && ctx->evals[er].op == FEMB_OP_IDENTITY) st = launch_rt0_mass_gather(ctx, er, brow, bcol, factor);
+        if (er == ec && flags == 0 && ctx->evals[er].op == FEMB_OP_IDENTITY) {
+            st = launch_rt0_mass_gather(ctx, er, brow, bcol, factor);
+            if (st == FEMB_ERR_UNSUPPORTED) st = launch_bdm1_mass_gather(ctx, er, brow, bcol, factor);
+        }
         else if (ctx->evals[er].op == FEMB_OP_DIVERGENCE && ctx->evals[ec].op == FEMB_OP_IDENTITY && (flags & ~FEMB_BIL_TRANSPOSE_COPY) == 0)
             st = launch_rt0_div(ctx, er, ec, brow, bcol, factor, flags);
     }

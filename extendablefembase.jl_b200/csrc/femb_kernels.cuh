@@ -68,4 +68,5 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
 int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu, int ei = -1, const RhsDev* rhs = nullptr, bool* rhs_done = nullptr);
 // femb_hdiv.cu: HDIVRT0 on tetrahedra in closed form (FEMB_ERR_UNSUPPORTED, without an error message, when not covered)
 int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor);
+int launch_bdm1_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor);
 int launch_rt0_div(femb_ctx* ctx, int er, int ec, int brow, int bcol, double factor, int flags);

@@ -1035,7 +1035,8 @@ static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off,
 }
 
 static bool hmap_space_ok(const femb_ctx* ctx, const FembSpace& s) {
-    if (s.family == FEMB_FAMILY_HDIV) return s.handler == FEMB_HANDLER_RT0_SIGNS && s.nd == s.nd_all && s.nd <= 4 && ctx->max_collen <= 254;  // RT0 (femb_hdiv.cu)
+    if (s.family == FEMB_FAMILY_HDIV)  // RT0 / BDM1 on tetrahedra (femb_hdiv.cu)
+        return ctx->max_collen <= 254 && ((s.handler == FEMB_HANDLER_RT0_SIGNS && s.nd == s.nd_all && s.nd <= 4) || (s.handler == FEMB_HANDLER_BDM1_3D && s.nd == 12));
     if (s.family != FEMB_FAMILY_H1 || s.handler != FEMB_HANDLER_NONE || s.nd != s.nd_all || s.nd % s.ncomp || ctx->max_collen > 254) return false;
     const int nds = s.nd / s.ncomp;
     return nds <= 12 && ((nds & 3) == 1 || (nds & 3) == 2);  // the last position word must have two spare bytes (k + first-touch flags)
