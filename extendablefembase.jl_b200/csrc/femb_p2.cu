@@ -7,10 +7,15 @@
 // evaluator's own quadrature tables for every local column (else the general kernel of femb_h1.cu runs).
 //
 // What this buys (ncu of the general kernel: L1 data pipe 72 %, long-scoreboard stalls at 16 warps / SM, 124 registers):
-//  * a vertex-column visit reads ONE 32-byte sector (G_k. and the local rhs entry) instead of a 96-byte record,
-//  * no quadrature tables, no h_q intermediates: ~70 registers, twice the resident warps,
+//  * a vertex-column visit needs ONE 32-byte sector (G_k. and the local rhs entry) instead of a 96-byte record; the cell pre-pass
+//    writes those sectors in VISIT order, so the vertex-column kernel streams them with the bulk copies of its map,
+//  * an edge-column visit reads exactly two sectors of the cell's 128-byte edge line,
+//  * no quadrature tables, no h_q intermediates: 75-95 registers,
 //  * the gather map is put into "role order" (self / other vertices / incident edges / opposite edges) once, so the numeric
-//    kernel has no per-lane indexing except one select chain over the local edge number.
+//    kernel has no per-lane indexing except one select chain over the local edge number,
+//  * the slice's map arrives by bulk copies (cp.async.bulk + mbarrier): one memory latency for all visits of a slice.
+// Timing experiments (compile-time): -DP2_DBG_REC (records forced into cache), -DP2_DBG_NOACC (no
+// shared-memory accumulation), -DP2_DBG_NOSTORE (no write-out), -DP2_NO_PREFETCH, -DP2_FILT_ON=0.
 #include <cstdlib>
 
 #include "femb_kernels.cuh"
@@ -35,16 +40,14 @@ namespace {
 #ifndef P2_DEPTH
 #define P2_DEPTH 1
 #endif
-#ifndef P2_DEPTH0
-#define P2_DEPTH0 2
-#endif
 #ifndef P2_MINB0
 #define P2_MINB0 4
 #endif
 
-// doubles per cell (the vertex part and the edge part are one aligned 128-byte line each): 4 vertex sectors [G_k,o1 G_k,o2 G_k,o3 bl_k],
-// then [G01 G02 G03 G12] and three sectors [G13 G23 bl_a bl_b], (a b) = (4 5) (6 7) (8 9): edge dof 4 + e reads sectors 4 and 5 + e / 2
-constexpr int P2_REC = 16;  // (round 2, later: the vertex sectors moved to the visit-order array `vrec`; the per-cell record is the edge line)
+// doubles per cell of the edge line (one aligned 128-byte line): [G01 G02 G03 G12] and three sectors [G13 G23 bl_a bl_b],
+// (a b) = (4 5) (6 7) (8 9): edge dof 4 + e reads sectors 0 and 1 + e / 2.  The vertex sectors [G_k,o1 G_k,o2 G_k,o3 bl_k] live
+// in the visit-order array FembHMap::vrec.
+constexpr int P2_REC = 16;
 
 struct P2Const {
     double alpha, beta, gd, go, mus, mud;
@@ -382,10 +385,12 @@ __device__ __forceinline__ void p2_visit(const P2Args& a, double (&cur)[8], int 
 // SPLIT = 1: one thread per column, 4 slices (warps) per CTA.  SPLIT = 4: one slice per CTA, warp w takes the visits
 // r = w (mod 4) and the shared-memory accumulation is serialised in visit order between barriers (same sums in the same
 // order as one thread per column).  Requires a complete map in role order, no value filter, no slot tracking.
-// Latency plan (the visit chain map entry -> record -> accumulate is what bounds this kernel, not a throughput): the slice's
-// whole map comes in with four bulk copies (cp.async.bulk + mbarrier, one memory latency for all visits), then every
-// record the slice will read is prefetched into L2 at once, and the visit loop loads records one visit ahead.
-// dynamic shared memory: [4 mbarriers | pad to 128 B][acc: maxlen x ncol doubles][map planes: (4 warps x) 4 x maxrows x 128 B]
+// Latency plan (the visit chain map entry -> record -> accumulate bounded the first versions, not a throughput): the slice's
+// whole map comes in with bulk copies (cp.async.bulk + mbarrier, one memory latency for all visits) — for vertex-dof slices
+// (MODE 0) together with the visit-order sectors, so that kernel issues no record loads at all; edge-dof slices prefetch all
+// their records into L2 at once and load them one visit ahead.
+// dynamic shared memory: [4 mbarriers | pad to 128 B][acc: (maxlen + 1) x ncol doubles][per slice: map planes (3 or 4) x maxrows x 128 B
+// (+ MODE 0: maxrows x 1 KB of sectors)]
 template <int SPLIT, int MODE>
 __global__ void __launch_bounds__(128, MODE == 0 ? P2_MINB0 : P2_MINB) k_p2_gather(const P2Args a) {
     constexpr unsigned ncol = 128 / SPLIT;
