@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get("FEMB_LIB") or os.path.join(HERE, "libfemb.so")  # FEMB_LIB: alternative build (tuning experiments)
 
 # enums of include/femb.h
-FAMILY = {"H1": 0, "Hdiv": 1, "L2": 2}
+FAMILY = {"H1": 0, "Hdiv": 1, "L2": 2, "Hcurl": 3}
 OP_IDENTITY, OP_GRADIENT, OP_DIVERGENCE = 0, 1, 2
 RHS_NONE, RHS_AFFINE, RHS_QPVALUES, RHS_EX210 = 0, 1, 2, 3
 FUNC_AFFINE, FUNC_EX210_U = 1, 2

@@ -5,6 +5,7 @@
 * ``prepare_assembly(A, b, FESu, FESp, sol)`` -> ``update_system(linear, nonlinear)``  <->
   ``Example210.prepare_assembly!`` (/root/reference/examples/Example210_LowLevelNavierStokes.jl:218-394)
 * ``assemble_hdiv_mixed`` : HDIVRT0/HDIVBDM1 mass + divergence blocks against L2P0 (config C4).
+* ``assemble_mass`` : mass matrix / load vector of one space with the Identity push-forward of its family (H1, L2, Hdiv, Hcurl).
 
 All arithmetic happens in libfemb.so (hand-written sm_100a CUDA) through the C ABI of
 include/femb.h; this module only extracts the raw arrays from the FESpace / FEEvaluator /
@@ -70,7 +71,7 @@ def _register_space(ctx, sid, fes, device_dofmap=False):
     signs = orient = None
     if handler in (1, 3, 4, 5):
         signs = grid["CellFaceSigns"]
-    elif handler == 2:
+    elif handler in (2, 6):
         signs = grid["CellEdgeSigns"]
     if handler == 5:
         orient = grid["CellFaceOrientations"]
@@ -236,6 +237,35 @@ def assemble_hdiv_mixed(A: FEMatrix, FESv, FESq, *, device=0, scatter=None):
     ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
     ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
     ctx.matrix_add_to(Ae.nzval)
+    return S
+
+
+# --------------------------------------------------------------------------------------
+# L2 mass system of one space (every family: H1 / L2 / Hdiv / Hcurl Identity push-forwards)
+# --------------------------------------------------------------------------------------
+def assemble_mass(A, b, fes, rhs=None, *, quadorder=None, device=0, scatter=None):
+    """``A += (u_j, u_k)`` and, with ``rhs``, ``b += (rhs, u_j)`` on the cells of ``fes``: the same loop as Example200:129-178 with the
+    Identity evaluator on both sides (feevaluator_h1.jl:2-14, feevaluator_hdiv.jl:2-19, feevaluator_hcurl.jl:2-16).  ``A`` is an
+    ``ExtendableSparseMatrix`` (pattern built on the device on first use), ``b`` a vector of length ``fes.ndofs``."""
+    ft = fes.fetype
+    g = fes.xgrid.geometry
+    qf = QuadratureRule(g, 2 * ft.get_polynomialorder(g) if quadorder is None else quadorder)
+    S = _session_for([fes], qf, device)
+    ctx = S.ctx
+    if scatter is not None:
+        ctx.set_scatter(scatter)
+    ei = S.evaluator(0, Identity)
+    fresh = S.ensure_pattern(A, [(0, 0)])
+    if fresh:
+        S.download_pattern(A)
+    ctx.matrix_zero()
+    ctx.assemble_bilinear(ei._eid, ei._eid, 0, 0, 1.0, 0, 0.0)
+    ctx.matrix_add_to(A.nzval)
+    if rhs is not None:
+        kind, data = _rhs_args(ctx, rhs, len(qf), ei.resultdim)
+        ctx.vector_zero()
+        ctx.assemble_linear(ei._eid, 0, 1.0, kind, data)
+        b += ctx.vector_get(b.shape[0])
     return S
 
 

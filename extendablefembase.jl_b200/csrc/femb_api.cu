@@ -231,8 +231,10 @@ int32_t femb_space_set(femb_ctx* ctx, int32_t id, int32_t family, int32_t ncomp,
         case FEMB_HANDLER_RT0_SIGNS: nsign = ctx->dim + 1; break;
         case FEMB_HANDLER_BDM1_2D: nsign = 3; break;
         case FEMB_HANDLER_BDM1_3D: nsign = 4; break;
+        case FEMB_HANDLER_N0_EDGESIGNS3D: nsign = 6; break;
         default: return femb_fail(ctx, FEMB_ERR_ARG, "unknown handler %d", handler);
     }
+    if (handler == FEMB_HANDLER_N0_EDGESIGNS3D && ctx->dim != 3) return femb_fail(ctx, FEMB_ERR_ARG, "handler %d is the tetrahedral one (CellEdgeSigns)", handler);
     if (nsign && !signs) return femb_fail(ctx, FEMB_ERR_ARG, "handler %d needs the sign array", handler);
     if (handler == FEMB_HANDLER_BDM1_3D && !orient) return femb_fail(ctx, FEMB_ERR_ARG, "HDIVBDM1{3} needs CellFaceOrientations");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -280,6 +282,8 @@ int32_t femb_evaluator_set(femb_ctx* ctx, int32_t id, int32_t space_id, int32_t 
     if (op != FEMB_OP_IDENTITY && op != FEMB_OP_GRADIENT && op != FEMB_OP_DIVERGENCE)
         return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "operator %d is not on the assembly path (Identity, Gradient, Divergence)", op);
     if (op == FEMB_OP_GRADIENT && s.family == FEMB_FAMILY_HDIV) return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "Gradient of Hdiv functions is out of scope");
+    if (op != FEMB_OP_IDENTITY && s.family == FEMB_FAMILY_HCURL)
+        return femb_fail(ctx, FEMB_ERR_UNSUPPORTED, "Hcurl spaces: only the Identity push-forward (feevaluator_hcurl.jl:2-16) is on the path");
     if (op == FEMB_OP_IDENTITY && !refvals) return femb_fail(ctx, FEMB_ERR_ARG, "Identity needs refvals");
     if (op != FEMB_OP_IDENTITY && !refderivs) return femb_fail(ctx, FEMB_ERR_ARG, "derivative operators need refderivs");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -139,6 +139,8 @@ __device__ __forceinline__ double coef_of(const SpaceDev& s, int64_t cell, int d
     switch (s.handler) {
         case FEMB_HANDLER_RT0_SIGNS:  // hdiv_rt0.jl:114-124
             return (double)__ldg(s.signs + cell * s.nsign + dof);
+        case FEMB_HANDLER_N0_EDGESIGNS3D:  // hcurl_n0.jl:156-166
+            return (double)__ldg(s.signs + cell * 6 + dof);
         case FEMB_HANDLER_BDM1_2D:  // hdiv_bdm1.jl:200-212
             return (dof & 1) ? 1.0 : (double)__ldg(s.signs + cell * 3 + (dof >> 1));
         case FEMB_HANDLER_BDM1_3D: {  // hdiv_bdm1.jl:215-228
@@ -161,7 +163,7 @@ __device__ __forceinline__ void eval_op(const SpaceDev& s, int op, const Geo<DIM
                                         double* out) {
     const int sub = subset_of(s, cell, dof);
     const int nc = s.ncomp;
-    if (s.family != FEMB_FAMILY_HDIV) {
+    if (s.family != FEMB_FAMILY_HDIV && s.family != FEMB_FAMILY_HCURL) {
         if (op == FEMB_OP_IDENTITY) {  // feevaluator_h1.jl:2-14
             const double* v = refvals + ((size_t)qp * s.nd_all + sub) * nc;
             if (RT > 0) {
@@ -212,6 +214,18 @@ __device__ __forceinline__ void eval_op(const SpaceDev& s, int op, const Geo<DIM
                 t = (k == 0) ? a : t + a;
             }
             out[0] = t;
+        }
+    } else if (s.family == FEMB_FAMILY_HCURL) {
+        if (op == FEMB_OP_IDENTITY) {  // feevaluator_hcurl.jl:2-16: covariant Piola map, (sum_l L2GAinv[k,l] phi[sub,l]) * coeff
+            const double cf = coef_of(s, cell, dof);
+            const double* v = refvals + ((size_t)qp * s.nd_all + sub) * DIM;
+#pragma unroll
+            for (int k = 0; k < DIM; k++) {
+                double a = 0.0;
+#pragma unroll
+                for (int l = 0; l < DIM; l++) a += g.M[k][l] * v[l];
+                if (RT == 0 || k < RT) out[k] = a * cf;
+            }
         }
     } else {
         const double cf = coef_of(s, cell, dof);

@@ -632,7 +632,7 @@ int launch_linear(femb_ctx* ctx, int ev, int brow, double factor, const RhsDev& 
     FEMB_TRY(femb_flush_zero(ctx, false, true));
     unsigned grid = (unsigned)((s.ndofs + 127) / 128);
     QuadDev q = quad_dev(E, ctx->dim);
-    const bool light = s.family != FEMB_FAMILY_HDIV && E.op == FEMB_OP_IDENTITY;
+    const bool light = s.family != FEMB_FAMILY_HDIV && s.family != FEMB_FAMILY_HCURL && E.op == FEMB_OP_IDENTITY;
     if (light && E.refvals && ctx->ncells) {
         const size_t need = (size_t)ctx->ncells * E.nqp * rhs.ncomp;
         if (ctx->cellrhs_n < need) {

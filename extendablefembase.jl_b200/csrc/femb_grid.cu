@@ -354,8 +354,10 @@ int32_t femb_space_set_from_pattern(femb_ctx* ctx, int32_t id, int32_t family, i
         case FEMB_HANDLER_RT0_SIGNS: nsign = ctx->dim + 1; break;
         case FEMB_HANDLER_BDM1_2D: nsign = 3; break;
         case FEMB_HANDLER_BDM1_3D: nsign = 4; break;
+        case FEMB_HANDLER_N0_EDGESIGNS3D: nsign = 6; sign_kind = 1; break;
         default: return femb_fail(ctx, FEMB_ERR_ARG, "unknown handler %d", handler);
     }
+    if (handler == FEMB_HANDLER_N0_EDGESIGNS3D && ctx->dim != 3) return femb_fail(ctx, FEMB_ERR_ARG, "handler %d is the tetrahedral one (CellEdgeSigns)", handler);
     PatArgs a;
     memset(&a, 0, sizeof(a));
     a.nseg = nseg; a.ncomp = ncomp; a.nd = nd; a.nnpc = ctx->nnpc;

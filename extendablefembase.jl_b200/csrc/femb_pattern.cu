@@ -923,7 +923,7 @@ int femb_hmap_set_canon(femb_ctx* ctx, FembHMap& H, bool canon) {
 // builds the map of the (component-diagonal part of the) square block of space `sid` whose rows / columns start at row_off / col_off
 static int build_hmap_into(femb_ctx* ctx, FembHMap& H, int sid, int64_t row_off, int64_t col_off, bool subrange) {
     const FembSpace& s = ctx->spaces[sid];
-    const int nds = s.family == FEMB_FAMILY_HDIV ? s.nd : s.nd / s.ncomp;  // (Hdiv: vector-valued functions, one block of nd dofs)
+    const int nds = (s.family == FEMB_FAMILY_HDIV || s.family == FEMB_FAMILY_HCURL) ? s.nd : s.nd / s.ncomp;  // (Hdiv / Hcurl: vector-valued functions, one block of nd dofs)
     const int64_t nslices = (s.ndofs + 31) / 32;
     const int nwords = (nds + 5) / 4;  // the position bytes + two spare bytes (k, first-touch flags) in the last word
     int32_t *deg = nullptr, *clen = nullptr;

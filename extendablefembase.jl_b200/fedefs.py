@@ -230,6 +230,15 @@ def _hdiv_rt0(dim):
     return [_vec(3, [2 * x, 2 * y, 2 * (z - 1)]), _vec(3, [2 * x, 2 * (y - 1), 2 * z]), _vec(3, [2 * x, 2 * y, 2 * z]), _vec(3, [2 * (x - 1), 2 * y, 2 * z])]
 
 
+def _hcurl_n0(dim):
+    if dim == 2:  # hcurl_n0.jl:94-104
+        _, (x, y) = _bary(2)
+        return [_vec(2, [1 - y, x]), _vec(2, [-y, x]), _vec(2, [-y, x - 1])]
+    _, (x, y, z) = _bary(3)  # hcurl_n0.jl:120-142 (local edges [1 2; 1 3; 1 4; 2 3; 2 4; 3 4])
+    return [_vec(3, [1 - y - z, x, x]), _vec(3, [y, 1 - z - x, y]), _vec(3, [z, z, 1 - x - y]),
+            _vec(3, [-y, x, 0]), _vec(3, [-z, 0, x]), _vec(3, [0, -z, y])]
+
+
 def _hdiv_bdm1(dim):
     if dim == 2:  # hdiv_bdm1.jl:73-90
         _, (x, y) = _bary(2)
@@ -260,6 +269,7 @@ HANDLER_H1_EDGESWAP3D = 2  # h1_p3.jl:220-241: same with CellEdgeSigns on tets
 HANDLER_RT0_SIGNS = 3      # hdiv_rt0.jl:114-124
 HANDLER_BDM1_2D = 4        # hdiv_bdm1.jl:200-212
 HANDLER_BDM1_3D = 5        # hdiv_bdm1.jl:215-249 (signs + orientation subset)
+HANDLER_N0_EDGESIGNS3D = 6  # hcurl_n0.jl:156-166 (CellEdgeSigns)
 
 _DIM = {"Triangle2D": 2, "Tetrahedron3D": 3}
 _NNODES = {"Triangle2D": 3, "Tetrahedron3D": 4}
@@ -418,6 +428,23 @@ class _HDIVRT0(FEType):
         return _NFACES[geometry]
 
 
+class _HCURLN0(FEType):
+    """Lowest-order Nedelec space of the first kind (hcurl_n0.jl): one tangential flux per face (2-D) / edge (3-D)."""
+
+    family = "Hcurl"
+    handler2d = HANDLER_RT0_SIGNS  # CellFaceSigns on every function (hcurl_n0.jl:144-154), as for RT0
+    handler3d = HANDLER_N0_EDGESIGNS3D
+
+    def get_dofmap_pattern(self, geometry):
+        return "f1" if _DIM[geometry] == 2 else "e1"  # hcurl_n0.jl:31-34
+
+    def reference_basis(self, geometry):
+        return (_hcurl_n0(_DIM[geometry]),)
+
+    def get_ndofs(self, geometry):
+        return 3 if _DIM[geometry] == 2 else 6
+
+
 class _HDIVBDM1(FEType):
     family = "Hdiv"
     handler2d = HANDLER_BDM1_2D
@@ -464,6 +491,11 @@ def L2P0(ncomponents=1):
 @lru_cache(maxsize=None)
 def HDIVRT0(edim=2):
     return _HDIVRT0(f"HDIVRT0{{{edim}}}", edim, edim, 1)
+
+
+@lru_cache(maxsize=None)
+def HCURLN0(edim=2):
+    return _HCURLN0(f"HCURLN0{{{edim}}}", edim, edim, 1)
 
 
 @lru_cache(maxsize=None)

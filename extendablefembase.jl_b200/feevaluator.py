@@ -53,7 +53,7 @@ class FEEvaluator:
         self.derivorder = NeededDerivative4Operator(operator)
         self.citem = 0
         self.cvals = np.zeros((self.resultdim, self.ndofs4item, len(qf)))  # Julia shape (resultdim, ndofs, nqp)
-        if operator == Identity and ft.family != "Hdiv" and ft.handler(g) == 0:
+        if operator == Identity and ft.family not in ("Hdiv", "Hcurl") and ft.handler(g) == 0:
             # filled once in the constructor, never changes per cell (feevaluator.jl:158-161)
             self.cvals[:] = np.transpose(vals[:, : self.ndofs4item, :], (2, 1, 0))
 

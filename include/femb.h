@@ -44,8 +44,8 @@ enum {
     FEMB_ERR_NCCL = 5
 };
 
-/* FE class of a space: selects the push-forward (src/feevaluator_h1.jl vs feevaluator_hdiv.jl) */
-enum { FEMB_FAMILY_H1 = 0, FEMB_FAMILY_HDIV = 1, FEMB_FAMILY_L2 = 2 };
+/* FE class of a space: selects the push-forward (src/feevaluator_h1.jl, feevaluator_hdiv.jl, feevaluator_hcurl.jl) */
+enum { FEMB_FAMILY_H1 = 0, FEMB_FAMILY_HDIV = 1, FEMB_FAMILY_L2 = 2, FEMB_FAMILY_HCURL = 3 };
 
 /* per-cell coefficient / subset handlers (get_coefficients, get_basissubset of src/fedefs) */
 enum {
@@ -54,7 +54,8 @@ enum {
     FEMB_HANDLER_H1_EDGESWAP3D = 2, /* h1_p3.jl:220-241 */
     FEMB_HANDLER_RT0_SIGNS = 3,     /* hdiv_rt0.jl:114-124 */
     FEMB_HANDLER_BDM1_2D = 4,       /* hdiv_bdm1.jl:200-212 */
-    FEMB_HANDLER_BDM1_3D = 5        /* hdiv_bdm1.jl:215-249 */
+    FEMB_HANDLER_BDM1_3D = 5,       /* hdiv_bdm1.jl:215-249 */
+    FEMB_HANDLER_N0_EDGESIGNS3D = 6 /* hcurl_n0.jl:156-166 (CellEdgeSigns; HCURLN0{2} takes FEMB_HANDLER_RT0_SIGNS: face signs, :144-154) */
 };
 
 /* function operators implemented on the device (src/functionoperators.jl:132-196) */

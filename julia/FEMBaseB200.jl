@@ -18,7 +18,7 @@ using SparseArrays
 const libfemb = get(ENV, "LIBFEMB", joinpath(@__DIR__, "..", "extendablefembase.jl_b200", "libfemb.so"))
 
 # enums of include/femb.h
-const FAMILY_H1, FAMILY_HDIV, FAMILY_L2 = Int32(0), Int32(1), Int32(2)
+const FAMILY_H1, FAMILY_HDIV, FAMILY_L2, FAMILY_HCURL = Int32(0), Int32(1), Int32(2), Int32(3)
 const OP_IDENTITY, OP_GRADIENT, OP_DIVERGENCE = Int32(0), Int32(1), Int32(2)
 const RHS_NONE, RHS_AFFINE, RHS_QPVALUES, RHS_EX210 = Int32(0), Int32(1), Int32(2), Int32(3)
 const BIL_TRANSPOSE_COPY = Int32(1)
@@ -52,6 +52,7 @@ end
 
 family(::Type{<:ExtendableFEMBase.AbstractH1FiniteElement}) = FAMILY_H1
 family(::Type{<:ExtendableFEMBase.AbstractHdivFiniteElement}) = FAMILY_HDIV
+family(::Type{<:ExtendableFEMBase.AbstractHcurlFiniteElement}) = FAMILY_HCURL
 family(::Type{<:L2P0}) = FAMILY_L2
 
 # per-cell handlers (get_basissubset / get_coefficients of src/fedefs/*.jl) -> FEMB_HANDLER_* of include/femb.h
@@ -61,6 +62,7 @@ function handler(FEType, EG)
     (FEType <: H1Pk && get_polynomialorder(FEType, EG) >= 3) && return Int32(1)
     FEType <: HDIVRT0 && return Int32(3)
     FEType <: HDIVBDM1 && return dim == 2 ? Int32(4) : Int32(5)
+    FEType <: HCURLN0 && return dim == 2 ? Int32(3) : Int32(6)   # face signs (hcurl_n0.jl:144-154) / edge signs (:156-166)
     return Int32(0)
 end
 
@@ -72,7 +74,7 @@ function space_set!(ctx::Context, id::Integer, FES::FESpace)
     nd = get_ndofs(ON_CELLS, FEType, EG)
     nd_all = get_ndofs_all(ON_CELLS, FEType, EG)
     h = handler(FEType, EG)
-    signs = h in (1, 3, 4, 5) ? xgrid[CellFaceSigns] : (h == 2 ? xgrid[CellEdgeSigns] : nothing)
+    signs = h in (1, 3, 4, 5) ? xgrid[CellFaceSigns] : (h in (2, 6) ? xgrid[CellEdgeSigns] : nothing)
     orient = h == 5 ? xgrid[CellFaceOrientations] : nothing
     entries = celldofs isa Matrix ? celldofs : celldofs.colentries
     # scalar P1: CellDofs is CellNodes (pattern "N1"); pass NULL so the library aliases the mesh array

@@ -131,12 +131,13 @@ def _stroud(order: int):
 # reference bases.  f(x) with x[..., dim] (float or complex) -> [..., nd_all, ncomp]
 # ---------------------------------------------------------------------------------------------
 class Element:
-    """name in {H1P1,H1P2,H1P3,H1Pk,HDIVRT0,HDIVBDM1,L2P0}; ncomp; order (H1Pk)."""
+    """name in {H1P1,H1P2,H1P3,H1Pk,HDIVRT0,HDIVBDM1,HCURLN0,L2P0}; ncomp; order (H1Pk)."""
 
     def __init__(self, name, ncomp=1, order=None):
         self.name, self.ncomp = name, int(ncomp)
-        self.order = {"H1P1": 1, "H1P2": 2, "H1P3": 3, "L2P0": 0, "HDIVRT0": 1, "HDIVBDM1": 1}.get(name, order)
-        self.family = "Hdiv" if name.startswith("HDIV") else ("L2" if name.startswith("L2") else "H1")
+        self.order = {"H1P1": 1, "H1P2": 2, "H1P3": 3, "L2P0": 0, "HDIVRT0": 1, "HDIVBDM1": 1, "HCURLN0": 1}.get(name, order)
+        self.family = "Hdiv" if name.startswith("HDIV") else ("Hcurl" if name.startswith("HCURL") else ("L2" if name.startswith("L2") else "H1"))
+        self.vector_valued = self.family in ("Hdiv", "Hcurl")  # one block of nd vector functions instead of ncomp scalar blocks
 
     def polyorder(self):
         return self.order
@@ -147,6 +148,7 @@ class Element:
             "H1P1": "N1", "H1P2": "N1F1" if d == 2 else "N1E1", "H1P3": "N1F2I1" if d == 2 else "N1E2F1",
             "H1Pk": "N1" if o == 1 else ("N1F1" if o == 2 else f"N1F{o - 1}I{(o - 2) * (o - 1) // 2}"),
             "HDIVRT0": "f1", "HDIVBDM1": "f2" if d == 2 else "f3", "L2P0": "I1",
+            "HCURLN0": "f1" if d == 2 else "e1",  # hcurl_n0.jl:31-34
         }[self.name]
 
     def scalar_basis(self, g, x):
@@ -194,7 +196,7 @@ class Element:
     def basis(self, g, x):
         x = np.asarray(x)
         d = DIM[g]
-        if self.family != "Hdiv":
+        if not self.vector_valued:
             sb = self.scalar_basis(g, x)
             nds = len(sb)
             out = np.zeros(x.shape[:-1] + (nds * self.ncomp, self.ncomp), dtype=x.dtype)
@@ -228,6 +230,16 @@ class Element:
                     [2 * (x1 - 1), 2 * x2, 2 * x3],
                     [24 * (l - x2), 24 * x2, z], [-24 * (l - x3), z, -24 * x3], [-24 * (x3 - x2), -24 * x2, 24 * x3],
                 ]
+        elif self.name == "HCURLN0":
+            one = np.ones(x.shape[:-1], dtype=x.dtype)
+            if d == 2:  # hcurl_n0.jl:94-104
+                x1, x2 = xs
+                rows = [[one - x2, x1], [-x2, x1], [-x2, x1 - 1]]
+            else:  # hcurl_n0.jl:120-142
+                x1, x2, x3 = xs
+                z = 0 * x1
+                rows = [[one - x2 - x3, x1, x1], [x2, one - x3 - x1, x2], [x3, x3, one - x1 - x2],
+                        [-x2, x1, z], [-x3, z, x1], [z, -x3, x2]]
         else:
             raise ValueError(self.name)
         out = np.zeros(x.shape[:-1] + (len(rows), d), dtype=x.dtype)
@@ -340,13 +352,15 @@ def basis_subset(el: Element, g, ncells, facesigns=None, edgesigns=None, orient=
     return sub
 
 
-def coefficients(el: Element, g, ncells, facesigns=None):
+def coefficients(el: Element, g, ncells, facesigns=None, edgesigns=None):
     """coefficients[cell, dof] (identical for all components in every on-path element) — get_coefficients"""
     nd = el.nd(g)
     co = np.ones((ncells, nd))
     d = DIM[g]
     if el.name == "HDIVRT0":  # hdiv_rt0.jl:114-124
         co[:] = facesigns
+    elif el.name == "HCURLN0":  # hcurl_n0.jl:144-166: face signs on triangles, edge signs on tetrahedra
+        co[:] = facesigns if d == 2 else edgesigns
     elif el.name == "HDIVBDM1":
         if d == 2:  # hdiv_bdm1.jl:200-212
             co[:, 0::2] = facesigns
@@ -405,9 +419,9 @@ def update_basis(el: Element, op: str, g, xref, coords, cellnodes, facesigns=Non
     vals, der = el.tabulate(g, xref)  # [qp, da, comp], [qp, da, comp, j]
     A, b, det, M = l2g(coords, cellnodes)
     sub = basis_subset(el, g, nc, facesigns, edgesigns, orient)  # [cell, dof]
-    ncomp = el.ncomp if el.family != "Hdiv" else d
+    ncomp = el.ncomp if not el.vector_valued else d
     nd, nq = el.nd(g), xref.shape[0]
-    if el.family != "Hdiv":
+    if not el.vector_valued:
         if op == "Identity":  # feevaluator_h1.jl:2-14
             v = vals[:, sub, :]  # [qp, cell, dof, comp]
             return np.ascontiguousarray(np.transpose(v, (1, 3, 2, 0)))
@@ -428,7 +442,18 @@ def update_basis(el: Element, op: str, g, xref, coords, cellnodes, facesigns=Non
                     acc = acc + M[None, :, k, j, None] * dsub[:, :, :, k, j]
             return np.transpose(acc, (1, 2, 0))[:, None, :, :]
         raise ValueError(op)
-    co = coefficients(el, g, nc, facesigns)  # [cell, dof]
+    co = coefficients(el, g, nc, facesigns, edgesigns)  # [cell, dof]
+    if el.family == "Hcurl":
+        if op != "Identity":
+            raise ValueError(op)
+        v = vals[:, sub, :]  # feevaluator_hcurl.jl:2-16: (sum_l L2GAinv[k,l] phi[sub, l]) * coeff
+        out = np.zeros((nc, d, nd, nq))
+        for k in range(d):
+            acc = np.zeros((nq, nc, nd))
+            for l in range(d):
+                acc = acc + M[None, :, k, l, None] * v[:, :, :, l]
+            out[:, k, :, :] = np.transpose(acc * co[None], (1, 2, 0))
+        return out
     if op == "Identity":  # feevaluator_hdiv.jl:2-19: (sum_l A[k,l] phi[sub, l]) * coeff / det
         v = vals[:, sub, :]  # [qp, cell, dof, l]
         out = np.zeros((nc, d, nd, nq))
@@ -459,12 +484,12 @@ def parse_pattern(p):
 def celldofs_from_pattern(el: Element, g, nnodes, cellnodes, cellfaces=None, nfaces=0, celledges=None, nedges=0):
     segs = parse_pattern(el.pattern(g))
     ncells = cellnodes.shape[0]
-    ncomp = el.ncomp if el.family != "Hdiv" else 1
+    ncomp = el.ncomp if not el.vector_valued else 1
     # dofs per component = coffset (finiteelements.jl:395-449)
     cnt = {"N": nnodes, "F": nfaces, "E": nedges, "I": ncells}
     coffset = sum(cnt[t] * q for t, q in segs if t.isupper())
-    ndofs = coffset * (el.ncomp if el.family != "Hdiv" else 1) + sum(cnt[t.upper()] * q for t, q in segs if t.islower())
-    if el.family == "Hdiv":
+    ndofs = coffset * (el.ncomp if not el.vector_valued else 1) + sum(cnt[t.upper()] * q for t, q in segs if t.islower())
+    if el.vector_valued:
         coffset, ncomp = 0, 0
     out = []
     for cell in range(ncells):
@@ -493,7 +518,7 @@ def celldofs_from_pattern(el: Element, g, nnodes, cellnodes, cellfaces=None, nfa
                     for m in range(q):
                         row.append(cell + 1 + off)
                         off += ncells
-        off = (el.ncomp if el.family != "Hdiv" else 0) * coffset
+        off = (el.ncomp if not el.vector_valued else 0) * coffset
         for t, q in segs:
             if t.isupper():
                 continue
@@ -803,6 +828,16 @@ def interpolate_hdiv(el: Element, g, coords, facenodes, u):
     for m in range(nmom):
         res[m * nf:(m + 1) * nf] = out[m::nmom]
     return res
+
+
+def interpolate_hcurl(coords, entitynodes, u):
+    """HCURLN0 interpolation (hcurl_n0.jl:44-56): dof_e = int_e u . t ds with t pointing from the first to the second node of the
+    entity (2-D: the faces, t = the rotated FaceNormal (-n_2, n_1); 3-D: the edges, t = EdgeTangents); 2-point Gauss rule."""
+    x = coords[entitynodes.astype(np.int64) - 1]  # [entity, 2, dim]
+    gp, gw = np.polynomial.legendre.leggauss(2)
+    t = x[:, 1, :] - x[:, 0, :]  # |e| t
+    pts = x[:, None, 0, :] + (0.5 * gp + 0.5)[None, :, None] * t[:, None, :]
+    return np.einsum("eqk,ek->eq", u(pts), t) @ (0.5 * gw)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ def _oracle_el(ft):
 def _signs(grid, ft):
     h = ft.handler(grid.geometry)
     fs = grid["CellFaceSigns"] if h in (1, 3, 4, 5) else None
-    es = grid["CellEdgeSigns"] if h == 2 else None
+    es = grid["CellEdgeSigns"] if h in (2, 6) else None
     ori = grid["CellFaceOrientations"] if h == 5 else None
     return fs, es, ori
 
@@ -53,12 +53,13 @@ EVAL_CASES = [
     (lambda: fb.HDIVRT0(2), 2, "Identity", 2), (lambda: fb.HDIVRT0(2), 2, "Divergence", 2), (lambda: fb.HDIVBDM1(2), 2, "Identity", 2),
     (lambda: fb.HDIVRT0(3), 3, "Identity", 2), (lambda: fb.HDIVRT0(3), 3, "Divergence", 2), (lambda: fb.HDIVBDM1(3), 3, "Identity", 2),
     (lambda: fb.HDIVBDM1(3), 3, "Divergence", 2), (lambda: fb.L2P0(1), 3, "Identity", 2),
+    (lambda: fb.HCURLN0(2), 2, "Identity", 2), (lambda: fb.HCURLN0(3), 3, "Identity", 2),
 ]
 
 
 @pytest.mark.parametrize("mk,dim,op,qorder", EVAL_CASES)
 def test_update_basis(mk, dim, op, qorder):
-    """femb_evaluator_eval == oracle update_basis! (feevaluator_h1.jl / feevaluator_hdiv.jl) for all cells."""
+    """femb_evaluator_eval == oracle update_basis! (feevaluator_h1.jl / feevaluator_hdiv.jl / feevaluator_hcurl.jl) for all cells."""
     ft = mk()
     grid = _grid2d(5, True) if dim == 2 else _grid3d(3, True)
     g = grid.geometry
@@ -284,6 +285,71 @@ def _check_hdiv_mixed(grid, ft):
     # divergence theorem: B^T 1_v-coefficients of a constant field ... row sums of the (q, v) block = sum_f sign * 1 -> net flux 0 for interior
     Msp = E.to_scipy()
     assert abs(Msp - Msp.T).max() <= RTOL * scale
+
+
+@pytest.mark.parametrize("dim,device_dofmap", [(2, False), (3, False), (3, True)])
+def test_hcurl_n0_mass_system(dim, device_dofmap):
+    """HCURLN0 mass matrix and load vector (Identity push-forward feevaluator_hcurl.jl:2-16, coefficients hcurl_n0.jl:144-166) against
+    the oracle; solving the system with a constant load returns its tangential-flux interpolant (the L2 projection onto N0 is exact
+    for constant fields: the reference's exactness order 0, test/test_interpolators.jl:15,44)."""
+    import scipy.sparse.linalg as spla
+
+    grid = _grid2d(6, True) if dim == 2 else _grid3d(4, True)
+    if device_dofmap:
+        grid.instantiate_on_device()
+    g = grid.geometry
+    ft = fb.HCURLN0(dim)
+    fes = fb.FESpace(ft, grid)
+    A = fb.ExtendableSparseMatrixCSC(fes.ndofs, fes.ndofs)
+    b = np.zeros(fes.ndofs)
+    cvec = np.array([0.7, -1.3, 0.4])[:dim]
+    rhs = fb.AffineFunction(list(cvec), [[0.0] * dim] * dim)
+    S = fb.assemble_mass(A, b, fes, rhs)
+    if device_dofmap:  # signs and CellDofs generated on the device from the pattern "e1" (femb_space_set_from_pattern): same system
+        from femb_b200.assembly import _Session
+
+        S2 = _Session([fes], S.qf, device_dofmaps=True)
+        ei = S2.evaluator(0, "Identity")
+        S2.ctx.pattern_build([(0, 0)])
+        S2.ctx.matrix_zero()
+        S2.ctx.assemble_bilinear(ei._eid, ei._eid, 0, 0, 1.0, 0, 0.0)
+        cp, rv = S2.ctx.pattern_get(fes.ndofs)
+        assert np.array_equal(cp, A.colptr) and np.array_equal(rv, A.rowval)
+        assert np.abs(S2.ctx.matrix_get() - A.nzval).max() <= RTOL * np.abs(A.nzval).max()  # (atomic scatter: summation order differs)
+        S2.ctx.close()
+    el = orc.Element("HCURLN0", dim)
+    xref, w = orc.quadrature(g, 2)
+    fs, es, _ = _signs(grid, ft)
+    fs = grid["CellFaceSigns"]
+    V = orc.update_basis(el, "Identity", g, xref, grid["Coordinates"], grid["CellNodes"], fs, es)
+    vol = grid["CellVolumes"]
+    M = orc.bilinear_local(V, V, w, vol)
+    cd = fes["CellDofs"]
+    I, J, Vv = orc.block_triplets(M, cd, cd)
+    colptr, rowval, nzval = orc.flush_csc(fes.ndofs, fes.ndofs, I, J, Vv)
+    assert np.array_equal(A.colptr, colptr) and np.array_equal(A.rowval, rowval)
+    scale = np.abs(M).max()
+    assert np.abs(A.nzval - nzval).max() <= RTOL * scale
+    # load vector: b_j = sum_cells |T| sum_qp w_qp <phi_j(x_qp), c>
+    bl = np.einsum("crdq,r,q,c->cd", V, cvec, w, vol)
+    bo = np.zeros(fes.ndofs)
+    np.add.at(bo, cd.astype(np.int64) - 1, bl)
+    assert np.abs(b - bo).max() <= RTOL * max(np.abs(bl).max(), 1e-300) * 8
+    # M x = b  =>  x = interpolant of the constant field
+    x = spla.spsolve(A.to_scipy().tocsc(), b)
+    enodes = grid["FaceNodes"] if dim == 2 else grid["EdgeNodes"]
+    want = orc.interpolate_hcurl(grid["Coordinates"], enodes, lambda p: np.broadcast_to(cvec, p.shape))
+    assert np.abs(x - want).max() < 1e-10 * np.abs(want).max()
+
+
+def test_hcurl_unsupported_operators_are_statuses():
+    grid = _grid2d(3)
+    fes = fb.FESpace(fb.HCURLN0(2), grid)
+    from femb_b200.assembly import _Session
+
+    S = _Session([fes], fb.QuadratureRule(grid.geometry, 2))
+    with pytest.raises(_lib.FembError):
+        S.evaluator(0, "Gradient")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -601,7 +667,7 @@ DOFMAP_CASES = [
     (lambda: fb.H1P1(1), 2), (lambda: fb.H1P1(2), 2), (lambda: fb.H1P2(1, 2), 2), (lambda: fb.H1Pk(2, 2, 2), 2), (lambda: fb.H1P3(1, 2), 2),
     (lambda: fb.H1Pk(1, 2, 4), 2), (lambda: fb.HDIVRT0(2), 2), (lambda: fb.HDIVBDM1(2), 2), (lambda: fb.L2P0(1), 2),
     (lambda: fb.H1P1(1), 3), (lambda: fb.H1P2(1, 3), 3), (lambda: fb.H1P2(3, 3), 3), (lambda: fb.H1P3(1, 3), 3), (lambda: fb.HDIVRT0(3), 3),
-    (lambda: fb.HDIVBDM1(3), 3), (lambda: fb.L2P0(3), 3),
+    (lambda: fb.HDIVBDM1(3), 3), (lambda: fb.L2P0(3), 3), (lambda: fb.HCURLN0(2), 2), (lambda: fb.HCURLN0(3), 3),
 ]
 
 

@@ -329,6 +329,44 @@ def test_interpolation_roundtrip_hdiv(name, order, dim):
     assert np.abs(divh - div).max() < 1e-8
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_interpolation_roundtrip_hcurl(dim):
+    """(4) test/test_interpolators.jl:15,44 (HCURLN0{2} / HCURLN0{3} => order 0): tangential-flux interpolation of a constant field, then
+    evaluation through the covariant Piola map (feevaluator_hcurl.jl:2-16) with the CellFaceSigns / CellEdgeSigns coefficients
+    (hcurl_n0.jl:144-166) reproduces the field; so does a rigid rotation a + w x (x), the rest of the first-kind Nedelec space."""
+    grid = _grids()[dim - 2]
+    g = grid.geometry
+    el = orc.Element("HCURLN0", dim)
+    ft = fb.HCURLN0(dim)
+    fes = fb.FESpace(ft, grid)
+    celldofs = fes["CellDofs"]
+    cd2, ndofs2 = orc.celldofs_from_pattern(el, g, grid.nnodes, grid["CellNodes"], grid["CellFaces"], grid.nfaces,
+                                            grid["CellEdges"] if dim == 3 else None, grid.nedges if dim == 3 else 0)
+    assert ndofs2 == fes.ndofs == (grid.nfaces if dim == 2 else grid.nedges) and np.array_equal(cd2, celldofs)
+    # product tables == oracle tables
+    xq, _ = orc.quadrature(g, 2)
+    v1, d1 = ft.tabulate(g, xq)
+    v2, d2 = el.tabulate(g, xq)
+    assert np.abs(v1 - v2).max() < 1e-15 and np.abs(d1 - d2).max() < 1e-15
+    enodes = grid["FaceNodes"] if dim == 2 else grid["EdgeNodes"]
+    A, b, _, _ = orc.l2g(grid["Coordinates"], grid["CellNodes"])
+    x = orc.eval_trafo(A, b, xq)
+    cv = orc.update_basis(el, "Identity", g, xq, grid["Coordinates"], grid["CellNodes"], grid["CellFaceSigns"],
+                          grid["CellEdgeSigns"] if dim == 3 else None)
+    const = _poly(dim, 0, dim)
+
+    def rot(x):
+        if dim == 2:
+            return np.stack([0.3 - 0.7 * x[..., 1], -0.2 + 0.7 * x[..., 0]], axis=-1)
+        w = np.array([0.4, -0.9, 0.6])
+        return np.array([0.1, 0.2, -0.3]) + np.cross(np.broadcast_to(w, x.shape), x)
+
+    for u in (const, rot):
+        sol = orc.interpolate_hcurl(grid["Coordinates"], enodes, u)
+        uh = np.einsum("crdq,cd->cqr", cv, sol[celldofs.astype(np.int64) - 1])
+        assert np.abs(uh - u(x)).max() < TOL
+
+
 # ---------------------------------------------------------------------------------------------
 def test_block_offsets():
     """(5) test/test_fematrix_and_vector.jl: block (i,j) starts at row sum(ndofs X[<i]) / col sum(ndofs Y[<j])."""
