@@ -71,6 +71,7 @@ SIGNATURES = {
     "femb_vector_set": (_i32, [_p, _i32, _p]),
     "femb_set_scatter": (_i32, [_p, _i32]),
     "femb_assemble_bilinear": (_i32, [_p, _i32, _i32, _i32, _i32, _f64, _i32, _f64]),
+    "femb_assemble_hdiv_mixed": (_i32, [_p, _i32, _i32, _i32, _f64, _f64]),
     "femb_assemble_linear": (_i32, [_p, _i32, _i32, _f64, _i32, _p]),
     "femb_assemble_poisson": (_i32, [_p, _i32, _i32, _f64, _i32, _p, _f64]),
     "femb_assemble_poisson_host": (_i32, [_p, _i32, _i32, _f64, _i32, _p, _f64, _p, _p, _p, _p, _p, _i32]),
@@ -392,6 +393,9 @@ class Context:
     # ---- assembly -------------------------------------------------------
     def assemble_bilinear(self, er, ec, brow, bcol, factor=1.0, flags=0, drop_tol=0.0):
         self._ck(self.lib.femb_assemble_bilinear(self.h, er, ec, brow, bcol, factor, flags, drop_tol))
+
+    def assemble_hdiv_mixed(self, e_id, e_div, e_q, factor_mass=1.0, factor_div=1.0):
+        self._ck(self.lib.femb_assemble_hdiv_mixed(self.h, e_id, e_div, e_q, factor_mass, factor_div))
 
     def assemble_linear(self, ev, brow, factor, rhs_kind, data):
         data = _arr(data, np.float64)

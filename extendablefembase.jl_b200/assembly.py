@@ -234,8 +234,7 @@ def assemble_hdiv_mixed(A: FEMatrix, FESv, FESq, *, device=0, scatter=None):
     if fresh:
         S.download_pattern(Ae)
     ctx.matrix_zero()
-    ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
-    ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
+    ctx.assemble_hdiv_mixed(eid._eid, ediv._eid, eq._eid, 1.0, 1.0)
     ctx.matrix_add_to(Ae.nzval)
     return S
 

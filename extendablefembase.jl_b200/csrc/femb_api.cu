@@ -46,6 +46,7 @@ int32_t femb_create(int32_t device, femb_ctx** out) {
         return FEMB_ERR_CUDA;
     }
     femb_ctx* ctx = new femb_ctx();
+    femb_reset_block_counts(ctx);
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -355,6 +356,7 @@ int32_t femb_matrix_zero(femb_ctx* ctx) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->dirty_A = false;
     ctx->zero_pending_A = true;  // applied lazily (femb_flush_zero) or skipped by write-once kernels
+    ctx->zero_mask = ~0ull;
     if (ctx->touched) CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 0, ctx->nnz, ctx->stream));
     return FEMB_OK;
 }

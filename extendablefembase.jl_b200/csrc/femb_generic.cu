@@ -42,16 +42,113 @@ SpaceDev space_dev(const FembSpace& s) {
     return d;
 }
 
-// apply the lazy zeroing requested by femb_matrix_zero / femb_vector_zero for kernels that accumulate
+// ---- lazy zeroing (femb_matrix_zero / femb_vector_zero) -------------------------------------------------
+// The rows of a layout block form one contiguous run in every column of the block (rowval ascending): [lo, hi) by two binary searches.
+__device__ __forceinline__ void block_run(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int64_t col, int64_t r0, int64_t r1, int64_t& lo,
+                                          int64_t& hi) {
+    const int64_t b = colptr[col] - 1, e = colptr[col + 1] - 1;
+    int64_t l = b, h = e;
+    while (l < h) {
+        const int64_t m = (l + h) >> 1;
+        if (rowval[m] <= r0) l = m + 1;  // 1-based rows of the block: r0 + 1 .. r1
+        else h = m;
+    }
+    lo = l;
+    h = e;
+    while (l < h) {
+        const int64_t m = (l + h) >> 1;
+        if (rowval[m] <= r1) l = m + 1;
+        else h = m;
+    }
+    hi = l;
+}
+
+// one warp per column of the block: zero the run
+__global__ void k_zero_block(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int64_t c0, int64_t c1, int64_t r0, int64_t r1,
+                             double* __restrict__ nzval) {
+    const int64_t col = c0 + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    if (col >= c1) return;
+    int64_t lo, hi;
+    block_run(colptr, rowval, col, r0, r1, lo, hi);
+    for (int64_t p = lo + (threadIdx.x & 31); p < hi; p += 32) nzval[p] = 0.0;
+}
+
+__global__ void k_count_block(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, int64_t c0, int64_t c1, int64_t r0, int64_t r1,
+                              unsigned long long* __restrict__ count) {
+    const int64_t col = c0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t lo = 0, hi = 0;
+    if (col < c1) block_run(colptr, rowval, col, r0, r1, lo, hi);
+    unsigned long long n = (unsigned long long)(hi - lo);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
+}
+
+// number of pattern entries inside layout block (brow, bcol); cached until the pattern changes
+int femb_block_entries(femb_ctx* ctx, int brow, int bcol, int64_t* n) {
+    if (brow < 0 || brow >= ctx->nrs || bcol < 0 || bcol >= ctx->ncs || !ctx->colptr) return femb_fail(ctx, FEMB_ERR_ARG, "block (%d,%d): no such block / no pattern", brow, bcol);
+    int64_t& cached = ctx->block_nnz[brow][bcol];
+    if (cached < 0) {
+        const int64_t c0 = ctx->col_off[bcol], c1 = ctx->col_off[bcol + 1];
+        unsigned long long* cnt = nullptr;
+        unsigned long long h = 0;
+        CUDA_TRY(ctx, cudaMalloc(&cnt, sizeof(*cnt)));
+        cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(*cnt), ctx->stream);
+        if (e == cudaSuccess && c1 > c0) {
+            k_count_block<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, ctx->stream>>>(ctx->colptr, ctx->rowval, c0, c1, ctx->row_off[brow], ctx->row_off[brow + 1], cnt);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(cnt);
+        if (e != cudaSuccess) return femb_fail(ctx, FEMB_ERR_CUDA, "femb_block_entries: %s", cudaGetErrorString(e));
+        cached = (int64_t)h;
+    }
+    *n = cached;
+    return FEMB_OK;
+}
+
+// A kernel that overwrites every pattern entry of block (brow, bcol) takes the block out of the pending zero: true = store, do not add.
+bool femb_claim_block(femb_ctx* ctx, int brow, int bcol) {
+    static const bool on = [] { const char* e = getenv("FEMB_BLOCK_CLAIMS"); return !(e && e[0] == '0'); }();  // 0: always zero, then add (A/B timing)
+    if (!on || !ctx->zero_pending_A) return false;
+    const uint64_t bit = 1ull << (brow * FEMB_MAX_SPACES + bcol);
+    if (!(ctx->zero_mask & bit)) return false;
+    ctx->zero_mask &= ~bit;
+    return true;
+}
+
+// apply the lazy zeroing for kernels that accumulate: the whole array, or — after claims — the runs of the blocks nobody has overwritten
 int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec) {
     if (mat && ctx->zero_pending_A) {
-        if (ctx->nzval) CUDA_TRY(ctx, cudaMemsetAsync(ctx->nzval, 0, sizeof(double) * ctx->nnz, ctx->stream));
+        if (ctx->nzval && ctx->zero_mask == ~0ull) {
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->nzval, 0, sizeof(double) * ctx->nnz, ctx->stream));
+        } else if (ctx->nzval) {
+            for (int br = 0; br < ctx->nrs; br++)
+                for (int bc = 0; bc < ctx->ncs; bc++) {
+                    const int64_t c0 = ctx->col_off[bc], c1 = ctx->col_off[bc + 1];
+                    if (!(ctx->zero_mask & (1ull << (br * FEMB_MAX_SPACES + bc))) || c1 <= c0 || ctx->row_off[br + 1] <= ctx->row_off[br]) continue;
+                    int64_t n = 0;
+                    FEMB_TRY(femb_block_entries(ctx, br, bc, &n));
+                    if (n == 0) continue;
+                    k_zero_block<<<(unsigned)((c1 - c0 + 7) / 8), 256, 0, ctx->stream>>>(ctx->colptr, ctx->rowval, c0, c1, ctx->row_off[br], ctx->row_off[br + 1], ctx->nzval);
+                    KERNEL_CHECK(ctx);
+                }
+        }
         ctx->zero_pending_A = false;
+        ctx->zero_mask = ~0ull;
     }
     if (vec && ctx->zero_pending_b) {
         if (ctx->bvec) CUDA_TRY(ctx, cudaMemsetAsync(ctx->bvec, 0, sizeof(double) * ctx->nrows, ctx->stream));
         ctx->zero_pending_b = false;
     }
+    return FEMB_OK;
+}
+
+// the single-kernel paths read zero_pending_A as "every entry is still to be zeroed": settle the blocks left over by earlier claims first
+int femb_settle_partial_zero(femb_ctx* ctx) {
+    if (ctx->zero_pending_A && ctx->zero_mask != ~0ull) return femb_flush_zero(ctx, true, false);
     return FEMB_OK;
 }
 
@@ -715,6 +812,27 @@ extern "C" int32_t femb_assemble_bilinear(femb_ctx* ctx, int32_t er, int32_t ec,
     if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, er, ec, ctx->evals[er].op, ctx->evals[ec].op, brow, bcol, factor, flags, drop_tol);
     if (st != FEMB_OK) return st;
     return femb_timer_end(ctx);
+}
+
+extern "C" int32_t femb_assemble_hdiv_mixed(femb_ctx* ctx, int32_t e_id, int32_t e_div, int32_t e_q, double factor_mass, double factor_div) {
+    FEMB_CHECK_CTX(ctx);
+    FEMB_TRY(check_eval(ctx, e_id));
+    FEMB_TRY(check_eval(ctx, e_div));
+    FEMB_TRY(check_eval(ctx, e_q));
+    FEMB_TRY(require_pattern(ctx));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->scatter == FEMB_SCATTER_GATHER && !ctx->touched) {
+        FEMB_TRY(femb_timer_begin(ctx));
+        const int st = launch_rt0_mixed(ctx, e_id, e_div, e_q, factor_mass, factor_div);
+        if (st == FEMB_OK) {
+            ctx->dirty_A = true;
+            return femb_timer_end(ctx);
+        }
+        if (st != FEMB_ERR_UNSUPPORTED) return st;
+    }
+    // everything else: the two assemblies one after the other (last_ms then reports the second one only)
+    FEMB_TRY(femb_assemble_bilinear(ctx, e_id, e_id, 0, 0, factor_mass, 0, 0.0));
+    return femb_assemble_bilinear(ctx, e_div, e_q, 0, 1, factor_div, FEMB_BIL_TRANSPOSE_COPY, 0.0);
 }
 
 extern "C" int32_t femb_assemble_linear(femb_ctx* ctx, int32_t ev, int32_t brow, double factor, int32_t rhs_kind, const double* data) {

@@ -796,6 +796,7 @@ int launch_h1_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     HArgs a;
     a.coef = ctx->cellcoef; a.hslice_ptr = H.slice_ptr; a.hslice_zero = H.slice_zero; a.hmap = H.map; a.hstride = H.stride; a.colptr = ctx->colptr; a.sub0 = a.sublen = nullptr; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag; a.drop_tol = drop_tol;
+    FEMB_TRY(femb_settle_partial_zero(ctx));
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
     a.has_rhs = rhs.kind != FEMB_RHS_NONE;

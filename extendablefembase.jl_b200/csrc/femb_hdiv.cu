@@ -27,7 +27,8 @@ __device__ __forceinline__ unsigned lds32(unsigned addr) {
 __host__ __device__ constexpr int rt0_opp(int j) { return j == 0 ? 3 : (j == 1 ? 2 : (j == 2 ? 0 : 1)); }
 
 __global__ void __launch_bounds__(128) k_cell_rt0rec(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol,
-                                                     const int32_t* __restrict__ signs, int64_t ncells, const uint32_t* __restrict__ finv, double* __restrict__ out) {
+                                                     const int32_t* __restrict__ signs, int64_t ncells, const uint32_t* __restrict__ finv, double* __restrict__ out,
+                                                     const int32_t* __restrict__ dslots, double fdiv, double* __restrict__ nzval) {
     const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (cell < ncells) {
         double x[4][3];
@@ -66,7 +67,33 @@ __global__ void __launch_bounds__(128) k_cell_rt0rec(const double* __restrict__ 
             double* o = out + (size_t)__ldg(finv + cell * 4 + k) * 4;
             asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(o), "d"(m[0]), "d"(m[1]), "d"(m[2]), "d"(m[3]) : "memory");
         }
+        if (dslots) {
+            // mixed pass: the (div v_j, q_T) entries of the cell's own column of block (0,1) — one sector, stored, not added (k_rt0_div's value)
+#pragma unroll
+            for (int j = 0; j < 4; j++) nzval[__ldg(dslots + cell * 4 + j)] = (fdiv * (sg[j] / det)) * vol;
+        }
     }
+}
+
+// mixed pass: per visit (cell, local face k) of the gather map the slot of the cell's (0,1) entry and the position of its transposed copy
+// in the (1,0) run that follows the mass run of the face column; bad counts what the fused gather does not cover
+__global__ void k_hdiv_xsrc(const uint32_t* __restrict__ map, size_t stride, int nw, const int32_t* __restrict__ celldofs, const int64_t* __restrict__ colptr,
+                            const int32_t* __restrict__ sub0, const int32_t* __restrict__ sublen, const int32_t* __restrict__ slots01, const int32_t* __restrict__ slots10,
+                            uint32_t* __restrict__ xsrc, int32_t* __restrict__ bad) {
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= stride) return;
+    const unsigned k = (map[(size_t)nw * stride + idx] >> 16) & 0xFu;
+    uint32_t v = 0u;
+    if (k < 4u) {
+        const int64_t cell = map[idx];
+        const int64_t col = celldofs[cell * 4 + k] - 1;
+        const int32_t src = slots01[cell * 4 + k], dst = slots10[cell * 4 + k];
+        const int64_t rank = (int64_t)dst - (colptr[col] - 1 + sublen[col]);
+        const int64_t dlen = (colptr[col + 1] - colptr[col]) - sublen[col];
+        if (src < 0 || dst < 0 || sub0[col] != 0 || rank < 0 || rank > 1 || rank >= dlen || dlen > 2) atomicAdd(bad, 1);
+        else v = (uint32_t)src | ((uint32_t)rank << 31);
+    }
+    xsrc[idx] = v;
 }
 
 // finv[cell * nd + k] = entry (row * 32 + lane) of the (local dof k of the cell, cell) visit in the gather map (nw position words)
@@ -91,14 +118,18 @@ struct RGArgs {
     int acc_A;
     int64_t slice_begin, slice_end;
     int maxlen, maxrows;
+    const uint32_t* xsrc;  // MIX
 };
 
 // one thread per face-dof column, 4 slices (warps) per CTA; ND local dofs per cell (RT0: 4, BDM1: 12).  Map planes (NW position
 // words; the cell plane is not needed) staged by bulk copies together with the visit-order records (ND doubles per visit).
 // dynamic shared memory: [4 mbarriers | pad to 128 B][acc: maxlen x 128 doubles][4 warps x (NW + 2 ND) x maxrows x 128 B]
-template <int ND>
+// MIX (RT0 in a [v; q] layout, fresh matrix): the thread also owns the (1,0) run that follows the mass run of its column — the transposed
+// copies of the (div v, q) entries the pre-pass has just stored in block (0,1), fetched through one more staged plane — and writes the
+// whole column in one piece (maxlen counts the two extra accumulator rows).
+template <int ND, bool MIX = false>
 __global__ void __launch_bounds__(128, ND == 4 ? 8 : 4) k_hdiv_mass_gather(const RGArgs a) {
-    constexpr unsigned NW = (ND + 5) / 4, STG = NW + 2u * ND;
+    constexpr unsigned NW = (ND + 5) / 4, STG = NW + 2u * ND, STGX = STG + (MIX ? 1u : 0u);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + warp;
@@ -106,7 +137,7 @@ __global__ void __launch_bounds__(128, ND == 4 ? 8 : 4) k_hdiv_mass_gather(const
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned pst = (unsigned)a.maxrows * 128u;
     const unsigned mbar = smem0 + warp * 8u;
-    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * 1024u + warp * STG * pst;
+    const unsigned sstw = smem0 + 128u + (unsigned)a.maxlen * 1024u + warp * STGX * pst;
     const int64_t c = slice * 32 + lane;
     const bool valid = c < a.ndofs;
     const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
@@ -114,8 +145,12 @@ __global__ void __launch_bounds__(128, ND == 4 ? 8 : 4) k_hdiv_mass_gather(const
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const unsigned bytes = (unsigned)nrows * 128u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * STG) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * STGX) : "memory");
         const uint32_t* g = a.map + ((size_t)row0 << 5) + a.stride;
+        if (MIX)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + STG * pst), "l"(a.xsrc + ((size_t)row0 << 5)),
+                         "r"(bytes), "r"(mbar)
+                         : "memory");
 #pragma unroll
         for (int p = 0; p < (int)NW; p++)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst), "l"(g + (size_t)p * a.stride),
@@ -127,12 +162,13 @@ __global__ void __launch_bounds__(128, ND == 4 ? 8 : 4) k_hdiv_mass_gather(const
     }
     const bool zero_first = __ldg(a.slice_zero + slice) != 0;
     int64_t base = 0;
-    int len = 0;
+    int len = 0, dlen = 0;
     if (valid) {
         base = a.colptr[c] - 1;
         len = (int)(a.colptr[c + 1] - 1 - base);
         if (a.sub0) {  // the block's run of the column
-            base += a.sub0[c];
+            if (MIX) dlen = len - a.sublen[c];  // (sub0 == 0, checked when xsrc was built: the (1,0) run follows directly)
+            else base += a.sub0[c];
             len = a.sublen[c];
         }
     }
@@ -168,20 +204,26 @@ __global__ void __launch_bounds__(128, ND == 4 ? 8 : 4) k_hdiv_mass_gather(const
         for (int j = 0; j < ND; j++) o[j] = lds64_unless(ad[j], (first >> j) & 1u);
 #pragma unroll
         for (int j = 0; j < ND; j++) sts64(ad[j], o[j] + v[j] * a.factor);
+        if (MIX) {
+            const unsigned xs = lds32(sstw + STG * pst + lane * 4u + (unsigned)r * 128u);
+            sts64(sacc + (unsigned)(len + (int)(xs >> 31)) * 1024u, __ldg(a.nzval + (xs & 0x7FFFFFFFu)));
+        }
     }
     if (!valid) return;
     double* out = a.nzval + base;
+    len += dlen;
     for (int i = 0; i < len; i++) {
         const double t = lds64(sacc + i * 1024u);
         out[i] = a.acc_A ? out[i] + t : t;
     }
 }
 
-// (div v_j, q_T) and its transposed copy: one contributing cell per entry -> plain adds through the slot maps
+// (div v_j, q_T) and its transposed copy: one contributing cell per entry -> plain adds through the slot maps, or plain stores
+// (store bit 0: the block, bit 1: its transposed copy) when the block was claimed from the pending zero
 // (ndl local dofs per cell, the flux function of face j is local dof j * fstep: RT0 4 / 1, BDM1 12 / 3 — the other BDM1 functions are divergence-free)
 __global__ void k_rt0_div(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol, const int32_t* __restrict__ signs,
                           int64_t ncells, double f0, double f1, double f2, double f3, const int32_t* __restrict__ slots, const int32_t* __restrict__ slots_t,
-                          double* __restrict__ nzval, int32_t* __restrict__ errflag, int ndl, int fstep) {
+                          double* __restrict__ nzval, int32_t* __restrict__ errflag, int ndl, int fstep, int store) {
     const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (cell >= ncells) return;
     double x[4][3];
@@ -201,11 +243,11 @@ __global__ void k_rt0_div(const double* __restrict__ coords, const int32_t* __re
         const double v = (f[j] * ((double)__ldg(signs + cell * 4 + j) / det)) * vol;
         const int32_t s = __ldg(slots + cell * ndl + j * fstep);
         if (s < 0) err = 1u;
-        else nzval[s] += v;
+        else nzval[s] = (store & 1) ? v : nzval[s] + v;
         if (slots_t) {
             const int32_t st = __ldg(slots_t + cell * ndl + j * fstep);
             if (st < 0) err = 1u;
-            else nzval[st] += v;
+            else nzval[st] = (store & 2) ? v : nzval[st] + v;
         }
     }
     if (err) atomicAdd(errflag, 1);
@@ -332,8 +374,14 @@ bool is_rt0_3d(const femb_ctx* ctx, const FembSpace& s) {
 
 }  // namespace
 
+struct HdivMix {
+    double fdiv;             // (sum_q w_q div phi_ref q_ref) * factor, the same for the four RT0 functions
+    const int32_t* slots01;  // [cell][4] slots of block (0,1)
+};
+
 // shared tail of the RT0 / BDM1 mass paths: gather map of block (0,0), inverse slot map, cell pre-pass, column gather
-static int hdiv_mass_gather(femb_ctx* ctx, const FembEval& E, int nd, double factor, const Bdm1Tab* tab) {
+// mix != nullptr (RT0, all three blocks still awaiting the lazy zero, H.xsrc built): the divergence blocks ride along
+static int hdiv_mass_gather(femb_ctx* ctx, const FembEval& E, int nd, double factor, const Bdm1Tab* tab, const HdivMix* mix = nullptr) {
     const FembSpace& s = ctx->spaces[E.space];
     int st = femb_build_hmap_vec(ctx);
     if (st != FEMB_OK) return st;
@@ -354,8 +402,9 @@ static int hdiv_mass_gather(femb_ctx* ctx, const FembEval& E, int nd, double fac
         }
         H.cranges = out;
     }
-    const size_t stg = (size_t)nw + 2 * (size_t)nd;
-    auto smem_of = [stg](const FembHMap::Range& r) { return 128 + (size_t)std::max(1, r.maxlen) * 1024 + 4 * stg * (size_t)r.maxrows * 128; };
+    const size_t stg = (size_t)nw + 2 * (size_t)nd + (mix ? 1 : 0);
+    const int xrows = mix ? 2 : 0;  // accumulator rows of the (1,0) run
+    auto smem_of = [stg, xrows](const FembHMap::Range& r) { return 128 + (size_t)(std::max(1, r.maxlen) + xrows) * 1024 + 4 * stg * (size_t)r.maxrows * 128; };
     size_t need = 0;
     for (auto& r : H.cranges) need = std::max(need, smem_of(r));
     if (need > 200 * 1024) return FEMB_ERR_UNSUPPORTED;
@@ -371,10 +420,14 @@ static int hdiv_mass_gather(femb_ctx* ctx, const FembEval& E, int nd, double fac
         }
     }
     if (ctx->ncells == 0) return FEMB_OK;
-    const bool fresh = ctx->zero_pending_A;  // right after femb_matrix_zero the runs are overwritten, not read-modify-written
-    FEMB_TRY(femb_flush_zero(ctx, true, false));
+    // right after femb_matrix_zero the gather claims its block: every run is overwritten (not read, added to and written back) and the
+    // zeroing of the block is skipped altogether; the other blocks keep waiting for their own kernels or femb_flush_zero
+    const bool fresh = femb_claim_block(ctx, 0, 0);
+    if (mix && !(fresh && femb_claim_block(ctx, 0, 1) && femb_claim_block(ctx, 1, 0))) return femb_fail(ctx, FEMB_ERR_ARG, "mixed RT0 pass on a matrix that is not freshly zeroed");
+    if (!fresh) FEMB_TRY(femb_flush_zero(ctx, true, false));
     if (nd == 4) {
-        k_cell_rt0rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.signs, ctx->ncells, H.vinv, ctx->rt0rec);
+        k_cell_rt0rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, s.signs, ctx->ncells, H.vinv, ctx->rt0rec,
+                                                                                     mix ? mix->slots01 : nullptr, mix ? mix->fdiv : 0.0, ctx->nzval);
     } else {
         k_cell_bdm1rec<<<(unsigned)((ctx->ncells + 9) / 10), 120, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, space_dev(s), ctx->ncells, *tab, H.vinv,
                                                                                          ctx->rt0rec);
@@ -385,14 +438,15 @@ static int hdiv_mass_gather(femb_ctx* ctx, const FembEval& E, int nd, double fac
     a.colptr = ctx->colptr + H.col_off; a.sub0 = H.sub0; a.sublen = H.sublen; a.ndofs = s.ndofs; a.nzval = ctx->nzval;
     a.factor = factor;
     a.acc_A = fresh ? 0 : 1;
-    const void* kern = nd == 4 ? (const void*)k_hdiv_mass_gather<4> : (const void*)k_hdiv_mass_gather<12>;
+    a.xsrc = mix ? H.xsrc : nullptr;
+    const void* kern = nd == 4 ? (mix ? (const void*)k_hdiv_mass_gather<4, true> : (const void*)k_hdiv_mass_gather<4>) : (const void*)k_hdiv_mass_gather<12>;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (auto& r : H.cranges) {
         if (r.s1 <= r.s0) continue;
         a.slice_begin = r.s0;
         a.slice_end = r.s1;
-        a.maxlen = std::max(1, r.maxlen);
+        a.maxlen = std::max(1, r.maxlen) + xrows;
         a.maxrows = r.maxrows;
         void* params[1] = {(void*)&a};
         CUDA_TRY(ctx, cudaLaunchKernel(kern, dim3((unsigned)((r.s1 - r.s0 + 3) / 4)), dim3(128), params, smem_of(r), ctx->stream));
@@ -448,11 +502,18 @@ int launch_bdm1_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double fa
     return hdiv_mass_gather(ctx, E, 12, factor, &tab);
 }
 
+static int rt0_mass_checked(femb_ctx* ctx, int er, double factor, const HdivMix* mix);
+
 int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor) {
+    if (brow != 0 || bcol != 0) return FEMB_ERR_UNSUPPORTED;
+    return rt0_mass_checked(ctx, er, factor, nullptr);
+}
+
+static int rt0_mass_checked(femb_ctx* ctx, int er, double factor, const HdivMix* mix) {
     if (!rt0_enabled()) return FEMB_ERR_UNSUPPORTED;
     const FembEval& E = ctx->evals[er];
     const FembSpace& s = ctx->spaces[E.space];
-    if (!is_rt0_3d(ctx, s) || brow != 0 || bcol != 0 || ctx->nrs < 1 || ctx->row_spaces[0] != E.space || ctx->col_spaces[0] != E.space) return FEMB_ERR_UNSUPPORTED;
+    if (!is_rt0_3d(ctx, s) || ctx->nrs < 1 || ctx->row_spaces[0] != E.space || ctx->col_spaces[0] != E.space) return FEMB_ERR_UNSUPPORTED;
     if (E.h_refvals.size() != (size_t)E.nqp * 4 * 3) return FEMB_ERR_UNSUPPORTED;
     {
         // the closed form must reproduce  |T| sum_q w_q (A phi_j(q) / det).(A phi_k(q) / det)  of the evaluator's table on a test cell
@@ -486,7 +547,7 @@ int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double fac
                 if (fabs(ref - closed) > 1e-12 * fabs(closed) + 1e-14) return FEMB_ERR_UNSUPPORTED;
             }
     }
-    return hdiv_mass_gather(ctx, E, 4, factor, nullptr);
+    return hdiv_mass_gather(ctx, E, 4, factor, nullptr, mix);
 }
 
 int launch_rt0_div(femb_ctx* ctx, int er, int ec, int brow, int bcol, double factor, int flags) {
@@ -527,10 +588,90 @@ int launch_rt0_div(femb_ctx* ctx, int er, int ec, int brow, int bcol, double fac
         else if (fn % 4 == 0) f[fn / 4] = t * factor;  // the RT0 function of face fn / 4 (subset index 4 j, hdiv_bdm1.jl:240)
         else if (fabs(t) > 1e-13) return FEMB_ERR_UNSUPPORTED;  // the moment functions must be divergence-free in the mean
     }
-    FEMB_TRY(femb_flush_zero(ctx, true, false));
-    if (ctx->ncells == 0) return FEMB_OK;
+    if (ctx->ncells == 0) return femb_flush_zero(ctx, true, false);
+    // a block whose pattern holds nothing but the (face dof, cell) couplings — 4 per cell (RT0), 12 per cell with the exact zeros of the
+    // divergence-free BDM1 functions — is overwritten entry by entry: claim it from the pending zero (RT0) instead of zeroing and adding
+    int store = 0;
+    if (ctx->zero_pending_A && !bdm) {
+        int64_t n = 0, nt = 0;
+        FEMB_TRY(femb_block_entries(ctx, brow, bcol, &n));
+        if (blk_t) FEMB_TRY(femb_block_entries(ctx, tr, tc, &nt));
+        if (n == ctx->ncells * 4 && femb_claim_block(ctx, brow, bcol)) store |= 1;
+        if (blk_t && nt == ctx->ncells * 4 && femb_claim_block(ctx, tr, tc)) store |= 2;
+    }
+    if (store != (blk_t ? 3 : 1)) {
+        // something is added to: settle the rest of the pending zero (the claimed blocks stay out of it)
+        FEMB_TRY(femb_flush_zero(ctx, true, false));
+    }
     k_rt0_div<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, rs.signs, ctx->ncells, f[0], f[1], f[2], f[3], blk->slots,
-                                                                             blk_t ? blk_t->slots : nullptr, ctx->nzval, ctx->errflag, ndl, fstep);
+                                                                             blk_t ? blk_t->slots : nullptr, ctx->nzval, ctx->errflag, ndl, fstep, store);
     KERNEL_CHECK(ctx);
     return FEMB_OK;
+}
+
+// Mass block and both divergence blocks of a [v; q] layout (v: HDIVRT0 on tetrahedra, q: L2P0) in two kernels on a freshly zeroed matrix: the cell
+// pre-pass also stores the cell's own column of block (0,1) (one sector), the face-column gather also copies those values into the (1,0) run
+// that follows its mass run, so that every column of the matrix is written exactly once and in one piece — no zeroing, no partial sectors.
+// FEMB_ERR_UNSUPPORTED (the caller runs the two separate assemblies) whenever something is not exactly that.
+int launch_rt0_mixed(femb_ctx* ctx, int eid, int ediv, int eq, double fmass, double fdivf) {
+    static const bool on = [] { const char* e = getenv("FEMB_RT0_MIXED"); return !(e && e[0] == '0'); }();
+    if (!on || !rt0_enabled()) return FEMB_ERR_UNSUPPORTED;
+    const FembEval& EI = ctx->evals[eid];
+    const FembEval& ED = ctx->evals[ediv];
+    const FembEval& EQ = ctx->evals[eq];
+    const FembSpace& vs = ctx->spaces[EI.space];
+    const FembSpace& qs = ctx->spaces[EQ.space];
+    if (!is_rt0_3d(ctx, vs) || ED.space != EI.space || EI.op != FEMB_OP_IDENTITY || ED.op != FEMB_OP_DIVERGENCE || EQ.op != FEMB_OP_IDENTITY) return FEMB_ERR_UNSUPPORTED;
+    if (qs.family != FEMB_FAMILY_L2 || qs.nd != 1 || qs.ncomp != 1 || ED.nqp != EQ.nqp) return FEMB_ERR_UNSUPPORTED;
+    if (ctx->nrs != 2 || ctx->ncs != 2 || ctx->row_spaces[0] != EI.space || ctx->col_spaces[0] != EI.space || ctx->row_spaces[1] != EQ.space || ctx->col_spaces[1] != EQ.space)
+        return FEMB_ERR_UNSUPPORTED;
+    if (!find_block(ctx, 0, 0) || !find_block(ctx, 0, 1) || !find_block(ctx, 1, 0) || ctx->ncells == 0) return FEMB_ERR_UNSUPPORTED;
+    const uint64_t bits = (1ull << 0) | (1ull << 1) | (1ull << FEMB_MAX_SPACES);
+    if (!ctx->zero_pending_A || (ctx->zero_mask & bits) != bits) return FEMB_ERR_UNSUPPORTED;  // something was assembled since femb_matrix_zero: add, do not store
+    if (ED.h_refderivs.size() != (size_t)ED.nqp * 4 * 9 || EQ.h_refvals.size() != (size_t)EQ.nqp) return FEMB_ERR_UNSUPPORTED;
+    double f[4];
+    for (int fn = 0; fn < 4; fn++) {
+        double t = 0.0;
+        for (int q = 0; q < ED.nqp; q++) {
+            double tr3 = 0.0;
+            for (int d = 0; d < 3; d++) tr3 += ED.h_refderivs[((size_t)q * 4 + fn) * 9 + d * 3 + d];
+            t += ED.w[q] * tr3 * EQ.h_refvals[q];
+        }
+        f[fn] = t * fdivf;
+    }
+    if (f[1] != f[0] || f[2] != f[0] || f[3] != f[0]) return FEMB_ERR_UNSUPPORTED;
+    int64_t n01 = 0, n10 = 0;
+    FEMB_TRY(femb_block_entries(ctx, 0, 1, &n01));
+    FEMB_TRY(femb_block_entries(ctx, 1, 0, &n10));
+    if (n01 != ctx->ncells * 4 || n10 != ctx->ncells * 4) return FEMB_ERR_UNSUPPORTED;  // entries beyond the (face dof, cell) couplings would stay unwritten
+    int st = femb_build_hmap_vec(ctx);
+    if (st != FEMB_OK) return st;
+    FembHMap& H = ctx->hm_vec;
+    if (H.space != EI.space || !H.complete || H.words != 2 || !H.sub0 || !H.sublen) return FEMB_ERR_UNSUPPORTED;
+    FEMB_TRY(femb_build_slotmaps(ctx, 0, 1));
+    FEMB_TRY(femb_build_slotmaps(ctx, 1, 0));
+    const FembBlock* b01 = find_block(ctx, 0, 1);
+    const FembBlock* b10 = find_block(ctx, 1, 0);
+    if (H.xsrc_state == 0) {
+        int32_t* bad = nullptr;
+        int32_t hbad = 0;
+        FEMB_TRY(femb_alloc(ctx, &H.xsrc, std::max<size_t>(H.stride, 1)));
+        CUDA_TRY(ctx, cudaMalloc(&bad, sizeof(int32_t)));
+        cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(int32_t), ctx->stream);
+        if (e == cudaSuccess && H.stride) {
+            k_hdiv_xsrc<<<(unsigned)((H.stride + 255) / 256), 256, 0, ctx->stream>>>(H.map, H.stride, 2, vs.celldofs, ctx->colptr + H.col_off, H.sub0, H.sublen, b01->slots, b10->slots,
+                                                                                    H.xsrc, bad);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(bad);
+        if (e != cudaSuccess) return femb_fail(ctx, FEMB_ERR_CUDA, "k_hdiv_xsrc: %s", cudaGetErrorString(e));
+        H.xsrc_state = hbad == 0 ? 1 : -1;
+    }
+    if (H.xsrc_state != 1) return FEMB_ERR_UNSUPPORTED;
+    // the closed-form mass matrix must pass the same table check as the stand-alone gather (launch_rt0_mass_gather); run it through that door
+    HdivMix mix{f[0], b01->slots};
+    return rt0_mass_checked(ctx, eid, fmass, &mix);
 }

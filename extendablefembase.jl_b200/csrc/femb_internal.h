@@ -81,6 +81,9 @@ struct FembHMap {
     int32_t* vrow = nullptr;        // femb_p2.cu (3-D): per slice the first row of its vertex-dof sectors in vrec, -1 = none
     uint32_t* vinv = nullptr;       // [cell][4]: slot in vrec of the cell's vertex-dof visits
     double* vrec = nullptr;         // vertex-dof sectors in visit order (4 doubles per slot)
+    uint32_t* xsrc = nullptr;       // femb_hdiv.cu (mixed RT0 pass): per visit the nzval slot of the (face dof, cell) entry of block (0,1), bit 31 = position of
+                                    // its transposed copy in the (1,0) run of the face column; xsrc_state 0 = not built, 1 = usable, -1 = layout not covered
+    int xsrc_state = 0;
     std::vector<Range> cranges;     // femb_p2.cu: `ranges` cut where the kind of dof changes (mode 0 = vertex dofs, 1 = edge dofs, 2 = both)
 };
 
@@ -135,6 +138,7 @@ struct femb_ctx {
     int64_t* rowval = nullptr;
     int max_collen = 0;
     std::vector<FembBlock> blocks;
+    int64_t block_nnz[FEMB_MAX_SPACES][FEMB_MAX_SPACES];  // pattern entries per layout block, -1 = not counted yet (femb_block_entries)
     std::vector<int64_t> extra_diag;
     // P1 gather map, sliced ELL (slice = 32 consecutive dofs = one warp), structure of arrays: plane p lives at
     // gmap + p * gmap_stride, element [row][lane].  Planes: 0 = na, 1 = nb (the e-th adjacent cell's other nodes in
@@ -161,6 +165,8 @@ struct femb_ctx {
 
     double* nzval = nullptr;      // nnz
     bool zero_pending_A = false;  // femb_matrix_zero is lazy: write-once kernels skip the memset
+    uint64_t zero_mask = ~0ull;   // while zero_pending_A: layout blocks (bit brow * FEMB_MAX_SPACES + bcol) still awaiting the zero; a write-once
+                                  // kernel that overwrites every entry of a block claims it (femb_claim_block), femb_flush_zero zeroes the rest
     bool zero_pending_b = false;
     bool dirty_A = false, dirty_b = false;  // something was assembled / set since the last femb_matrix_zero / femb_vector_zero
     uint8_t* touched = nullptr;   // nnz (only when tracking)
@@ -303,6 +309,13 @@ void femb_free_saved(femb_ctx* ctx);
 void femb_free_system(femb_ctx* ctx);
 // assemble.cu
 int femb_flush_zero(femb_ctx* ctx, bool mat, bool vec);
+bool femb_claim_block(femb_ctx* ctx, int brow, int bcol);   // true: the caller overwrites EVERY pattern entry of the block instead of adding to it
+int femb_settle_partial_zero(femb_ctx* ctx);                // afterwards zero_pending_A means "the whole matrix" again (single-kernel paths)
+int femb_block_entries(femb_ctx* ctx, int brow, int bcol, int64_t* n);
+inline void femb_reset_block_counts(femb_ctx* ctx) {
+    for (auto& r : ctx->block_nnz)
+        for (auto& v : r) v = -1;
+}
 int femb_build_coloring(femb_ctx* ctx);
 int femb_timer_begin(femb_ctx* ctx);
 int femb_timer_end(femb_ctx* ctx);

@@ -70,3 +70,4 @@ int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu, int ei = -1, const Rh
 int launch_rt0_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor);
 int launch_bdm1_mass_gather(femb_ctx* ctx, int er, int brow, int bcol, double factor);
 int launch_rt0_div(femb_ctx* ctx, int er, int ec, int brow, int bcol, double factor, int flags);
+int launch_rt0_mixed(femb_ctx* ctx, int eid, int ediv, int eq, double fmass, double fdiv);

@@ -547,6 +547,7 @@ static int prepare_p1_gather(femb_ctx* ctx, int eg, int ei, double mu, const Rhs
     a.coords = ctx->coords; a.cellvol = ctx->cellvol; a.gvol = nullptr; a.gslice_ptr = ctx->gslice_ptr; a.gmap = ctx->gmap; a.gstride = ctx->gmap_stride;
     a.colptr = ctx->colptr; a.ndofs = s.ndofs; a.nzval = ctx->nzval; a.touched = ctx->touched; a.bvec = ctx->bvec; a.errflag = ctx->errflag;
     a.mu = mu; a.drop_tol = drop_tol;
+    FEMB_TRY(femb_settle_partial_zero(ctx));
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
     ctx->zero_pending_A = false;
@@ -788,6 +789,7 @@ extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t
         if (!ctx->stream_d2h) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking));
         ctx->gvol_valid = false;
         ctx->zero_pending_A = true;
+        ctx->zero_mask = ~0ull;
         ctx->zero_pending_b = true;
         FEMB_TRY(femb_timer_begin(ctx));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coords, coords, sizeof(double) * ctx->nnodes * 3, cudaMemcpyHostToDevice, ctx->stream_h2d));
@@ -830,6 +832,7 @@ extern "C" int32_t femb_assemble_poisson_host(femb_ctx* ctx, int32_t eg, int32_t
     FEMB_TRY(plan_chunks(ctx, nchunks, nslices, s.ndofs));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // earlier kernels may still read the mesh arrays
     ctx->zero_pending_A = true;  // "zero + assemble": the write-once kernel overwrites
+    ctx->zero_mask = ~0ull;
     ctx->zero_pending_b = true;
     P1Launch L;
     ctx->gvol_valid = false;  // this call uploads new volumes chunk by chunk: the visit-order copy is not used and goes stale

@@ -978,6 +978,7 @@ static int launch_p2_gather2d(femb_ctx* ctx, FembHMap& H, const FembEval& EG, co
         a.acc_A = vec_fresh ? 0 : 1;  // the columns also hold rows of other blocks: the caller flushed the lazy zero, only the block's runs are touched
         a.acc_b = 1;
     } else {
+        FEMB_TRY(femb_settle_partial_zero(ctx));
         a.acc_A = ctx->zero_pending_A ? 0 : 1;
         a.acc_b = ctx->zero_pending_b ? 0 : 1;
         ctx->zero_pending_A = false;
@@ -1031,6 +1032,7 @@ int launch_p2_gather_vec(femb_ctx* ctx, int eg, double mu, int ei, const RhsDev*
     FembHMap& H = ctx->hm_vec;
     if (H.space != EG.space || !H.complete) return P2_UNSUPPORTED;
     // right after femb_matrix_zero the runs can be overwritten instead of read, added to and written back
+    FEMB_TRY(femb_settle_partial_zero(ctx));
     const bool fresh = ctx->zero_pending_A;
     FEMB_TRY(femb_flush_zero(ctx, true, false));
     // the load of the same space rides along (Example210:304-318): its local entries come from the pre-pass, the gather sums them
@@ -1094,6 +1096,7 @@ int launch_p2_gather(femb_ctx* ctx, int eg, int ei, double mu, const RhsDev& rhs
     P2Args a;
     a.rec = ctx->p2rec; a.slice_ptr = H.slice_ptr; a.slice_zero = H.slice_zero; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr; a.sub0 = a.sublen = nullptr; a.ndofs = s.ndofs;
     a.nzval = ctx->nzval; a.bvec = ctx->bvec;
+    FEMB_TRY(femb_settle_partial_zero(ctx));
     a.acc_A = ctx->zero_pending_A ? 0 : 1;
     a.acc_b = ctx->zero_pending_b ? 0 : 1;
     a.has_rhs = rhs.kind != FEMB_RHS_NONE;

@@ -36,6 +36,7 @@ void femb_free_pattern(femb_ctx* ctx) {
     femb_free(&ctx->p2vrhs);
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
+    femb_reset_block_counts(ctx);
     ctx->nnz = 0;
     ctx->max_collen = 0;
     femb_free(&ctx->color_perm);
@@ -529,6 +530,7 @@ extern "C" int32_t femb_pattern_compress(femb_ctx* ctx, int64_t* nnz_out) {
     // swap in the compressed arrays (keep exact-size copies)
     std::vector<FembBlock> blocks = ctx->blocks;
     for (auto& b : ctx->blocks) femb_free(&b.slots);
+    femb_reset_block_counts(ctx);
     femb_free(&ctx->rowval);
     femb_free(&ctx->nzval);
     femb_free(&ctx->touched);
@@ -877,6 +879,8 @@ void femb_free_hmap(FembHMap& H) {
     femb_free(&H.vrow);
     femb_free(&H.vinv);
     femb_free(&H.vrec);
+    femb_free(&H.xsrc);
+    H.xsrc_state = 0;
 }
 
 // in-place permutation of the position bytes and first-touch flags of every map entry: role order <-> local dof order

@@ -253,6 +253,13 @@ int32_t femb_set_scatter(femb_ctx* ctx, int32_t policy);
  * brow/bcol index into the row/col space lists of femb_matrix_layout (0-based). */
 int32_t femb_assemble_bilinear(femb_ctx* ctx, int32_t eval_row, int32_t eval_col, int32_t brow, int32_t bcol,
                                double factor, int32_t flags, double drop_tol);
+/* The blocks of a mixed (Darcy-type) system over the layout [v; q], v an Hdiv space, q = L2P0, in one call (config C4 of BASELINE.json):
+ *   A[0,0] += factor_mass (v_j, v_k),  A[0,1] += factor_div (div v_j, q),  A[1,0] += its transpose
+ * — the cell loop of Example200:129-161 with the evaluators of src/feevaluator_hdiv.jl:2-19 (Identity) and :66-83 (Divergence); equal to
+ * femb_assemble_bilinear(e_id, e_id, 0, 0, factor_mass, 0, 0) + femb_assemble_bilinear(e_div, e_q, 0, 1, factor_div,
+ * FEMB_BIL_TRANSPOSE_COPY, 0).  For HDIVRT0 on tetrahedra right after femb_matrix_zero every column of the matrix is written once and in
+ * one piece by two kernels (closed-form cell pre-pass + owner-computes column gather), without zeroing. */
+int32_t femb_assemble_hdiv_mixed(femb_ctx* ctx, int32_t eval_id, int32_t eval_div, int32_t eval_q, double factor_mass, double factor_div);
 /* b[off(brow)+dof_j] += factor * |T| * sum_qp w_qp <op_j(qp), f(x_qp)>   (Example200:165-178, Example210:304-318) */
 int32_t femb_assemble_linear(femb_ctx* ctx, int32_t eval_id, int32_t brow, double factor, int32_t rhs_kind,
                              const double* params_or_fvals);

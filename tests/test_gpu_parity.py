@@ -352,6 +352,91 @@ def test_hcurl_unsupported_operators_are_statuses():
         S.evaluator(0, "Gradient")
 
 
+def test_hdiv_blockwise_lazy_zero():
+    """After femb_matrix_zero the RT0 kernels claim the blocks they overwrite entry by entry and the memset is skipped; everything
+    the reference's fill!(A.nzval, 0) + assembly sequence guarantees must still hold: poisoned storage is never visible, blocks no
+    kernel wrote read as zeros, a second assembly without zeroing accumulates, and a pattern with entries beyond the (face, cell)
+    couplings falls back to zero + add."""
+    import scipy.sparse as sp
+    from femb_b200.assembly import _Session
+
+    grid = _grid3d(4, True)
+    FESv, FESq = fb.FESpace(fb.HDIVRT0(3), grid), fb.FESpace(fb.L2P0(1), grid)
+    S = _Session([FESv, FESq], fb.QuadratureRule(grid.geometry, 2))
+    ctx = S.ctx
+    eid, ediv, eq = S.evaluator(0, "Identity"), S.evaluator(0, "Divergence"), S.evaluator(1, "Identity")
+    ctx.pattern_build([(0, 0), (0, 1), (1, 0)])
+    nall = FESv.ndofs + FESq.ndofs
+
+    def mass():
+        ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
+
+    def div():
+        ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
+
+    def poison():  # fill the device array with garbage through an accumulating call sequence, then request the lazy zero
+        ctx.matrix_zero(); mass(); div(); mass(); div(); mass()
+        ctx.matrix_zero()
+
+    ctx.matrix_zero(); mass(); div()
+    ref = ctx.matrix_get().copy()
+    colptr, rowval = ctx.pattern_get(nall)
+    cols = np.repeat(np.arange(nall), np.diff(colptr))
+    in_mass = (rowval <= FESv.ndofs) & (cols < FESv.ndofs)
+    assert np.abs(ref[in_mass]).max() > 0 and np.abs(ref[~in_mass]).max() > 0
+    # both orders, repeated
+    for order in ((mass, div), (div, mass)):
+        poison()
+        for f in order:
+            f()
+        assert np.array_equal(ctx.matrix_get(), ref)
+    # the same three blocks in one call (femb_assemble_hdiv_mixed): fresh matrix -> two kernels writing every column once;
+    # matrix already holding something -> the two assemblies, added
+    mixed = lambda: ctx.assemble_hdiv_mixed(eid._eid, ediv._eid, eq._eid, 1.0, 1.0)
+    poison(); mixed()
+    assert np.array_equal(ctx.matrix_get(), ref)
+    mixed()
+    assert np.abs(ctx.matrix_get() - 2.0 * ref).max() <= RTOL * np.abs(ref).max()
+    poison(); mass(); mixed()
+    got = ctx.matrix_get()
+    assert np.abs(got[in_mass] - 2.0 * ref[in_mass]).max() <= RTOL * np.abs(ref).max() and np.array_equal(got[~in_mass], ref[~in_mass])
+    poison()
+    ctx.assemble_hdiv_mixed(eid._eid, ediv._eid, eq._eid, 0.5, -2.0)
+    got = ctx.matrix_get()
+    assert np.array_equal(got[in_mass], 0.5 * ref[in_mass]) and np.array_equal(got[~in_mass], -2.0 * ref[~in_mass])
+    # only one of the two: the blocks nobody wrote are zeros
+    poison(); mass()
+    got = ctx.matrix_get()
+    assert np.array_equal(got[in_mass], ref[in_mass]) and not got[~in_mass].any()
+    poison(); div()
+    got = ctx.matrix_get()
+    assert np.array_equal(got[~in_mass], ref[~in_mass]) and not got[in_mass].any()
+    # no zeroing in between: accumulation (mass block: gather adds; divergence blocks: plain adds)
+    poison(); mass(); div(); div(); mass()
+    assert np.abs(ctx.matrix_get() - 2.0 * ref).max() <= RTOL * np.abs(ref).max()
+    # claim, then a consumer in between (femb_matrix_get settles the pending blocks), then the rest
+    poison(); mass()
+    ctx.matrix_get()
+    div()
+    assert np.array_equal(ctx.matrix_get(), ref)
+    # a pattern with additional entries in the divergence blocks: they must read as zeros, the rest is unchanged
+    A = sp.csc_matrix((ref, rowval - 1, colptr - 1), shape=(nall, nall))
+    cd = FESv["CellDofs"]
+    free = lambda c: int(np.setdiff1d(np.arange(1, 12), cd[c])[0]) - 1  # a face dof (0-based) that is not one of cell c's
+    ex = [(free(1), FESv.ndofs + 1), (free(7), FESv.ndofs + 7), (FESv.ndofs + 2, free(2))]
+    extra = sp.csc_matrix((np.ones(3), ([e[0] for e in ex], [e[1] for e in ex])), shape=(nall, nall))
+    P = (abs(A) + extra).tocsc()
+    P.sort_indices()
+    ctx.pattern_adopt(nall, nall, P.indptr.astype(np.int64) + 1, P.indices.astype(np.int64) + 1, [(0, 0), (0, 1), (1, 0)])
+    for run in (lambda: (mass(), div()), mixed):
+        ctx.matrix_zero(); mass(); div(); mass(); div()
+        ctx.matrix_zero(); run()
+        got = sp.csc_matrix((ctx.matrix_get(), P.indices, P.indptr), shape=(nall, nall))
+        assert abs(got - A).max() <= RTOL * np.abs(ref).max()
+        assert P.nnz == A.nnz + 3 and all(got[i, j] == 0.0 for i, j in ex)
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # error behaviour
 # ---------------------------------------------------------------------------------------------

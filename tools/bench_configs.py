@@ -103,8 +103,7 @@ def c4_hdiv(m, steps, warmup, name, scatter=None):
 
     def step():
         ctx.matrix_zero()
-        ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
-        ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0)
+        ctx.assemble_hdiv_mixed(eid._eid, ediv._eid, eq._eid, 1.0, 1.0)
 
     ms = timeit(step, ctx, steps, warmup)
     return {"config": f"C4 HDIV{name}{{3}} mass + (div v, q) vs L2P0, Kuhn m={m}" + ("" if scatter is None else f", scatter policy {scatter}"), "ncells": grid.ncells, "ndofs": FESv.ndofs + FESq.ndofs, "nnz": nnz,
@@ -294,6 +293,8 @@ if __name__ == "__main__":
         elif w == "c4":
             res.append(c4_hdiv(a.m4, a.steps, a.warmup, "RT0", a.scatter))
             res.append(c4_hdiv(a.m4, a.steps, a.warmup, "BDM1", a.scatter))
+        elif w == "c4rt0":
+            res.append(c4_hdiv(a.m4, a.steps, a.warmup, "RT0", a.scatter))
         elif w == "c5":
             res += c5_taylor_hood(a.n5, a.steps, a.warmup)
         elif w == "topo":
