@@ -379,4 +379,47 @@ function prepare_assembly!(A, b, FESu, FESp, sol; teval = 0, mu = 1.0e-2, device
     return update_system!
 end
 
+"""
+    assemble_hdiv_mixed!(A::FEMatrix, FESv, FESq; device = 0)
+
+Blocks of a mixed system over `[FESv; FESq]` (`FESv` an Hdiv space such as `HDIVRT0{3}`, `FESq = L2P0{1}`): `A[1,1] += (v_j, v_k)`,
+`A[1,2] += (div v_j, q)`, `A[2,1] +=` its transpose — the cell loop of Example200:129-161 with the Identity / Divergence evaluators of
+src/feevaluator_hdiv.jl (order-2 rule).  One `femb_assemble_hdiv_mixed` call; for HDIVRT0 on tetrahedra a fused write-once pass.
+"""
+function assemble_hdiv_mixed!(A, FESv, FESq; device = 0)
+    Ae = A.entries
+    xgrid = FESv.xgrid
+    EG = xgrid[UniqueCellGeometries][1]
+    qf = QuadratureRule{Float64, EG}(2)
+    ctx = Context(device)
+    mesh_set!(ctx, xgrid)
+    space_set!(ctx, 0, FESv); space_set!(ctx, 1, FESq)
+    quadrature_set!(ctx, qf)
+    evaluator_set!(ctx, 0, 0, FEEvaluator(FESv, Identity, qf), OP_IDENTITY)
+    evaluator_set!(ctx, 1, 0, FEEvaluator(FESv, Divergence, qf), OP_DIVERGENCE)
+    evaluator_set!(ctx, 2, 1, FEEvaluator(FESq, Identity, qf), OP_IDENTITY)
+    sp = Int32[0, 1]
+    check(ctx, ccall((:femb_matrix_layout, libfemb), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Int32, Ptr{Int32}), ctx.h, 2, sp, 2, sp))
+    brow, bcol = Int32[0, 0, 1], Int32[0, 1, 0]
+    flush!(Ae)
+    csc = Ae.cscmatrix
+    if nnz(csc) == 0
+        nnzref = Ref{Int64}(0)
+        check(ctx, ccall((:femb_pattern_build, libfemb), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Int64, Ptr{Int64}, Ref{Int64}), ctx.h, 3, brow, bcol, 0, C_NULL, nnzref))
+        n = size(csc, 1)
+        colptr = Vector{Int64}(undef, n + 1); rowval = Vector{Int64}(undef, nnzref[])
+        check(ctx, ccall((:femb_pattern_get, libfemb), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), ctx.h, colptr, rowval))
+        Ae.cscmatrix = SparseMatrixCSC{Float64, Int64}(n, n, colptr, rowval, zeros(Float64, nnzref[]))
+    else
+        check(ctx, ccall((:femb_pattern_adopt, libfemb), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{Int32}),
+            ctx.h, size(csc, 1), size(csc, 2), nnz(csc), csc.colptr, csc.rowval, 3, brow, bcol))
+    end
+    check(ctx, ccall((:femb_matrix_zero, libfemb), Int32, (Ptr{Cvoid},), ctx.h))
+    check(ctx, ccall((:femb_assemble_hdiv_mixed, libfemb), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Float64, Float64), ctx.h, 0, 1, 2, 1.0, 1.0))
+    check(ctx, ccall((:femb_matrix_add_to, libfemb), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, Ae.cscmatrix.nzval))
+    return nothing
+end
+
 end # module

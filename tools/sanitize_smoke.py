@@ -42,6 +42,22 @@ for ft in (fb.HDIVRT0(3), fb.HDIVBDM1(3), fb.HDIVRT0(2), fb.HDIVBDM1(2)):
     A = fb.FEMatrix([FESv, FESq])
     fb.assemble_hdiv_mixed(A, FESv, FESq)
     print(ft, A.entries.nnz)
+# block-wise lazy zero: one block claimed, the others settled by the consumer; then the separate divergence kernel with claims
+FESv, FESq = fb.FESpace(fb.HDIVRT0(3), g3), fb.FESpace(fb.L2P0(1), g3)
+S = _Session([FESv, FESq], fb.QuadratureRule(g3.geometry, 2))
+eid, ediv, eq = S.evaluator(0, "Identity"), S.evaluator(0, "Divergence"), S.evaluator(1, "Identity")
+S.ctx.pattern_build([(0, 0), (0, 1), (1, 0)])
+S.ctx.matrix_zero(); S.ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
+print("claimed mass only", float(np.abs(S.ctx.matrix_get()).max()))
+S.ctx.matrix_zero(); S.ctx.assemble_bilinear(ediv._eid, eq._eid, 0, 1, 1.0, _lib.BIL_TRANSPOSE_COPY, 0.0); S.ctx.assemble_bilinear(eid._eid, eid._eid, 0, 0, 1.0, 0, 0.0)
+print("div then mass", float(np.abs(S.ctx.matrix_get()).max()))
+S.ctx.close()
+# Hcurl mass system
+for ft, g in ((fb.HCURLN0(2), g2), (fb.HCURLN0(3), g3)):
+    fes = fb.FESpace(ft, g)
+    A, b = fb.ExtendableSparseMatrixCSC(fes.ndofs, fes.ndofs), np.zeros(fes.ndofs)
+    fb.assemble_mass(A, b, fes, fb.AffineFunction([1.0] * ft.edim, [[0.0] * ft.edim] * ft.edim))
+    print(ft, A.nnz, float(np.abs(b).max()))
 # coloured scatter, device topology / dofmaps, boundary dofs, penalisation, residual, block products, compute_error
 for ft in (fb.HDIVBDM1(3), fb.H1P3(1, 3)):
     FESv, FESq = fb.FESpace(ft, g3), fb.FESpace(fb.L2P0(1), g3)
