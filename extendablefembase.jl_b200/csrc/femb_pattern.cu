@@ -197,6 +197,7 @@ static int set_blocks(femb_ctx* ctx, int nblocks, const int32_t* brows, const in
 static int finish_pattern(femb_ctx* ctx) {
     FEMB_TRY(femb_alloc(ctx, &ctx->nzval, (size_t)ctx->nnz));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->nzval, 0, sizeof(double) * ctx->nnz, ctx->stream));
+    ctx->zero_mask = ~0ull;  // (claims refer to the blocks of the previous array)
     if (ctx->track) {
         FEMB_TRY(femb_alloc(ctx, &ctx->touched, (size_t)ctx->nnz));
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->touched, 0, ctx->nnz, ctx->stream));
