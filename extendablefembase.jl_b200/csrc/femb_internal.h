@@ -84,6 +84,7 @@ struct FembHMap {
     uint32_t* xsrc = nullptr;       // femb_hdiv.cu (mixed RT0 pass): per visit the nzval slot of the (face dof, cell) entry of block (0,1), bit 31 = position of
                                     // its transposed copy in the (1,0) run of the face column; xsrc_state 0 = not built, 1 = usable, -1 = layout not covered
     int xsrc_state = 0;
+    int th_state = 0;               // femb_ns.cu (owner-computes div-pressure blocks): 0 = column layout not checked, 1 = as expected, -1 = not covered
     std::vector<Range> cranges;     // femb_p2.cu: `ranges` cut where the kind of dof changes (mode 0 = vertex dofs, 1 = edge dofs, 2 = both)
 };
 
@@ -159,6 +160,7 @@ struct femb_ctx {
     double* cellrhs = nullptr;     // [cell][qp][comp]: factor w_q |T| f(x_q), pre-pass of the Identity rhs gather
     size_t cellrhs_n = 0;
     double* p2vrhs = nullptr;      // [cell][6][2]: local entries of a two-component load on P2 triangles (fused rhs of Example210, femb_p2.cu)
+    double* threc = nullptr;       // [cell][4]: |T| d_c lambda_a, a = 1, 2 (femb_ns.cu, owner-computes div-pressure blocks)
     double* rt0rec = nullptr;      // [cell][16]: local RT0 mass matrix, one 32-byte column per face dof (femb_hdiv.cu)
     double* p2rec = nullptr;       // [cell][28]: per-cell record of the closed-form P2 gather (femb_p2.cu)
     double* cellcoef = nullptr;    // [cell][FEMB_COEF_STRIDE]: Kc (3 / 6) then |T| f(x_q) per quadrature point (pre-pass of the gather)

@@ -274,8 +274,194 @@ __global__ void __launch_bounds__(128) k_th_divpressure2d(const double* __restri
     if (err) atomicAdd(errflag, 1);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same blocks written by the column owners (no reductions, every entry stored once), for a matrix that was zero when
+// femb_assemble_navierstokes started.  No map beyond the component-diagonal gather map of the velocity block is needed: the vertex dofs
+// of P2 are the dofs of the P1 pressure, hence
+//   * the pressure rows [p rows] that follow the [ux rows | uy rows] of a velocity column are that column's vertex rows in the same
+//     order: the position bytes the map holds for local dofs 0..2 of every visit address them;
+//   * the pressure column of node v has the rows, visits and positions of the velocity column of vertex dof v (ux part, and the uy
+//     part one run length further down).
+// One thread per scalar velocity dof j (both components: twins): (p, ux_j), (p, uy_j) and, for vertex dofs, column p_j.
+// Records: |T| d_c lambda_a for a = 1, 2 (one sector per cell).  Map words in role order (femb_p2.cu: perm[k][role] = local dof).
+// dynamic shared memory: [4 mbarriers | pad to 128 B][acc: nacc x R rows x 128 doubles][4 warps x 3 planes x maxrows x 128 B],
+// nacc = 4 (vertex-dof slices: P_x, P_y, Q_x, Q_y) or 2.
+// ---------------------------------------------------------------------------------------------------
+struct ThGArgs {
+    const double* rec;  // [cell][4] = D[0][1], D[1][1], D[0][2], D[1][2]
+    const int32_t* slice_ptr;
+    const uint32_t* map;
+    size_t stride;
+    const int64_t* colptr;  // of the whole matrix
+    const int32_t* sublen;  // run length of the component-diagonal block per velocity column
+    int64_t n;              // scalar dofs per component
+    int64_t nnodes;         // vertex dofs = pressure dofs
+    int64_t ucol0, pcol0;   // first velocity / pressure column of the matrix
+    double* nzval;
+    double factor;
+    int64_t slice_begin, slice_end;
+    int R, nacc, maxrows;
+    uint8_t perm[6][6];
+};
+
+__device__ __forceinline__ double th_pick(int a, double x0, double x1, double x2) { return a == 0 ? x0 : (a == 1 ? x1 : x2); }
+
+// -|T| int d_c phi_i lambda_a without the factor, D = (D_c0, D_c1, D_c2): the arithmetic of k_th_divpressure2d
+__device__ __forceinline__ double th_value(int i, int a, double d0, double d1, double d2) {
+    if (i < 3) return i == a ? th_pick(a, d0, d1, d2) * (1.0 / 3.0) : 0.0;
+    const int ea = (i == 3) ? 0 : ((i == 4) ? 1 : 0), eb = (i == 3) ? 1 : 2;
+    const double ma = (ea == a) ? (1.0 / 6.0) : (1.0 / 12.0), mb = (eb == a) ? (1.0 / 6.0) : (1.0 / 12.0);
+    return 4.0 * (ma * th_pick(eb, d0, d1, d2) + mb * th_pick(ea, d0, d1, d2));
+}
+
+__global__ void __launch_bounds__(128) k_th_rec(const double* __restrict__ coords, const int32_t* __restrict__ cellnodes, const double* __restrict__ cellvol, int64_t ncells,
+                                                double* __restrict__ rec) {
+    const int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cell >= ncells) return;
+    double x[3][2];
+    load_nodes<2>(coords, cellnodes, cell, x);
+    const double a00 = x[1][0] - x[0][0], a01 = x[2][0] - x[0][0], a10 = x[1][1] - x[0][1], a11 = x[2][1] - x[0][1];
+    const double det = a00 * a11 - a01 * a10;
+    const double vol = cellvol ? __ldg(cellvol + cell) : fabs(det) * 0.5;
+    const double sc = vol / det;
+    double* o = rec + cell * 4;
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(o), "d"(a11 * sc), "d"(-a01 * sc), "d"(-a10 * sc), "d"(a00 * sc) : "memory");
+}
+
+// what the gather takes for granted about the columns, checked once per pattern: velocity column = [ux rows | uy rows | p rows] with
+// equally long ux / uy parts (= the run of the component-diagonal block), the vertex rows first in a run and as many as there are
+// pressure rows; pressure column of node v = [ux rows | uy rows | ...] with the run length of velocity column v
+__global__ void k_th_layout_check(const int64_t* __restrict__ colptr, const int64_t* __restrict__ rowval, const int32_t* __restrict__ sub0, const int32_t* __restrict__ sublen,
+                                  int64_t n, int64_t nnodes, int64_t ucol0, int64_t pcol0, int64_t urow0, int64_t prow0, int32_t* __restrict__ bad) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    bool ok = true;
+    const int L = sublen[j];
+    ok = ok && sublen[j + n] == L && sub0[j] == 0 && sub0[j + n] == L;
+    for (int c = 0; c < 2 && ok; c++) {
+        const int64_t b = colptr[ucol0 + j + c * n] - 1, e = colptr[ucol0 + j + c * n + 1] - 1;
+        const int np = (int)(e - b) - 2 * L;
+        ok = ok && np >= 0 && np <= L;
+        if (!ok) break;
+        // rows (1-based): ux part in (urow0, urow0 + n], uy part in (urow0 + n, urow0 + 2n], p part in (prow0, prow0 + nnodes]
+        if (L > 0) ok = ok && rowval[b] > urow0 && rowval[b + L - 1] <= urow0 + n && rowval[b + L] > urow0 + n && rowval[b + 2 * L - 1] <= urow0 + 2 * n;
+        if (np > 0) ok = ok && rowval[b + 2 * L] > prow0 && rowval[e - 1] <= prow0 + nnodes;
+        // vertex rows of the run: exactly np, at its start
+        if (np > 0) ok = ok && rowval[b + c * L + np - 1] <= urow0 + c * n + nnodes;
+        if (np < L) ok = ok && rowval[b + c * L + np] > urow0 + c * n + nnodes;
+    }
+    if (ok && j < nnodes) {
+        const int64_t b = colptr[pcol0 + j] - 1, e = colptr[pcol0 + j + 1] - 1;
+        ok = ok && (e - b) >= 2 * L;
+        if (ok && L > 0) ok = ok && rowval[b] > urow0 && rowval[b + L - 1] <= urow0 + n && rowval[b + L] > urow0 + n && rowval[b + 2 * L - 1] <= urow0 + 2 * n;
+        if (ok && (e - b) > 2 * L) ok = ok && rowval[b + 2 * L] > urow0 + 2 * n;
+    }
+    if (!ok) atomicAdd(bad, 1);
+}
+
+__device__ __forceinline__ unsigned th_lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_th_divp_gather(const ThGArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int64_t slice = a.slice_begin + (int64_t)blockIdx.x * 4 + warp;
+    if (slice >= a.slice_end) return;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned pst = (unsigned)a.maxrows * 128u;
+    const unsigned mbar = smem0 + warp * 8u;
+    const unsigned plane = 128u * 8u;                      // one accumulator row: 128 doubles
+    const unsigned asz = (unsigned)a.R * plane;            // one accumulator array
+    const unsigned sstw = smem0 + 128u + (unsigned)a.nacc * asz + warp * 3u * pst;
+    const int64_t j = slice * 32 + lane;
+    const bool valid = j < a.n;
+    const int row0 = __ldg(a.slice_ptr + slice), nrows = __ldg(a.slice_ptr + slice + 1) - row0;
+    if (nrows > 0 && lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)nrows * 128u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes * 3u) : "memory");
+        const uint32_t* g = a.map + ((size_t)row0 << 5);
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sstw + (unsigned)p * pst), "l"(g + (size_t)p * a.stride),
+                         "r"(bytes), "r"(mbar)
+                         : "memory");
+    }
+    const int L = valid ? __ldg(a.sublen + j) : 0;
+    const bool isv = valid && j < a.nnodes && a.nacc == 4;
+    int64_t ub[2] = {0, 0};
+    int np[2] = {0, 0};
+    if (valid) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            ub[c] = a.colptr[a.ucol0 + j + c * a.n] - 1;
+            np[c] = (int)(a.colptr[a.ucol0 + j + c * a.n + 1] - 1 - ub[c]) - 2 * L;
+        }
+    }
+    const unsigned sP = smem0 + 128u + tid * 8u;  // P_c at sP + c * asz, Q_c at sP + (2 + c) * asz
+    for (int i = 0; i < max(np[0], np[1]); i++) {
+        sts64(sP + i * plane, 0.0);
+        sts64(sP + asz + i * plane, 0.0);
+    }
+    if (isv)
+        for (int i = 0; i < L; i++) {
+            sts64(sP + 2u * asz + i * plane, 0.0);
+            sts64(sP + 3u * asz + i * plane, 0.0);
+        }
+    __syncwarp();
+    const unsigned sst = sstw + lane * 4u;
+    if (nrows > 0) {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+    }
+    for (int r = 0; r < nrows; r++) {
+        const unsigned ra = sst + (unsigned)r * 128u;
+        const unsigned cell = th_lds32(ra), wa = th_lds32(ra + pst), wb = th_lds32(ra + 2u * pst);
+        const unsigned k = (wb >> 16) & 0xFu;
+        if (k == 0xFu || !valid) continue;
+        double d01, d11, d02, d12;
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(d01), "=d"(d11), "=d"(d02), "=d"(d12) : "l"(a.rec + (size_t)cell * 4));
+        const double d00 = -(d01 + d02), d10 = -(d11 + d12);
+#pragma unroll
+        for (int rr = 0; rr < 6; rr++) {
+            const unsigned pos = ((rr < 4 ? wa : wb) >> (8 * (rr & 3))) & 0xFFu;
+            const int il = a.perm[k][rr];  // local dof of the cell in this role
+            if (il < 3 && pos < (unsigned)a.R) {
+                // pressure row of local vertex il in the columns (ux_j, uy_j): -|T| int d_c phi_k lambda_il
+                const unsigned ad = sP + pos * plane;
+                sts64(ad, lds64(ad) + th_value((int)k, il, d00, d01, d02) * a.factor);
+                sts64(ad + asz, lds64(ad + asz) + th_value((int)k, il, d10, d11, d12) * a.factor);
+            }
+            if (isv && pos < (unsigned)a.R) {
+                // pressure column of this vertex (local index k): rows ux / uy of local dof il
+                const unsigned ad = sP + 2u * asz + pos * plane;
+                sts64(ad, lds64(ad) + th_value(il, (int)k, d00, d01, d02) * a.factor);
+                sts64(ad + asz, lds64(ad + asz) + th_value(il, (int)k, d10, d11, d12) * a.factor);
+            }
+        }
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        double* out = a.nzval + ub[c] + 2 * L;
+        for (int i = 0; i < np[c]; i++) out[i] = lds64(sP + (unsigned)c * asz + i * plane);
+    }
+    if (isv) {
+        double* out = a.nzval + (a.colptr[a.pcol0 + j] - 1);
+        for (int i = 0; i < L; i++) out[i] = lds64(sP + 2u * asz + i * plane);
+        for (int i = 0; i < L; i++) out[L + i] = lds64(sP + 3u * asz + i * plane);
+    }
+}
+
 // FEMB_ERR_UNSUPPORTED (no message) when the closed form does not apply
-static int launch_th_divpressure(femb_ctx* ctx, int egu, int eip, double factor) {
+static int launch_th_divp_gather(femb_ctx* ctx, const FembSpace& us, const FembSpace& ps, double factor);
+
+static int launch_th_divpressure(femb_ctx* ctx, int egu, int eip, double factor, bool zero_at_entry) {
     static const bool on = [] { const char* e = getenv("FEMB_TH_CLOSED"); return !(e && e[0] == '0'); }();
     const FembEval& EG = ctx->evals[egu];
     const FembEval& EP = ctx->evals[eip];
@@ -307,6 +493,11 @@ static int launch_th_divpressure(femb_ctx* ctx, int egu, int eip, double factor)
                     if (fabs(ref2 - closed) > 5e-12) return FEMB_ERR_UNSUPPORTED;
                 }
     }
+    if (zero_at_entry && ctx->scatter == FEMB_SCATTER_GATHER) {
+        // nothing but zeros in the (u,p) / (p,u) blocks so far: the column owners store them, no reductions
+        const int st = launch_th_divp_gather(ctx, us, ps, factor);
+        if (st != FEMB_ERR_UNSUPPORTED) return st;
+    }
     FEMB_TRY(femb_build_slotmaps(ctx, 0, 1));
     FEMB_TRY(femb_build_slotmaps(ctx, 1, 0));
     const FembBlock* b01 = find_block(ctx, 0, 1);
@@ -317,6 +508,90 @@ static int launch_th_divpressure(femb_ctx* ctx, int egu, int eip, double factor)
     k_th_divpressure2d<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, factor, b01->slots, b10->slots,
                                                                                       ctx->nzval, ctx->errflag);
     KERNEL_CHECK(ctx);
+    return FEMB_OK;
+}
+
+static int launch_th_divp_gather(femb_ctx* ctx, const FembSpace& us, const FembSpace& ps, double factor) {
+    static const bool on = [] { const char* e = getenv("FEMB_TH_GATHER"); return !(e && e[0] == '0'); }();
+    if (!on || ctx->ncells == 0 || !find_block(ctx, 0, 0) || !find_block(ctx, 0, 1) || !find_block(ctx, 1, 0)) return FEMB_ERR_UNSUPPORTED;
+    int st = femb_build_hmap_vec(ctx);
+    if (st != FEMB_OK) return st;
+    FembHMap& H = ctx->hm_vec;
+    if (H.space != ctx->row_spaces[0] || !H.complete || H.words != 2 || H.twins != 2 || !H.sub0 || !H.sublen) return FEMB_ERR_UNSUPPORTED;
+    for (auto& r : H.ranges)
+        if (r.split != 1) return FEMB_ERR_UNSUPPORTED;
+    const int64_t n = us.ndofs / 2, nnodes = ps.ndofs;
+    if (nnodes > n || nnodes != ctx->nnodes) return FEMB_ERR_UNSUPPORTED;
+    if (H.th_state == 0) {
+        int32_t* bad = nullptr;
+        int32_t hbad = 0;
+        CUDA_TRY(ctx, cudaMalloc(&bad, sizeof(int32_t)));
+        cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(int32_t), ctx->stream);
+        if (e == cudaSuccess) {
+            k_th_layout_check<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->colptr, ctx->rowval, H.sub0, H.sublen, n, nnodes, ctx->col_off[0], ctx->col_off[1], ctx->row_off[0],
+                                                                                   ctx->row_off[1], bad);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(bad);
+        if (e != cudaSuccess) return femb_fail(ctx, FEMB_ERR_CUDA, "k_th_layout_check: %s", cudaGetErrorString(e));
+        // (the stores cover the two blocks entirely by construction: the whole pressure run of every velocity column, both velocity runs of every
+        // pressure column; the transposed blocks must at least agree in size)
+        int64_t n01 = 0, n10 = 0;
+        FEMB_TRY(femb_block_entries(ctx, 0, 1, &n01));
+        FEMB_TRY(femb_block_entries(ctx, 1, 0, &n10));
+        H.th_state = (hbad == 0 && n01 == n10) ? 1 : -1;
+    }
+    if (H.th_state != 1) return FEMB_ERR_UNSUPPORTED;
+    if (H.cranges.empty()) {
+        const int64_t nslices = (us.ndofs + 31) / 32;
+        std::vector<int32_t> hptr((size_t)nslices + 1);
+        CUDA_TRY(ctx, cudaMemcpyAsync(hptr.data(), H.slice_ptr, sizeof(int32_t) * (nslices + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<FembHMap::Range> out = H.ranges;
+        for (auto& c : out) {
+            c.maxrows = 1;
+            for (int64_t sl = c.s0; sl < c.s1; sl++) c.maxrows = std::max(c.maxrows, hptr[sl + 1] - hptr[sl]);
+        }
+        H.cranges = out;
+    }
+    FEMB_TRY(femb_hmap_set_canon(ctx, H, true));
+    if (!ctx->threc) FEMB_TRY(femb_alloc(ctx, &ctx->threc, (size_t)ctx->ncells * 4));
+    FEMB_TRY(femb_flush_zero(ctx, true, false));  // (normally a no-op here: the Laplacian has settled the lazy zero)
+    k_th_rec<<<(unsigned)((ctx->ncells + 127) / 128), 128, 0, ctx->stream>>>(ctx->coords, ctx->cellnodes, ctx->cellvol, ctx->ncells, ctx->threc);
+    KERNEL_CHECK(ctx);
+    ThGArgs a;
+    a.rec = ctx->threc; a.slice_ptr = H.slice_ptr; a.map = H.map; a.stride = H.stride; a.colptr = ctx->colptr; a.sublen = H.sublen;
+    a.n = n; a.nnodes = nnodes; a.ucol0 = ctx->col_off[0]; a.pcol0 = ctx->col_off[1]; a.nzval = ctx->nzval; a.factor = factor;
+    uint8_t perm[12][12];
+    femb_p2_role_perm(perm, 2);
+    for (int k = 0; k < 6; k++)
+        for (int r = 0; r < 6; r++) a.perm[k][r] = perm[k][r];
+    const int64_t vend = (nnodes + 31) / 32, send = (n + 31) / 32;  // slices with vertex dofs (they also own the pressure columns) / all slices of component 0
+    size_t maxsmem = 0;
+    auto smem_of = [](const FembHMap::Range& r, int nacc) { return 128 + (size_t)nacc * (size_t)std::max(1, r.maxlen) * 1024 + 4 * 3 * (size_t)r.maxrows * 128; };
+    for (auto& r : H.cranges) {
+        if (r.s0 < vend) maxsmem = std::max(maxsmem, smem_of(r, 4));
+        if (r.s1 > vend && r.s0 < send) maxsmem = std::max(maxsmem, smem_of(r, 2));
+    }
+    if (maxsmem > 200 * 1024) return FEMB_ERR_UNSUPPORTED;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_th_divp_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxsmem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_th_divp_gather, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (auto& r : H.cranges) {
+        for (int part = 0; part < 2; part++) {
+            const int64_t s0 = part == 0 ? r.s0 : std::max(r.s0, vend), s1 = part == 0 ? std::min(r.s1, vend) : std::min(r.s1, send);
+            if (s1 <= s0) continue;
+            a.slice_begin = s0;
+            a.slice_end = s1;
+            a.nacc = part == 0 ? 4 : 2;
+            a.R = std::max(1, r.maxlen);  // (ranges of a block map carry the longest run of the block, not the longest column)
+            a.maxrows = r.maxrows;
+            k_th_divp_gather<<<(unsigned)((s1 - s0 + 3) / 4), 128, smem_of(r, a.nacc), ctx->stream>>>(a);
+            KERNEL_CHECK(ctx);
+        }
+    }
     return FEMB_OK;
 }
 
@@ -340,6 +615,7 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
     RhsDev rhs;
     double* dev_f = nullptr;
     FEMB_TRY(make_rhs(ctx, linear ? rhs_kind : FEMB_RHS_NONE, data, 2, EG.nqp, rhs, &dev_f));
+    const bool zero_at_entry = ctx->zero_pending_A && ctx->zero_mask == ~0ull && !ctx->dirty_A;  // femb_matrix_zero was the last thing that happened to A
     ctx->dirty_A = ctx->dirty_b = true;
     int st = femb_timer_begin(ctx);
     if (st == FEMB_OK && linear) {
@@ -353,7 +629,7 @@ extern "C" int32_t femb_assemble_navierstokes(femb_ctx* ctx, int32_t egu, int32_
         if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, egu, egu, FEMB_OP_GRADIENT, FEMB_OP_GRADIENT, 0, 0, mu, 0, 0.0);
         // Bloc[j,k] = -sum_qp w (g[1,j]+g[4,j]) psi_k * |T| into (u,p) and (p,u) (Example210:293-301,376-380)
         if (st == FEMB_OK) {
-            st = launch_th_divpressure(ctx, egu, eip, -1.0);  // closed form for the P2 / P1 pair on triangles
+            st = launch_th_divpressure(ctx, egu, eip, -1.0, zero_at_entry);  // closed form for the P2 / P1 pair on triangles
             if (st == FEMB_ERR_UNSUPPORTED) st = launch_bilinear(ctx, egu, eip, FEMB_OP_GRADTRACE, FEMB_OP_IDENTITY, 0, 1, -1.0, FEMB_BIL_TRANSPOSE_COPY, 0.0);
         }
         if (st == FEMB_OK && rhs.kind != FEMB_RHS_NONE && !rhs_done) st = launch_linear(ctx, eiu, 0, 1.0, rhs);

@@ -33,6 +33,7 @@ void femb_free_pattern(femb_ctx* ctx) {
     femb_free(&ctx->cellcoef);
     femb_free(&ctx->p2rec);
     femb_free(&ctx->rt0rec);
+    femb_free(&ctx->threc);
     femb_free(&ctx->p2vrhs);
     for (auto& b : ctx->blocks) femb_free(&b.slots);
     ctx->blocks.clear();
@@ -882,6 +883,7 @@ void femb_free_hmap(FembHMap& H) {
     femb_free(&H.vrec);
     femb_free(&H.xsrc);
     H.xsrc_state = 0;
+    H.th_state = 0;
 }
 
 // in-place permutation of the position bytes and first-touch flags of every map entry: role order <-> local dof order

@@ -250,6 +250,27 @@ def test_example210(n, jit):
         assert np.abs(b.entries - b2).max() <= RTOL * max(np.abs(b2).max(), 1e-300)
 
 
+def test_example210_divpressure_owner_computes_and_reductions_agree():
+    """Linear part on a freshly zeroed matrix: the (u,p) / (p,u) blocks are stored by the column owners (k_th_divp_gather); on a matrix
+    that already holds something they are added by the per-cell kernel.  Assembling twice without zeroing must give twice the first."""
+    grid = _grid2d(12, True)
+    FESu, FESp = fb.FESpace(fb.H1Pk(2, 2, 2), grid), fb.FESpace(fb.H1Pk(1, 2, 1), grid)
+    sol = fb.FEVector([FESu, FESp])
+    A, b = fb.FEMatrix([FESu, FESp]), fb.FEVector([FESu, FESp])
+    upd = fb.prepare_assembly(A, b, FESu, FESp, sol, mu=0.3)
+    upd(True, False)
+    ctx = upd.session.ctx
+    first = ctx.matrix_get().copy()
+    S = upd.session
+    egu, eiu, eip = S.evaluator(0, "Gradient"), S.evaluator(0, "Identity"), S.evaluator(1, "Identity")
+    ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, 0.3, True, False, _lib.RHS_NONE, None)  # no femb_matrix_zero in between
+    twice = ctx.matrix_get()
+    assert np.abs(twice - 2.0 * first).max() <= RTOL * np.abs(first).max()
+    ctx.matrix_zero()
+    ctx.assemble_navierstokes(egu._eid, eiu._eid, eip._eid, 0.3, True, False, _lib.RHS_NONE, None)
+    assert np.array_equal(ctx.matrix_get(), first)  # write-once paths: bit-reproducible
+
+
 # ---------------------------------------------------------------------------------------------
 # Hdiv mass + divergence blocks (config C4)
 # ---------------------------------------------------------------------------------------------
